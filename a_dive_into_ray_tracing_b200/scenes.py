@@ -1,0 +1,344 @@
+"""Flattened scenes of the reference's configurations (BASELINE.json `configs`).
+
+The reference hard-codes its scenes inside `main()`s; here they are data:
+  weekend()    rt_in_one_weekend/main.cpp:86-131 random_scene() under glibc's default
+               seed, extracted once from the compiled reference (tools/make_golden.py)
+               and stored float-rounded in tests/golden/weekend_scene.npy;
+  final_cu()   accelerated-rt-cuda/final.cu:100-143 distribution (cuRAND stream not
+               reproducible -> Philox-free numpy generator with the same law);
+  next_week()  rt_next_week/cuda/main.cu:153-198 (moving spheres, checker ground);
+  obj_room()   triangles/cuda/obj_render.cu:384-524 (mesh in a lit, mirrored room).
+"""
+import os
+
+import numpy as np
+
+from .ctypes_defs import (MATERIAL_DT, QUAD_DT, RT_FLAG_DEPTH_BACKGROUND, RT_FLAG_FLIP_NORMALS,
+                          RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_LAMBERTIAN, RT_MAT_METAL,
+                          RT_PROFILE_FINAL_CU, RT_PROFILE_NEXT_WEEK, RT_PROFILE_WEEKEND_CPU, RT_TEX_CHECKER,
+                          RT_TEX_SOLID, SPHERE_DT, TRIANGLE_DT, Scene, camera_from_lookat)
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _mat(mtype, albedo=(0, 0, 0), param=0.0, texture=RT_TEX_SOLID, albedo2=(0, 0, 0)):
+    m = np.zeros((), MATERIAL_DT)
+    m["type"] = mtype
+    m["texture"] = texture
+    m["albedo"] = albedo
+    m["param"] = param
+    m["albedo2"] = albedo2
+    return m
+
+
+def _sphere(c0, r, mat, c1=None, t0=0.0, t1=1.0):
+    s = np.zeros((), SPHERE_DT)
+    s["center0"] = c0
+    s["radius"] = r
+    s["center1"] = c0 if c1 is None else c1
+    s["material"] = mat
+    s["time0"] = t0
+    s["time1"] = t1
+    s["moving"] = 0 if c1 is None else 1
+    return s
+
+
+def scene_from_rows(rows, name="rows"):
+    """rows [n][12] = cx cy cz r kind a0 a1 a2 param (oracle/ref_harness.cpp l0_scene_get).
+    One material per sphere, as the reference allocates them."""
+    rows = np.asarray(rows, np.float64)
+    n = len(rows)
+    spheres = np.zeros(n, SPHERE_DT)
+    mats = np.zeros(n, MATERIAL_DT)
+    spheres["center0"] = rows[:, 0:3]
+    spheres["center1"] = rows[:, 0:3]
+    spheres["radius"] = rows[:, 3]
+    spheres["material"] = np.arange(n)
+    spheres["time1"] = 1.0
+    mats["type"] = rows[:, 4].astype(np.int32)
+    mats["albedo"] = rows[:, 5:8]
+    mats["param"] = rows[:, 8]
+    return Scene(spheres=spheres, materials=mats, name=name)
+
+
+def rows_from_scene(scene):
+    """Inverse of scene_from_rows (float values widened exactly to double)."""
+    n = len(scene.spheres)
+    rows = np.zeros((n, 12), np.float64)
+    rows[:, 0:3] = scene.spheres["center0"]
+    rows[:, 3] = scene.spheres["radius"]
+    m = scene.materials[scene.spheres["material"]]
+    rows[:, 4] = m["type"]
+    rows[:, 5:8] = m["albedo"]
+    rows[:, 8] = m["param"]
+    return rows
+
+
+def weekend_camera(aspect, dtype=np.float64):
+    """main.cpp:304-311: lookfrom (13,2,3), lookat 0, vfov 20, aperture 0.1, focus 10."""
+    return camera_from_lookat((13, 2, 3), (0, 0, 0), (0, 1, 0), 20.0, aspect, 0.1, 10.0, dtype=dtype)
+
+
+def weekend(width=1200, height=800):
+    """Configs 1, 2, 5: the reference's deterministic 487-sphere scene."""
+    rows = np.load(os.path.join(GOLDEN_DIR, "weekend_scene.npy"))
+    sc = scene_from_rows(rows, "weekend")
+    sc.camera = weekend_camera(width / height)
+    sc.sky_gradient = 1
+    sc.t_min = 1e-3
+    sc.max_depth = 50
+    sc.profile = RT_PROFILE_WEEKEND_CPU
+    return sc
+
+
+def _random_spheres(rng, moving):
+    """The 22x22 grid law shared by final.cu:105-131 and main.cu:153-198."""
+    spheres, mats = [], []
+
+    def add(s, m):
+        s["material"] = len(mats)
+        spheres.append(s)
+        mats.append(m)
+
+    R = lambda: np.float32(rng.random())
+    for a in range(-11, 11):
+        for b in range(-11, 11):
+            choose = R()
+            center = (np.float32(a) + R(), np.float32(0.2), np.float32(b) + R())
+            if choose < 0.8:
+                c1 = None
+                if moving:
+                    c1 = (center[0], center[1] + R() * np.float32(0.5), center[2])
+                add(_sphere(center, 0.2, 0, c1), _mat(RT_MAT_LAMBERTIAN, (R() * R(), R() * R(), R() * R())))
+            elif choose < 0.95:
+                alb = tuple(np.float32(0.5) * (np.float32(1.0) + R()) for _ in range(3))
+                add(_sphere(center, 0.2, 0), _mat(RT_MAT_METAL, alb, np.float32(0.5) * R()))
+            else:
+                add(_sphere(center, 0.2, 0), _mat(RT_MAT_DIELECTRIC, param=1.5))
+    add(_sphere((0, 1, 0), 1.0, 0), _mat(RT_MAT_DIELECTRIC, param=1.5))
+    add(_sphere((-4, 1, 0), 1.0, 0), _mat(RT_MAT_LAMBERTIAN, (0.4, 0.2, 0.1)))
+    add(_sphere((4, 1, 0), 1.0, 0), _mat(RT_MAT_METAL, (0.7, 0.6, 0.5), 0.0))
+    return spheres, mats
+
+
+def final_cu(width=1200, height=800, seed=1984):
+    """accelerated-rt-cuda/final.cu:100-143: 488 spheres, ground at (0,-1000,-1), vfov 30."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    spheres, mats = _random_spheres(rng, moving=False)
+    ground = _sphere((0, -1000.0, -1), 1000, 0)
+    ground["material"] = len(mats)
+    spheres.insert(0, ground)
+    mats.append(_mat(RT_MAT_LAMBERTIAN, (0.5, 0.5, 0.5)))
+    sc = Scene(spheres=np.array(spheres, SPHERE_DT), materials=np.array(mats, MATERIAL_DT), name="final_cu")
+    sc.camera = camera_from_lookat((13, 2, 3), (0, 0, 0), (0, 1, 0), 30.0, np.float32(width) / np.float32(height),
+                                   0.1, 10.0, dtype=np.float32)
+    sc.profile = RT_PROFILE_FINAL_CU
+    return sc
+
+
+def next_week(width=1200, height=800, seed=1984):
+    """Config 4 — rt_next_week/cuda/main.cu:153-198 + :402-407,462-465: checker ground,
+    80 % moving lambertian, camera vfov 20, aperture 0.05, focus |lookfrom-lookat|,
+    shutter [0,1], constant background (0.7,0.8,1.0)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    spheres, mats = _random_spheres(rng, moving=True)
+    ground = _sphere((0, -1000.0, -1), 1000, 0)
+    ground["material"] = len(mats)
+    spheres.insert(0, ground)
+    mats.append(_mat(RT_MAT_LAMBERTIAN, (0.2, 0.3, 0.1), texture=RT_TEX_CHECKER, albedo2=(0.9, 0.9, 0.9)))
+    sc = Scene(spheres=np.array(spheres, SPHERE_DT), materials=np.array(mats, MATERIAL_DT), name="next_week")
+    lookfrom = np.array([13, 2, 3], np.float32)
+    focus = np.sqrt(np.dot(lookfrom, lookfrom), dtype=np.float32)
+    sc.camera = camera_from_lookat(lookfrom, (0, 0, 0), (0, 1, 0), 20.0, np.float32(width) / np.float32(height),
+                                   0.05, focus, 0.0, 1.0, dtype=np.float32)
+    sc.background = (0.70, 0.80, 1.00)
+    sc.sky_gradient = 0
+    sc.t_min = 1e-3
+    sc.profile = RT_PROFILE_NEXT_WEEK
+    return sc
+
+
+# ---------------------------------------------------------------- triangles / OBJ
+
+def triangle_record(v0, v1, v2, vn0, vn1, vn2, material):
+    """triangle ctor — triangles/cuda/include/triangle.h:17-53 (float32 arithmetic):
+    face normal = +-cross(v1-v0, v2-v0), oriented to agree with -(vn0+vn1+vn2)/3."""
+    f = np.float32
+    v0, v1, v2 = (np.asarray(x, f) for x in (v0, v1, v2))
+    vn0, vn1, vn2 = (np.asarray(x, f) for x in (vn0, vn1, vn2))
+    avg = -(((vn0 + vn1).astype(f) + vn2).astype(f)) * (f(1) / f(3.0))
+    ab = (v1 - v0).astype(f)
+    ac = (v2 - v0).astype(f)
+    cand = np.array([ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]], f)
+    d = f(f(f(cand[0] * avg[0]) + f(cand[1] * avg[1])) + f(cand[2] * avg[2]))
+    n = cand if d > 0 else -cand
+    t = np.zeros((), TRIANGLE_DT)
+    t["v0"], t["v1"], t["v2"], t["normal"], t["material"] = v0, v1, v2, n, material
+    return t
+
+
+def read_obj_triangles(path):
+    """read_triangles — triangles/cuda/include/triangle.h:217-300: `v`, `vn`, `f a/b/c`
+    x3 (or a//c); the face is emitted with vertex indices [6],[3],[0] and normal indices
+    [8],[5],[2] of the flattened a/b/c list, i.e. with REVERSED winding. Returns
+    (v[n][3][3], vn[n][3][3]) float32, un-transformed."""
+    vs, vns, tv, tn = [], [], [], []
+    with open(path) as fh:
+        for line in fh:
+            parts = line.split()
+            if not parts:
+                continue
+            if parts[0] == "vn":
+                vns.append([float(x) for x in parts[1:4]])
+            elif parts[0] == "v":
+                vs.append([float(x) for x in parts[1:4]])
+            elif parts[0] == "f":
+                idx = []
+                for sec in parts[1:]:
+                    for num in sec.split("/"):
+                        idx.append(int(num) - 1 if num else -1)
+                    # std::getline drops a trailing empty field: "1//" cannot occur in valid OBJ
+                tv.append([vs[idx[6]], vs[idx[3]], vs[idx[0]]])
+                tn.append([vns[idx[8]], vns[idx[5]], vns[idx[2]]])
+    return np.array(tv, np.float32).reshape(-1, 3, 3), np.array(tn, np.float32).reshape(-1, 3, 3)
+
+
+def make_blob_mesh(path, subdivisions=2, seed=1984):
+    """Procedural stand-in for the missing objs/blender_monkey.obj (SURVEY.md §7 hard part
+    6): a displaced, subdivided icosphere (subdivisions=2 -> 320 faces, 3 -> 1280) written
+    in the `v` / `vn` / `f a//n b//n c//n` form the reference parser accepts."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    verts = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+             (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    verts = [np.array(v, np.float64) / np.linalg.norm(v) for v in verts]
+    faces = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2),
+             (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11),
+             (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = verts[a] + verts[b]
+                verts.append(m / np.linalg.norm(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+
+        for a, b, c in faces:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        faces = nf
+    V = np.array(verts)
+    rng = np.random.Generator(np.random.Philox(seed))
+    k = rng.normal(size=(4, 3))
+    disp = 1.0 + 0.12 * np.sin(3.0 * V @ k[0]) + 0.08 * np.sin(5.0 * V @ k[1] + 1.0) + 0.05 * np.cos(7.0 * V @ k[2])
+    P = V * disp[:, None]
+    # vertex normals: area-weighted face normals
+    N = np.zeros_like(P)
+    for a, b, c in faces:
+        fn = np.cross(P[b] - P[a], P[c] - P[a])
+        N[a] += fn
+        N[b] += fn
+        N[c] += fn
+    N /= np.linalg.norm(N, axis=1)[:, None]
+    with open(path, "w") as fh:
+        fh.write("# procedural blob mesh (stand-in asset), %d faces\n" % len(faces))
+        for p in P:
+            fh.write("v %.6f %.6f %.6f\n" % tuple(p))
+        for n in N:
+            fh.write("vn %.6f %.6f %.6f\n" % tuple(n))
+        for a, b, c in faces:
+            fh.write("f %d//%d %d//%d %d//%d\n" % (a + 1, a + 1, b + 1, b + 1, c + 1, c + 1))
+    return len(faces)
+
+
+def bake_instance(tv, scale=2.5, angle_deg=30.0, offset=(0.0, 1.5, 0.0)):
+    """translate(rotate_y(triangle(v*scale), angle), offset) — obj_render.cu:498-511 —
+    baked into the vertices. rotate_y::hit maps object p to world as
+    x' = cos*x + sin*z, z' = -sin*x + cos*z (rt_next_week/cuda/hittable.h:176-180);
+    translate then adds the offset (:73). float32 throughout."""
+    f = np.float32
+    rad = f(angle_deg) * f(3.1415926535897932385) / f(180.0)
+    s, c = f(np.sin(rad, dtype=f)), f(np.cos(rad, dtype=f))
+    v = (np.asarray(tv, f) * f(scale)).astype(f)
+    x = (c * v[..., 0] + s * v[..., 2]).astype(f)
+    z = (-s * v[..., 0] + c * v[..., 2]).astype(f)
+    out = np.stack([x, v[..., 1], z], -1).astype(f)
+    return (out + np.asarray(offset, f)).astype(f)
+
+
+def rotate_normals(tn, angle_deg=30.0):
+    f = np.float32
+    rad = f(angle_deg) * f(3.1415926535897932385) / f(180.0)
+    s, c = f(np.sin(rad, dtype=f)), f(np.cos(rad, dtype=f))
+    n = np.asarray(tn, f)
+    x = (c * n[..., 0] + s * n[..., 2]).astype(f)
+    z = (-s * n[..., 0] + c * n[..., 2]).astype(f)
+    return np.stack([x, n[..., 1], z], -1).astype(f)
+
+
+def obj_room(obj_path=None, width=800, height=800, subdivisions=2):
+    """Config 3 — triangles/cuda/obj_render.cu:384-524 (obj_model) with camera
+    :716-724,736-738: (1,3,7)->(0,2,0), vfov 60, aperture 0, black background,
+    t_min 1e-5 (:33), flipping normals (include/hittable.h:29)."""
+    if obj_path is None:
+        obj_path = os.path.join(GOLDEN_DIR, "blob_%d.obj" % subdivisions)
+        if not os.path.exists(obj_path):
+            make_blob_mesh(obj_path, subdivisions)
+    tv, tn = read_obj_triangles(obj_path)
+    mats, spheres, quads = [], [], []
+
+    def M(m):
+        mats.append(m)
+        return len(mats) - 1
+
+    c256 = lambda r, g, b: (np.float32(r) / np.float32(256.0), np.float32(g) / np.float32(256.0),
+                            np.float32(b) / np.float32(256.0))
+    blue_1 = M(_mat(RT_MAT_LAMBERTIAN, c256(0, 129, 167)))
+    red_1 = M(_mat(RT_MAT_LAMBERTIAN, c256(240, 113, 103)))
+    yellow_1 = M(_mat(RT_MAT_LAMBERTIAN, c256(253, 252, 220)))
+    gold = M(_mat(RT_MAT_METAL, c256(255, 215, 0), 0.5))
+    light = M(_mat(RT_MAT_DIFFUSE_LIGHT, (5.0, 5.0, 5.0)))  # color(20,20,20)*0.25
+    pink = M(_mat(RT_MAT_DIFFUSE_LIGHT, tuple(np.float32(2) * np.array(c256(255, 59, 148), np.float32))))
+    green = M(_mat(RT_MAT_DIFFUSE_LIGHT, tuple(np.float32(2) * np.array(c256(166, 253, 41), np.float32))))
+    mirror = lambda: M(_mat(RT_MAT_METAL, (0.8, 0.8, 0.9), 0.0))
+
+    def quad(axis, a0, a1, b0, b1, k, m):
+        q = np.zeros((), QUAD_DT)
+        q["axis"], q["a0"], q["a1"], q["b0"], q["b1"], q["k"], q["material"] = axis, a0, a1, b0, b1, k, m
+        quads.append(q)
+
+    f = np.float32
+    spheres.append(_sphere((-1, f(3.69) + f(1), -2.5), 0.3, pink))
+    spheres.append(_sphere((1, f(3.69) + f(1), -2.5), 0.3, green))
+    XZ, XY, YZ = 1, 2, 0
+    quad(XZ, -4, 4, 3, 4, 4 + 1 - 0.01, light)
+    quad(XZ, -4, 4, 2, 3, -4 + 0.01, light)
+    quad(XY, -4, 4, -4, 4 + 1, -4, yellow_1)
+    quad(XY, -3, 3, -4, 4 + 1, -3.999, mirror())
+    quad(XZ, -40, 40, -40, 40, -4, red_1)
+    quad(XZ, -40, 40, -40, 40, 4 + 1, red_1)
+    quad(YZ, -4, 4 + 1, -4, 4, -4, blue_1)
+    quad(YZ, -4, 4 + 1, -4, 4, 4, blue_1)
+    quad(YZ, -1, 3 + 1, -4, 4, -3.999, mirror())
+    quad(YZ, -1, 3 + 1 - 0.001, -4, 4, 3.999, mirror())
+    wv = bake_instance(tv)
+    wn = rotate_normals(tn)
+    tris = np.zeros(len(wv), TRIANGLE_DT)
+    for i in range(len(wv)):
+        tris[i] = triangle_record(wv[i, 0], wv[i, 1], wv[i, 2], wn[i, 0], wn[i, 1], wn[i, 2], gold)
+    sc = Scene(spheres=np.array(spheres, SPHERE_DT), triangles=tris, quads=np.array(quads, QUAD_DT),
+               materials=np.array(mats, MATERIAL_DT), name="obj_room")
+    lookfrom = np.array([1, 3, 7], np.float32)
+    lookat = np.array([0, 2, 0], np.float32)
+    dv = lookfrom - lookat
+    focus = np.sqrt(np.dot(dv, dv), dtype=np.float32)
+    sc.camera = camera_from_lookat(lookfrom, lookat, (0, 1, 0), 60.0, np.float32(width) / np.float32(height), 0.0,
+                                   focus, 0.0, 1.0, dtype=np.float32)
+    sc.background = (0.0, 0.0, 0.0)
+    sc.sky_gradient = 0
+    sc.t_min = 1e-5
+    sc.flags = RT_FLAG_FLIP_NORMALS | RT_FLAG_DEPTH_BACKGROUND
+    sc.profile = RT_PROFILE_NEXT_WEEK
+    return sc

@@ -1,0 +1,226 @@
+/* rt_capi.h — C ABI of the B200 path-tracer core (libb200rt.so).
+ *
+ * The reference (xyloid/a_dive_into_ray_tracing) has no FFI; its renderers are
+ * single translation units whose host code launches CUDA kernels directly.
+ * Each entry point below replaces one of those launch sites / host loops and
+ * is what a maintainer's host C++ would call instead:
+ *
+ *   rt_create / rt_destroy      cudaMalloc/cudaFree + checkCudaErrors->exit(99)
+ *                               accelerated-rt-cuda/final.cu:13-24,176-203,234-245
+ *   rt_scene_upload             create_world<<<1,1>>> (device-side `new` of every
+ *                               sphere/material/camera) final.cu:100-143,
+ *                               rt_next_week/cuda/main.cu:386-467,
+ *                               triangles/cuda/obj_render.cu:631-741
+ *   rt_accel_build              `new bvh_node(list,0,n,t0,t1,rng)`
+ *                               rt_next_week/cuda/bvh.h:139-196 (one GPU thread)
+ *   rt_trace_closest            hittable::hit — hittable_list.h:20-34 (CPU),
+ *                               accelerated-rt-cuda/hittable_list.h:22-37,
+ *                               rt_next_week/cuda/bvh.h:78-137   (parity hook)
+ *   rt_render                   worker() rt_in_one_weekend/main.cpp:267-290;
+ *                               render_init+render<<<grid,8x8>>> final.cu:62-96,
+ *                               main.cu:113-149, obj_render.cu:94-130
+ *   rt_resolve                  write_color rt_in_one_weekend/color.h:14-28;
+ *                               the /ns, sqrt in final.cu:91-95 and the
+ *                               int(255.99*x) loop final.cu:223-232
+ *   rt_last_error               the std::cerr text of check_cuda final.cu:15-24
+ *
+ * Conventions: plain pointers and sizes only; every function returns an
+ * rt_status (0 = OK) and never throws, prints or exits; the caller owns all
+ * host buffers, the library owns all device buffers it allocates; a context is
+ * bound to ONE CUDA device and is single-host-thread; separate contexts are
+ * independent (multi-GPU = one context per device, see rt_render's spp range).
+ *
+ * Pixel indexing everywhere: index = j*W + i with j = 0 the BOTTOM row, as in
+ * the reference (main.cpp:274-275, final.cu:80-81); writers flip rows.
+ */
+#ifndef RT_CAPI_H
+#define RT_CAPI_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_CAPI_VERSION 1
+
+typedef struct rt_ctx rt_ctx;
+
+typedef enum rt_status {
+  RT_OK = 0,
+  RT_ERR_INVALID = 1,  /* bad argument / malformed scene */
+  RT_ERR_CUDA = 2,     /* a CUDA runtime call failed; see rt_last_error */
+  RT_ERR_STATE = 3,    /* call order (e.g. render before scene upload) */
+  RT_ERR_NOMEM = 4,
+  RT_ERR_NODEVICE = 5  /* no CUDA device: there is NO CPU fallback */
+} rt_status;
+
+/* Semantic profile = which reference renderer defines the expected image
+ * (SURVEY.md §7 table). */
+typedef enum rt_profile {
+  RT_PROFILE_WEEKEND_CPU = 0, /* rt_in_one_weekend (book v3, front_face, true Lambertian) */
+  RT_PROFILE_FINAL_CU = 1,    /* accelerated-rt-cuda/final.cu */
+  RT_PROFILE_NEXT_WEEK = 2    /* rt_next_week/cuda + triangles/cuda (emission, background) */
+} rt_profile;
+
+/* rt_config.flags / rt_scene_desc.flags */
+#define RT_FLAG_FLIP_NORMALS 1u      /* triangles/cuda/include/hittable.h:29 (normal faces the ray) */
+#define RT_FLAG_DEPTH_BACKGROUND 2u  /* obj_render.cu:78-83: depth exhausted -> unwound background */
+#define RT_FLAG_COUNTERS 4u          /* maintain node/prim test counters (slower kernel variant) */
+
+typedef enum rt_prim_type { RT_PRIM_SPHERE = 0, RT_PRIM_TRIANGLE = 1, RT_PRIM_QUAD = 2 } rt_prim_type;
+/* primitive id returned by rt_trace_closest: (type << 28) | index-within-type; -1 = miss */
+#define RT_PRIM_ID(type, index) ((int32_t)(((uint32_t)(type) << 28) | (uint32_t)(index)))
+#define RT_PRIM_TYPE_OF(id) ((int)(((uint32_t)(id)) >> 28))
+#define RT_PRIM_INDEX_OF(id) ((int)(((uint32_t)(id)) & 0x0FFFFFFFu))
+
+typedef enum rt_material_type {
+  RT_MAT_LAMBERTIAN = 0,
+  RT_MAT_METAL = 1,
+  RT_MAT_DIELECTRIC = 2,
+  RT_MAT_DIFFUSE_LIGHT = 3
+} rt_material_type;
+
+typedef enum rt_texture_type { RT_TEX_SOLID = 0, RT_TEX_CHECKER = 1 } rt_texture_type;
+
+typedef struct rt_config {
+  int32_t device;   /* CUDA device ordinal */
+  int32_t profile;  /* rt_profile */
+  uint32_t flags;
+  uint32_t reserved;
+  uint64_t seed;    /* Philox key */
+} rt_config;
+
+/* sphere / moving_sphere (sphere.h:10-11, moving_sphere.h:12-15) */
+typedef struct rt_sphere {
+  float center0[3];
+  float radius;      /* may be negative (hollow-glass trick, main.cpp:209) */
+  float center1[3];  /* == center0 when not moving */
+  int32_t material;
+  float time0, time1;
+  int32_t moving;    /* 0 = sphere, 1 = moving_sphere */
+  int32_t reserved;
+} rt_sphere;
+
+/* triangle (triangles/cuda/include/triangle.h:17-53): vertices as stored by the
+ * ctor and the oriented, UN-normalised face normal it computes (:42-44). */
+typedef struct rt_triangle {
+  float v0[3], v1[3], v2[3];
+  float normal[3];
+  int32_t material;
+} rt_triangle;
+
+/* xy_rect / xz_rect / yz_rect (aarect.h:15-17,70-72,126-128).
+ * axis = the constant axis: 2 -> xy_rect (a=x,b=y), 1 -> xz_rect (a=x,b=z),
+ * 0 -> yz_rect (a=y,b=z). */
+typedef struct rt_quad {
+  int32_t axis;
+  float a0, a1, b0, b1, k;
+  int32_t material;
+} rt_quad;
+
+typedef struct rt_material {
+  int32_t type;      /* rt_material_type */
+  int32_t texture;   /* rt_texture_type (albedo / emit) */
+  float albedo[3];   /* solid colour, or checker `even` (texture.h:33-53) */
+  float param;       /* metal: fuzz (already clamped to <=1); dielectric: index */
+  float albedo2[3];  /* checker `odd` */
+  float reserved;
+} rt_material;
+
+/* camera as its constructor leaves it (camera.h:8-45; rt_next_week/cuda/camera.h:25-61) */
+typedef struct rt_camera {
+  float origin[3];
+  float lower_left_corner[3];
+  float horizontal[3];
+  float vertical[3];
+  float u[3], v[3], w[3];
+  float lens_radius;
+  float time0, time1;
+} rt_camera;
+
+typedef struct rt_scene_desc {
+  int32_t n_spheres;   const rt_sphere *spheres;
+  int32_t n_triangles; const rt_triangle *triangles;
+  int32_t n_quads;     const rt_quad *quads;
+  int32_t n_materials; const rt_material *materials;
+  rt_camera camera;
+  float background[3]; /* profile 2: constant background (main.cu:96) */
+  int32_t sky_gradient;/* 1: lerp(white,(.5,.7,1)) miss shader (main.cpp:80-82) */
+  float t_min;         /* 1e-3 (main.cpp:65) / 1e-5 (obj_render.cu:33) */
+  int32_t max_depth;   /* 50 */
+  uint32_t flags;      /* RT_FLAG_FLIP_NORMALS | RT_FLAG_DEPTH_BACKGROUND */
+  uint32_t reserved;
+} rt_scene_desc;
+
+/* 32-byte packed BVH node as downloaded by rt_accel_download (device layout).
+ * Threaded (stackless) traversal: on a box hit go to `child` (inner) or test
+ * the primitive (leaf) and go to `escape`; on a miss go to `escape`.
+ * index == n_nodes terminates. */
+typedef struct rt_bvh_node {
+  float bmin[3];
+  int32_t escape;
+  float bmax[3];
+  int32_t payload; /* >= 0: index of first child (inner); < 0: ~prim_id (leaf) */
+} rt_bvh_node;
+
+typedef struct rt_stats_t {
+  uint64_t paths;          /* camera rays started since the last rt_stats_reset */
+  uint64_t segments;       /* closest-hit queries ("path-bounces") */
+  uint64_t box_tests;      /* only with RT_FLAG_COUNTERS */
+  uint64_t prim_tests;     /* only with RT_FLAG_COUNTERS */
+  uint64_t kernel_launches;/* kernels of this library launched */
+  float ms_upload, ms_build, ms_render, ms_resolve; /* last call of each phase (CUDA events) */
+  int32_t n_nodes, n_big_prims, smem_bytes, block_threads, grid_blocks, regs_per_thread;
+} rt_stats_t;
+
+int rt_version(void);
+int rt_device_count(void);
+
+int rt_create(rt_ctx **out, const rt_config *cfg);
+void rt_destroy(rt_ctx *ctx);
+const char *rt_last_error(const rt_ctx *ctx);
+
+int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *scene);
+
+/* quality: 0 = LBVH (Morton + radix sort + Karras), 1 = + SAH refinement. */
+int rt_accel_build(rt_ctx *ctx, int quality);
+int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nodes,
+                      int32_t *big_prims, int cap_big, int *n_big);
+
+/* rays: [n][8] floats = origin.xyz, time, direction.xyz, unused. use_accel 0 =
+ * brute force over the flattened arrays, 1 = through the BVH. */
+int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel,
+                     int32_t *prim_id, float *t);
+
+/* Accumulate samples [spp_begin, spp_begin+spp_count) of every pixel into the
+ * context's accumulation buffer (float4 per pixel: sum R,G,B and sample count).
+ * Counter-based RNG: the result for a given (pixel, sample) does not depend on
+ * which call / which GPU rendered it. */
+int rt_render(rt_ctx *ctx, int width, int height, int spp_begin, int spp_count);
+/* Same, into a caller-provided DEVICE buffer (float[H*W*4]) on a caller stream
+ * (cudaStream_t as void*; NULL = the context's stream). No host sync. */
+int rt_render_device(rt_ctx *ctx, int width, int height, int spp_begin, int spp_count, float *d_accum,
+                     void *stream);
+int rt_accum_clear(rt_ctx *ctx);
+int rt_accum_download(rt_ctx *ctx, float *rgba, size_t n_floats);     /* host <- device */
+int rt_accum_upload(rt_ctx *ctx, int width, int height, const float *rgba, size_t n_floats); /* resume */
+void *rt_accum_device_ptr(rt_ctx *ctx);
+
+/* Resolve = /count, sqrt (gamma 2), clamp, quantise — per profile:
+ * 0: int(256*clamp(sqrt(x),0,0.999)) color.h:21-27; 1,2: int(255.99*sqrt(x)) clamped to 255.
+ * linear_rgb: [H][W][3] mean radiance (bottom row first) or NULL;
+ * rgb8: [H][W][3] bytes, TOP row first (PPM order) or NULL. */
+int rt_resolve(rt_ctx *ctx, float *linear_rgb, uint8_t *rgb8);
+int rt_resolve_device(rt_ctx *ctx, int width, int height, const float *d_accum, float *linear_rgb,
+                      uint8_t *rgb8, void *stream);
+
+int rt_stats(rt_ctx *ctx, rt_stats_t *out);
+int rt_stats_reset(rt_ctx *ctx);
+int rt_sync(rt_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_CAPI_H */
