@@ -1,0 +1,729 @@
+// b200rt.cu — the C ABI (include/rt_capi.h) over the sm_100a kernels.
+// Single translation unit: nvcc -gencode arch=compute_100a,code=sm_100a (Makefile).
+// There is NO CPU fallback in this library: without a CUDA device rt_create fails
+// with RT_ERR_NODEVICE.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh_build.cuh"
+#include "scene_flatten.h"
+#include "render_kernels.cuh"
+
+#define RT_MAX_BIG 32
+#define RT_BIG_FRAC 0.30f
+#define RT_BIG_ROUNDS 3
+
+// ------------------------------------------------------------------ build kernels
+__global__ void k_prim_box(BuildArrays B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B.n_prims) body_prim_box(B, i);
+}
+__global__ void k_classify(BuildArrays B, int round, float frac) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B.n_prims) body_classify(B, i, round, frac);
+}
+__global__ void k_morton(BuildArrays B, int final_round) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B.n_pad) body_morton(B, i, final_round);
+}
+__global__ void k_bitonic(unsigned long long *a, int n_pad, int j, int k) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) body_bitonic(a, i, j, k);
+}
+// all (k, j) steps with j < tile inside one block's shared memory
+__global__ void k_bitonic_smem(unsigned long long *a, int n_pad, int k_begin, int k_end, int j_begin) {
+  extern __shared__ unsigned long long s_keys[];
+  const int tile = blockDim.x * 2;
+  const int base = blockIdx.x * tile;
+  for (int i = threadIdx.x; i < tile; i += blockDim.x) s_keys[i] = a[base + i];
+  __syncthreads();
+  for (int k = k_begin; k <= k_end; k <<= 1) {
+    for (int j = (k == k_begin ? j_begin : k >> 1); j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < tile; i += blockDim.x) {
+        int gi = base + i, ixj = i ^ j;
+        if (ixj > i) {
+          unsigned long long x = s_keys[i], y = s_keys[ixj];
+          bool up = (gi & k) == 0;
+          if ((x > y) == up) { s_keys[i] = y; s_keys[ixj] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < tile; i += blockDim.x) a[base + i] = s_keys[i];
+}
+__global__ void k_karras(BuildArrays B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B.n_small - 1) body_karras(B, i);
+}
+__global__ void k_fit(BuildArrays B, int rotate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B.n_small) body_fit(B, i, rotate);
+}
+__global__ void k_pack(BuildArrays B) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * B.n_small - 1) body_pack(B, i);
+}
+
+// ------------------------------------------------------------------ context
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+struct rt_ctx {
+  rt_config cfg;
+  std::string err;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 0, max_smem_optin = 0;
+  // host copy of the scene
+  bool have_scene = false, have_accel = false;
+  std::vector<rt_sphere> spheres;
+  std::vector<rt_triangle> tris;
+  std::vector<rt_quad> quads;
+  std::vector<rt_material> mats;
+  rt_scene_desc desc;
+  bool general = false;
+  // device scene
+  std::vector<DevBuf *> owned;
+  DevBuf d_nodes, d_sph, d_sph_mv, d_sph_t0, d_tri, d_tri_n, d_quad, d_sph_mat, d_tri_mat, d_quad_mat, d_mats, d_big,
+      d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad;
+  DevScene S;
+  DevCamera cam;
+  ShadeParams sp;
+  std::vector<int32_t> big_ids;
+  // frame
+  int W = 0, H = 0;
+  DevBuf d_accum, d_partial, d_counter, d_stats, d_linear, d_rgb8, d_rays, d_ids, d_ts;
+  rt_stats_t stats;
+  unsigned long long launches = 0;
+};
+
+static int fail(rt_ctx *c, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      return fail(ctx, RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static size_t pad16(size_t b) { return (b + 15) & ~(size_t)15; }
+
+static int dev_reserve(rt_ctx *ctx, DevBuf &b, size_t bytes) {
+  bytes = pad16(std::max<size_t>(bytes, 16));
+  if (b.bytes >= bytes) return RT_OK;
+  if (b.p) CK(cudaFree(b.p));
+  b.p = nullptr; b.bytes = 0;
+  CK(cudaMalloc(&b.p, bytes));
+  b.bytes = bytes;
+  return RT_OK;
+}
+static int dev_upload(rt_ctx *ctx, DevBuf &b, const void *src, size_t bytes) {
+  int rc = dev_reserve(ctx, b, bytes);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(b.p, 0, b.bytes, ctx->stream));
+  if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return RT_OK;
+}
+static void dev_free(DevBuf &b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr; b.bytes = 0;
+}
+
+extern "C" {
+
+int rt_version(void) { return RT_CAPI_VERSION; }
+
+int rt_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+const char *rt_last_error(const rt_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int rt_create(rt_ctx **out, const rt_config *cfg) {
+  if (!out || !cfg) return RT_ERR_INVALID;
+  *out = nullptr;
+  if (cfg->profile < 0 || cfg->profile > 2) return RT_ERR_INVALID;
+  int n = rt_device_count();
+  if (n <= 0) return RT_ERR_NODEVICE;
+  if (cfg->device < 0 || cfg->device >= n) return RT_ERR_INVALID;
+  rt_ctx *ctx = new (std::nothrow) rt_ctx();
+  if (!ctx) return RT_ERR_NOMEM;
+  ctx->cfg = *cfg;
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  memset(&ctx->S, 0, sizeof ctx->S);
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+  if (e == cudaSuccess)
+    e = cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return RT_ERR_CUDA;
+  }
+  *out = ctx;
+  return RT_OK;
+}
+
+void rt_destroy(rt_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  DevBuf *all[] = {&ctx->d_nodes, &ctx->d_sph, &ctx->d_sph_mv, &ctx->d_sph_t0, &ctx->d_tri, &ctx->d_tri_n, &ctx->d_quad,
+                   &ctx->d_sph_mat, &ctx->d_tri_mat, &ctx->d_quad_mat, &ctx->d_mats, &ctx->d_big, &ctx->d_sph_is_big,
+                   &ctx->d_raw_sph, &ctx->d_raw_tri, &ctx->d_raw_quad, &ctx->d_accum, &ctx->d_partial, &ctx->d_counter,
+                   &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts};
+  for (DevBuf *b : all) dev_free(*b);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int rt_sync(rt_ctx *ctx) {
+  if (!ctx) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RT_OK;
+}
+
+// Flatten the scene description into the device SoA layout (rt_common.cuh DevScene).
+int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
+  if (!ctx || !sc) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  HostFlat F;
+  {
+    int frc = flatten_scene(sc, ctx->cfg.profile, F, ctx->err);
+    if (frc) return frc;
+  }
+  const int profile = ctx->cfg.profile;
+  const bool any_moving = F.any_moving;
+  ctx->spheres.assign(sc->spheres, sc->spheres + sc->n_spheres);
+  ctx->tris.assign(sc->triangles, sc->triangles + sc->n_triangles);
+  ctx->quads.assign(sc->quads, sc->quads + sc->n_quads);
+  ctx->mats.assign(sc->materials, sc->materials + sc->n_materials);
+  ctx->desc = *sc;
+  ctx->desc.spheres = ctx->spheres.data();
+  ctx->desc.triangles = ctx->tris.data();
+  ctx->desc.quads = ctx->quads.data();
+  ctx->desc.materials = ctx->mats.data();
+  ctx->general = (profile == RT_PROFILE_NEXT_WEEK);
+
+  CK(cudaEventRecord(ctx->ev0, ctx->stream));
+  const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, nm = sc->n_materials;
+  int rc;
+#define UP(buf, vec) \
+  if ((rc = dev_upload(ctx, ctx->buf, (vec).data(), (vec).size() * sizeof((vec)[0])))) return rc
+  UP(d_sph, F.sph); UP(d_sph_mv, F.sph_mv); UP(d_sph_t0, F.sph_t0); UP(d_tri, F.tri); UP(d_tri_n, F.tri_n); UP(d_quad, F.quad);
+  UP(d_sph_mat, F.sph_mat); UP(d_tri_mat, F.tri_mat); UP(d_quad_mat, F.quad_mat); UP(d_mats, F.mats);
+  UP(d_raw_sph, ctx->spheres); UP(d_raw_tri, ctx->tris); UP(d_raw_quad, ctx->quads);
+#undef UP
+  std::vector<uint8_t> nobig(std::max(ns, 1), 0);
+  if ((rc = dev_upload(ctx, ctx->d_sph_is_big, nobig.data(), nobig.size()))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_big, 16))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_nodes, 32))) return rc;
+
+  DevScene &S = ctx->S;
+  S.nodes = (const float4 *)ctx->d_nodes.p;
+  S.sph = (const float4 *)ctx->d_sph.p;
+  S.sph_mv = (const float4 *)ctx->d_sph_mv.p;
+  S.sph_t0 = (const float *)ctx->d_sph_t0.p;
+  S.tri = (const float4 *)ctx->d_tri.p;
+  S.tri_n = (const float4 *)ctx->d_tri_n.p;
+  S.quad = (const float4 *)ctx->d_quad.p;
+  S.sph_mat = (const int32_t *)ctx->d_sph_mat.p;
+  S.tri_mat = (const int32_t *)ctx->d_tri_mat.p;
+  S.quad_mat = (const int32_t *)ctx->d_quad_mat.p;
+  S.mats = (const float4 *)ctx->d_mats.p;
+  S.big = (const int32_t *)ctx->d_big.p;
+  S.n_nodes = 0; S.n_big = 0;
+  S.n_spheres = ns; S.n_tris = nt; S.n_quads = nq; S.n_mats = nm;
+  S.any_moving = any_moving ? 1 : 0;
+
+  const rt_camera &c = sc->camera;
+  ctx->cam.origin = v3_from(c.origin);
+  ctx->cam.llc = v3_from(c.lower_left_corner);
+  ctx->cam.horizontal = v3_from(c.horizontal);
+  ctx->cam.vertical = v3_from(c.vertical);
+  ctx->cam.u = v3_from(c.u);
+  ctx->cam.v = v3_from(c.v);
+  ctx->cam.lens_radius = c.lens_radius;
+  ctx->cam.time0 = c.time0;
+  ctx->cam.time1 = c.time1;
+  ctx->sp.background = v3_from(sc->background);
+  ctx->sp.sky_gradient = sc->sky_gradient;
+  ctx->sp.flags = sc->flags | ctx->cfg.flags;
+  ctx->sp.t_min = sc->t_min;
+  ctx->sp.max_depth = sc->max_depth;
+  CK(cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaEventElapsedTime(&ctx->stats.ms_upload, ctx->ev0, ctx->ev1));
+  ctx->have_scene = true;
+  ctx->have_accel = false;
+  ctx->big_ids.clear();
+  ctx->stats.n_nodes = 0;
+  ctx->stats.n_big_prims = 0;
+  return RT_OK;
+}
+
+int rt_accel_build(rt_ctx *ctx, int quality) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->have_scene) return fail(ctx, RT_ERR_STATE, "rt_accel_build before rt_scene_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = ctx->stream;
+  const int ns = ctx->S.n_spheres, nt = ctx->S.n_tris, nq = ctx->S.n_quads;
+  const int n = ns + nt + nq;
+  ctx->big_ids.clear();
+  ctx->S.n_nodes = 0; ctx->S.n_big = 0;
+  ctx->stats.n_nodes = 0; ctx->stats.n_big_prims = 0;
+  if (n == 0) { ctx->have_accel = true; ctx->stats.ms_build = 0; return RT_OK; }
+  CK(cudaEventRecord(ctx->ev0, st));
+
+  BuildArrays B;
+  memset(&B, 0, sizeof B);
+  B.n_prims = n; B.n_spheres = ns; B.n_tris = nt; B.n_quads = nq;
+  B.spheres = (const rt_sphere *)ctx->d_raw_sph.p;
+  B.tris = (const rt_triangle *)ctx->d_raw_tri.p;
+  B.quads = (const rt_quad *)ctx->d_raw_quad.p;
+  B.thickness = (ctx->sp.flags & RT_FLAG_FLIP_NORMALS) ? 0.01f : 0.1f; // THICKNESS of the two trees
+  DevBuf t_lo, t_hi, t_flag, t_bounds, t_small, t_keys, t_left, t_right, t_parent, t_nflag, t_size, t_nlo, t_nhi;
+  DevBuf *temps[] = {&t_lo, &t_hi, &t_flag, &t_bounds, &t_small, &t_keys, &t_left, &t_right, &t_parent, &t_nflag, &t_size, &t_nlo, &t_nhi};
+  auto cleanup = [&]() { for (DevBuf *b : temps) dev_free(*b); };
+#define CKB(call)                                                                                  \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess) {                                                                       \
+      cleanup();                                                                                   \
+      return fail(ctx, RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    }                                                                                              \
+  } while (0)
+#define RSV(buf, bytes) do { int rc_ = dev_reserve(ctx, buf, (bytes)); if (rc_) { cleanup(); return rc_; } } while (0)
+  RSV(t_lo, sizeof(float4) * (size_t)n); RSV(t_hi, sizeof(float4) * (size_t)n); RSV(t_flag, sizeof(int) * (size_t)n);
+  RSV(t_bounds, sizeof(BuildBounds) * 4);
+  B.pbox_lo = (float4 *)t_lo.p; B.pbox_hi = (float4 *)t_hi.p; B.big_flag = (int *)t_flag.p;
+  B.bounds = (BuildBounds *)t_bounds.p;
+  {
+    BuildBounds init[4];
+    for (int r = 0; r < 4; r++)
+      for (int a = 0; a < 3; a++) { init[r].lo[a] = 0x7fffffff; init[r].hi[a] = (int)0x80000000; }
+    CKB(cudaMemcpyAsync(t_bounds.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+  }
+  const int TB = 256;
+  const int gp = (n + TB - 1) / TB;
+  k_prim_box<<<gp, TB, 0, st>>>(B);
+  ctx->launches++;
+  for (int r = 0; r < RT_BIG_ROUNDS; r++) {
+    k_classify<<<gp, TB, 0, st>>>(B, r, RT_BIG_FRAC);
+    ctx->launches++;
+  }
+  CKB(cudaGetLastError());
+  std::vector<int> flags(n);
+  CKB(cudaMemcpyAsync(flags.data(), t_flag.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CKB(cudaStreamSynchronize(st));
+  int n_big = 0;
+  for (int i = 0; i < n; i++) n_big += flags[i] ? 1 : 0;
+  int final_round = RT_BIG_ROUNDS;
+  if (n_big > RT_MAX_BIG) { // degenerate classification: keep everything in the tree
+    std::fill(flags.begin(), flags.end(), 0);
+    n_big = 0;
+    final_round = 0;
+  }
+  std::vector<int> small;
+  small.reserve(n - n_big);
+  std::vector<uint8_t> sph_is_big(std::max(ns, 1), 0);
+  for (int i = 0; i < n; i++) {
+    if (flags[i]) {
+      int32_t id = i < ns ? RT_PRIM_ID(RT_PRIM_SPHERE, i)
+                          : (i < ns + nt ? RT_PRIM_ID(RT_PRIM_TRIANGLE, i - ns) : RT_PRIM_ID(RT_PRIM_QUAD, i - ns - nt));
+      ctx->big_ids.push_back(id);
+      if (i < ns) sph_is_big[i] = 1;
+    } else small.push_back(i);
+  }
+  const int nsm = (int)small.size();
+  {
+    std::vector<int32_t> bigpad(std::max<size_t>(ctx->big_ids.size(), 4), 0);
+    std::copy(ctx->big_ids.begin(), ctx->big_ids.end(), bigpad.begin());
+    int rc = dev_upload(ctx, ctx->d_big, bigpad.data(), bigpad.size() * sizeof(int32_t));
+    if (!rc) rc = dev_upload(ctx, ctx->d_sph_is_big, sph_is_big.data(), sph_is_big.size());
+    if (rc) { cleanup(); return rc; }
+    ctx->S.big = (const int32_t *)ctx->d_big.p;
+    ctx->S.n_big = n_big;
+  }
+  int n_nodes = nsm > 0 ? 2 * nsm - 1 : 0;
+  if (nsm > 0) {
+    int n_pad = 1;
+    while (n_pad < nsm) n_pad <<= 1;
+    if (n_pad < 2) n_pad = 2;
+    B.n_small = nsm; B.n_pad = n_pad;
+    RSV(t_small, sizeof(int) * (size_t)nsm);
+    CKB(cudaMemcpyAsync(t_small.p, small.data(), sizeof(int) * (size_t)nsm, cudaMemcpyHostToDevice, st));
+    RSV(t_keys, sizeof(unsigned long long) * (size_t)n_pad);
+    RSV(t_left, sizeof(int) * (size_t)nsm); RSV(t_right, sizeof(int) * (size_t)nsm);
+    RSV(t_parent, sizeof(int) * (size_t)n_nodes); RSV(t_nflag, sizeof(int) * (size_t)nsm);
+    RSV(t_size, sizeof(int) * (size_t)n_nodes);
+    RSV(t_nlo, sizeof(float4) * (size_t)n_nodes); RSV(t_nhi, sizeof(float4) * (size_t)n_nodes);
+    { int rc = dev_reserve(ctx, ctx->d_nodes, sizeof(float4) * 2 * (size_t)n_nodes); if (rc) { cleanup(); return rc; } }
+    B.small_gid = (const int *)t_small.p;
+    B.keys = (unsigned long long *)t_keys.p;
+    B.left = (int *)t_left.p; B.right = (int *)t_right.p; B.parent = (int *)t_parent.p;
+    B.flag = (int *)t_nflag.p; B.size = (int *)t_size.p;
+    B.nbox_lo = (float4 *)t_nlo.p; B.nbox_hi = (float4 *)t_nhi.p;
+    B.packed = (float4 *)ctx->d_nodes.p;
+    k_morton<<<(n_pad + TB - 1) / TB, TB, 0, st>>>(B, final_round);
+    ctx->launches++;
+    // bitonic sort of the unique 64-bit keys: steps with j < TILE run in shared memory
+    const int SORT_THREADS = 512, TILE = 2 * SORT_THREADS;
+    if (n_pad <= TILE) {
+      k_bitonic_smem<<<1, n_pad / 2, sizeof(unsigned long long) * (size_t)n_pad, st>>>(B.keys, n_pad, 2, n_pad, 1);
+      ctx->launches++;
+    } else {
+      k_bitonic_smem<<<n_pad / TILE, SORT_THREADS, sizeof(unsigned long long) * TILE, st>>>(B.keys, n_pad, 2, TILE, 1);
+      ctx->launches++;
+      for (int k = 2 * TILE; k <= n_pad; k <<= 1) {
+        int j = k >> 1;
+        for (; j >= TILE; j >>= 1) {
+          k_bitonic<<<(n_pad + TB - 1) / TB, TB, 0, st>>>(B.keys, n_pad, j, k);
+          ctx->launches++;
+        }
+        k_bitonic_smem<<<n_pad / TILE, SORT_THREADS, sizeof(unsigned long long) * TILE, st>>>(B.keys, n_pad, k, k, j);
+        ctx->launches++;
+      }
+    }
+    if (nsm > 1) {
+      k_karras<<<(nsm - 1 + TB - 1) / TB, TB, 0, st>>>(B);
+      ctx->launches++;
+    }
+    const int rounds = quality > 0 ? 1 + 2 * std::min(quality, 4) : 1;
+    for (int r = 0; r < rounds; r++) {
+      if (r > 0) CKB(cudaMemsetAsync(B.flag, 0, sizeof(int) * (size_t)nsm, st));
+      k_fit<<<(nsm + TB - 1) / TB, TB, 0, st>>>(B, (quality > 0 && r < rounds - 1) ? 1 : 0);
+      ctx->launches++;
+    }
+    k_pack<<<(n_nodes + TB - 1) / TB, TB, 0, st>>>(B);
+    ctx->launches++;
+    CKB(cudaGetLastError());
+  }
+  CKB(cudaEventRecord(ctx->ev1, st));
+  CKB(cudaStreamSynchronize(st));
+  CKB(cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev0, ctx->ev1));
+  cleanup();
+#undef CKB
+#undef RSV
+  ctx->S.nodes = (const float4 *)ctx->d_nodes.p;
+  ctx->S.n_nodes = n_nodes;
+  ctx->stats.n_nodes = n_nodes;
+  ctx->stats.n_big_prims = n_big;
+  ctx->have_accel = true;
+  return RT_OK;
+}
+
+int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nodes, int32_t *big_prims, int cap_big,
+                      int *n_big) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->have_accel) return fail(ctx, RT_ERR_STATE, "rt_accel_download before rt_accel_build");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (n_nodes) *n_nodes = ctx->S.n_nodes;
+  if (n_big) *n_big = ctx->S.n_big;
+  if (nodes) {
+    if (cap_nodes < ctx->S.n_nodes) return fail(ctx, RT_ERR_INVALID, "node buffer too small");
+    if (ctx->S.n_nodes)
+      CK(cudaMemcpy(nodes, ctx->d_nodes.p, sizeof(rt_bvh_node) * (size_t)ctx->S.n_nodes, cudaMemcpyDeviceToHost));
+  }
+  if (big_prims) {
+    if (cap_big < ctx->S.n_big) return fail(ctx, RT_ERR_INVALID, "big-primitive buffer too small");
+    std::copy(ctx->big_ids.begin(), ctx->big_ids.end(), big_prims);
+  }
+  return RT_OK;
+}
+
+int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *prim_id,
+                     float *t) {
+  if (!ctx || n < 0 || (n && (!rays || !prim_id || !t))) return RT_ERR_INVALID;
+  if (!ctx->have_scene) return fail(ctx, RT_ERR_STATE, "rt_trace_closest before rt_scene_upload");
+  if (use_accel && !ctx->have_accel) return fail(ctx, RT_ERR_STATE, "use_accel=1 before rt_accel_build");
+  if (n == 0) return RT_OK;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc;
+  if ((rc = dev_reserve(ctx, ctx->d_rays, sizeof(float) * 8 * (size_t)n))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_ids, sizeof(int32_t) * (size_t)n))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_ts, sizeof(float) * (size_t)n))) return rc;
+  cudaStream_t st = ctx->stream;
+  CK(cudaMemcpyAsync(ctx->d_rays.p, rays, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
+  DevScene S = ctx->S;
+  if (!use_accel) { S.n_nodes = 0; S.n_big = 0; }
+  const int TB = 128, g = (n + TB - 1) / TB;
+  const uint8_t *isbig = (const uint8_t *)ctx->d_sph_is_big.p;
+  const float4 *dr = (const float4 *)ctx->d_rays.p;
+  int32_t *di = (int32_t *)ctx->d_ids.p;
+  float *dt = (float *)ctx->d_ts.p;
+  switch (ctx->cfg.profile) {
+  case 0: k_trace_closest<0, false><<<g, TB, 0, st>>>(S, isbig, dr, n, t_min, t_max, use_accel, di, dt); break;
+  case 1: k_trace_closest<1, false><<<g, TB, 0, st>>>(S, isbig, dr, n, t_min, t_max, use_accel, di, dt); break;
+  default: k_trace_closest<2, true><<<g, TB, 0, st>>>(S, isbig, dr, n, t_min, t_max, use_accel, di, dt); break;
+  }
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(prim_id, di, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(t, dt, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RT_OK;
+}
+
+// ------------------------------------------------------------------ render
+typedef void (*render_kernel_t)(const RenderParams);
+static render_kernel_t pick_render_kernel(int profile, bool smem, bool count) {
+#define PICK(P, G)                                                                 \
+  return smem ? (count ? k_render<P, G, true, true> : k_render<P, G, true, false>) \
+              : (count ? k_render<P, G, false, true> : k_render<P, G, false, false>)
+  if (profile == 0) { PICK(0, false); }
+  if (profile == 1) { PICK(1, false); }
+  PICK(2, true);
+#undef PICK
+}
+
+static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, float *d_accum, cudaStream_t st,
+                       bool timed) {
+  if (W < 2 || H < 2 || spp_count < 0 || spp_begin < 0) return fail(ctx, RT_ERR_INVALID, "bad frame parameters");
+  if (!ctx->have_scene) return fail(ctx, RT_ERR_STATE, "rt_render before rt_scene_upload");
+  if (!ctx->have_accel) {
+    int rc = rt_accel_build(ctx, 1);
+    if (rc) return rc;
+  }
+  if (spp_count == 0) return RT_OK;
+  const size_t n_pix = (size_t)W * H;
+  RenderParams P;
+  memset(&P, 0, sizeof P);
+  P.S = ctx->S; P.cam = ctx->cam; P.sp = ctx->sp;
+  P.W = W; P.H = H;
+  P.tiles_x = (W + RT_TILE_W - 1) / RT_TILE_W;
+  P.n_tiles = P.tiles_x * ((H + RT_TILE_H - 1) / RT_TILE_H);
+  const int grid = ctx->sm_count;
+  const int n_warps = grid * (RT_BLOCK / 32);
+  // chunking: balance end-of-frame imbalance (few work items per warp) against the
+  // per-item drain tail (~10 iterations): n_chunks ~ sqrt(0.133 * warps * spp / tiles)
+  double ideal = sqrt(0.133 * (double)n_warps * (double)spp_count / (double)P.n_tiles);
+  int n_chunks = (int)(ideal + 0.5);
+  n_chunks = std::max(1, std::min(n_chunks, std::min(spp_count, 64)));
+  P.chunk_spp = (spp_count + n_chunks - 1) / n_chunks;
+  P.n_chunks = (spp_count + P.chunk_spp - 1) / P.chunk_spp;
+  P.spp_begin = spp_begin; P.spp_count = spp_count;
+  P.n_work = P.n_tiles * P.n_chunks;
+  int rc;
+  if ((rc = dev_reserve(ctx, ctx->d_partial, sizeof(float4) * n_pix * (size_t)P.n_chunks))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_counter, 16))) return rc;
+  if (!ctx->d_stats.p) {
+    if ((rc = dev_reserve(ctx, ctx->d_stats, 64))) return rc;
+    CK(cudaMemsetAsync(ctx->d_stats.p, 0, 64, st));
+  }
+  P.partial = (float4 *)ctx->d_partial.p;
+  P.work_counter = (int *)ctx->d_counter.p;
+  P.stats = (unsigned long long *)ctx->d_stats.p;
+  P.seed_lo = (uint32_t)(ctx->cfg.seed & 0xffffffffu);
+  P.seed_hi = (uint32_t)(ctx->cfg.seed >> 32);
+  const DevScene &S = ctx->S;
+  P.b_nodes = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_nodes);
+  P.b_sph = (int)pad16(sizeof(float4) * (size_t)S.n_spheres);
+  P.b_sph_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_spheres);
+  P.b_mats = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_mats);
+  P.b_big = (int)pad16(sizeof(int32_t) * (size_t)S.n_big);
+  size_t scene_bytes = (size_t)P.b_nodes + P.b_sph + P.b_sph_mat + P.b_mats + P.b_big;
+  if (ctx->general) {
+    P.b_sph_mv = S.any_moving ? (int)pad16(sizeof(float4) * (size_t)S.n_spheres) : 0;
+    P.b_sph_t0 = S.any_moving ? (int)pad16(sizeof(float) * (size_t)S.n_spheres) : 0;
+    P.b_tri = (int)pad16(sizeof(float4) * 4 * (size_t)S.n_tris);
+    P.b_tri_n = (int)pad16(sizeof(float4) * (size_t)S.n_tris);
+    P.b_quad = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_quads);
+    P.b_tri_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_tris);
+    P.b_quad_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_quads);
+    scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat;
+  }
+  const size_t acc_bytes = (size_t)(RT_BLOCK / 32) * 128 * sizeof(float);
+  const bool smem = scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin;
+  const size_t smem_bytes = acc_bytes + (smem ? scene_bytes : 0);
+  const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
+  render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count);
+  CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  cudaFuncAttributes fa;
+  CK(cudaFuncGetAttributes(&fa, (const void *)kern));
+  CK(cudaMemsetAsync(P.work_counter, 0, 4, st));
+  if (timed) CK(cudaEventRecord(ctx->ev0, st));
+  kern<<<grid, RT_BLOCK, smem_bytes, st>>>(P);
+  CK(cudaGetLastError());
+  k_combine<<<(unsigned)((n_pix + 255) / 256), 256, 0, st>>>((float4 *)d_accum, P.partial, (int)n_pix, P.n_chunks);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  if (timed) CK(cudaEventRecord(ctx->ev1, st));
+  ctx->stats.smem_bytes = (int)smem_bytes;
+  ctx->stats.block_threads = RT_BLOCK;
+  ctx->stats.grid_blocks = grid;
+  ctx->stats.regs_per_thread = fa.numRegs;
+  return RT_OK;
+}
+
+static int ensure_frame(rt_ctx *ctx, int W, int H) {
+  if (ctx->W == W && ctx->H == H && ctx->d_accum.p) return RT_OK;
+  int rc = dev_reserve(ctx, ctx->d_accum, sizeof(float4) * (size_t)W * H);
+  if (rc) return rc;
+  CK(cudaMemsetAsync(ctx->d_accum.p, 0, sizeof(float4) * (size_t)W * H, ctx->stream));
+  ctx->W = W; ctx->H = H;
+  return RT_OK;
+}
+
+int rt_render(rt_ctx *ctx, int width, int height, int spp_begin, int spp_count) {
+  if (!ctx) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_frame(ctx, width, height);
+  if (rc) return rc;
+  rc = render_into(ctx, width, height, spp_begin, spp_count, (float *)ctx->d_accum.p, ctx->stream, true);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (spp_count > 0) CK(cudaEventElapsedTime(&ctx->stats.ms_render, ctx->ev0, ctx->ev1));
+  return RT_OK;
+}
+
+int rt_render_device(rt_ctx *ctx, int width, int height, int spp_begin, int spp_count, float *d_accum, void *stream) {
+  if (!ctx || !d_accum) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  return render_into(ctx, width, height, spp_begin, spp_count, d_accum, stream ? (cudaStream_t)stream : ctx->stream,
+                     false);
+}
+
+int rt_accum_clear(rt_ctx *ctx) {
+  if (!ctx) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (ctx->d_accum.p) CK(cudaMemsetAsync(ctx->d_accum.p, 0, sizeof(float4) * (size_t)ctx->W * ctx->H, ctx->stream));
+  return RT_OK;
+}
+
+int rt_accum_download(rt_ctx *ctx, float *rgba, size_t n_floats) {
+  if (!ctx || !rgba) return RT_ERR_INVALID;
+  if (!ctx->d_accum.p) return fail(ctx, RT_ERR_STATE, "no frame");
+  if (n_floats != (size_t)ctx->W * ctx->H * 4) return fail(ctx, RT_ERR_INVALID, "size mismatch");
+  CK(cudaSetDevice(ctx->cfg.device));
+  CK(cudaMemcpyAsync(rgba, ctx->d_accum.p, n_floats * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RT_OK;
+}
+
+int rt_accum_upload(rt_ctx *ctx, int width, int height, const float *rgba, size_t n_floats) {
+  if (!ctx || !rgba) return RT_ERR_INVALID;
+  if (n_floats != (size_t)width * height * 4) return fail(ctx, RT_ERR_INVALID, "size mismatch");
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc = ensure_frame(ctx, width, height);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(ctx->d_accum.p, rgba, n_floats * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return RT_OK;
+}
+
+void *rt_accum_device_ptr(rt_ctx *ctx) { return ctx ? ctx->d_accum.p : nullptr; }
+
+int rt_resolve_device(rt_ctx *ctx, int width, int height, const float *d_accum, float *linear_rgb, uint8_t *rgb8,
+                      void *stream) {
+  if (!ctx || !d_accum || width < 1 || height < 1) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const size_t n_pix = (size_t)width * height;
+  int rc;
+  if (linear_rgb && (rc = dev_reserve(ctx, ctx->d_linear, sizeof(float) * 3 * n_pix))) return rc;
+  if (rgb8 && (rc = dev_reserve(ctx, ctx->d_rgb8, 3 * n_pix))) return rc;
+  CK(cudaEventRecord(ctx->ev0, st));
+  k_resolve<<<(unsigned)((n_pix + 255) / 256), 256, 0, st>>>((const float4 *)d_accum, width, height, ctx->cfg.profile,
+                                                             linear_rgb ? (float *)ctx->d_linear.p : nullptr,
+                                                             rgb8 ? (uint8_t *)ctx->d_rgb8.p : nullptr);
+  ctx->launches++;
+  CK(cudaGetLastError());
+  if (linear_rgb)
+    CK(cudaMemcpyAsync(linear_rgb, ctx->d_linear.p, sizeof(float) * 3 * n_pix, cudaMemcpyDeviceToHost, st));
+  if (rgb8) CK(cudaMemcpyAsync(rgb8, ctx->d_rgb8.p, 3 * n_pix, cudaMemcpyDeviceToHost, st));
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->stats.ms_resolve, ctx->ev0, ctx->ev1));
+  return RT_OK;
+}
+
+int rt_resolve(rt_ctx *ctx, float *linear_rgb, uint8_t *rgb8) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->d_accum.p) return fail(ctx, RT_ERR_STATE, "rt_resolve before rt_render");
+  return rt_resolve_device(ctx, ctx->W, ctx->H, (const float *)ctx->d_accum.p, linear_rgb, rgb8, nullptr);
+}
+
+// FP32 FMA issue-rate microbenchmark: the roofline denominator of this compute-bound
+// path (MEASURED_PEAKS.json only holds HBM and bf16-tensor peaks).
+__global__ void k_fma_peak(float *out, int iters, float a, float b) {
+  float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      x0 = __fmaf_rn(x0, a, b); x1 = __fmaf_rn(x1, a, b); x2 = __fmaf_rn(x2, a, b); x3 = __fmaf_rn(x3, a, b);
+      x4 = __fmaf_rn(x4, a, b); x5 = __fmaf_rn(x5, a, b); x6 = __fmaf_rn(x6, a, b); x7 = __fmaf_rn(x7, a, b);
+    }
+  }
+  float s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+  if (s == 12345.678f) out[0] = s;
+}
+
+int rt_measure_fp32_peak(rt_ctx *ctx, float *tflops) {
+  if (!ctx || !tflops) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  int rc = dev_reserve(ctx, ctx->d_counter, 16);
+  if (rc) return rc;
+  const int iters = 4096, threads = 512, grid = ctx->sm_count * 4;
+  float best = 0.f;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    k_fma_peak<<<grid, threads, 0, ctx->stream>>>((float *)ctx->d_counter.p, iters, 0.999f, 0.001f);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    double flops = 2.0 * 64.0 * (double)iters * (double)threads * (double)grid;
+    float tf = (float)(flops / (ms * 1e-3) / 1e12);
+    if (rep > 0 && tf > best) best = tf;
+  }
+  ctx->launches += 4;
+  *tflops = best;
+  return RT_OK;
+}
+
+int rt_stats(rt_ctx *ctx, rt_stats_t *out) {
+  if (!ctx || !out) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  unsigned long long h[4] = {0, 0, 0, 0};
+  if (ctx->d_stats.p) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(h, ctx->d_stats.p, sizeof h, cudaMemcpyDeviceToHost));
+  }
+  ctx->stats.paths = h[0]; ctx->stats.segments = h[1]; ctx->stats.box_tests = h[2]; ctx->stats.prim_tests = h[3];
+  ctx->stats.kernel_launches = ctx->launches;
+  *out = ctx->stats;
+  return RT_OK;
+}
+
+int rt_stats_reset(rt_ctx *ctx) {
+  if (!ctx) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (ctx->d_stats.p) CK(cudaMemsetAsync(ctx->d_stats.p, 0, 64, ctx->stream));
+  ctx->launches = 0;
+  return RT_OK;
+}
+
+} // extern "C"

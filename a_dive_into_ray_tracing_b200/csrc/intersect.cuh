@@ -1,0 +1,232 @@
+// intersect.cuh — ray/primitive and ray/box tests + the threaded-BVH closest-hit
+// query. Replaces the reference's virtual `hittable::hit` family:
+//   sphere::hit         rt_in_one_weekend/sphere.h:21-55, accelerated-rt-cuda/sphere.h:20-49,
+//                       rt_next_week/cuda/sphere.h:43-77
+//   moving_sphere::hit  rt_next_week/cuda/moving_sphere.h:39-72
+//   triangle::hit       triangles/cuda/include/triangle.h:102-215
+//   xy/xz/yz_rect::hit  rt_next_week/cuda/aarect.h:38-65,93-121,149-176
+//   aabb::hit           rt_next_week/cuda/aabb.h:33-50
+//   hittable_list::hit  hittable_list.h:20-34     bvh_node::hit  rt_next_week/cuda/bvh.h:78-137
+// The arithmetic is re-derived for accuracy in FP32 (see DESIGN.md §"closest hit"):
+// results must agree with the reference's DOUBLE renderer to 1e-5 relative in t,
+// which the reference's own float formulas do not achieve (up to 3.6e-4 measured).
+#pragma once
+#include "rt_common.cuh"
+
+struct RayPre {
+  V3f inv_d;  // 1/d (inf where d == 0)
+  V3f ood;    // o/d
+  float inv_a; // 1/(d.d)
+};
+
+RT_HD RayPre ray_precompute(const Ray &r) {
+  RayPre p;
+  p.inv_d = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+  p.ood = v3(r.o.x * p.inv_d.x, r.o.y * p.inv_d.y, r.o.z * p.inv_d.z);
+  p.inv_a = 1.0f / dot(r.d, r.d);
+  return p;
+}
+
+struct HitAcc {
+  float t;    // closest accepted t so far (starts at t_max)
+  int32_t id; // RT_PRIM_ID or -1
+};
+
+// Interval + tie rule. closed: the reference accepts roots on [t_min, t_max] and the
+// LATER list item wins an exact tie (sphere.h:37-43 with hittable_list.h:26-31);
+// open: (t_min, t_max), the FIRST wins (accelerated-rt-cuda/sphere.h:29). List
+// order == primitive-id order, which makes the result independent of BVH order.
+RT_HD bool accept_root(float root, float t_min, bool closed, const HitAcc &h, int32_t id) {
+  bool lo = closed ? (root >= t_min) : (root > t_min);
+  bool better = (root < h.t) || (root == h.t && (closed ? (id > h.id) : (id < h.id)));
+  return lo && better;
+}
+
+// Sphere, FP32, cancellation-free: with g = c - o, q = (g.d)/(d.d) the parameter of
+// closest approach and l = g - q d the perpendicular from the ray to the centre,
+//   disc = r^2 - |l|^2,   roots = q -/+ sqrt(disc/(d.d)).
+// (|l| <= r whenever there is a hit, so no large numbers are subtracted.)
+RT_HD void hit_sphere(float4 s, V3f center, bool closed, const Ray &r, const RayPre &pre, float t_min, HitAcc &h,
+                      int32_t id) {
+  V3f g = center - r.o;
+  float q = dot(g, r.d) * pre.inv_a;
+  V3f l = madd(g, -q, r.d);
+  float disc = RT_FMA(s.w, s.w, -dot(l, l));
+  if (closed ? (disc < 0.0f) : !(disc > 0.0f)) return;
+  float sq = RT_SQRT(disc * pre.inv_a);
+  float root = q - sq;
+  if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; return; }
+  // the near root failed its range test: the reference then tries the far root
+  bool near_in_range = closed ? (root >= t_min && root <= h.t) : (root > t_min && root < h.t);
+  if (near_in_range) return; // it was in range but lost a tie: the far root cannot win either
+  root = q + sq;
+  if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; }
+}
+
+// Oversized spheres (the r = 1000 ground): FP64. With |c - o| ~ 1e3 the float
+// subtraction alone loses 3e-5 of the height above the surface; these primitives
+// are few (the always-tested "big" list) so double precision is affordable.
+RT_HD void hit_sphere_f64(float4 s, V3f center, bool closed, const Ray &r, float t_min, HitAcc &h, int32_t id) {
+  double gx = (double)center.x - (double)r.o.x, gy = (double)center.y - (double)r.o.y,
+         gz = (double)center.z - (double)r.o.z;
+  double dx = r.d.x, dy = r.d.y, dz = r.d.z;
+  double a = dx * dx + dy * dy + dz * dz;
+  double bp = gx * dx + gy * dy + gz * dz;
+  double c = gx * gx + gy * gy + gz * gz - (double)s.w * (double)s.w;
+  double disc = bp * bp - a * c;
+  if (closed ? (disc < 0.0) : !(disc > 0.0)) return;
+  double sq = sqrt(disc);
+  double inv = 1.0 / a;
+  float root = (float)((bp - sq) * inv);
+  if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; return; }
+  bool near_in_range = closed ? (root >= t_min && root <= h.t) : (root > t_min && root < h.t);
+  if (near_in_range) return;
+  root = (float)((bp + sq) * inv);
+  if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; }
+}
+
+// moving_sphere::center — moving_sphere.h:34-36. mv = {c1-c0, 1/(time1-time0)}.
+RT_HD V3f sphere_center_at(float4 s, float4 mv, float time0, float tm) {
+  float f = (tm - time0) * mv.w;
+  return v3(RT_FMA(f, mv.x, s.x), RT_FMA(f, mv.y, s.y), RT_FMA(f, mv.z, s.z));
+}
+
+// Triangle in plane form. The reference tests  |N.d| < 0.01 (un-normalised N and d,
+// triangle.h:123-128), t = (v0-o).N / N.d, t >= 0, t in [t_min,t_max], then three
+// edge tests dot(N^, cross(edge, p - vert)) >= 0 (:172-202). With
+// m_e = cross(N^, edge), k_e = m_e.vert the edge test is m_e.p - k_e >= 0.
+RT_HD void hit_triangle(float4 pl, float4 e0, float4 e1, float4 e2, const Ray &r, float t_min, HitAcc &h,
+                        int32_t id) {
+  V3f n = xyz(pl);
+  float nd = dot(n, r.d);
+  if (fabsf(nd) < 0.01f) return;
+  float t = (pl.w - dot(n, r.o)) / nd;
+  if (t < 0.0f) return;
+  if (!accept_root(t, t_min, true, h, id)) return;
+  V3f p = madd(r.o, t, r.d);
+  if (dot(xyz(e0), p) - e0.w < 0.0f) return;
+  if (dot(xyz(e1), p) - e1.w < 0.0f) return;
+  if (dot(xyz(e2), p) - e2.w < 0.0f) return;
+  h.t = t; h.id = id;
+}
+
+// Axis-aligned rectangle: q0 = {k, a0, a1, as_float(axis)}, q1 = {b0, b1, -, -}.
+RT_HD void hit_quad(float4 q0, float4 q1, const Ray &r, float t_min, HitAcc &h, int32_t id) {
+  int ax = RT_F2I(q0.w);
+  float oa = ax == 0 ? r.o.x : (ax == 1 ? r.o.y : r.o.z);
+  float da = ax == 0 ? r.d.x : (ax == 1 ? r.d.y : r.d.z);
+  float t = (q0.x - oa) / da;
+  if (!accept_root(t, t_min, true, h, id)) return;
+  // in-plane coordinates: axis 0 -> (y,z), 1 -> (x,z), 2 -> (x,y)
+  float o1 = ax == 0 ? r.o.y : r.o.x, d1 = ax == 0 ? r.d.y : r.d.x;
+  float o2 = ax == 2 ? r.o.y : r.o.z, d2 = ax == 2 ? r.d.y : r.d.z;
+  float a = RT_FMA(t, d1, o1), b = RT_FMA(t, d2, o2);
+  if (a < q0.y || a > q0.z || b < q1.x || b > q1.y) return;
+  h.t = t; h.id = id;
+}
+
+// Slab test against a packed node box (closed interval; NaNs from 0*inf are dropped
+// by fminf/fmaxf, which keeps the test conservative).
+RT_HD bool hit_box(float4 lo, float4 hi, const RayPre &pre, float t_min, float t_max) {
+  float x0 = RT_FMA(lo.x, pre.inv_d.x, -pre.ood.x), x1 = RT_FMA(hi.x, pre.inv_d.x, -pre.ood.x);
+  float y0 = RT_FMA(lo.y, pre.inv_d.y, -pre.ood.y), y1 = RT_FMA(hi.y, pre.inv_d.y, -pre.ood.y);
+  float z0 = RT_FMA(lo.z, pre.inv_d.z, -pre.ood.z), z1 = RT_FMA(hi.z, pre.inv_d.z, -pre.ood.z);
+  float tn = RT_FMAX(RT_FMAX(RT_FMIN(x0, x1), RT_FMIN(y0, y1)), RT_FMAX(RT_FMIN(z0, z1), t_min));
+  float tf = RT_FMIN(RT_FMIN(RT_FMAX(x0, x1), RT_FMAX(y0, y1)), RT_FMIN(RT_FMAX(z0, z1), t_max));
+  return tn <= tf;
+}
+
+// One primitive by RT_PRIM_ID. PROFILE selects the interval rule of static spheres.
+template <int PROFILE, bool GENERAL, bool F64>
+RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &pre, float t_min, HitAcc &h) {
+  if (!GENERAL) {
+    float4 s = S.sph[id];
+    if (F64) hit_sphere_f64(s, xyz(s), PROFILE == 0, r, t_min, h, id);
+    else hit_sphere(s, xyz(s), PROFILE == 0, r, pre, t_min, h, id);
+    return;
+  }
+  int type = RT_PRIM_TYPE_OF(id), idx = RT_PRIM_INDEX_OF(id);
+  if (type == RT_PRIM_SPHERE) {
+    float4 s = S.sph[idx];
+    V3f c = xyz(s);
+    bool closed = PROFILE == 0;
+    if (S.any_moving) {
+      float4 mv = S.sph_mv[idx];
+      if (mv.w != 0.0f) { c = sphere_center_at(s, mv, S.sph_t0[idx], r.tm); closed = true; }
+    }
+    if (F64) hit_sphere_f64(s, c, closed, r, t_min, h, id);
+    else hit_sphere(s, c, closed, r, pre, t_min, h, id);
+  } else if (type == RT_PRIM_TRIANGLE) {
+    const float4 *t = S.tri + 4 * idx;
+    hit_triangle(t[0], t[1], t[2], t[3], r, t_min, h, id);
+  } else {
+    const float4 *q = S.quad + 2 * idx;
+    hit_quad(q[0], q[1], r, t_min, h, id);
+  }
+}
+
+struct TraceCounters {
+  unsigned box_tests, prim_tests;
+};
+
+// Closest hit: always-tested big primitives first (they shrink t_max early), then
+// the threaded BVH — no stack: every node carries the index to continue with when
+// its box is missed (or its subtree is done).  while-while form: lanes first walk
+// to their next leaf, then the warp tests primitives together.
+template <int PROFILE, bool GENERAL, bool COUNT>
+RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r, float t_min, float t_max, TraceCounters *cnt) {
+  HitAcc h;
+  h.t = t_max;
+  h.id = -1;
+  RayPre pre = ray_precompute(r);
+  for (int i = 0; i < S.n_big; i++) {
+    int32_t id = S.big[i];
+    if (COUNT) cnt->prim_tests++;
+    bool is_sphere = !GENERAL || RT_PRIM_TYPE_OF(id) == RT_PRIM_SPHERE;
+    if (is_sphere) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
+    else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
+  }
+  int node = 0;
+  const int n_nodes = S.n_nodes;
+  while (node < n_nodes) {
+    int32_t leaf = -1;
+    while (node < n_nodes) {
+      float4 lo = S.nodes[2 * node], hi = S.nodes[2 * node + 1];
+      if (COUNT) cnt->box_tests++;
+      int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
+      if (hit_box(lo, hi, pre, t_min, h.t)) {
+        if (pay >= 0) { node = pay; continue; }
+        leaf = ~pay;
+        node = esc;
+        break;
+      }
+      node = esc;
+    }
+    if (leaf >= 0) {
+      if (COUNT) cnt->prim_tests++;
+      hit_prim<PROFILE, GENERAL, false>(S, leaf, r, pre, t_min, h);
+    }
+  }
+  return h;
+}
+
+// Brute force over the flattened arrays in list order (parity hook; the reference's
+// hittable_list::hit). Spheres in the big list still use the FP64 path so that the
+// result is identical to the BVH path's.
+template <int PROFILE, bool GENERAL>
+RT_HD HitAcc trace_brute(const DevScene &S, const uint8_t *is_big, const Ray &r, float t_min, float t_max) {
+  HitAcc h;
+  h.t = t_max;
+  h.id = -1;
+  RayPre pre = ray_precompute(r);
+  for (int i = 0; i < S.n_spheres; i++) {
+    int32_t id = RT_PRIM_ID(RT_PRIM_SPHERE, i);
+    if (is_big[i]) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
+    else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
+  }
+  if (GENERAL) {
+    for (int i = 0; i < S.n_tris; i++) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_TRIANGLE, i), r, pre, t_min, h);
+    for (int i = 0; i < S.n_quads; i++) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_QUAD, i), r, pre, t_min, h);
+  }
+  return h;
+}

@@ -1,0 +1,240 @@
+// render_kernels.cuh — the sm_100a kernels of the hot path.
+//
+//  k_render      persistent-thread path tracer. Replaces worker()
+//                (rt_in_one_weekend/main.cpp:267-290) and render_init+render<<<grid,8x8>>>
+//                (accelerated-rt-cuda/final.cu:62-96, rt_next_week/cuda/main.cu:113-149,
+//                triangles/cuda/obj_render.cu:94-130): one thread per pixel looping over
+//                all samples and up to 50 bounces there; here one resident CTA per SM,
+//                the whole scene staged in shared memory, and every warp draining a
+//                pool of (pixel, sample) items of one 8x4 tile: lanes whose path ended
+//                take the next items by ballot/popc rank ("warp-aggregated work fetch"),
+//                so all 32 lanes trace a segment in every iteration (path regeneration);
+//                tiles are fetched from a global atomic counter.
+//  k_combine     fixed-order sum of the per-chunk partial frames into the accumulation
+//                buffer (deterministic: no float atomics on global memory).
+//  k_resolve     /count, sqrt, clamp, 8-bit (color.h:14-28 / final.cu:91-95,223-232).
+//  k_trace_closest  one ray per thread closest-hit query (parity hook).
+#pragma once
+#include "shade.cuh"
+
+#ifndef RT_BLOCK
+#define RT_BLOCK 512
+#endif
+#define RT_TILE_W 8
+#define RT_TILE_H 4
+
+struct RenderParams {
+  DevScene S;
+  DevCamera cam;
+  ShadeParams sp;
+  int W, H, tiles_x, n_tiles;
+  int n_chunks, chunk_spp, spp_begin, spp_count, n_work;
+  float4 *partial;               // [n_chunks][H*W]
+  int *work_counter;
+  unsigned long long *stats;     // paths, segments, box tests, prim tests
+  uint32_t seed_lo, seed_hi;
+  // bytes of each array staged to shared memory (all multiples of 16)
+  int b_nodes, b_sph, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big;
+};
+
+__device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &off, const void *src, int bytes) {
+  unsigned char *dst = smem + off;
+  const int n16 = bytes >> 4;
+  const float4 *s = (const float4 *)src;
+  float4 *d = (float4 *)dst;
+  for (int i = threadIdx.x; i < n16; i += blockDim.x) d[i] = __ldg(s + i);
+  off += bytes;
+  return dst;
+}
+
+template <int PROFILE, bool GENERAL, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(RT_BLOCK, 1) k_render(const __grid_constant__ RenderParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  DevScene S = P.S;
+  int off = 0;
+  if (SMEM) {
+    S.nodes = (const float4 *)stage_to_smem(smem_raw, off, P.S.nodes, P.b_nodes);
+    S.sph = (const float4 *)stage_to_smem(smem_raw, off, P.S.sph, P.b_sph);
+    S.sph_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.sph_mat, P.b_sph_mat);
+    S.mats = (const float4 *)stage_to_smem(smem_raw, off, P.S.mats, P.b_mats);
+    S.big = (const int32_t *)stage_to_smem(smem_raw, off, P.S.big, P.b_big);
+    if (GENERAL) {
+      S.sph_mv = (const float4 *)stage_to_smem(smem_raw, off, P.S.sph_mv, P.b_sph_mv);
+      S.sph_t0 = (const float *)stage_to_smem(smem_raw, off, P.S.sph_t0, P.b_sph_t0);
+      S.tri = (const float4 *)stage_to_smem(smem_raw, off, P.S.tri, P.b_tri);
+      S.tri_n = (const float4 *)stage_to_smem(smem_raw, off, P.S.tri_n, P.b_tri_n);
+      S.quad = (const float4 *)stage_to_smem(smem_raw, off, P.S.quad, P.b_quad);
+      S.tri_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.tri_mat, P.b_tri_mat);
+      S.quad_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.quad_mat, P.b_quad_mat);
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *acc = (float *)(smem_raw + off) + warp * 128; // [32 pixels][4]
+  __syncthreads();
+
+  const unsigned FULL = 0xffffffffu;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  bool alive = false;
+  int pool_next = 0, pool_end = 0; // warp-uniform
+  int work = -1, tile_x0 = 0, tile_y0 = 0, s0 = 0, chunk = 0, chunk_n = 0;
+  Ray r;
+  r.o = v3(0, 0, 0); r.d = v3(0, 0, 1); r.tm = 0;
+  V3f beta = v3(1, 1, 1), L = v3(0, 0, 0);
+  int bounce = 0, pix = 0, smp = 0, pixel_index = 0;
+  unsigned n_seg = 0, n_paths = 0;
+  TraceCounters cnt;
+  cnt.box_tests = 0; cnt.prim_tests = 0;
+
+  for (;;) {
+    const unsigned dead = __ballot_sync(FULL, !alive);
+    if (dead) {
+      bool can_fetch = true;
+      if (pool_next >= pool_end) {
+        if (dead != FULL) {
+          can_fetch = false; // pool drained, some lanes still in flight
+        } else {
+          __syncwarp();
+          if (work >= 0) { // flush this tile's chunk: lane <-> pixel
+            const int i = tile_x0 + (lane & 7), j = tile_y0 + (lane >> 3);
+            if (i < P.W && j < P.H) {
+              float4 v = make_float4(acc[lane * 4 + 0], acc[lane * 4 + 1], acc[lane * 4 + 2], (float)chunk_n);
+              P.partial[(size_t)chunk * ((size_t)P.W * P.H) + (size_t)j * P.W + i] = v;
+            }
+          }
+          int w = 0;
+          if (lane == 0) w = atomicAdd(P.work_counter, 1);
+          w = __shfl_sync(FULL, w, 0);
+          if (w >= P.n_work) break;
+          work = w;
+          const int tile = w % P.n_tiles;
+          chunk = w / P.n_tiles;
+          tile_x0 = (tile % P.tiles_x) * RT_TILE_W;
+          tile_y0 = (tile / P.tiles_x) * RT_TILE_H;
+          s0 = P.spp_begin + chunk * P.chunk_spp;
+          chunk_n = min(P.chunk_spp, P.spp_count - chunk * P.chunk_spp);
+          pool_next = 0;
+          pool_end = chunk_n * 32;
+          acc[lane * 4 + 0] = 0.f; acc[lane * 4 + 1] = 0.f; acc[lane * 4 + 2] = 0.f; acc[lane * 4 + 3] = 0.f;
+          __syncwarp();
+        }
+      }
+      if (can_fetch) {
+        if (!alive) {
+          const int item = pool_next + __popc(dead & lt_mask);
+          if (item < pool_end) {
+            pix = item & 31;
+            smp = s0 + (item >> 5);
+            const int i = tile_x0 + (pix & 7), j = tile_y0 + (pix >> 3);
+            if (i < P.W && j < P.H) {
+              pixel_index = j * P.W + i;
+              Philox4 q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, 0u, 0u, P.seed_lo, P.seed_hi);
+              float x5 = 0.f;
+              if (PROFILE == 2 && P.cam.time1 != P.cam.time0)
+                x5 = u01(philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, 0u, 1u, P.seed_lo, P.seed_hi).x);
+              r = gen_camera_ray<PROFILE>(P.cam, P.W, P.H, i, j, u01(q.x), u01(q.y), u01(q.z), u01(q.w), x5);
+              beta = v3(1, 1, 1);
+              L = v3(0, 0, 0);
+              bounce = 0;
+              alive = true;
+              n_paths++;
+            }
+          }
+        }
+        pool_next = min(pool_end, pool_next + __popc(dead));
+      }
+    }
+    if (alive) {
+      HitAcc h = trace_closest<PROFILE, GENERAL, COUNT>(S, r, P.sp.t_min, INFINITY, &cnt);
+      n_seg++;
+      if (h.id < 0) {
+        V3f m = miss_radiance(P.sp, r.d);
+        L = L + beta * m;
+        alive = false;
+      } else {
+        Philox4 q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo,
+                                  P.seed_hi);
+        bool cont = shade_hit<PROFILE, GENERAL>(S, P.sp, r, h, beta, L, q);
+        bounce++;
+        if (!cont) {
+          alive = false; // absorbed (contributes L, which is 0 for profiles 0/1) or hit a light
+        } else if (bounce >= P.sp.max_depth) {
+          alive = false;
+          if (PROFILE == 2) {
+            if (P.sp.flags & RT_FLAG_DEPTH_BACKGROUND) L = L + beta * P.sp.background; // obj_render.cu:78-83
+            else L = P.sp.background;                                                    // main.cu:104
+          } else {
+            L = v3(0, 0, 0); // main.cpp:58-60, final.cu:53
+          }
+        }
+      }
+      if (!alive) {
+        atomicAdd(&acc[pix * 4 + 0], L.x);
+        atomicAdd(&acc[pix * 4 + 1], L.y);
+        atomicAdd(&acc[pix * 4 + 2], L.z);
+      }
+    }
+  }
+  // statistics: one atomic per warp
+  unsigned long long a = n_paths, b = n_seg, c = cnt.box_tests, d = cnt.prim_tests;
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_down_sync(FULL, a, o);
+    b += __shfl_down_sync(FULL, b, o);
+    if (COUNT) { c += __shfl_down_sync(FULL, c, o); d += __shfl_down_sync(FULL, d, o); }
+  }
+  if (lane == 0) {
+    atomicAdd(&P.stats[0], a);
+    atomicAdd(&P.stats[1], b);
+    if (COUNT) { atomicAdd(&P.stats[2], c); atomicAdd(&P.stats[3], d); }
+  }
+}
+
+// accum[p] += sum over chunks (fixed order) of partial[c][p]
+__global__ void k_combine(float4 *__restrict__ accum, const float4 *__restrict__ partial, int n_pix, int n_chunks) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  float4 a = accum[p];
+  for (int c = 0; c < n_chunks; c++) {
+    float4 v = __ldcs(partial + (size_t)c * n_pix + p);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  accum[p] = a;
+}
+
+// Resolve. linear: [H][W][3] bottom row first (may be null). rgb8: [H][W][3] TOP row
+// first (PPM order; may be null).
+__global__ void k_resolve(const float4 *__restrict__ accum, int W, int H, int profile, float *__restrict__ linear,
+                          uint8_t *__restrict__ rgb8) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= W * H) return;
+  float4 a = accum[p];
+  float inv = a.w > 0.f ? 1.0f / a.w : 0.f;
+  float c[3] = {a.x * inv, a.y * inv, a.z * inv};
+  if (linear) { linear[3 * p + 0] = c[0]; linear[3 * p + 1] = c[1]; linear[3 * p + 2] = c[2]; }
+  if (rgb8) {
+    int i = p % W, j = p / W;
+    size_t o = ((size_t)(H - 1 - j) * W + i) * 3;
+    for (int k = 0; k < 3; k++) {
+      float g = sqrtf(fmaxf(c[k], 0.f));
+      int q;
+      if (profile == 0) q = (int)(256.0f * fminf(fmaxf(g, 0.0f), 0.999f)); // color.h:21-27
+      else q = min(255, (int)(255.99f * g));                                // final.cu:227-229 (clamped)
+      rgb8[o + k] = (uint8_t)q;
+    }
+  }
+}
+
+template <int PROFILE, bool GENERAL>
+__global__ void k_trace_closest(const DevScene S, const uint8_t *__restrict__ sphere_is_big,
+                                const float4 *__restrict__ rays, int n, float t_min, float t_max, int use_accel,
+                                int32_t *__restrict__ out_id, float *__restrict__ out_t) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  float4 a = rays[2 * k], b = rays[2 * k + 1];
+  Ray r;
+  r.o = v3(a.x, a.y, a.z); r.tm = a.w; r.d = v3(b.x, b.y, b.z);
+  HitAcc h;
+  if (use_accel) h = trace_closest<PROFILE, GENERAL, false>(S, r, t_min, t_max, nullptr);
+  else h = trace_brute<PROFILE, GENERAL>(S, sphere_is_big, r, t_min, t_max);
+  out_id[k] = h.id;
+  out_t[k] = h.id >= 0 ? h.t : 0.f;
+}

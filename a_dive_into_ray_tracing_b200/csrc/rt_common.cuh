@@ -1,0 +1,99 @@
+// rt_common.cuh — device-side data layout and small math helpers of the B200
+// path-tracer core. Everything here is `__host__ __device__` so that
+// tests/emu can single-step the per-lane code on the CPU while debugging; the
+// product library only ever runs it on the GPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#include "../../include/rt_capi.h"
+
+#define RT_HD __host__ __device__ __forceinline__
+#define RT_D __device__ __forceinline__
+
+#ifdef __CUDA_ARCH__
+#define RT_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define RT_FMIN(a, b) fminf((a), (b))
+#define RT_FMAX(a, b) fmaxf((a), (b))
+#define RT_F2I(x) __float_as_int(x)
+#define RT_I2F(x) __int_as_float(x)
+#define RT_RSQRT(x) rsqrtf(x)
+#define RT_RCP(x) __frcp_rn(x)
+#define RT_SQRT(x) __fsqrt_rn(x)
+#define RT_MULHI(a, b) __umulhi((a), (b))
+#else
+static inline int rt_host_f2i(float x) { int i; memcpy(&i, &x, 4); return i; }
+static inline float rt_host_i2f(int i) { float x; memcpy(&x, &i, 4); return x; }
+#define RT_FMA(a, b, c) fmaf((a), (b), (c))
+#define RT_FMIN(a, b) fminf((a), (b))
+#define RT_FMAX(a, b) fmaxf((a), (b))
+#define RT_F2I(x) rt_host_f2i(x)
+#define RT_I2F(x) rt_host_i2f(x)
+#define RT_RSQRT(x) (1.0f / sqrtf(x))
+#define RT_RCP(x) (1.0f / (x))
+#define RT_SQRT(x) sqrtf(x)
+#define RT_MULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
+#endif
+
+struct V3f {
+  float x, y, z;
+};
+RT_HD V3f v3(float x, float y, float z) { V3f r = {x, y, z}; return r; }
+RT_HD V3f operator+(V3f a, V3f b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+RT_HD V3f operator-(V3f a, V3f b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+RT_HD V3f operator-(V3f a) { return v3(-a.x, -a.y, -a.z); }
+RT_HD V3f operator*(float t, V3f a) { return v3(t * a.x, t * a.y, t * a.z); }
+RT_HD V3f operator*(V3f a, V3f b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
+RT_HD float dot(V3f a, V3f b) { return RT_FMA(a.z, b.z, RT_FMA(a.y, b.y, a.x * b.x)); }
+RT_HD V3f cross(V3f u, V3f w) {
+  return v3(RT_FMA(u.y, w.z, -u.z * w.y), RT_FMA(u.z, w.x, -u.x * w.z), RT_FMA(u.x, w.y, -u.y * w.x));
+}
+// a + t*b
+RT_HD V3f madd(V3f a, float t, V3f b) { return v3(RT_FMA(t, b.x, a.x), RT_FMA(t, b.y, a.y), RT_FMA(t, b.z, a.z)); }
+RT_HD V3f normalize(V3f a) { float s = RT_RSQRT(dot(a, a)); return s * a; }
+RT_HD V3f v3_from(const float *p) { return v3(p[0], p[1], p[2]); }
+RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
+
+// ---------------------------------------------------------------- scene on device
+// All arrays live in HBM (uploaded once per scene) and are staged into shared
+// memory by the render kernel when they fit ("data layout").
+//
+//  nodes   float4[2*n_nodes]   {bmin.xyz, escape} {bmax.xyz, payload}   32 B/node
+//  sph     float4[n_spheres]   {c0.xyz, radius}                         16 B
+//  sph_mv  float4[n_spheres]   {c1-c0, 1/(time1-time0)} (only if any sphere moves;
+//                              .w == 0 marks a static sphere; time0 in sph_t0)
+//  tri     float4[4*n_tris]    {N.xyz (un-normalised), v0.N}, then three edge
+//                              planes {m_e.xyz, k_e}: inside <=> m_e.p - k_e >= 0
+//  tri_n   float4[n_tris]      {unit N.xyz, 0} (shading only)
+//  quad    float4[2*n_quads]   {k, a0, a1, as_float(axis)} {b0, b1, 0, 0}
+//  *_mat   int32 per primitive material index
+//  mats    float4[2*n_mats]    {albedo.rgb, as_float(type | texture<<8)} {albedo2.rgb, param}
+//  big     int32[n_big]        RT_PRIM_IDs tested for every ray before traversal
+struct DevScene {
+  const float4 *nodes;
+  const float4 *sph;
+  const float4 *sph_mv;
+  const float *sph_t0;
+  const float4 *tri;
+  const float4 *tri_n;
+  const float4 *quad;
+  const int32_t *sph_mat;
+  const int32_t *tri_mat;
+  const int32_t *quad_mat;
+  const float4 *mats;
+  const int32_t *big;
+  int n_nodes, n_spheres, n_tris, n_quads, n_mats, n_big;
+  int any_moving;
+};
+
+struct DevCamera {
+  V3f origin, llc, horizontal, vertical, u, v;
+  float lens_radius, time0, time1;
+};
+
+struct Ray {
+  V3f o, d;
+  float tm;
+};

@@ -1,0 +1,116 @@
+// scene_flatten.h — host-side flattening of an rt_scene_desc into the SoA arrays the
+// kernels read (layout documented in rt_common.cuh DevScene). Replaces the device-side
+// `new sphere(...)/new lambertian(...)` object graph of create_world<<<1,1>>>
+// (accelerated-rt-cuda/final.cu:100-143, rt_next_week/cuda/main.cu:386-467).
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "rt_common.cuh"
+
+struct HostFlat {
+  std::vector<float4> sph, sph_mv, tri, tri_n, quad, mats;
+  std::vector<float> sph_t0;
+  std::vector<int32_t> sph_mat, tri_mat, quad_mat;
+  bool any_moving = false;
+};
+
+static inline int flat_fail(std::string &err, const char *fmt, ...) {
+  char buf[256];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  err = buf;
+  return RT_ERR_INVALID;
+}
+
+static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &F, std::string &err) {
+#define FAIL(...) return flat_fail(err, __VA_ARGS__)
+  if (sc->n_spheres < 0 || sc->n_triangles < 0 || sc->n_quads < 0 || sc->n_materials < 0)
+    FAIL("negative count");
+  if ((sc->n_spheres && !sc->spheres) || (sc->n_triangles && !sc->triangles) || (sc->n_quads && !sc->quads) ||
+      (sc->n_materials && !sc->materials))
+    FAIL("null array with non-zero count");
+  if (sc->n_spheres >= (1 << 28) || sc->n_triangles >= (1 << 28) || sc->n_quads >= (1 << 28))
+    FAIL("too many primitives");
+  if (sc->max_depth < 1) FAIL("max_depth must be >= 1");
+  bool any_moving = false;
+  for (int i = 0; i < sc->n_spheres; i++) {
+    const rt_sphere &s = sc->spheres[i];
+    if (s.material < 0 || s.material >= sc->n_materials) FAIL("sphere %d: material index", i);
+    if (s.radius == 0.0f) FAIL("sphere %d: zero radius", i);
+    if (s.moving) {
+      any_moving = true;
+      if (s.time1 == s.time0) FAIL("moving sphere %d: time0 == time1", i);
+    }
+  }
+  for (int i = 0; i < sc->n_triangles; i++)
+    if (sc->triangles[i].material < 0 || sc->triangles[i].material >= sc->n_materials)
+      FAIL("triangle %d: material index", i);
+  for (int i = 0; i < sc->n_quads; i++) {
+    const rt_quad &q = sc->quads[i];
+    if (q.material < 0 || q.material >= sc->n_materials) FAIL("quad %d: material index", i);
+    if (q.axis < 0 || q.axis > 2) FAIL("quad %d: axis", i);
+  }
+  for (int i = 0; i < sc->n_materials; i++) {
+    const rt_material &m = sc->materials[i];
+    if (m.type < 0 || m.type > 3) FAIL("material %d: type", i);
+    if (profile != RT_PROFILE_NEXT_WEEK && (m.type == RT_MAT_DIFFUSE_LIGHT || m.texture != RT_TEX_SOLID))
+      FAIL("material %d: lights/textures need profile 2", i);
+  }
+  if (profile != RT_PROFILE_NEXT_WEEK && (sc->n_triangles || sc->n_quads || any_moving))
+    FAIL("triangles, rects and moving spheres need profile 2 (next-week / triangles trees)");
+
+  const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, nm = sc->n_materials;
+  std::vector<float4> &sph = F.sph, &sph_mv = F.sph_mv, &tri = F.tri, &tri_n = F.tri_n, &quad = F.quad, &mats = F.mats;
+  std::vector<float> &sph_t0 = F.sph_t0;
+  std::vector<int32_t> &sph_mat = F.sph_mat, &tri_mat = F.tri_mat, &quad_mat = F.quad_mat;
+  sph.assign(ns, make_float4(0, 0, 0, 0)); sph_mv.assign(ns, make_float4(0, 0, 0, 0));
+  tri.assign(4 * (size_t)nt, make_float4(0, 0, 0, 0)); tri_n.assign(nt, make_float4(0, 0, 0, 0));
+  quad.assign(2 * (size_t)nq, make_float4(0, 0, 0, 0)); mats.assign(2 * (size_t)nm, make_float4(0, 0, 0, 0));
+  sph_t0.assign(ns, 0.f); sph_mat.assign(ns, 0); tri_mat.assign(nt, 0); quad_mat.assign(nq, 0);
+  for (int i = 0; i < ns; i++) {
+    const rt_sphere &s = sc->spheres[i];
+    sph[i] = make_float4(s.center0[0], s.center0[1], s.center0[2], s.radius);
+    if (s.moving)
+      sph_mv[i] = make_float4(s.center1[0] - s.center0[0], s.center1[1] - s.center0[1], s.center1[2] - s.center0[2],
+                              1.0f / (s.time1 - s.time0));
+    else
+      sph_mv[i] = make_float4(0, 0, 0, 0);
+    sph_t0[i] = s.time0;
+    sph_mat[i] = s.material;
+  }
+  for (int i = 0; i < nt; i++) {
+    const rt_triangle &t = sc->triangles[i];
+    V3f v0 = v3_from(t.v0), v1 = v3_from(t.v1), v2 = v3_from(t.v2), N = v3_from(t.normal);
+    float len = sqrtf(N.x * N.x + N.y * N.y + N.z * N.z);
+    if (!(len > 0.f)) FAIL("triangle %d: degenerate normal", i);
+    V3f Nu = (1.0f / len) * N; // unit_vector(face_normal), triangle.h:49
+    V3f e[3] = {v1 - v0, v2 - v1, v0 - v2};
+    V3f vert[3] = {v0, v1, v2};
+    tri[4 * (size_t)i] = make_float4(N.x, N.y, N.z, dot(v0, N));
+    for (int k = 0; k < 3; k++) {
+      V3f m = cross(Nu, e[k]);
+      tri[4 * (size_t)i + 1 + k] = make_float4(m.x, m.y, m.z, dot(m, vert[k]));
+    }
+    tri_n[i] = make_float4(Nu.x, Nu.y, Nu.z, 0.f);
+    tri_mat[i] = t.material;
+  }
+  for (int i = 0; i < nq; i++) {
+    const rt_quad &q = sc->quads[i];
+    quad[2 * (size_t)i] = make_float4(q.k, q.a0, q.a1, RT_I2F(q.axis));
+    quad[2 * (size_t)i + 1] = make_float4(q.b0, q.b1, 0.f, 0.f);
+    quad_mat[i] = q.material;
+  }
+  for (int i = 0; i < nm; i++) {
+    const rt_material &m = sc->materials[i];
+    mats[2 * (size_t)i] = make_float4(m.albedo[0], m.albedo[1], m.albedo[2], RT_I2F(m.type | (m.texture << 8)));
+    mats[2 * (size_t)i + 1] = make_float4(m.albedo2[0], m.albedo2[1], m.albedo2[2], m.param);
+  }
+  F.any_moving = any_moving;
+  return RT_OK;
+#undef FAIL
+}

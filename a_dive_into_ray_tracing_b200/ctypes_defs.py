@@ -1,8 +1,7 @@
 """ctypes / numpy mirrors of the plain-C structs in include/rt_capi.h.
 
-Kept free of any library loading so that both the product binding
-(`capi.py`, loads libb200rt.so) and the test-only oracle binding
-(`oracle/pyoracle.py`) can describe the same flattened scene.
+Kept free of any library loading: it only describes the flattened scene
+(structs, dtypes, camera construction, deterministic primary rays).
 """
 import ctypes as C
 

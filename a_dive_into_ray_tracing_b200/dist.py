@@ -1,0 +1,37 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), sample-space split.
+
+The path shards by SAMPLES: rank g of G renders the global sample
+indices [g*spp/G, (g+1)*spp/G) of every pixel into its own float4 accumulation frame;
+Philox counters are (pixel, global sample, event), so the reduced image does not depend
+on G up to fp32 summation order. The one real exchange step is a sum-reduce of the
+frames to rank 0 (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def sample_range(spp, rank, world):
+    """Contiguous, exhaustive, non-overlapping split of [0, spp) over `world` ranks."""
+    begin = (spp * rank) // world
+    end = (spp * (rank + 1)) // world
+    return begin, end - begin
+
+
+def reduce_frames(accum, dst=0):
+    """Sum the per-rank accumulation frames onto `dst` (in place on dst)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
+    return accum
+
+
+def render_frame(ctx, W, H, spp, accum, rank=0, world=1, stream=None):
+    """Render this rank's share of `spp` samples into the CUDA tensor `accum`
+    ([H, W, 4] float32, zeroed by the caller) on the current torch stream, then
+    reduce to rank 0. No host synchronisation."""
+    assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
+    assert tuple(accum.shape) == (H, W, 4)
+    begin, count = sample_range(spp, rank, world)
+    s = stream if stream is not None else torch.cuda.current_stream()
+    ctx.render_device(W, H, count, begin, accum.data_ptr(), s.cuda_stream)
+    reduce_frames(accum)
+    return accum

@@ -220,6 +220,10 @@ int rt_stats(rt_ctx *ctx, rt_stats_t *out);
 int rt_stats_reset(rt_ctx *ctx);
 int rt_sync(rt_ctx *ctx);
 
+/* Diagnostic: measured FP32 FMA throughput of the device (TFLOP/s, FMA = 2 flops), the
+ * roofline denominator for this compute-bound path. */
+int rt_measure_fp32_peak(rt_ctx *ctx, float *tflops);
+
 #ifdef __cplusplus
 }
 #endif

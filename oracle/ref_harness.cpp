@@ -58,6 +58,11 @@ struct count_proxy : public hittable {
   }
 };
 
+struct null_buf : public std::streambuf {
+  int overflow(int c) override { return c == EOF ? 0 : c; }
+  std::streamsize xsputn(const char *, std::streamsize n) override { return n; }
+};
+
 bool g_cam_override = false;
 double g_cam22[22];
 
@@ -258,8 +263,8 @@ double l0_worker_timed(int W, int H, int spp, int depth, const double *cam13, un
   std::vector<shared_ptr<color>> img((size_t)W * H);
   srand(seed);
   std::streambuf *old = std::cerr.rdbuf();
-  std::ostringstream sink;
-  std::cerr.rdbuf(sink.rdbuf()); // worker() prints its range on stderr
+  static null_buf sink;          // stateless: safe to share between the worker threads
+  std::cerr.rdbuf(&sink);        // worker() prints its range on stderr (main.cpp:271)
   int size = end - start;
   int batch = (size + threads - 1) / threads;
   auto t0 = std::chrono::steady_clock::now();

@@ -1,0 +1,59 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol the header
+declares, and refuses to run without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from a_dive_into_ray_tracing_b200 import capi, ctypes_defs as D
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "rt_capi.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    capi.build_library()
+    lib = C.CDLL(capi.LIB_PATH)
+    syms = header_symbols()
+    assert len(syms) >= 18
+    assert sorted(capi.SYMBOLS) == syms
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert capi.load_library().rt_version() == 1
+
+
+def test_struct_sizes_match_header():
+    # include/rt_capi.h: plain structs, natural alignment
+    assert C.sizeof(D.RtConfig) == 24
+    assert C.sizeof(D.RtCamera) == 96
+    assert C.sizeof(D.RtStats) == 80
+    assert D.SPHERE_DT.itemsize == 48 and D.TRIANGLE_DT.itemsize == 52 and D.QUAD_DT.itemsize == 28
+    assert D.MATERIAL_DT.itemsize == 40 and D.BVH_NODE_DT.itemsize == 32
+    assert C.sizeof(D.RtSceneDesc) == 4 * 16 + 96 + 32
+
+
+def test_no_cpu_fallback():
+    from tests.conftest import HAS_GPU
+    if HAS_GPU:
+        pytest.skip("GPU present")
+    assert capi.device_count() == 0
+    with pytest.raises(capi.RtError) as e:
+        capi.Context(profile=0)
+    assert e.value.code == 5  # RT_ERR_NODEVICE
+
+
+def test_product_never_touches_the_oracle():
+    """Nothing under the package or include/ may reference oracle/ (the checker)."""
+    pkg = os.path.join(ROOT, "a_dive_into_ray_tracing_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "pyoracle" not in txt and "liboracle" not in txt and "libref_l0" not in txt, f
+                assert "libemu" not in txt and "tests.emu" not in txt, f
