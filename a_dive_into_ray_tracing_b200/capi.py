@@ -49,10 +49,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("B200RT_LIB", LIB_PATH)  # tuning builds (csrc/Makefile variants)
+    if not os.path.exists(path):
         raise OSError("libb200rt.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); "
                       "there is no CPU fallback")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     L.rt_version.restype = C.c_int
     L.rt_device_count.restype = C.c_int
     L.rt_create.restype = C.c_int
@@ -173,8 +174,17 @@ class Context:
         self.W, self.H = W, H
         return self
 
+    @staticmethod
+    def _stream(stream_ptr):
+        # None -> the context's own stream (NULL in the C ABI); torch's default stream has
+        # handle 0, which must be spelled cudaStreamLegacy (0x1) to be distinguishable.
+        if stream_ptr is None:
+            return None
+        return 1 if int(stream_ptr) == 0 else int(stream_ptr)
+
     def render_device(self, W, H, spp_count, spp_begin, d_accum_ptr, stream_ptr=None):
-        self._ck(self.lib.rt_render_device(self.h, W, H, spp_begin, spp_count, d_accum_ptr, stream_ptr))
+        self._ck(self.lib.rt_render_device(self.h, W, H, spp_begin, spp_count, d_accum_ptr,
+                                           self._stream(stream_ptr)))
 
     def clear(self):
         self._ck(self.lib.rt_accum_clear(self.h))
@@ -202,7 +212,7 @@ class Context:
         lin = np.empty((H, W, 3), np.float32) if want_linear else None
         rgb = np.empty((H, W, 3), np.uint8) if want_rgb8 else None
         self._ck(self.lib.rt_resolve_device(self.h, W, H, d_accum_ptr, lin.ctypes.data if want_linear else None,
-                                            rgb.ctypes.data if want_rgb8 else None, stream_ptr))
+                                            rgb.ctypes.data if want_rgb8 else None, self._stream(stream_ptr)))
         return lin, rgb
 
     def stats(self):

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -91,7 +92,7 @@ struct rt_ctx {
   bool general = false;
   // device scene
   std::vector<DevBuf *> owned;
-  DevBuf d_nodes, d_sph, d_sph_mv, d_sph_t0, d_tri, d_tri_n, d_quad, d_sph_mat, d_tri_mat, d_quad_mat, d_mats, d_big,
+  DevBuf d_nodes, d_sph, d_sph_k, d_sph_mv, d_sph_t0, d_tri, d_tri_n, d_quad, d_sph_mat, d_tri_mat, d_quad_mat, d_mats, d_big,
       d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad;
   DevScene S;
   DevCamera cam;
@@ -186,7 +187,7 @@ void rt_destroy(rt_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf *all[] = {&ctx->d_nodes, &ctx->d_sph, &ctx->d_sph_mv, &ctx->d_sph_t0, &ctx->d_tri, &ctx->d_tri_n, &ctx->d_quad,
+  DevBuf *all[] = {&ctx->d_nodes, &ctx->d_sph, &ctx->d_sph_k, &ctx->d_sph_mv, &ctx->d_sph_t0, &ctx->d_tri, &ctx->d_tri_n, &ctx->d_quad,
                    &ctx->d_sph_mat, &ctx->d_tri_mat, &ctx->d_quad_mat, &ctx->d_mats, &ctx->d_big, &ctx->d_sph_is_big,
                    &ctx->d_raw_sph, &ctx->d_raw_tri, &ctx->d_raw_quad, &ctx->d_accum, &ctx->d_partial, &ctx->d_counter,
                    &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts};
@@ -231,7 +232,7 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   int rc;
 #define UP(buf, vec) \
   if ((rc = dev_upload(ctx, ctx->buf, (vec).data(), (vec).size() * sizeof((vec)[0])))) return rc
-  UP(d_sph, F.sph); UP(d_sph_mv, F.sph_mv); UP(d_sph_t0, F.sph_t0); UP(d_tri, F.tri); UP(d_tri_n, F.tri_n); UP(d_quad, F.quad);
+  UP(d_sph, F.sph); UP(d_sph_k, F.sph_k); UP(d_sph_mv, F.sph_mv); UP(d_sph_t0, F.sph_t0); UP(d_tri, F.tri); UP(d_tri_n, F.tri_n); UP(d_quad, F.quad);
   UP(d_sph_mat, F.sph_mat); UP(d_tri_mat, F.tri_mat); UP(d_quad_mat, F.quad_mat); UP(d_mats, F.mats);
   UP(d_raw_sph, ctx->spheres); UP(d_raw_tri, ctx->tris); UP(d_raw_quad, ctx->quads);
 #undef UP
@@ -245,6 +246,7 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   S.sph = (const float4 *)ctx->d_sph.p;
   S.sph_mv = (const float4 *)ctx->d_sph_mv.p;
   S.sph_t0 = (const float *)ctx->d_sph_t0.p;
+  S.sph_k = (const float *)ctx->d_sph_k.p;
   S.tri = (const float4 *)ctx->d_tri.p;
   S.tri_n = (const float4 *)ctx->d_tri_n.p;
   S.quad = (const float4 *)ctx->d_quad.p;
@@ -541,9 +543,10 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   P.b_nodes = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_nodes);
   P.b_sph = (int)pad16(sizeof(float4) * (size_t)S.n_spheres);
   P.b_sph_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_spheres);
+  P.b_sph_k = (int)pad16(sizeof(float) * (size_t)S.n_spheres);
   P.b_mats = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_mats);
   P.b_big = (int)pad16(sizeof(int32_t) * (size_t)S.n_big);
-  size_t scene_bytes = (size_t)P.b_nodes + P.b_sph + P.b_sph_mat + P.b_mats + P.b_big;
+  size_t scene_bytes = (size_t)P.b_nodes + P.b_sph + P.b_sph_k + P.b_sph_mat + P.b_mats + P.b_big;
   if (ctx->general) {
     P.b_sph_mv = S.any_moving ? (int)pad16(sizeof(float4) * (size_t)S.n_spheres) : 0;
     P.b_sph_t0 = S.any_moving ? (int)pad16(sizeof(float) * (size_t)S.n_spheres) : 0;

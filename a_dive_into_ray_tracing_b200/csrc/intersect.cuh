@@ -63,25 +63,30 @@ RT_HD void hit_sphere(float4 s, V3f center, bool closed, const Ray &r, const Ray
   if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; }
 }
 
-// Oversized spheres (the r = 1000 ground): FP64. With |c - o| ~ 1e3 the float
-// subtraction alone loses 3e-5 of the height above the surface; these primitives
-// are few (the always-tested "big" list) so double precision is affordable.
-RT_HD void hit_sphere_f64(float4 s, V3f center, bool closed, const Ray &r, float t_min, HitAcc &h, int32_t id) {
-  double gx = (double)center.x - (double)r.o.x, gy = (double)center.y - (double)r.o.y,
-         gz = (double)center.z - (double)r.o.z;
-  double dx = r.d.x, dy = r.d.y, dz = r.d.z;
-  double a = dx * dx + dy * dy + dz * dz;
-  double bp = gx * dx + gy * dy + gz * dz;
-  double c = gx * gx + gy * gy + gz * gz - (double)s.w * (double)s.w;
-  double disc = bp * bp - a * c;
-  if (closed ? (disc < 0.0) : !(disc > 0.0)) return;
-  double sq = sqrt(disc);
-  double inv = 1.0 / a;
-  float root = (float)((bp - sq) * inv);
+// Oversized spheres (the r = 1000 ground, always-tested "big" list). With |c - o| ~ 1e3
+// the subtraction c - o alone loses 3e-5 of the height above the surface in FP32, so
+// the quadratic is expanded around the ORIGIN instead:  f = |o-c|^2 - r^2 =
+// |o|^2 - 2 o.c + K  with K = |c|^2 - r^2 precomputed in double on the host (0 for the
+// reference's ground sphere): no large terms cancel for origins near the surface.
+// Roots from the numerically stable pair  s = bp + sign(bp) sqrt(bp^2 - a f):
+// t_a = f / s, t_b = s / a.   (bp = (c-o).d, a = d.d)
+RT_HD void hit_sphere_big(float4 s, float K, bool closed, const Ray &r, const RayPre &pre, float t_min, HitAcc &h,
+                          int32_t id) {
+  const V3f c = xyz(s);
+  const float f = RT_FMA(-2.0f, dot(r.o, c), dot(r.o, r.o)) + K;
+  const float a = dot(r.d, r.d);
+  const float bp = dot(c, r.d) - dot(r.o, r.d);
+  const float disc = RT_FMA(bp, bp, -a * f);
+  if (closed ? (disc < 0.0f) : !(disc > 0.0f)) return;
+  const float sq = RT_SQRT(disc);
+  const float s1 = bp + (bp >= 0.0f ? sq : -sq);
+  const float ta = (s1 != 0.0f) ? f / s1 : 0.0f;
+  const float tb = s1 * pre.inv_a;
+  float root = RT_FMIN(ta, tb);
   if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; return; }
   bool near_in_range = closed ? (root >= t_min && root <= h.t) : (root > t_min && root < h.t);
   if (near_in_range) return;
-  root = (float)((bp + sq) * inv);
+  root = RT_FMAX(ta, tb);
   if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; }
 }
 
@@ -137,11 +142,11 @@ RT_HD bool hit_box(float4 lo, float4 hi, const RayPre &pre, float t_min, float t
 }
 
 // One primitive by RT_PRIM_ID. PROFILE selects the interval rule of static spheres.
-template <int PROFILE, bool GENERAL, bool F64>
+template <int PROFILE, bool GENERAL, bool BIG>
 RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &pre, float t_min, HitAcc &h) {
   if (!GENERAL) {
     float4 s = S.sph[id];
-    if (F64) hit_sphere_f64(s, xyz(s), PROFILE == 0, r, t_min, h, id);
+    if (BIG) hit_sphere_big(s, S.sph_k[id], PROFILE == 0, r, pre, t_min, h, id);
     else hit_sphere(s, xyz(s), PROFILE == 0, r, pre, t_min, h, id);
     return;
   }
@@ -150,11 +155,12 @@ RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &p
     float4 s = S.sph[idx];
     V3f c = xyz(s);
     bool closed = PROFILE == 0;
+    bool moving = false;
     if (S.any_moving) {
       float4 mv = S.sph_mv[idx];
-      if (mv.w != 0.0f) { c = sphere_center_at(s, mv, S.sph_t0[idx], r.tm); closed = true; }
+      if (mv.w != 0.0f) { c = sphere_center_at(s, mv, S.sph_t0[idx], r.tm); closed = true; moving = true; }
     }
-    if (F64) hit_sphere_f64(s, c, closed, r, t_min, h, id);
+    if (BIG && !moving) hit_sphere_big(s, S.sph_k[idx], closed, r, pre, t_min, h, id);
     else hit_sphere(s, c, closed, r, pre, t_min, h, id);
   } else if (type == RT_PRIM_TRIANGLE) {
     const float4 *t = S.tri + 4 * idx;
@@ -211,7 +217,7 @@ RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r, float t_min, float t
 }
 
 // Brute force over the flattened arrays in list order (parity hook; the reference's
-// hittable_list::hit). Spheres in the big list still use the FP64 path so that the
+// hittable_list::hit). Spheres in the big list still use the big-sphere formula so that the
 // result is identical to the BVH path's.
 template <int PROFILE, bool GENERAL>
 RT_HD HitAcc trace_brute(const DevScene &S, const uint8_t *is_big, const Ray &r, float t_min, float t_max) {

@@ -18,7 +18,7 @@
 #include "shade.cuh"
 
 #ifndef RT_BLOCK
-#define RT_BLOCK 512
+#define RT_BLOCK 1024
 #endif
 #define RT_TILE_W 8
 #define RT_TILE_H 4
@@ -34,7 +34,7 @@ struct RenderParams {
   unsigned long long *stats;     // paths, segments, box tests, prim tests
   uint32_t seed_lo, seed_hi;
   // bytes of each array staged to shared memory (all multiples of 16)
-  int b_nodes, b_sph, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big;
+  int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big;
 };
 
 __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &off, const void *src, int bytes) {
@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 1) k_render(const __grid_constant__ 
     S.nodes = (const float4 *)stage_to_smem(smem_raw, off, P.S.nodes, P.b_nodes);
     S.sph = (const float4 *)stage_to_smem(smem_raw, off, P.S.sph, P.b_sph);
     S.sph_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.sph_mat, P.b_sph_mat);
+    S.sph_k = (const float *)stage_to_smem(smem_raw, off, P.S.sph_k, P.b_sph_k);
     S.mats = (const float4 *)stage_to_smem(smem_raw, off, P.S.mats, P.b_mats);
     S.big = (const int32_t *)stage_to_smem(smem_raw, off, P.S.big, P.b_big);
     if (GENERAL) {

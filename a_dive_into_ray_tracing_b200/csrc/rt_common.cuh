@@ -62,6 +62,7 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 //
 //  nodes   float4[2*n_nodes]   {bmin.xyz, escape} {bmax.xyz, payload}   32 B/node
 //  sph     float4[n_spheres]   {c0.xyz, radius}                         16 B
+//  sph_k   float[n_spheres]    |c0|^2 - r^2 (big-sphere intersection, intersect.cuh)
 //  sph_mv  float4[n_spheres]   {c1-c0, 1/(time1-time0)} (only if any sphere moves;
 //                              .w == 0 marks a static sphere; time0 in sph_t0)
 //  tri     float4[4*n_tris]    {N.xyz (un-normalised), v0.N}, then three edge
@@ -74,6 +75,7 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 struct DevScene {
   const float4 *nodes;
   const float4 *sph;
+  const float *sph_k;   // |c0|^2 - r^2 per sphere (double precision on the host, rounded once)
   const float4 *sph_mv;
   const float *sph_t0;
   const float4 *tri;

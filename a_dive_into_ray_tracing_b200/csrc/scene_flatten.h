@@ -12,7 +12,7 @@
 
 struct HostFlat {
   std::vector<float4> sph, sph_mv, tri, tri_n, quad, mats;
-  std::vector<float> sph_t0;
+  std::vector<float> sph_t0, sph_k;
   std::vector<int32_t> sph_mat, tri_mat, quad_mat;
   bool any_moving = false;
 };
@@ -71,7 +71,7 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
   sph.assign(ns, make_float4(0, 0, 0, 0)); sph_mv.assign(ns, make_float4(0, 0, 0, 0));
   tri.assign(4 * (size_t)nt, make_float4(0, 0, 0, 0)); tri_n.assign(nt, make_float4(0, 0, 0, 0));
   quad.assign(2 * (size_t)nq, make_float4(0, 0, 0, 0)); mats.assign(2 * (size_t)nm, make_float4(0, 0, 0, 0));
-  sph_t0.assign(ns, 0.f); sph_mat.assign(ns, 0); tri_mat.assign(nt, 0); quad_mat.assign(nq, 0);
+  sph_t0.assign(ns, 0.f); F.sph_k.assign(ns, 0.f); sph_mat.assign(ns, 0); tri_mat.assign(nt, 0); quad_mat.assign(nq, 0);
   for (int i = 0; i < ns; i++) {
     const rt_sphere &s = sc->spheres[i];
     sph[i] = make_float4(s.center0[0], s.center0[1], s.center0[2], s.radius);
@@ -81,6 +81,8 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
     else
       sph_mv[i] = make_float4(0, 0, 0, 0);
     sph_t0[i] = s.time0;
+    F.sph_k[i] = (float)((double)s.center0[0] * s.center0[0] + (double)s.center0[1] * s.center0[1] +
+                         (double)s.center0[2] * s.center0[2] - (double)s.radius * s.radius);
     sph_mat[i] = s.material;
   }
   for (int i = 0; i < nt; i++) {

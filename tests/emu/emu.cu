@@ -29,7 +29,7 @@ struct EmuScene {
 static void bind(EmuScene &E, const rt_scene_desc *sc) {
   DevScene &S = E.S;
   memset(&S, 0, sizeof S);
-  S.nodes = E.nodes.data(); S.sph = E.F.sph.data(); S.sph_mv = E.F.sph_mv.data(); S.sph_t0 = E.F.sph_t0.data();
+  S.nodes = E.nodes.data(); S.sph = E.F.sph.data(); S.sph_mv = E.F.sph_mv.data(); S.sph_t0 = E.F.sph_t0.data(); S.sph_k = E.F.sph_k.data();
   S.tri = E.F.tri.data(); S.tri_n = E.F.tri_n.data(); S.quad = E.F.quad.data();
   S.sph_mat = E.F.sph_mat.data(); S.tri_mat = E.F.tri_mat.data(); S.quad_mat = E.F.quad_mat.data();
   S.mats = E.F.mats.data(); S.big = E.big.data();

@@ -270,3 +270,31 @@ def test_gallery_image(golden_dir):
     psnr = SU.psnr(ds, ref)
     assert psnr > 38.0, psnr  # the unmodified CPU reference at 6 spp scores 45.5 dB
     assert np.all(np.abs(ds.mean((0, 1)) - ref.mean((0, 1))) < 0.01)
+
+
+def test_render_into_torch_tensor_on_torch_stream():
+    """rt_render_device on a caller stream / caller buffer (the multi-GPU plumbing path)
+    produces the same bits as rt_render into the context's own frame."""
+    import torch
+    from a_dive_into_ray_tracing_b200.dist import render_frame
+    W, H, spp = 64, 48, 16
+    sc = scenes.weekend(W, H)
+    with capi.Context(profile=0, seed=11) as ctx:
+        ctx.upload(sc).build_accel(1)
+        ctx.render(W, H, spp)
+        ref = ctx.accum()
+        acc = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)
+        render_frame(ctx, W, H, spp, acc)                      # default (legacy) stream
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(acc.cpu().numpy(), ref)
+        s = torch.cuda.Stream()
+        acc2 = torch.zeros(H, W, 4, device="cuda", dtype=torch.float32)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            render_frame(ctx, W, H, spp, acc2)
+            e1.record()
+        s.synchronize()
+        assert e0.elapsed_time(e1) > 0.05  # the kernel really ran on THAT stream
+        np.testing.assert_array_equal(acc2.cpu().numpy(), ref)
