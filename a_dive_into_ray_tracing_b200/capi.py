@@ -67,7 +67,7 @@ def load_library():
     L.rt_accel_build.restype = C.c_int
     L.rt_accel_build.argtypes = [_vp, C.c_int]
     L.rt_accel_download.restype = C.c_int
-    L.rt_accel_download.argtypes = [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]
+    L.rt_accel_download.argtypes = [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]
     L.rt_trace_closest.restype = C.c_int
     L.rt_trace_closest.argtypes = [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_int, _vp, _vp]
     L.rt_render.restype = C.c_int
@@ -150,13 +150,16 @@ class Context:
         return self
 
     def accel(self):
-        nn, nb = C.c_int(), C.c_int()
-        self._ck(self.lib.rt_accel_download(self.h, None, 0, C.addressof(nn), None, 0, C.addressof(nb)))
+        """(nodes, leaf_prims, big): the packed threaded BVH as the kernels read it."""
+        nn, nl, nb = C.c_int(), C.c_int(), C.c_int()
+        self._ck(self.lib.rt_accel_download(self.h, None, 0, C.addressof(nn), None, 0, C.addressof(nl), None, 0,
+                                            C.addressof(nb)))
         nodes = np.zeros(max(nn.value, 1), BVH_NODE_DT)
+        leaf = np.zeros(max(nl.value, 1), np.int32)
         big = np.zeros(max(nb.value, 1), np.int32)
-        self._ck(self.lib.rt_accel_download(self.h, nodes.ctypes.data, len(nodes), None, big.ctypes.data, len(big),
-                                            None))
-        return nodes[:nn.value], big[:nb.value]
+        self._ck(self.lib.rt_accel_download(self.h, nodes.ctypes.data, len(nodes), None, leaf.ctypes.data, len(leaf),
+                                            None, big.ctypes.data, len(big), None))
+        return nodes[:nn.value], leaf[:nl.value], big[:nb.value]
 
     def trace_closest(self, rays, t_min=1e-3, t_max=np.inf, use_accel=True):
         rays = np.ascontiguousarray(rays, np.float32)

@@ -93,11 +93,12 @@ struct rt_ctx {
   // device scene
   std::vector<DevBuf *> owned;
   DevBuf d_nodes, d_sph, d_sph_k, d_sph_mv, d_sph_t0, d_tri, d_tri_n, d_quad, d_sph_mat, d_tri_mat, d_quad_mat, d_mats, d_big,
-      d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad;
+      d_leaf_prims, d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad;
   DevScene S;
   DevCamera cam;
   ShadeParams sp;
   std::vector<int32_t> big_ids;
+  int n_leaf_prims = 0, max_leaf = 1;
   // frame
   int W = 0, H = 0;
   DevBuf d_accum, d_partial, d_counter, d_stats, d_linear, d_rgb8, d_rays, d_ids, d_ts;
@@ -188,7 +189,7 @@ void rt_destroy(rt_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf *all[] = {&ctx->d_nodes, &ctx->d_sph, &ctx->d_sph_k, &ctx->d_sph_mv, &ctx->d_sph_t0, &ctx->d_tri, &ctx->d_tri_n, &ctx->d_quad,
-                   &ctx->d_sph_mat, &ctx->d_tri_mat, &ctx->d_quad_mat, &ctx->d_mats, &ctx->d_big, &ctx->d_sph_is_big,
+                   &ctx->d_sph_mat, &ctx->d_tri_mat, &ctx->d_quad_mat, &ctx->d_mats, &ctx->d_big, &ctx->d_leaf_prims, &ctx->d_sph_is_big,
                    &ctx->d_raw_sph, &ctx->d_raw_tri, &ctx->d_raw_quad, &ctx->d_accum, &ctx->d_partial, &ctx->d_counter,
                    &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts};
   for (DevBuf *b : all) dev_free(*b);
@@ -239,6 +240,7 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   std::vector<uint8_t> nobig(std::max(ns, 1), 0);
   if ((rc = dev_upload(ctx, ctx->d_sph_is_big, nobig.data(), nobig.size()))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_big, 16))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_leaf_prims, 16))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_nodes, 32))) return rc;
 
   DevScene &S = ctx->S;
@@ -255,6 +257,7 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   S.quad_mat = (const int32_t *)ctx->d_quad_mat.p;
   S.mats = (const float4 *)ctx->d_mats.p;
   S.big = (const int32_t *)ctx->d_big.p;
+  S.leaf_prims = (const int32_t *)ctx->d_leaf_prims.p;
   S.n_nodes = 0; S.n_big = 0;
   S.n_spheres = ns; S.n_tris = nt; S.n_quads = nq; S.n_mats = nm;
   S.any_moving = any_moving ? 1 : 0;
@@ -293,7 +296,7 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   const int ns = ctx->S.n_spheres, nt = ctx->S.n_tris, nq = ctx->S.n_quads;
   const int n = ns + nt + nq;
   ctx->big_ids.clear();
-  ctx->S.n_nodes = 0; ctx->S.n_big = 0;
+  ctx->S.n_nodes = 0; ctx->S.n_big = 0; ctx->n_leaf_prims = 0;
   ctx->stats.n_nodes = 0; ctx->stats.n_big_prims = 0;
   if (n == 0) { ctx->have_accel = true; ctx->stats.ms_build = 0; return RT_OK; }
   CK(cudaEventRecord(ctx->ev0, st));
@@ -305,8 +308,8 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   B.tris = (const rt_triangle *)ctx->d_raw_tri.p;
   B.quads = (const rt_quad *)ctx->d_raw_quad.p;
   B.thickness = (ctx->sp.flags & RT_FLAG_FLIP_NORMALS) ? 0.01f : 0.1f; // THICKNESS of the two trees
-  DevBuf t_lo, t_hi, t_flag, t_bounds, t_small, t_keys, t_left, t_right, t_parent, t_nflag, t_size, t_nlo, t_nhi;
-  DevBuf *temps[] = {&t_lo, &t_hi, &t_flag, &t_bounds, &t_small, &t_keys, &t_left, &t_right, &t_parent, &t_nflag, &t_size, &t_nlo, &t_nhi};
+  DevBuf t_lo, t_hi, t_flag, t_bounds, t_small, t_keys, t_left, t_right, t_parent, t_nflag, t_size, t_lcnt, t_nlo, t_nhi;
+  DevBuf *temps[] = {&t_lo, &t_hi, &t_flag, &t_bounds, &t_small, &t_keys, &t_left, &t_right, &t_parent, &t_nflag, &t_size, &t_lcnt, &t_nlo, &t_nhi};
   auto cleanup = [&]() { for (DevBuf *b : temps) dev_free(*b); };
 #define CKB(call)                                                                                  \
   do {                                                                                             \
@@ -379,13 +382,21 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     RSV(t_keys, sizeof(unsigned long long) * (size_t)n_pad);
     RSV(t_left, sizeof(int) * (size_t)nsm); RSV(t_right, sizeof(int) * (size_t)nsm);
     RSV(t_parent, sizeof(int) * (size_t)n_nodes); RSV(t_nflag, sizeof(int) * (size_t)nsm);
-    RSV(t_size, sizeof(int) * (size_t)n_nodes);
+    RSV(t_size, sizeof(int) * (size_t)n_nodes); RSV(t_lcnt, sizeof(int) * (size_t)n_nodes);
+    { int rc = dev_reserve(ctx, ctx->d_leaf_prims, sizeof(int32_t) * (size_t)nsm); if (rc) { cleanup(); return rc; } }
     RSV(t_nlo, sizeof(float4) * (size_t)n_nodes); RSV(t_nhi, sizeof(float4) * (size_t)n_nodes);
     { int rc = dev_reserve(ctx, ctx->d_nodes, sizeof(float4) * 2 * (size_t)n_nodes); if (rc) { cleanup(); return rc; } }
     B.small_gid = (const int *)t_small.p;
     B.keys = (unsigned long long *)t_keys.p;
     B.left = (int *)t_left.p; B.right = (int *)t_right.p; B.parent = (int *)t_parent.p;
-    B.flag = (int *)t_nflag.p; B.size = (int *)t_size.p;
+    B.flag = (int *)t_nflag.p; B.size = (int *)t_size.p; B.lcnt = (int *)t_lcnt.p;
+    B.leaf_prims = (int32_t *)ctx->d_leaf_prims.p;
+    {
+      const char *e = getenv("B200RT_MAX_LEAF"); // tuning knob (leaf size)
+      int ml = e ? atoi(e) : 1; // while-while traversal: single-primitive leaves measured fastest
+      B.max_leaf = ml < 1 ? 1 : (ml > 8 ? 8 : ml);
+      ctx->max_leaf = B.max_leaf;
+    }
     B.nbox_lo = (float4 *)t_nlo.p; B.nbox_hi = (float4 *)t_nhi.p;
     B.packed = (float4 *)ctx->d_nodes.p;
     k_morton<<<(n_pad + TB - 1) / TB, TB, 0, st>>>(B, final_round);
@@ -421,6 +432,10 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     k_pack<<<(n_nodes + TB - 1) / TB, TB, 0, st>>>(B);
     ctx->launches++;
     CKB(cudaGetLastError());
+    int kept = 0; // nodes that survive leaf collapsing = kept size of the root (build node 0)
+    CKB(cudaMemcpyAsync(&kept, B.size, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CKB(cudaStreamSynchronize(st));
+    n_nodes = kept;
   }
   CKB(cudaEventRecord(ctx->ev1, st));
   CKB(cudaStreamSynchronize(st));
@@ -429,6 +444,8 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
 #undef CKB
 #undef RSV
   ctx->S.nodes = (const float4 *)ctx->d_nodes.p;
+  ctx->S.leaf_prims = (const int32_t *)ctx->d_leaf_prims.p;
+  ctx->n_leaf_prims = nsm;
   ctx->S.n_nodes = n_nodes;
   ctx->stats.n_nodes = n_nodes;
   ctx->stats.n_big_prims = n_big;
@@ -436,17 +453,24 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   return RT_OK;
 }
 
-int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nodes, int32_t *big_prims, int cap_big,
-                      int *n_big) {
+int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nodes, int32_t *leaf_prims, int cap_leaf,
+                      int *n_leaf, int32_t *big_prims, int cap_big, int *n_big) {
   if (!ctx) return RT_ERR_INVALID;
   if (!ctx->have_accel) return fail(ctx, RT_ERR_STATE, "rt_accel_download before rt_accel_build");
   CK(cudaSetDevice(ctx->cfg.device));
   if (n_nodes) *n_nodes = ctx->S.n_nodes;
+  if (n_leaf) *n_leaf = ctx->n_leaf_prims;
   if (n_big) *n_big = ctx->S.n_big;
   if (nodes) {
     if (cap_nodes < ctx->S.n_nodes) return fail(ctx, RT_ERR_INVALID, "node buffer too small");
     if (ctx->S.n_nodes)
       CK(cudaMemcpy(nodes, ctx->d_nodes.p, sizeof(rt_bvh_node) * (size_t)ctx->S.n_nodes, cudaMemcpyDeviceToHost));
+  }
+  if (leaf_prims) {
+    if (cap_leaf < ctx->n_leaf_prims) return fail(ctx, RT_ERR_INVALID, "leaf-primitive buffer too small");
+    if (ctx->n_leaf_prims)
+      CK(cudaMemcpy(leaf_prims, ctx->d_leaf_prims.p, sizeof(int32_t) * (size_t)ctx->n_leaf_prims,
+                    cudaMemcpyDeviceToHost));
   }
   if (big_prims) {
     if (cap_big < ctx->S.n_big) return fail(ctx, RT_ERR_INVALID, "big-primitive buffer too small");
@@ -517,7 +541,8 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   P.tiles_x = (W + RT_TILE_W - 1) / RT_TILE_W;
   P.n_tiles = P.tiles_x * ((H + RT_TILE_H - 1) / RT_TILE_H);
   const int grid = ctx->sm_count;
-  const int n_warps = grid * (RT_BLOCK / 32);
+  const int block = RT_BLOCK_OF(ctx->general);
+  const int n_warps = grid * (block / 32);
   // chunking: balance end-of-frame imbalance (few work items per warp) against the
   // per-item drain tail (~10 iterations): n_chunks ~ sqrt(0.133 * warps * spp / tiles)
   double ideal = sqrt(0.133 * (double)n_warps * (double)spp_count / (double)P.n_tiles);
@@ -546,7 +571,8 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   P.b_sph_k = (int)pad16(sizeof(float) * (size_t)S.n_spheres);
   P.b_mats = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_mats);
   P.b_big = (int)pad16(sizeof(int32_t) * (size_t)S.n_big);
-  size_t scene_bytes = (size_t)P.b_nodes + P.b_sph + P.b_sph_k + P.b_sph_mat + P.b_mats + P.b_big;
+  P.b_leaf_prims = (int)pad16(sizeof(int32_t) * (size_t)ctx->n_leaf_prims);
+  size_t scene_bytes = (size_t)P.b_nodes + P.b_sph + P.b_sph_k + P.b_sph_mat + P.b_mats + P.b_big + P.b_leaf_prims;
   if (ctx->general) {
     P.b_sph_mv = S.any_moving ? (int)pad16(sizeof(float4) * (size_t)S.n_spheres) : 0;
     P.b_sph_t0 = S.any_moving ? (int)pad16(sizeof(float) * (size_t)S.n_spheres) : 0;
@@ -557,7 +583,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
     P.b_quad_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_quads);
     scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat;
   }
-  const size_t acc_bytes = (size_t)(RT_BLOCK / 32) * 128 * sizeof(float);
+  const size_t acc_bytes = (size_t)(block / 32) * 128 * sizeof(float);
   const bool smem = scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin;
   const size_t smem_bytes = acc_bytes + (smem ? scene_bytes : 0);
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
@@ -567,14 +593,14 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   CK(cudaFuncGetAttributes(&fa, (const void *)kern));
   CK(cudaMemsetAsync(P.work_counter, 0, 4, st));
   if (timed) CK(cudaEventRecord(ctx->ev0, st));
-  kern<<<grid, RT_BLOCK, smem_bytes, st>>>(P);
+  kern<<<grid, block, smem_bytes, st>>>(P);
   CK(cudaGetLastError());
   k_combine<<<(unsigned)((n_pix + 255) / 256), 256, 0, st>>>((float4 *)d_accum, P.partial, (int)n_pix, P.n_chunks);
   CK(cudaGetLastError());
   ctx->launches += 2;
   if (timed) CK(cudaEventRecord(ctx->ev1, st));
   ctx->stats.smem_bytes = (int)smem_bytes;
-  ctx->stats.block_threads = RT_BLOCK;
+  ctx->stats.block_threads = block;
   ctx->stats.grid_blocks = grid;
   ctx->stats.regs_per_thread = fa.numRegs;
   return RT_OK;

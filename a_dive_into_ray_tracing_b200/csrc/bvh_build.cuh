@@ -55,7 +55,10 @@ struct BuildArrays {
   int *left, *right;         // [n_small-1]
   int *parent;               // [2*n_small-1]
   int *flag;                 // [n_small-1]
-  int *size;                 // [2*n_small-1] nodes in subtree
+  int *size;                 // [2*n_small-1] KEPT nodes in subtree (after leaf collapsing)
+  int *lcnt;                 // [2*n_small-1] primitives (build leaves) in subtree
+  int max_leaf;              // subtrees with <= max_leaf primitives become ONE leaf node (1..8)
+  int32_t *leaf_prims;       // [n_small] RT_PRIM_IDs in depth-first leaf order
   float4 *nbox_lo, *nbox_hi; // [2*n_small-1]
   float4 *packed;            // [2*(2*n_small-1)] output nodes
 };
@@ -206,6 +209,7 @@ RT_HD void body_fit(const BuildArrays &B, int leaf, int rotate) {
   B.nbox_lo[node] = B.pbox_lo[gid];
   B.nbox_hi[node] = B.pbox_hi[gid];
   B.size[node] = 1;
+  B.lcnt[node] = 1;
   if (n == 1) { B.parent[node] = -1; return; }
   int p = B.parent[node];
   while (p >= 0) {
@@ -248,7 +252,9 @@ RT_HD void body_fit(const BuildArrays &B, int leaf, int rotate) {
         float4 olo = (which < 2) ? rlo : llo, ohi = (which < 2) ? rhi : lhi;
         B.nbox_lo[c] = f4min(klo, olo);
         B.nbox_hi[c] = f4max(khi, ohi);
-        B.size[c] = 1 + RT_LDCG_I(&B.size[keep]) + RT_LDCG_I(&B.size[o]);
+        const int lc_c = RT_LDCG_I(&B.lcnt[keep]) + RT_LDCG_I(&B.lcnt[o]);
+        B.lcnt[c] = lc_c;
+        B.size[c] = lc_c <= B.max_leaf ? 1 : 1 + RT_LDCG_I(&B.size[keep]) + RT_LDCG_I(&B.size[o]);
         RT_FENCE();
         if (which < 2) { r = up; rlo = RT_LDCG4(&B.nbox_lo[r]); rhi = RT_LDCG4(&B.nbox_hi[r]);
                          llo = f4min(klo, olo); lhi = f4max(khi, ohi); }
@@ -258,30 +264,39 @@ RT_HD void body_fit(const BuildArrays &B, int leaf, int rotate) {
     }
     B.nbox_lo[p] = f4min(llo, rlo);
     B.nbox_hi[p] = f4max(lhi, rhi);
-    B.size[p] = 1 + RT_LDCG_I(&B.size[l]) + RT_LDCG_I(&B.size[r]);
+    const int lc_p = RT_LDCG_I(&B.lcnt[l]) + RT_LDCG_I(&B.lcnt[r]);
+    B.lcnt[p] = lc_p;
+    B.size[p] = lc_p <= B.max_leaf ? 1 : 1 + RT_LDCG_I(&B.size[l]) + RT_LDCG_I(&B.size[r]);
     p = RT_LDCG_I(&B.parent[p]);
   }
 }
 
-// ---- kernel 7: depth-first threaded layout + 32-byte packing. Node `v` (build id)
-// gets position = #nodes before it in DFS preorder (walk to the root); its escape
-// index is position + subtree size; boxes are padded by a few ulps so that the
-// FP32 slab test stays conservative.
+// ---- kernel 7: depth-first threaded layout + 32-byte packing. A build node `v` is
+// emitted unless it lies strictly inside a collapsed subtree (an ancestor holds
+// <= max_leaf primitives and became a multi-primitive leaf). Its position = number of
+// emitted nodes before it in DFS preorder (walk to the root); escape = position +
+// kept subtree size. Leaves reference leaf_prims[first .. first+count): payload =
+// ~(first << 3 | count-1). Boxes are padded by a few ulps so that the FP32 slab test
+// stays conservative.
 RT_HD void body_pack(const BuildArrays &B, int v) {
   const int n = B.n_small;
-  int pos = 0, cur = v;
+  int pos = 0, lpos = 0, cur = v;
   for (int p = B.parent[cur]; p >= 0; p = B.parent[cur]) {
     pos += 1;
-    if (B.right[p] == cur) pos += B.size[B.left[p]];
+    if (B.right[p] == cur) { pos += B.size[B.left[p]]; lpos += B.lcnt[B.left[p]]; }
     cur = p;
   }
+  const bool build_leaf = v >= n - 1;
+  if (build_leaf) B.leaf_prims[lpos] = gid_to_prim_id(B, (int)(B.keys[v - (n - 1)] & 0xffffffffull));
+  const int par = B.parent[v];
+  if (par >= 0 && B.lcnt[par] <= B.max_leaf) return; // inside a collapsed subtree
   float4 lo = B.nbox_lo[v], hi = B.nbox_hi[v];
   float e[3] = {fmaxf(fabsf(lo.x), fabsf(hi.x)), fmaxf(fabsf(lo.y), fabsf(hi.y)), fmaxf(fabsf(lo.z), fabsf(hi.z))};
   lo.x -= RT_FMA(e[0], 4e-7f, 1e-9f); lo.y -= RT_FMA(e[1], 4e-7f, 1e-9f); lo.z -= RT_FMA(e[2], 4e-7f, 1e-9f);
   hi.x += RT_FMA(e[0], 4e-7f, 1e-9f); hi.y += RT_FMA(e[1], 4e-7f, 1e-9f); hi.z += RT_FMA(e[2], 4e-7f, 1e-9f);
-  int escape = pos + B.size[v];
+  const int escape = pos + B.size[v];
   int payload;
-  if (v >= n - 1) payload = ~gid_to_prim_id(B, (int)(B.keys[v - (n - 1)] & 0xffffffffull));
+  if (build_leaf || B.lcnt[v] <= B.max_leaf) payload = ~((lpos << 3) | (B.lcnt[v] - 1));
   else payload = pos + 1;
   lo.w = RT_I2F(escape);
   hi.w = RT_I2F(payload);

@@ -194,23 +194,28 @@ RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r, float t_min, float t
   }
   int node = 0;
   const int n_nodes = S.n_nodes;
-  while (node < n_nodes) {
-    int32_t leaf = -1;
-    while (node < n_nodes) {
-      float4 lo = S.nodes[2 * node], hi = S.nodes[2 * node + 1];
-      if (COUNT) cnt->box_tests++;
-      int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
-      if (hit_box(lo, hi, pre, t_min, h.t)) {
-        if (pay >= 0) { node = pay; continue; }
-        leaf = ~pay;
+  int first = 0, left = 0; // pending primitives of the last hit leaf: leaf_prims[first .. first+left)
+  while (node < n_nodes || left > 0) {
+    if (left == 0) {
+      while (node < n_nodes) {
+        float4 lo = S.nodes[2 * node], hi = S.nodes[2 * node + 1];
+        if (COUNT) cnt->box_tests++;
+        int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
+        if (hit_box(lo, hi, pre, t_min, h.t)) {
+          if (pay >= 0) { node = pay; continue; }
+          first = (~pay) >> 3;
+          left = ((~pay) & 7) + 1;
+          node = esc;
+          break;
+        }
         node = esc;
-        break;
       }
-      node = esc;
     }
-    if (leaf >= 0) {
+    if (left > 0) { // one primitive per outer iteration keeps the warp converged here
       if (COUNT) cnt->prim_tests++;
-      hit_prim<PROFILE, GENERAL, false>(S, leaf, r, pre, t_min, h);
+      hit_prim<PROFILE, GENERAL, false>(S, S.leaf_prims[first], r, pre, t_min, h);
+      first++;
+      left--;
     }
   }
   return h;

@@ -17,9 +17,16 @@
 #pragma once
 #include "shade.cuh"
 
+// Threads per CTA (one CTA per SM). The sphere-only kernels fit 64 registers -> 1024
+// threads; the general kernel (triangles, rects, moving spheres, textures) is capped at 64 too
+// (a few bytes of spills): measured faster than 768 threads x 72 registers.
 #ifndef RT_BLOCK
 #define RT_BLOCK 1024
 #endif
+#ifndef RT_BLOCK_GENERAL
+#define RT_BLOCK_GENERAL 1024
+#endif
+#define RT_BLOCK_OF(GENERAL) ((GENERAL) ? RT_BLOCK_GENERAL : RT_BLOCK)
 #define RT_TILE_W 8
 #define RT_TILE_H 4
 
@@ -34,7 +41,7 @@ struct RenderParams {
   unsigned long long *stats;     // paths, segments, box tests, prim tests
   uint32_t seed_lo, seed_hi;
   // bytes of each array staged to shared memory (all multiples of 16)
-  int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big;
+  int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big, b_leaf_prims;
 };
 
 __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &off, const void *src, int bytes) {
@@ -48,7 +55,7 @@ __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &o
 }
 
 template <int PROFILE, bool GENERAL, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(RT_BLOCK, 1) k_render(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevScene S = P.S;
   int off = 0;
@@ -59,6 +66,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 1) k_render(const __grid_constant__ 
     S.sph_k = (const float *)stage_to_smem(smem_raw, off, P.S.sph_k, P.b_sph_k);
     S.mats = (const float4 *)stage_to_smem(smem_raw, off, P.S.mats, P.b_mats);
     S.big = (const int32_t *)stage_to_smem(smem_raw, off, P.S.big, P.b_big);
+    S.leaf_prims = (const int32_t *)stage_to_smem(smem_raw, off, P.S.leaf_prims, P.b_leaf_prims);
     if (GENERAL) {
       S.sph_mv = (const float4 *)stage_to_smem(smem_raw, off, P.S.sph_mv, P.b_sph_mv);
       S.sph_t0 = (const float *)stage_to_smem(smem_raw, off, P.S.sph_t0, P.b_sph_t0);

@@ -61,6 +61,8 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 // memory by the render kernel when they fit ("data layout").
 //
 //  nodes   float4[2*n_nodes]   {bmin.xyz, escape} {bmax.xyz, payload}   32 B/node
+//                              payload >= 0: first child; < 0: ~(first<<3 | count-1) into leaf_prims
+//  leaf_prims int32[n_small]   RT_PRIM_IDs in depth-first leaf order
 //  sph     float4[n_spheres]   {c0.xyz, radius}                         16 B
 //  sph_k   float[n_spheres]    |c0|^2 - r^2 (big-sphere intersection, intersect.cuh)
 //  sph_mv  float4[n_spheres]   {c1-c0, 1/(time1-time0)} (only if any sphere moves;
@@ -86,6 +88,7 @@ struct DevScene {
   const int32_t *quad_mat;
   const float4 *mats;
   const int32_t *big;
+  const int32_t *leaf_prims; // RT_PRIM_IDs in depth-first leaf order (leaves hold ranges of it)
   int n_nodes, n_spheres, n_tris, n_quads, n_mats, n_big;
   int any_moving;
 };

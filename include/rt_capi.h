@@ -156,13 +156,15 @@ typedef struct rt_scene_desc {
 
 /* 32-byte packed BVH node as downloaded by rt_accel_download (device layout).
  * Threaded (stackless) traversal: on a box hit go to `child` (inner) or test
- * the primitive (leaf) and go to `escape`; on a miss go to `escape`.
+ * the leaf's primitives and go to `escape`; on a miss go to `escape`.
  * index == n_nodes terminates. */
 typedef struct rt_bvh_node {
   float bmin[3];
   int32_t escape;
   float bmax[3];
-  int32_t payload; /* >= 0: index of first child (inner); < 0: ~prim_id (leaf) */
+  int32_t payload; /* >= 0: index of first child (inner);
+                    * < 0: leaf, ~payload = first << 3 | (count - 1): the leaf holds
+                    * leaf_prims[first .. first + count), count <= 8 */
 } rt_bvh_node;
 
 typedef struct rt_stats_t {
@@ -186,8 +188,10 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *scene);
 
 /* quality: 0 = LBVH (Morton + radix sort + Karras), 1 = + SAH refinement. */
 int rt_accel_build(rt_ctx *ctx, int quality);
-int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nodes,
-                      int32_t *big_prims, int cap_big, int *n_big);
+/* nodes: threaded BVH; leaf_prims: RT_PRIM_IDs in depth-first leaf order; big_prims: the
+ * always-tested oversized primitives. Any output pointer may be NULL (counts only). */
+int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nodes, int32_t *leaf_prims,
+                      int cap_leaf, int *n_leaf, int32_t *big_prims, int cap_big, int *n_big);
 
 /* rays: [n][8] floats = origin.xyz, time, direction.xyz, unused. use_accel 0 =
  * brute force over the flattened arrays, 1 = through the BVH. */

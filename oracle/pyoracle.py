@@ -44,7 +44,7 @@ class L1:
                                   C.c_uint64, _vp, _vp, _vp]
         self._packed = getattr(self.lib, p + "closest_hit_packed")
         self._packed.restype = C.c_int
-        self._packed.argtypes = [C.POINTER(RtSceneDesc), C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int,
+        self._packed.argtypes = [C.POINTER(RtSceneDesc), C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int,
                                  C.c_double, C.c_double, _vp, _vp, _vp]
         self._render = getattr(self.lib, p + "render")
         self._render.restype = C.c_uint64
@@ -74,17 +74,19 @@ class L1:
         assert rc == 0
         return ids, ts, cnt
 
-    def closest_hit_packed(self, scene, profile, nodes, big, rays, t_min=1e-3, t_max=np.inf):
+    def closest_hit_packed(self, scene, profile, nodes, leaf_prims, big, rays, t_min=1e-3, t_max=np.inf):
         rays = np.ascontiguousarray(rays, np.float32)
         nodes = np.ascontiguousarray(nodes, BVH_NODE_DT)
         big = np.ascontiguousarray(big, np.int32)
+        leaf_prims = np.ascontiguousarray(leaf_prims, np.int32)
         n = len(rays)
         ids = np.empty(n, np.int32)
         ts = np.empty(n, np.float64)
         cnt = np.zeros(2, np.uint64)
         d = scene.desc()
         tmax = 3.4e38 if not np.isfinite(t_max) else float(t_max)
-        rc = self._packed(C.byref(d), profile, nodes.ctypes.data, len(nodes), big.ctypes.data, len(big),
+        rc = self._packed(C.byref(d), profile, nodes.ctypes.data, len(nodes), leaf_prims.ctypes.data,
+                          big.ctypes.data, len(big),
                           rays.ctypes.data, n, float(t_min), tmax, ids.ctypes.data, ts.ctypes.data, cnt.ctypes.data)
         assert rc == 0
         return ids, ts, cnt

@@ -643,7 +643,7 @@ int FN(closest_hit)(const rt_scene_desc *sc, int profile, const float *rays, int
  * with the reference's own primitive tests. Counts box and primitive tests —
  * the N_box / N_prim figures of the roofline model. */
 int FN(closest_hit_packed)(const rt_scene_desc *sc, int profile, const rt_bvh_node *nodes, int n_nodes,
-                           const int32_t *big, int n_big, const float *rays, int n, double t_min, double t_max,
+                           const int32_t *leaf_prims, const int32_t *big, int n_big, const float *rays, int n, double t_min, double t_max,
                            int32_t *prim_id, double *t_out, uint64_t *counters /*[2]*/) {
   FN(World) w = {sc, profile, sc->flags, 0, 0};
   for (int k = 0; k < n; k++) {
@@ -675,7 +675,9 @@ int FN(closest_hit_packed)(const rt_scene_desc *sc, int profile, const rt_bvh_no
       }
       if (ok) {
         if (nd->payload >= 0) { node = nd->payload; continue; }
-        if (FN(prim_hit)(&w, ~nd->payload, &r, (REAL)t_min, closest, &tmp)) { any = 1; closest = tmp.t; rec = tmp; }
+        int enc = ~nd->payload, first = enc >> 3, count = (enc & 7) + 1;
+        for (int q2 = 0; q2 < count; q2++)
+          if (FN(prim_hit)(&w, leaf_prims[first + q2], &r, (REAL)t_min, closest, &tmp)) { any = 1; closest = tmp.t; rec = tmp; }
       }
       node = nd->escape;
     }

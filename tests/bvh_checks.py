@@ -32,22 +32,30 @@ def prim_boxes(sc, thickness):
     return boxes
 
 
-def check_packed_bvh(sc, nodes, big):
+def check_packed_bvh(sc, nodes, leaf_prims, big, max_leaf=8):
     n = len(nodes)
     thickness = 0.01 if (sc.flags & D.RT_FLAG_FLIP_NORMALS) else 0.1
     boxes = prim_boxes(sc, thickness)
     all_ids = set(boxes)
     big_ids = set(int(b) for b in big)
-    assert big_ids <= all_ids
+    assert big_ids <= all_ids and len(big_ids) == len(big)
     n_small = len(all_ids) - len(big_ids)
-    assert n == (2 * n_small - 1 if n_small else 0)
-    if n == 0:
+    # every non-big primitive appears exactly once in the leaf order
+    assert sorted(int(x) for x in leaf_prims) == sorted(all_ids - big_ids)
+    if n_small == 0:
+        assert n == 0
         return
     esc, pay = nodes["escape"], nodes["payload"]
     leaves = pay < 0
-    leaf_ids = [int(~p) for p in pay[leaves]]
-    # every non-big primitive in exactly one leaf
-    assert sorted(leaf_ids) == sorted(all_ids - big_ids)
+    enc = ~pay[leaves]
+    first, count = enc >> 3, (enc & 7) + 1
+    assert np.all(count >= 1) and np.all(count <= max_leaf)
+    # leaves tile leaf_prims in depth-first order: each primitive in exactly one leaf
+    order = np.argsort(np.where(leaves)[0])
+    assert np.array_equal(first[order], np.concatenate([[0], np.cumsum(count[order])[:-1]]))
+    assert int(count.sum()) == n_small
+    n_leaves = int(leaves.sum())
+    assert n == 2 * n_leaves - 1  # full binary tree
     # threaded layout: depth-first preorder
     assert np.all(esc > np.arange(n)) and np.all(esc <= n) and esc[0] == n
     inner = ~leaves
@@ -60,9 +68,10 @@ def check_packed_bvh(sc, nodes, big):
         r = esc[l]
         assert r < n and esc[r] == esc[i]  # the two children tile the parent's range
         assert np.all(lo[i] <= np.minimum(lo[l], lo[r]) + 1e-12) and np.all(hi[i] >= np.maximum(hi[l], hi[r]) - 1e-12)
-    for i in np.where(leaves)[0]:
-        blo, bhi = boxes[int(~pay[i])]
-        assert np.all(lo[i] <= blo) and np.all(hi[i] >= bhi)  # node box contains the primitive box
+    for i, f, c in zip(np.where(leaves)[0], first, count):
+        for pid in leaf_prims[f:f + c]:
+            blo, bhi = boxes[int(pid)]
+            assert np.all(lo[i] <= blo) and np.all(hi[i] >= bhi)  # node box contains the primitive boxes
 
 
 def sah_cost(nodes):

@@ -18,7 +18,7 @@
 struct EmuScene {
   HostFlat F;
   std::vector<float4> nodes;
-  std::vector<int32_t> big;
+  std::vector<int32_t> big, leaf_prims;
   std::vector<uint8_t> sph_is_big;
   DevScene S;
   DevCamera cam;
@@ -32,7 +32,7 @@ static void bind(EmuScene &E, const rt_scene_desc *sc) {
   S.nodes = E.nodes.data(); S.sph = E.F.sph.data(); S.sph_mv = E.F.sph_mv.data(); S.sph_t0 = E.F.sph_t0.data(); S.sph_k = E.F.sph_k.data();
   S.tri = E.F.tri.data(); S.tri_n = E.F.tri_n.data(); S.quad = E.F.quad.data();
   S.sph_mat = E.F.sph_mat.data(); S.tri_mat = E.F.tri_mat.data(); S.quad_mat = E.F.quad_mat.data();
-  S.mats = E.F.mats.data(); S.big = E.big.data();
+  S.mats = E.F.mats.data(); S.big = E.big.data(); S.leaf_prims = E.leaf_prims.data();
   S.n_nodes = (int)E.nodes.size() / 2; S.n_big = (int)E.big.size();
   S.n_spheres = sc->n_spheres; S.n_tris = sc->n_triangles; S.n_quads = sc->n_quads; S.n_mats = sc->n_materials;
   S.any_moving = E.F.any_moving;
@@ -46,9 +46,9 @@ static void bind(EmuScene &E, const rt_scene_desc *sc) {
 }
 
 // serial replay of rt_accel_build (csrc/b200rt.cu) with the same kernel bodies
-static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_frac, int big_rounds, int shuffle) {
+static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_frac, int big_rounds, int shuffle, int max_leaf) {
   const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, n = ns + nt + nq;
-  E.nodes.clear(); E.big.clear(); E.sph_is_big.assign(std::max(ns, 1), 0);
+  E.nodes.clear(); E.big.clear(); E.leaf_prims.clear(); E.sph_is_big.assign(std::max(ns, 1), 0);
   if (n == 0) return;
   BuildArrays B;
   memset(&B, 0, sizeof B);
@@ -80,11 +80,14 @@ static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_f
   while (n_pad < nsm) n_pad <<= 1;
   B.n_small = nsm; B.n_pad = n_pad; B.small_gid = small.data();
   std::vector<unsigned long long> keys(n_pad);
-  std::vector<int> left(nsm), right(nsm), parent(n_nodes), nflag(nsm), size(n_nodes);
+  std::vector<int> left(nsm), right(nsm), parent(n_nodes), nflag(nsm), size(n_nodes), lcnt(n_nodes);
+  E.leaf_prims.assign(nsm, 0);
   std::vector<float4> nlo(n_nodes), nhi(n_nodes);
   E.nodes.assign(2 * (size_t)n_nodes, make_float4(0, 0, 0, 0));
   B.keys = keys.data(); B.left = left.data(); B.right = right.data(); B.parent = parent.data(); B.flag = nflag.data();
-  B.size = size.data(); B.nbox_lo = nlo.data(); B.nbox_hi = nhi.data(); B.packed = E.nodes.data();
+  B.size = size.data(); B.lcnt = lcnt.data(); B.leaf_prims = E.leaf_prims.data();
+  B.max_leaf = max_leaf < 1 ? 1 : (max_leaf > 8 ? 8 : max_leaf);
+  B.nbox_lo = nlo.data(); B.nbox_hi = nhi.data(); B.packed = E.nodes.data();
   for (int i = 0; i < n_pad; i++) body_morton(B, i, final_round);
   for (int k = 2; k <= n_pad; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) for (int i = 0; i < n_pad; i++) body_bitonic(B.keys, i, j, k);
   for (int i = 0; i < nsm - 1; i++) body_karras(B, i);
@@ -103,6 +106,7 @@ static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_f
     }
   }
   for (int v = 0; v < n_nodes; v++) body_pack(B, v);
+  E.nodes.resize(2 * (size_t)size[0]); // kept nodes after leaf collapsing
 }
 
 template <int PROFILE, bool GENERAL>
@@ -148,20 +152,21 @@ static void render_t(EmuScene *E, int W, int H, int spp_begin, int spp_count, ui
 
 extern "C" {
 
-void *emu_create(const rt_scene_desc *sc, int profile, int quality, float big_frac, int big_rounds, int shuffle, char *err, int errcap) {
+void *emu_create(const rt_scene_desc *sc, int profile, int quality, float big_frac, int big_rounds, int shuffle, int max_leaf, char *err, int errcap) {
   EmuScene *E = new EmuScene();
   std::string e;
   E->profile = profile;
   if (flatten_scene(sc, profile, E->F, e)) { snprintf(err, errcap, "%s", e.c_str()); delete E; return nullptr; }
-  build(*E, sc, quality, big_frac, big_rounds, shuffle);
+  build(*E, sc, quality, big_frac, big_rounds, shuffle, max_leaf);
   bind(*E, sc);
   return E;
 }
 void emu_destroy(void *p) { delete (EmuScene *)p; }
-int emu_counts(void *p, int *n_nodes, int *n_big) { EmuScene *E = (EmuScene *)p; *n_nodes = E->S.n_nodes; *n_big = E->S.n_big; return 0; }
-int emu_download(void *p, rt_bvh_node *nodes, int32_t *big) {
+int emu_counts(void *p, int *n_nodes, int *n_leaf, int *n_big) { EmuScene *E = (EmuScene *)p; *n_nodes = E->S.n_nodes; *n_leaf = (int)E->leaf_prims.size(); *n_big = E->S.n_big; return 0; }
+int emu_download(void *p, rt_bvh_node *nodes, int32_t *leaf, int32_t *big) {
   EmuScene *E = (EmuScene *)p;
   memcpy(nodes, E->nodes.data(), sizeof(float4) * E->nodes.size());
+  memcpy(leaf, E->leaf_prims.data(), sizeof(int32_t) * E->leaf_prims.size());
   memcpy(big, E->big.data(), sizeof(int32_t) * E->big.size());
   return 0;
 }

@@ -24,21 +24,22 @@ def build(force=False):
 
 
 class Emu:
-    def __init__(self, scene, profile=None, quality=1, big_frac=0.30, big_rounds=3, shuffle=0):
+    def __init__(self, scene, profile=None, quality=1, big_frac=0.30, big_rounds=3, shuffle=0, max_leaf=4):
         build()
         self.lib = L = C.CDLL(PATH)
         L.emu_create.restype = _vp
-        L.emu_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_char_p, C.c_int]
+        L.emu_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                                 C.c_int]
         L.emu_destroy.argtypes = [_vp]
-        L.emu_counts.argtypes = [_vp, _vp, _vp]
-        L.emu_download.argtypes = [_vp, _vp, _vp]
+        L.emu_counts.argtypes = [_vp, _vp, _vp, _vp]
+        L.emu_download.argtypes = [_vp, _vp, _vp, _vp]
         L.emu_trace.argtypes = [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]
         L.emu_render.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, _vp, _vp, _vp]
         self.scene = scene
         self.profile = scene.profile if profile is None else profile
         d = scene.desc()
         err = C.create_string_buffer(256)
-        self.h = L.emu_create(C.byref(d), self.profile, quality, big_frac, big_rounds, shuffle, err, 256)
+        self.h = L.emu_create(C.byref(d), self.profile, quality, big_frac, big_rounds, shuffle, max_leaf, err, 256)
         if not self.h:
             raise ValueError(err.value.decode())
 
@@ -48,12 +49,13 @@ class Emu:
             self.h = None
 
     def accel(self):
-        nn, nb = C.c_int(), C.c_int()
-        self.lib.emu_counts(self.h, C.addressof(nn), C.addressof(nb))
+        nn, nl, nb = C.c_int(), C.c_int(), C.c_int()
+        self.lib.emu_counts(self.h, C.addressof(nn), C.addressof(nl), C.addressof(nb))
         nodes = np.zeros(max(nn.value, 1), BVH_NODE_DT)
+        leaf = np.zeros(max(nl.value, 1), np.int32)
         big = np.zeros(max(nb.value, 1), np.int32)
-        self.lib.emu_download(self.h, nodes.ctypes.data, big.ctypes.data)
-        return nodes[:nn.value], big[:nb.value]
+        self.lib.emu_download(self.h, nodes.ctypes.data, leaf.ctypes.data, big.ctypes.data)
+        return nodes[:nn.value], leaf[:nl.value], big[:nb.value]
 
     def trace(self, rays, t_min=1e-3, t_max=np.inf, use_accel=1):
         rays = np.ascontiguousarray(rays, np.float32)

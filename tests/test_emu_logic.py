@@ -19,18 +19,18 @@ def weekend_emu():
 
 def test_lbvh_invariants_weekend(weekend_emu):
     sc = weekend_emu.scene
-    nodes, big = weekend_emu.accel()
+    nodes, leaf, big = weekend_emu.accel()
     assert big.tolist() == [0]  # the r=1000 ground sphere is split off
-    assert len(nodes) == 2 * (sc.n_prims - 1) - 1
-    check_packed_bvh(sc, nodes, big)
+    assert len(leaf) == sc.n_prims - 1 and len(nodes) % 2 == 1 and len(nodes) <= 2 * (sc.n_prims - 1) - 1
+    check_packed_bvh(sc, nodes, leaf, big)
 
 
 @pytest.mark.parametrize("quality,shuffle", [(0, 0), (1, 0), (2, 1)])
 def test_lbvh_invariants_other_scenes(quality, shuffle):
     for sc in (scenes.next_week(120, 80), scenes.obj_room(width=64, height=64, subdivisions=1)):
         e = Emu(sc, quality=quality, shuffle=shuffle)
-        nodes, big = e.accel()
-        check_packed_bvh(sc, nodes, big)
+        nodes, leaf, big = e.accel()
+        check_packed_bvh(sc, nodes, leaf, big)
 
 
 def test_emulated_closest_hit_matches_reference(weekend_emu, hits_primary, hits_bounce):
@@ -93,3 +93,17 @@ def test_emulated_closest_hit_general_scenes(l1_64):
         same = (~mism) & (io >= 0)
         rel = np.abs(ta[same] - to[same]) / to[same]
         assert np.percentile(rel, 99.9) < 1e-5, (sc.name, rel.max())
+
+
+@pytest.mark.parametrize("max_leaf", [1, 2, 4, 8])
+def test_leaf_collapsing(max_leaf, hits_primary):
+    """Subtrees with <= max_leaf primitives become one leaf: same hits, fewer nodes."""
+    sc = scenes.weekend(400, 225)
+    e = Emu(sc, quality=1, shuffle=1, max_leaf=max_leaf)
+    nodes, leaf, big = e.accel()
+    check_packed_bvh(sc, nodes, leaf, big, max_leaf=max_leaf)
+    if max_leaf == 1:
+        assert len(nodes) == 2 * 486 - 1
+    rays = hits_primary["rays"][:3000]
+    ia, ta, cnt = e.trace(rays, use_accel=1)
+    np.testing.assert_array_equal(ia, hits_primary["ids"][:3000])

@@ -54,19 +54,19 @@ def test_closest_hit_full_grid_vs_oracle(weekend_ctx, l1_64):
 
 def test_bvh_structure_and_quality(weekend_ctx, l1_64, hits_primary):
     sc = scenes.weekend(400, 225)
-    nodes, big = weekend_ctx.accel()
-    assert big.tolist() == [0] and len(nodes) == 971
-    check_packed_bvh(sc, nodes, big)
+    nodes, leaf, big = weekend_ctx.accel()
+    assert big.tolist() == [0] and len(leaf) == 486 and len(nodes) <= 971
+    check_packed_bvh(sc, nodes, leaf, big)
     # the oracle traversing the SAME packed tree finds the same hits and counts the work
-    io, to, cnt = l1_64.closest_hit_packed(sc, 0, nodes, big, hits_primary["rays"])
+    io, to, cnt = l1_64.closest_hit_packed(sc, 0, nodes, leaf, big, hits_primary["rays"])
     np.testing.assert_array_equal(io, hits_primary["ids"])
-    assert cnt[0] / len(io) < 40 and cnt[1] / len(io) < 5
+    assert cnt[0] / len(io) < 40 and cnt[1] / len(io) < 12
     # SAH refinement does not make the tree worse than plain LBVH
     weekend_ctx.build_accel(0)
-    n0, _ = weekend_ctx.accel()
-    check_packed_bvh(sc, n0, big)
+    n0, l0_, _ = weekend_ctx.accel()
+    check_packed_bvh(sc, n0, l0_, big)
     weekend_ctx.build_accel(1)
-    n1, _ = weekend_ctx.accel()
+    n1, _, _ = weekend_ctx.accel()
     assert sah_cost(n1) <= sah_cost(n0) * 1.0001
 
 
@@ -79,8 +79,8 @@ def test_bvh_edge_cases():
         sc.camera = base.camera
         with capi.Context(profile=0) as ctx:
             ctx.upload(sc).build_accel(1)
-            nodes, big = ctx.accel()
-            check_packed_bvh(sc, nodes, big)
+            nodes, leaf, big = ctx.accel()
+            check_packed_bvh(sc, nodes, leaf, big)
             ia, ta = ctx.trace_closest(rays, use_accel=True)
             ib, tb = ctx.trace_closest(rays, use_accel=False)
             np.testing.assert_array_equal(ia, ib)
@@ -150,8 +150,8 @@ def test_closest_hit_general_scenes(l1_64):
     for sc, W, H in ((scenes.next_week(160, 100), 160, 100), (scenes.obj_room(width=96, height=96), 96, 96)):
         with capi.Context(profile=2) as ctx:
             ctx.upload(sc).build_accel(1)
-            nodes, big = ctx.accel()
-            check_packed_bvh(sc, nodes, big)
+            nodes, leaf, big = ctx.accel()
+            check_packed_bvh(sc, nodes, leaf, big)
             rays = D.primary_rays(sc.camera, W, H, sc.profile, time=0.37)
             ia, ta = ctx.trace_closest(rays, t_min=sc.t_min, use_accel=True)
             ib, tb = ctx.trace_closest(rays, t_min=sc.t_min, use_accel=False)
