@@ -543,10 +543,12 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   const int grid = ctx->sm_count;
   const int block = RT_BLOCK_OF(ctx->general);
   const int n_warps = grid * (block / 32);
-  // chunking: balance end-of-frame imbalance (few work items per warp) against the
-  // per-item drain tail (~10 iterations): n_chunks ~ sqrt(0.133 * warps * spp / tiles)
-  double ideal = sqrt(0.133 * (double)n_warps * (double)spp_count / (double)P.n_tiles);
-  int n_chunks = (int)(ideal + 0.5);
+  // chunking: a work item is (tile, chunk of samples). Measured on B200: the
+  // end-of-frame imbalance (few items per warp) costs far more than the per-item drain
+  // tail, so aim for >= 64 items per resident warp while keeping >= 8 samples per item.
+  int n_chunks = (int)((64LL * n_warps + P.n_tiles - 1) / P.n_tiles);
+  n_chunks = std::min(n_chunks, std::max(1, spp_count / 8));
+  if (const char *e = getenv("B200RT_CHUNKS")) n_chunks = atoi(e); // tuning knob
   n_chunks = std::max(1, std::min(n_chunks, std::min(spp_count, 64)));
   P.chunk_spp = (spp_count + n_chunks - 1) / n_chunks;
   P.n_chunks = (spp_count + P.chunk_spp - 1) / P.chunk_spp;

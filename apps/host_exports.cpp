@@ -1,0 +1,43 @@
+// apps/host_exports.cpp — C exports of the C++ host layer for the Python tests: build a
+// scene with the rtx classes, flatten it, hand the flattened arrays back. No CUDA here.
+#include <cstring>
+#include "scenes.h"
+
+static flat_scene g_flat;
+static rt_camera g_cam;
+
+extern "C" {
+// which: 0 = weekend random_scene() under srand(seed) (seed 1 = glibc default), 1 = next_week
+int rtx_host_build(int which, unsigned seed, double aspect, const char *obj_path) {
+  srand(seed);
+  g_flat = flat_scene();
+  if (which == 0) {
+    hittable_list w = random_scene();
+    w.flatten(g_flat, transform());
+    g_cam = camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.1, 10.0).describe();
+  } else if (which == 1) {
+    std::vector<hittable *> d_list(22 * 22 + 1 + 3 + 1);
+    hittable *root = next_week_random_scene(d_list.data());
+    root->flatten(g_flat, transform());
+    g_cam = camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.05,
+                   (point3(13, 2, 3) - point3(0, 0, 0)).length(), 0.0, 1.0, true).describe();
+  } else {
+    hittable *root = obj_model(obj_path);
+    root->flatten(g_flat, transform());
+    g_cam = camera(point3(1, 3, 7), point3(0, 2, 0), vec3(0, 1, 0), 60, aspect, 0.0,
+                   (point3(1, 3, 7) - point3(0, 2, 0)).length(), 0.0, 1.0, true).describe();
+  }
+  return 0;
+}
+void rtx_host_counts(int *n) {
+  n[0] = (int)g_flat.spheres.size(); n[1] = (int)g_flat.triangles.size();
+  n[2] = (int)g_flat.quads.size(); n[3] = (int)g_flat.materials.size(); n[4] = g_flat.wants_accel;
+}
+void rtx_host_get(rt_sphere *s, rt_triangle *t, rt_quad *q, rt_material *m, rt_camera *c) {
+  if (s) memcpy(s, g_flat.spheres.data(), sizeof(rt_sphere) * g_flat.spheres.size());
+  if (t) memcpy(t, g_flat.triangles.data(), sizeof(rt_triangle) * g_flat.triangles.size());
+  if (q) memcpy(q, g_flat.quads.data(), sizeof(rt_quad) * g_flat.quads.size());
+  if (m) memcpy(m, g_flat.materials.data(), sizeof(rt_material) * g_flat.materials.size());
+  if (c) *c = g_cam;
+}
+}

@@ -1,0 +1,81 @@
+// apps/render_cli.cpp — the reference's `main()`s as one host program over the B200 core:
+// builds a scene with the reference's own scene-description classes, renders it through
+// the C ABI and writes a P3 PPM on stdout / timing on stderr exactly like
+// rt_in_one_weekend/main.cpp:292-360 and accelerated-rt-cuda/final.cu:155-246.
+//   render_cli [--scene weekend|next_week|obj] [--obj file.obj] [--width W] [--height H]
+//              [--spp N] [--seed S] [--device D] [--binary]
+#include <chrono>
+#include <cstring>
+#include <iostream>
+
+#include "scenes.h"
+
+int main(int argc, char **argv) {
+  std::string scene = "weekend", obj;
+  int W = 1200, H = 800, spp = 500, device = 0;
+  unsigned long long seed = 1984;
+  bool binary = false;
+  for (int i = 1; i < argc; i++) {
+    auto is = [&](const char *f) { return !strcmp(argv[i], f) && i + 1 < argc; };
+    if (is("--scene")) scene = argv[++i];
+    else if (is("--obj")) obj = argv[++i];
+    else if (is("--width")) W = atoi(argv[++i]);
+    else if (is("--height")) H = atoi(argv[++i]);
+    else if (is("--spp")) spp = atoi(argv[++i]);
+    else if (is("--seed")) seed = strtoull(argv[++i], nullptr, 10);
+    else if (is("--device")) device = atoi(argv[++i]);
+    else if (!strcmp(argv[i], "--binary")) binary = true;
+    else { std::cerr << "unknown argument " << argv[i] << "\n"; return 2; }
+  }
+  try {
+    render_options opt;
+    opt.device = device;
+    opt.seed = seed;
+    const double aspect = double(W) / H;
+    hittable_list world;
+    hittable *root = nullptr;
+    std::vector<hittable *> d_list(22 * 22 + 1 + 3 + 1);
+    if (scene == "weekend") { // main.cpp:292-311
+      world = random_scene();
+      root = &world;
+    } else if (scene == "next_week") { // main.cu:402-407,462-465
+      root = next_week_random_scene(d_list.data());
+      opt.profile = RT_PROFILE_NEXT_WEEK;
+      opt.sky_gradient = false;
+      opt.background = color(0.70, 0.80, 1.00);
+    } else if (scene == "obj") { // obj_render.cu:716-724
+      if (obj.empty()) { std::cerr << "--scene obj needs --obj file.obj\n"; return 2; }
+      root = obj_model(obj);
+      opt.profile = RT_PROFILE_NEXT_WEEK;
+      opt.sky_gradient = false;
+      opt.background = color(0, 0, 0);
+      opt.t_min = 0.00001;
+      opt.flags = RT_FLAG_FLIP_NORMALS | RT_FLAG_DEPTH_BACKGROUND;
+    } else { std::cerr << "unknown scene " << scene << "\n"; return 2; }
+    camera cam = scene == "weekend"
+                     ? camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.1, 10.0)
+                 : scene == "next_week"
+                     ? camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.05,
+                              (point3(13, 2, 3) - point3(0, 0, 0)).length(), 0.0, 1.0, true)
+                     : camera(point3(1, 3, 7), point3(0, 2, 0), vec3(0, 1, 0), 60, aspect, 0.0,
+                              (point3(1, 3, 7) - point3(0, 2, 0)).length(), 0.0, 1.0, true);
+    renderer r(opt);
+    r.set_scene(*root, cam);
+    std::cerr << "Rendering a " << W << "x" << H << " image with " << spp << " samples per pixel ("
+              << r.flat.spheres.size() << " spheres, " << r.flat.triangles.size() << " triangles, " << r.flat.quads.size()
+              << " rects)\n";
+    auto t0 = std::chrono::steady_clock::now();
+    r.render(W, H, spp);
+    image8 im = r.resolve();
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    rt_stats_t st = r.stats();
+    std::cerr << "took " << secs << " seconds. (" << st.segments / 1e6 / (st.ms_render * 1e-3) << " Mpath-bounces/s, BVH "
+              << st.n_nodes << " nodes built in " << st.ms_build << " ms)\n";
+    if (binary) im.write_ppm_binary(std::cout);
+    else im.write_ppm(std::cout);
+  } catch (const std::exception &e) {
+    std::cerr << "error: " << e.what() << "\n";
+    return 99; // the reference exits 99 on CUDA errors (final.cu:22)
+  }
+  return 0;
+}

@@ -1,0 +1,8 @@
+// hittable_list.h — drop-in for the reference header of the same name: the scene-description
+// classes live in rtx.h (namespace rtx) and are exported to the global namespace here so
+// that existing scene code (`#include "hittable_list.h"`, -Iinclude/rtx) compiles unchanged.
+#ifndef RTX_COMPAT_HITTABLE_LIST_H
+#define RTX_COMPAT_HITTABLE_LIST_H
+#include "rtx.h"
+using namespace rtx;
+#endif

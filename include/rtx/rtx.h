@@ -1,0 +1,569 @@
+// rtx.h — host-side scene-description surface of the reference, kept source-compatible
+// so that existing scenes drop in: the same class names and constructor
+// signatures as
+//   vec3/point3/color   rt_in_one_weekend/vec3.h:10-101
+//   camera              rt_in_one_weekend/camera.h:8-45, rt_next_week/cuda/camera.h:25-61
+//   hittable, hittable_list   hittable.h:29-33, hittable_list.h:6-18,
+//                             accelerated-rt-cuda/hittable_list.h:9-12 (raw-pointer form)
+//   sphere, moving_sphere, triangle, xy/xz/yz_rect   sphere.h:10-11, moving_sphere.h:12-15,
+//                             triangles/cuda/include/triangle.h:17-20, aarect.h:15-17,70-72,126-128
+//   translate, rotate_y, bvh_node   rt_next_week/cuda/hittable.h:49-190, bvh.h:45-46
+//   lambertian, metal, dielectric, diffuse_light, solid_color, checker_texture
+//                             material.h:9-97, rt_next_week/cuda/material.h:27-176, texture.h:13-53
+// These are DESCRIPTION objects only: nothing here intersects rays. `flatten()` turns an
+// object graph into the plain-C rt_scene_desc (include/rt_capi.h) that the GPU core
+// consumes; instances (translate / rotate_y) are baked into the vertices, and a
+// bvh_node is a request ("build an acceleration structure over these") honoured by
+// rt_accel_build on the device.
+#ifndef RTX_RTX_H
+#define RTX_RTX_H
+
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <limits>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../rt_capi.h"
+
+namespace rtx {
+
+using std::make_shared;
+using std::shared_ptr;
+
+// The CUDA trees of the reference pass raw `new`-ed pointers around and share them
+// (one material on several rects) without ever freeing them; raw-pointer overloads
+// therefore BORROW (no ownership), exactly as leaky as the original.
+template <class T> inline shared_ptr<T> borrow(T *p) { return shared_ptr<T>(p, [](T *) {}); }
+
+const double infinity = std::numeric_limits<double>::infinity();
+const double pi = 3.1415926535897932385;
+inline double degrees_to_radians(double d) { return d * pi / 180.0; }
+// rtweekend.h:21-29 — the reference's generator (glibc rand), for scenes that call it
+inline double random_double() { return rand() / (RAND_MAX + 1.0); }
+inline double random_double(double lo, double hi) { return lo + (hi - lo) * random_double(); }
+
+class vec3 {
+public:
+  vec3() : e{0, 0, 0} {}
+  vec3(double e0, double e1, double e2) : e{e0, e1, e2} {}
+  double x() const { return e[0]; }
+  double y() const { return e[1]; }
+  double z() const { return e[2]; }
+  vec3 operator-() const { return vec3(-e[0], -e[1], -e[2]); }
+  double operator[](int i) const { return e[i]; }
+  double &operator[](int i) { return e[i]; }
+  vec3 &operator+=(const vec3 &v) { e[0] += v.e[0]; e[1] += v.e[1]; e[2] += v.e[2]; return *this; }
+  vec3 &operator*=(double t) { e[0] *= t; e[1] *= t; e[2] *= t; return *this; }
+  vec3 &operator/=(double t) { return *this *= 1 / t; }
+  double length_squared() const { return e[0] * e[0] + e[1] * e[1] + e[2] * e[2]; }
+  double length() const { return std::sqrt(length_squared()); }
+  // vec3.h:46-49: g++ evaluates the three arguments right to left; spelled out here
+  static vec3 random() { double c = random_double(), b = random_double(), a = random_double(); return vec3(a, b, c); }
+  static vec3 random(double lo, double hi) {
+    double c = random_double(lo, hi), b = random_double(lo, hi), a = random_double(lo, hi);
+    return vec3(a, b, c);
+  }
+  double e[3];
+};
+using point3 = vec3;
+using color = vec3;
+inline vec3 operator+(const vec3 &u, const vec3 &v) { return vec3(u.e[0] + v.e[0], u.e[1] + v.e[1], u.e[2] + v.e[2]); }
+inline vec3 operator-(const vec3 &u, const vec3 &v) { return vec3(u.e[0] - v.e[0], u.e[1] - v.e[1], u.e[2] - v.e[2]); }
+inline vec3 operator*(const vec3 &u, const vec3 &v) { return vec3(u.e[0] * v.e[0], u.e[1] * v.e[1], u.e[2] * v.e[2]); }
+inline vec3 operator*(double t, const vec3 &v) { return vec3(t * v.e[0], t * v.e[1], t * v.e[2]); }
+inline vec3 operator*(const vec3 &v, double t) { return t * v; }
+inline vec3 operator/(vec3 v, double t) { return (1 / t) * v; }
+inline double dot(const vec3 &u, const vec3 &v) { return u.e[0] * v.e[0] + u.e[1] * v.e[1] + u.e[2] * v.e[2]; }
+inline vec3 cross(const vec3 &u, const vec3 &v) {
+  return vec3(u.e[1] * v.e[2] - u.e[2] * v.e[1], u.e[2] * v.e[0] - u.e[0] * v.e[2], u.e[0] * v.e[1] - u.e[1] * v.e[0]);
+}
+inline vec3 unit_vector(vec3 v) { return v / v.length(); }
+inline std::ostream &operator<<(std::ostream &o, const vec3 &v) { return o << v.e[0] << ' ' << v.e[1] << ' ' << v.e[2]; }
+
+// ---------------------------------------------------------------- textures, materials
+class abstract_texture {
+public:
+  virtual ~abstract_texture() {}
+  virtual bool describe(rt_material &m, bool second) const = 0;
+};
+class solid_color : public abstract_texture {
+public:
+  solid_color() {}
+  solid_color(color c) : color_value(c) {}
+  solid_color(double r, double g, double b) : color_value(r, g, b) {}
+  bool describe(rt_material &m, bool second) const override {
+    float *dst = second ? m.albedo2 : m.albedo;
+    for (int a = 0; a < 3; a++) dst[a] = (float)color_value[a];
+    return true;
+  }
+  color color_value;
+};
+class checker_texture : public abstract_texture {
+public:
+  checker_texture(color c1, color c2) : even(make_shared<solid_color>(c1)), odd(make_shared<solid_color>(c2)) {}
+  checker_texture(shared_ptr<abstract_texture> e, shared_ptr<abstract_texture> o) : even(e), odd(o) {}
+  bool describe(rt_material &m, bool) const override {
+    m.texture = RT_TEX_CHECKER;
+    return even->describe(m, false) && odd->describe(m, true);
+  }
+  shared_ptr<abstract_texture> even, odd;
+};
+
+class material {
+public:
+  virtual ~material() {}
+  virtual rt_material describe() const = 0;
+};
+class lambertian : public material {
+public:
+  lambertian(const color &a) : albedo(make_shared<solid_color>(a)) {}
+  lambertian(shared_ptr<abstract_texture> a) : albedo(a) {}
+  lambertian(abstract_texture *a) : albedo(borrow(a)) {}
+  rt_material describe() const override {
+    rt_material m = {};
+    m.type = RT_MAT_LAMBERTIAN;
+    albedo->describe(m, false);
+    return m;
+  }
+  shared_ptr<abstract_texture> albedo;
+};
+class metal : public material {
+public:
+  metal(const color &a, double f) : albedo(a), fuzz(f < 1 ? f : 1) {}
+  rt_material describe() const override {
+    rt_material m = {};
+    m.type = RT_MAT_METAL;
+    for (int a = 0; a < 3; a++) m.albedo[a] = (float)albedo[a];
+    m.param = (float)fuzz;
+    return m;
+  }
+  color albedo;
+  double fuzz;
+};
+class dielectric : public material {
+public:
+  dielectric(double index_of_refraction) : ir(index_of_refraction) {}
+  rt_material describe() const override {
+    rt_material m = {};
+    m.type = RT_MAT_DIELECTRIC;
+    m.param = (float)ir;
+    return m;
+  }
+  double ir;
+};
+class diffuse_light : public material {
+public:
+  diffuse_light(color c) : emit(make_shared<solid_color>(c)) {}
+  diffuse_light(shared_ptr<abstract_texture> a) : emit(a) {}
+  rt_material describe() const override {
+    rt_material m = {};
+    m.type = RT_MAT_DIFFUSE_LIGHT;
+    emit->describe(m, false);
+    return m;
+  }
+  shared_ptr<abstract_texture> emit;
+};
+
+// ---------------------------------------------------------------- flattening
+// rotate about Y then translate (the only instance transforms the reference has)
+struct transform {
+  double c = 1, s = 0; // x' = c x + s z ; z' = -s x + c z   (hittable.h:176-180)
+  vec3 offset;
+  double scale = 1;
+  bool identity() const { return c == 1 && s == 0 && offset[0] == 0 && offset[1] == 0 && offset[2] == 0 && scale == 1; }
+  // float arithmetic, as the device-side wrappers of the reference compute it
+  void apply(const float in[3], float out[3]) const {
+    float x = in[0] * (float)scale, y = in[1] * (float)scale, z = in[2] * (float)scale;
+    float fc = (float)c, fs = (float)s;
+    out[0] = fc * x + fs * z + (float)offset[0];
+    out[1] = y + (float)offset[1];
+    out[2] = -fs * x + fc * z + (float)offset[2];
+  }
+  void rotate(const float in[3], float out[3]) const {
+    float fc = (float)c, fs = (float)s;
+    out[0] = fc * in[0] + fs * in[2];
+    out[1] = in[1];
+    out[2] = -fs * in[0] + fc * in[2];
+  }
+  transform then_rotate_y(double deg) const { // inner rotation applied before *this
+    transform t = *this;
+    double r = degrees_to_radians(deg), ci = std::cos(r), si = std::sin(r);
+    t.c = c * ci - s * si;
+    t.s = c * si + s * ci;
+    return t;
+  }
+  transform then_translate(const vec3 &d) const { // inner translation applied before *this
+    transform t = *this;
+    t.offset = vec3(c * d[0] + s * d[2] + offset[0], d[1] + offset[1], -s * d[0] + c * d[2] + offset[2]);
+    return t;
+  }
+};
+
+class flat_scene {
+public:
+  std::vector<rt_sphere> spheres;
+  std::vector<rt_triangle> triangles;
+  std::vector<rt_quad> quads;
+  std::vector<rt_material> materials;
+  bool wants_accel = false;
+  int add_material(const material *m) {
+    if (!m) throw std::invalid_argument("primitive without material");
+    for (size_t i = 0; i < seen.size(); i++)
+      if (seen[i] == m) return (int)i;
+    seen.push_back(m);
+    materials.push_back(m->describe());
+    return (int)materials.size() - 1;
+  }
+
+private:
+  std::vector<const material *> seen;
+};
+
+class hittable {
+public:
+  virtual ~hittable() {}
+  virtual void flatten(flat_scene &out, const transform &xf) const = 0;
+};
+
+// triangle ctor — triangles/cuda/include/triangle.h:17-53 in float arithmetic
+inline void triangle_face_normal(const float v0[3], const float v1[3], const float v2[3], const float vn0[3],
+                                 const float vn1[3], const float vn2[3], float n[3]) {
+  float avg[3], ab[3], ac[3];
+  for (int a = 0; a < 3; a++) {
+    avg[a] = -((vn0[a] + vn1[a]) + vn2[a]) * (1.0f / 3.0f);
+    ab[a] = v1[a] - v0[a];
+    ac[a] = v2[a] - v0[a];
+  }
+  float c[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+  float d = c[0] * avg[0] + c[1] * avg[1] + c[2] * avg[2];
+  for (int a = 0; a < 3; a++) n[a] = d > 0.0f ? c[a] : -c[a];
+}
+
+class sphere : public hittable {
+public:
+  sphere() {}
+  sphere(point3 cen, double r, shared_ptr<material> m) : center(cen), radius(r), mat_ptr(m) {}
+  sphere(point3 cen, double r, material *m) : center(cen), radius(r), mat_ptr(borrow(m)) {}
+  void flatten(flat_scene &out, const transform &xf) const override {
+    rt_sphere s = {};
+    float c[3] = {(float)center[0], (float)center[1], (float)center[2]};
+    if (xf.identity()) for (int a = 0; a < 3; a++) s.center0[a] = c[a];
+    else xf.apply(c, s.center0);
+    for (int a = 0; a < 3; a++) s.center1[a] = s.center0[a];
+    s.radius = (float)(radius * xf.scale);
+    s.material = out.add_material(mat_ptr.get());
+    s.time0 = 0; s.time1 = 1; s.moving = 0;
+    out.spheres.push_back(s);
+  }
+  point3 center;
+  double radius = 0;
+  shared_ptr<material> mat_ptr;
+};
+
+class moving_sphere : public hittable {
+public:
+  moving_sphere(point3 c0, point3 c1, double t0, double t1, double r, shared_ptr<material> m)
+      : center0(c0), center1(c1), time0(t0), time1(t1), radius(r), mat_ptr(m) {}
+  moving_sphere(point3 c0, point3 c1, double t0, double t1, double r, material *m)
+      : center0(c0), center1(c1), time0(t0), time1(t1), radius(r), mat_ptr(borrow(m)) {}
+  void flatten(flat_scene &out, const transform &xf) const override {
+    rt_sphere s = {};
+    float a0[3] = {(float)center0[0], (float)center0[1], (float)center0[2]};
+    float a1[3] = {(float)center1[0], (float)center1[1], (float)center1[2]};
+    if (xf.identity()) for (int a = 0; a < 3; a++) { s.center0[a] = a0[a]; s.center1[a] = a1[a]; }
+    else { xf.apply(a0, s.center0); xf.apply(a1, s.center1); }
+    s.radius = (float)(radius * xf.scale);
+    s.material = out.add_material(mat_ptr.get());
+    s.time0 = (float)time0; s.time1 = (float)time1; s.moving = 1;
+    out.spheres.push_back(s);
+  }
+  point3 center0, center1;
+  double time0, time1, radius;
+  shared_ptr<material> mat_ptr;
+};
+
+class triangle : public hittable {
+public:
+  triangle(vec3 _v0, vec3 _v1, vec3 _v2, vec3 _vn0, vec3 _vn1, vec3 _vn2, shared_ptr<material> m)
+      : v0(_v0), v1(_v1), v2(_v2), vn0(_vn0), vn1(_vn1), vn2(_vn2), mat_ptr(m) {}
+  triangle(vec3 _v0, vec3 _v1, vec3 _v2, vec3 _vn0, vec3 _vn1, vec3 _vn2, material *m)
+      : v0(_v0), v1(_v1), v2(_v2), vn0(_vn0), vn1(_vn1), vn2(_vn2), mat_ptr(borrow(m)) {}
+  void flatten(flat_scene &out, const transform &xf) const override {
+    rt_triangle t = {};
+    const vec3 *v[3] = {&v0, &v1, &v2}, *vn[3] = {&vn0, &vn1, &vn2};
+    float fv[3][3], fn[3][3];
+    for (int k = 0; k < 3; k++) {
+      float a[3] = {(float)(*v[k])[0], (float)(*v[k])[1], (float)(*v[k])[2]};
+      float b[3] = {(float)(*vn[k])[0], (float)(*vn[k])[1], (float)(*vn[k])[2]};
+      if (xf.identity()) { for (int q = 0; q < 3; q++) { fv[k][q] = a[q]; fn[k][q] = b[q]; } }
+      else { xf.apply(a, fv[k]); xf.rotate(b, fn[k]); }
+    }
+    for (int q = 0; q < 3; q++) { t.v0[q] = fv[0][q]; t.v1[q] = fv[1][q]; t.v2[q] = fv[2][q]; }
+    triangle_face_normal(fv[0], fv[1], fv[2], fn[0], fn[1], fn[2], t.normal);
+    t.material = out.add_material(mat_ptr.get());
+    out.triangles.push_back(t);
+  }
+  vec3 v0, v1, v2, vn0, vn1, vn2;
+  shared_ptr<material> mat_ptr;
+};
+
+// aarect.h: axis-aligned rectangles; only translation-free use is supported when flattened
+// under a rotation (the reference never rotates its rects in the in-scope scenes).
+class aa_rect : public hittable {
+public:
+  aa_rect(int axis_, double a0_, double a1_, double b0_, double b1_, double k_, shared_ptr<material> m)
+      : axis(axis_), a0(a0_), a1(a1_), b0(b0_), b1(b1_), k(k_), mp(m) {}
+  void flatten(flat_scene &out, const transform &xf) const override {
+    if (xf.s != 0 || xf.c != 1 || xf.scale != 1) throw std::invalid_argument("rotated/scaled rect: not an axis-aligned rect");
+    int ia = (axis == 0) ? 1 : 0, ib = (axis == 2) ? 1 : 2;
+    rt_quad q = {};
+    q.axis = axis;
+    q.a0 = (float)(a0 + xf.offset[ia]); q.a1 = (float)(a1 + xf.offset[ia]);
+    q.b0 = (float)(b0 + xf.offset[ib]); q.b1 = (float)(b1 + xf.offset[ib]);
+    q.k = (float)(k + xf.offset[axis]);
+    q.material = out.add_material(mp.get());
+    out.quads.push_back(q);
+  }
+  int axis;
+  double a0, a1, b0, b1, k;
+  shared_ptr<material> mp;
+};
+class xy_rect : public aa_rect {
+public:
+  xy_rect(double x0, double x1, double y0, double y1, double k, shared_ptr<material> m) : aa_rect(2, x0, x1, y0, y1, k, m) {}
+  xy_rect(double x0, double x1, double y0, double y1, double k, material *m) : aa_rect(2, x0, x1, y0, y1, k, borrow(m)) {}
+};
+class xz_rect : public aa_rect {
+public:
+  xz_rect(double x0, double x1, double z0, double z1, double k, shared_ptr<material> m) : aa_rect(1, x0, x1, z0, z1, k, m) {}
+  xz_rect(double x0, double x1, double z0, double z1, double k, material *m) : aa_rect(1, x0, x1, z0, z1, k, borrow(m)) {}
+};
+class yz_rect : public aa_rect {
+public:
+  yz_rect(double y0, double y1, double z0, double z1, double k, shared_ptr<material> m) : aa_rect(0, y0, y1, z0, z1, k, m) {}
+  yz_rect(double y0, double y1, double z0, double z1, double k, material *m) : aa_rect(0, y0, y1, z0, z1, k, borrow(m)) {}
+};
+
+class hittable_list : public hittable {
+public:
+  hittable_list() {}
+  hittable_list(shared_ptr<hittable> object) { add(object); }
+  hittable_list(hittable **l, int n) { for (int i = 0; i < n; i++) objects.push_back(borrow(l[i])); }
+  void clear() { objects.clear(); }
+  void add(shared_ptr<hittable> object) { objects.push_back(object); }
+  void flatten(flat_scene &out, const transform &xf) const override {
+    for (const auto &o : objects) o->flatten(out, xf);
+  }
+  std::vector<shared_ptr<hittable>> objects;
+};
+
+class translate : public hittable {
+public:
+  translate(shared_ptr<hittable> p, const vec3 &d) : ptr(p), offset(d) {}
+  translate(hittable *p, const vec3 &d) : ptr(borrow(p)), offset(d) {}
+  void flatten(flat_scene &out, const transform &xf) const override { ptr->flatten(out, xf.then_translate(offset)); }
+  shared_ptr<hittable> ptr;
+  vec3 offset;
+};
+class rotate_y : public hittable {
+public:
+  rotate_y(shared_ptr<hittable> p, double angle_deg) : ptr(p), angle(angle_deg) {}
+  rotate_y(hittable *p, double angle_deg) : ptr(borrow(p)), angle(angle_deg) {}
+  void flatten(flat_scene &out, const transform &xf) const override { ptr->flatten(out, xf.then_rotate_y(angle)); }
+  shared_ptr<hittable> ptr;
+  double angle;
+};
+// bvh_node(list, start, end, time0, time1[, rng]) — bvh.h:45-46: a request for an
+// acceleration structure over the range; the device builds one LBVH over everything.
+class bvh_node : public hittable {
+public:
+  bvh_node(const hittable_list &l, double = 0, double = 1) { for (const auto &o : l.objects) objects.push_back(o); }
+  bvh_node(hittable **l, size_t start, size_t end, double = 0, double = 1, void * = nullptr) {
+    for (size_t i = start; i < end; i++) objects.push_back(borrow(l[i]));
+  }
+  void flatten(flat_scene &out, const transform &xf) const override {
+    out.wants_accel = true;
+    for (const auto &o : objects) o->flatten(out, xf);
+  }
+  std::vector<shared_ptr<hittable>> objects;
+};
+
+// ---------------------------------------------------------------- camera
+class camera {
+public:
+  // double arithmetic = camera.h:8-45 (CPU); use_float = accelerated-rt-cuda/camera.h:20-53
+  camera(point3 lookfrom, point3 lookat, vec3 vup, double vfov, double aspect_ratio, double aperture, double focus_dist,
+         double _time0 = 0, double _time1 = 0, bool use_float = false) {
+    time0 = _time0; time1 = _time1;
+    if (!use_float) {
+      double theta = degrees_to_radians(vfov), h = std::tan(theta / 2);
+      double viewport_height = 2.0 * h, viewport_width = aspect_ratio * viewport_height;
+      w = unit_vector(lookfrom - lookat);
+      u = unit_vector(cross(vup, w));
+      v = cross(w, u);
+      origin = lookfrom;
+      horizontal = focus_dist * viewport_width * u;
+      vertical = focus_dist * viewport_height * v;
+      lower_left_corner = origin - horizontal / 2 - vertical / 2 - focus_dist * w;
+      lens_radius = aperture / 2;
+    } else {
+      auto F = [](double x) { return (double)(float)x; };
+      float theta = (float)((double)(float)vfov * M_PI / 180);
+      float half_height = (float)std::tan((double)(theta / 2)), half_width = (float)aspect_ratio * half_height;
+      float fd = (float)focus_dist;
+      float lf[3] = {(float)lookfrom[0], (float)lookfrom[1], (float)lookfrom[2]};
+      float wv[3], uv[3], vv[3];
+      float d[3] = {lf[0] - (float)lookat[0], lf[1] - (float)lookat[1], lf[2] - (float)lookat[2]};
+      float il = 1.0f / std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      for (int a = 0; a < 3; a++) wv[a] = il * d[a];
+      float up[3] = {(float)vup[0], (float)vup[1], (float)vup[2]};
+      float c[3] = {up[1] * wv[2] - up[2] * wv[1], up[2] * wv[0] - up[0] * wv[2], up[0] * wv[1] - up[1] * wv[0]};
+      il = 1.0f / std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+      for (int a = 0; a < 3; a++) uv[a] = il * c[a];
+      vv[0] = wv[1] * uv[2] - wv[2] * uv[1]; vv[1] = wv[2] * uv[0] - wv[0] * uv[2]; vv[2] = wv[0] * uv[1] - wv[1] * uv[0];
+      float hs = fd * 2.0f * half_width, vs = fd * 2.0f * half_height;
+      for (int a = 0; a < 3; a++) {
+        float hz = hs * uv[a], vt = vs * vv[a];
+        horizontal[a] = F(hz); vertical[a] = F(vt);
+        lower_left_corner[a] = F(((lf[a] - hz * 0.5f) - vt * 0.5f) - fd * wv[a]);
+        origin[a] = F(lf[a]); u[a] = F(uv[a]); v[a] = F(vv[a]); w[a] = F(wv[a]);
+      }
+      lens_radius = F((float)aperture / 2.0f);
+    }
+  }
+  rt_camera describe() const {
+    rt_camera c = {};
+    for (int a = 0; a < 3; a++) {
+      c.origin[a] = (float)origin[a]; c.lower_left_corner[a] = (float)lower_left_corner[a];
+      c.horizontal[a] = (float)horizontal[a]; c.vertical[a] = (float)vertical[a];
+      c.u[a] = (float)u[a]; c.v[a] = (float)v[a]; c.w[a] = (float)w[a];
+    }
+    c.lens_radius = (float)lens_radius; c.time0 = (float)time0; c.time1 = (float)time1;
+    return c;
+  }
+  point3 origin, lower_left_corner;
+  vec3 horizontal, vertical, u, v, w;
+  double lens_radius, time0, time1;
+};
+
+// read_triangles — triangles/cuda/include/triangle.h:217-300: `v`, `vn`, `f a/b/c` x3; the
+// face is emitted with vertex indices [6],[3],[0] and normal indices [8],[5],[2] of the
+// flattened index list (reversed winding).
+inline void read_triangles(const std::string &filename, std::vector<shared_ptr<hittable>> &out, shared_ptr<material> mat,
+                           double scale = 1.0) {
+  std::ifstream in(filename);
+  if (!in.is_open()) throw std::runtime_error("read failed: " + filename);
+  std::vector<vec3> vs, vns;
+  std::string line;
+  while (std::getline(in, line)) {
+    std::istringstream ls(line);
+    std::string type;
+    ls >> type;
+    double x, y, z;
+    if (type == "vn") { ls >> x >> y >> z; vns.push_back(vec3(x, y, z)); }
+    else if (type == "v") { ls >> x >> y >> z; vs.push_back(vec3(x, y, z)); }
+    else if (type == "f") {
+      std::vector<int> idx;
+      std::string sec;
+      while (ls >> sec) {
+        std::istringstream ss(sec);
+        std::string num;
+        while (std::getline(ss, num, '/')) idx.push_back(num.empty() ? -1 : std::stoi(num) - 1);
+      }
+      if (idx.size() < 9) continue;
+      out.push_back(make_shared<triangle>(vs.at(idx[6]) * scale, vs.at(idx[3]) * scale, vs.at(idx[0]) * scale,
+                                          vns.at(idx[8]), vns.at(idx[5]), vns.at(idx[2]), mat));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- render entry
+struct render_options {
+  int profile = RT_PROFILE_WEEKEND_CPU;
+  int device = 0;
+  uint64_t seed = 1984;
+  color background = color(0, 0, 0);
+  bool sky_gradient = true;
+  double t_min = 0.001;
+  int max_depth = 50;
+  uint32_t flags = 0;
+};
+
+struct image8 {
+  int width = 0, height = 0;
+  std::vector<uint8_t> rgb; // top row first
+  // P3 text on a stream, as the reference writes it (main.cpp:344-355)
+  void write_ppm(std::ostream &out) const {
+    out << "P3\n" << width << ' ' << height << "\n255\n";
+    for (size_t i = 0; i + 2 < rgb.size(); i += 3) out << (int)rgb[i] << ' ' << (int)rgb[i + 1] << ' ' << (int)rgb[i + 2] << '\n';
+  }
+  void write_ppm_binary(std::ostream &out) const {
+    out << "P6\n" << width << ' ' << height << "\n255\n";
+    out.write((const char *)rgb.data(), (std::streamsize)rgb.size());
+  }
+};
+
+// The drop-in for worker()/render<<<>>>: flatten -> rt_scene_upload -> rt_accel_build ->
+// rt_render -> rt_resolve. Throws std::runtime_error with rt_last_error() on failure.
+class renderer {
+public:
+  renderer(const render_options &o = render_options()) : opt(o) {
+    rt_config cfg = {};
+    cfg.device = o.device; cfg.profile = o.profile; cfg.flags = 0; cfg.seed = o.seed;
+    int rc = rt_create(&ctx, &cfg);
+    if (rc) throw std::runtime_error(rc == RT_ERR_NODEVICE ? "no CUDA device (there is no CPU fallback)" : "rt_create failed");
+  }
+  ~renderer() { if (ctx) rt_destroy(ctx); }
+  renderer(const renderer &) = delete;
+  renderer &operator=(const renderer &) = delete;
+
+  static rt_scene_desc describe(const flat_scene &fs, const camera &cam, const render_options &o) {
+    rt_scene_desc d = {};
+    d.n_spheres = (int)fs.spheres.size(); d.spheres = fs.spheres.data();
+    d.n_triangles = (int)fs.triangles.size(); d.triangles = fs.triangles.data();
+    d.n_quads = (int)fs.quads.size(); d.quads = fs.quads.data();
+    d.n_materials = (int)fs.materials.size(); d.materials = fs.materials.data();
+    d.camera = cam.describe();
+    for (int a = 0; a < 3; a++) d.background[a] = (float)o.background[a];
+    d.sky_gradient = o.sky_gradient ? 1 : 0;
+    d.t_min = (float)o.t_min; d.max_depth = o.max_depth; d.flags = o.flags;
+    return d;
+  }
+  void set_scene(const hittable &world, const camera &cam) {
+    flat = flat_scene();
+    world.flatten(flat, transform());
+    rt_scene_desc d = describe(flat, cam, opt);
+    check(rt_scene_upload(ctx, &d));
+    check(rt_accel_build(ctx, 1));
+  }
+  void render(int width, int height, int samples_per_pixel, int spp_begin = 0) {
+    W = width; H = height;
+    check(rt_render(ctx, width, height, spp_begin, samples_per_pixel));
+  }
+  image8 resolve() {
+    image8 im;
+    im.width = W; im.height = H;
+    im.rgb.resize((size_t)W * H * 3);
+    check(rt_resolve(ctx, nullptr, im.rgb.data()));
+    return im;
+  }
+  rt_stats_t stats() { rt_stats_t s; check(rt_stats(ctx, &s)); return s; }
+  rt_ctx *handle() { return ctx; }
+  flat_scene flat;
+
+private:
+  void check(int rc) { if (rc) throw std::runtime_error(std::string("b200rt: ") + rt_last_error(ctx)); }
+  render_options opt;
+  rt_ctx *ctx = nullptr;
+  int W = 0, H = 0;
+};
+
+} // namespace rtx
+#endif
