@@ -465,6 +465,10 @@ int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nod
     if (cap_nodes < ctx->S.n_nodes) return fail(ctx, RT_ERR_INVALID, "node buffer too small");
     if (ctx->S.n_nodes)
       CK(cudaMemcpy(nodes, ctx->d_nodes.p, sizeof(rt_bvh_node) * (size_t)ctx->S.n_nodes, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < ctx->S.n_nodes; i++) { // device links are byte offsets; the ABI speaks indices
+      nodes[i].escape >>= RT_NODE_SHIFT;
+      if (nodes[i].payload >= 0) nodes[i].payload >>= RT_NODE_SHIFT;
+    }
   }
   if (leaf_prims) {
     if (cap_leaf < ctx->n_leaf_prims) return fail(ctx, RT_ERR_INVALID, "leaf-primitive buffer too small");
@@ -566,6 +570,13 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   P.stats = (unsigned long long *)ctx->d_stats.p;
   P.seed_lo = (uint32_t)(ctx->cfg.seed & 0xffffffffu);
   P.seed_hi = (uint32_t)(ctx->cfg.seed >> 32);
+  {
+    const char *e = getenv("B200RT_BATCH"), *f = getenv("B200RT_FRAC8"); // tuning knobs
+    P.batch = e ? atoi(e) : 24;
+    P.frac8 = f ? atoi(f) : 5;
+    P.batch = std::max(1, std::min(P.batch, 32));
+    P.frac8 = std::max(0, std::min(P.frac8, 8));
+  }
   const DevScene &S = ctx->S;
   P.b_nodes = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_nodes);
   P.b_sph = (int)pad16(sizeof(float4) * (size_t)S.n_spheres);

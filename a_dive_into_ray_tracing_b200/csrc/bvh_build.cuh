@@ -298,8 +298,10 @@ RT_HD void body_pack(const BuildArrays &B, int v) {
   int payload;
   if (build_leaf || B.lcnt[v] <= B.max_leaf) payload = ~((lpos << 3) | (B.lcnt[v] - 1));
   else payload = pos + 1;
-  lo.w = RT_I2F(escape);
-  hi.w = RT_I2F(payload);
+  // links are stored as BYTE offsets (index * 32) so that traversal needs no address
+  // arithmetic; rt_accel_download converts them back to indices
+  lo.w = RT_I2F(escape << RT_NODE_SHIFT);
+  hi.w = RT_I2F(payload >= 0 ? (payload << RT_NODE_SHIFT) : payload);
   B.packed[2 * pos] = lo;
   B.packed[2 * pos + 1] = hi;
 }

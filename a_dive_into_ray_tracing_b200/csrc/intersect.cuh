@@ -192,13 +192,14 @@ RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r, float t_min, float t
     if (is_sphere) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
     else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
   }
-  int node = 0;
-  const int n_nodes = S.n_nodes;
+  int node = 0; // byte offset of the current node
+  const int n_nodes = S.n_nodes << RT_NODE_SHIFT;
   int first = 0, left = 0; // pending primitives of the last hit leaf: leaf_prims[first .. first+left)
   while (node < n_nodes || left > 0) {
     if (left == 0) {
       while (node < n_nodes) {
-        float4 lo = S.nodes[2 * node], hi = S.nodes[2 * node + 1];
+        const float4 *np = (const float4 *)((const char *)S.nodes + node);
+        float4 lo = np[0], hi = np[1];
         if (COUNT) cnt->box_tests++;
         int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
         if (hit_box(lo, hi, pre, t_min, h.t)) {

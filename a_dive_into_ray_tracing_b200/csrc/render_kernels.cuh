@@ -40,6 +40,8 @@ struct RenderParams {
   int *work_counter;
   unsigned long long *stats;     // paths, segments, box tests, prim tests
   uint32_t seed_lo, seed_hi;
+  int batch;  // shade/regenerate when this many lanes are DONE or DEAD (warp-voted scheduler)
+  int frac8;  // a BVH burst ends when fewer than frac8/8 of its entry lanes are still searching
   // bytes of each array staged to shared memory (all multiples of 16)
   int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big, b_leaf_prims;
 };
@@ -83,7 +85,29 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
 
   const unsigned FULL = 0xffffffffu;
   const unsigned lt_mask = (1u << lane) - 1u;
+  // Lane state machine with WARP-VOTED phases (design evaluated with tests/emu/warpsim:
+  // 75 -> ~60 warp-instructions per segment). Every lane owns one path; its state is
+  //   SEARCH  walking the threaded BVH (one node per step)
+  //   LEAF    a hit leaf's primitives are pending
+  //   DONE    traversal finished: shade / terminate
+  //   DEAD    no path: take the next (pixel, sample) item of the tile's pool
+  // The warp (1) steps the BVH while at least `frac` of the lanes that entered the burst
+  // are still searching, (2) runs the pending primitive tests together, (3) shades and
+  // regenerates once `batch` lanes are DONE/DEAD (or nobody is traversing) while the
+  // remaining lanes keep their traversal state in registers.
+  // Encoding: `alive` (the lane owns a path) and `node`:
+  //   0 <= node < node_end   SEARCH: byte offset of the next BVH node
+  //   node == node_end       traversal finished (DONE if alive, else DEAD)
+  //   node < 0               LEAF: a hit leaf is pending, node = its payload
+  //                          ~(first << 3 | count-1) into leaf_prims; `resume` = where to go on
+  const int node_end = S.n_nodes << RT_NODE_SHIFT;
   bool alive = false;
+  int node = node_end, resume = 0;
+  HitAcc h;
+  h.t = INFINITY; h.id = -1;
+  RayPre pre;
+  pre.inv_d = v3(0, 0, 0); pre.ood = v3(0, 0, 0); pre.inv_a = 0.f;
+  const float t_min = P.sp.t_min;
   int pool_next = 0, pool_end = 0; // warp-uniform
   int work = -1, tile_x0 = 0, tile_y0 = 0, s0 = 0, chunk = 0, chunk_n = 0;
   Ray r;
@@ -93,41 +117,98 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   unsigned n_seg = 0, n_paths = 0;
   TraceCounters cnt;
   cnt.box_tests = 0; cnt.prim_tests = 0;
+  // node fetch: 2 x LDS.128 straight from a 32-bit shared address (no generic-pointer
+  // arithmetic in the loop); global path for scenes that do not fit shared memory
+  const uint32_t nodes_s = SMEM ? (uint32_t)__cvta_generic_to_shared(S.nodes) : 0u;
+  const char *nodes_g = (const char *)S.nodes;
+
+  // start a segment: per-ray constants, the always-tested big primitives, enter at the root
+  auto begin_segment = [&]() {
+    pre = ray_precompute(r);
+    h.t = INFINITY; h.id = -1;
+    for (int i = 0; i < S.n_big; i++) {
+      const int32_t id = S.big[i];
+      if (COUNT) cnt.prim_tests++;
+      const bool is_sphere = !GENERAL || RT_PRIM_TYPE_OF(id) == RT_PRIM_SPHERE;
+      if (is_sphere) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
+      else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
+    }
+    node = 0;
+  };
 
   for (;;) {
-    const unsigned dead = __ballot_sync(FULL, !alive);
-    if (dead) {
-      bool can_fetch = true;
-      if (pool_next >= pool_end) {
-        if (dead != FULL) {
-          can_fetch = false; // pool drained, some lanes still in flight
+    // ---- phase 1: a burst of BVH steps (branch-free body: lanes that are not searching
+    // fetch node 0 and discard the result)
+    const int ns0 = __popc(__ballot_sync(FULL, (unsigned)node < (unsigned)node_end));
+    if (ns0 > 0) {
+      const int thr = max(1, (ns0 * P.frac8) >> 3);
+      for (;;) {
+        const bool searching = (unsigned)node < (unsigned)node_end;
+        if (__popc(__ballot_sync(FULL, searching)) < thr) break;
+        const int at = searching ? node : 0;
+        float4 lo, hi;
+        if (SMEM) {
+          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(nodes_s + at));
+          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nodes_s + at));
         } else {
-          __syncwarp();
-          if (work >= 0) { // flush this tile's chunk: lane <-> pixel
-            const int i = tile_x0 + (lane & 7), j = tile_y0 + (lane >> 3);
-            if (i < P.W && j < P.H) {
-              float4 v = make_float4(acc[lane * 4 + 0], acc[lane * 4 + 1], acc[lane * 4 + 2], (float)chunk_n);
-              P.partial[(size_t)chunk * ((size_t)P.W * P.H) + (size_t)j * P.W + i] = v;
+          lo = __ldg((const float4 *)(nodes_g + at));
+          hi = __ldg((const float4 *)(nodes_g + at) + 1);
+        }
+        if (COUNT) cnt.box_tests += searching ? 1u : 0u;
+        const int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
+        const int nxt = hit_box(lo, hi, pre, t_min, h.t) ? pay : esc; // inner: child; leaf: payload < 0
+        if (searching) { node = nxt; resume = esc; }
+      }
+    }
+    // ---- phase 2: pending primitive tests (one per lane per round)
+    if (__ballot_sync(FULL, node < 0)) {
+      if (node < 0) {
+        const int enc = ~node;
+        if (COUNT) cnt.prim_tests++;
+        hit_prim<PROFILE, GENERAL, false>(S, S.leaf_prims[enc >> 3], r, pre, t_min, h);
+        node = (enc & 7) ? node - 7 : resume; // next primitive of the leaf (first+1, count-1) or go on
+      }
+    }
+    // ---- phase 3: shade + regenerate once enough lanes are out of the traversal
+    const unsigned m_out = __ballot_sync(FULL, node == node_end);
+    const int n_out = __popc(m_out);
+    if (n_out < P.batch && n_out < 32) continue;
+    const bool pool_has = pool_next < pool_end;
+    const bool done = alive && node == node_end;
+    if (__ballot_sync(FULL, done || (!alive && pool_has))) {
+      if (done) {
+        n_seg++;
+        if (h.id < 0) {
+          L = L + beta * miss_radiance(P.sp, r.d);
+          alive = false;
+        } else {
+          Philox4 q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo,
+                                    P.seed_hi);
+          const bool cont = shade_hit<PROFILE, GENERAL>(S, P.sp, r, h, beta, L, q);
+          bounce++;
+          if (!cont) {
+            alive = false; // absorbed (L is 0 for profiles 0/1) or hit a light
+          } else if (bounce >= P.sp.max_depth) {
+            alive = false;
+            if (PROFILE == 2) {
+              if (P.sp.flags & RT_FLAG_DEPTH_BACKGROUND) L = L + beta * P.sp.background; // obj_render.cu:78-83
+              else L = P.sp.background;                                                    // main.cu:104
+            } else {
+              L = v3(0, 0, 0); // main.cpp:58-60, final.cu:53
             }
           }
-          int w = 0;
-          if (lane == 0) w = atomicAdd(P.work_counter, 1);
-          w = __shfl_sync(FULL, w, 0);
-          if (w >= P.n_work) break;
-          work = w;
-          const int tile = w % P.n_tiles;
-          chunk = w / P.n_tiles;
-          tile_x0 = (tile % P.tiles_x) * RT_TILE_W;
-          tile_y0 = (tile / P.tiles_x) * RT_TILE_H;
-          s0 = P.spp_begin + chunk * P.chunk_spp;
-          chunk_n = min(P.chunk_spp, P.spp_count - chunk * P.chunk_spp);
-          pool_next = 0;
-          pool_end = chunk_n * 32;
-          acc[lane * 4 + 0] = 0.f; acc[lane * 4 + 1] = 0.f; acc[lane * 4 + 2] = 0.f; acc[lane * 4 + 3] = 0.f;
-          __syncwarp();
+        }
+        if (alive) {
+          begin_segment();
+        } else {
+          atomicAdd(&acc[pix * 4 + 0], L.x);
+          atomicAdd(&acc[pix * 4 + 1], L.y);
+          atomicAdd(&acc[pix * 4 + 2], L.z);
+          node = node_end;
         }
       }
-      if (can_fetch) {
+      const unsigned dead = __ballot_sync(FULL, !alive);
+      if (pool_has && dead) {
         if (!alive) {
           const int item = pool_next + __popc(dead & lt_mask);
           if (item < pool_end) {
@@ -146,42 +227,39 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
               bounce = 0;
               alive = true;
               n_paths++;
+              begin_segment();
             }
           }
         }
         pool_next = min(pool_end, pool_next + __popc(dead));
       }
+      continue;
     }
-    if (alive) {
-      HitAcc h = trace_closest<PROFILE, GENERAL, COUNT>(S, r, P.sp.t_min, INFINITY, &cnt);
-      n_seg++;
-      if (h.id < 0) {
-        V3f m = miss_radiance(P.sp, r.d);
-        L = L + beta * m;
-        alive = false;
-      } else {
-        Philox4 q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo,
-                                  P.seed_hi);
-        bool cont = shade_hit<PROFILE, GENERAL>(S, P.sp, r, h, beta, L, q);
-        bounce++;
-        if (!cont) {
-          alive = false; // absorbed (contributes L, which is 0 for profiles 0/1) or hit a light
-        } else if (bounce >= P.sp.max_depth) {
-          alive = false;
-          if (PROFILE == 2) {
-            if (P.sp.flags & RT_FLAG_DEPTH_BACKGROUND) L = L + beta * P.sp.background; // obj_render.cu:78-83
-            else L = P.sp.background;                                                    // main.cu:104
-          } else {
-            L = v3(0, 0, 0); // main.cpp:58-60, final.cu:53
-          }
-        }
-      }
-      if (!alive) {
-        atomicAdd(&acc[pix * 4 + 0], L.x);
-        atomicAdd(&acc[pix * 4 + 1], L.y);
-        atomicAdd(&acc[pix * 4 + 2], L.z);
+    if (n_out < 32) continue; // some lanes still traversing, nothing to shade or regenerate
+    // ---- the tile's pool is drained and every path has ended: flush, fetch the next tile
+    __syncwarp();
+    if (work >= 0) { // lane <-> pixel
+      const int i = tile_x0 + (lane & 7), j = tile_y0 + (lane >> 3);
+      if (i < P.W && j < P.H) {
+        float4 v = make_float4(acc[lane * 4 + 0], acc[lane * 4 + 1], acc[lane * 4 + 2], (float)chunk_n);
+        P.partial[(size_t)chunk * ((size_t)P.W * P.H) + (size_t)j * P.W + i] = v;
       }
     }
+    int w = 0;
+    if (lane == 0) w = atomicAdd(P.work_counter, 1);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= P.n_work) break;
+    work = w;
+    const int tile = w % P.n_tiles;
+    chunk = w / P.n_tiles;
+    tile_x0 = (tile % P.tiles_x) * RT_TILE_W;
+    tile_y0 = (tile / P.tiles_x) * RT_TILE_H;
+    s0 = P.spp_begin + chunk * P.chunk_spp;
+    chunk_n = min(P.chunk_spp, P.spp_count - chunk * P.chunk_spp);
+    pool_next = 0;
+    pool_end = chunk_n * 32;
+    acc[lane * 4 + 0] = 0.f; acc[lane * 4 + 1] = 0.f; acc[lane * 4 + 2] = 0.f; acc[lane * 4 + 3] = 0.f;
+    __syncwarp();
   }
   // statistics: one atomic per warp
   unsigned long long a = n_paths, b = n_seg, c = cnt.box_tests, d = cnt.prim_tests;

@@ -37,6 +37,8 @@ static inline float rt_host_i2f(int i) { float x; memcpy(&x, &i, 4); return x; }
 #define RT_MULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
 #endif
 
+#define RT_NODE_SHIFT 5 // log2(sizeof packed node): node links are byte offsets
+
 struct V3f {
   float x, y, z;
 };
@@ -61,6 +63,7 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 // memory by the render kernel when they fit ("data layout").
 //
 //  nodes   float4[2*n_nodes]   {bmin.xyz, escape} {bmax.xyz, payload}   32 B/node
+//                              escape / child links are BYTE offsets (index << 5)
 //                              payload >= 0: first child; < 0: ~(first<<3 | count-1) into leaf_prims
 //  leaf_prims int32[n_small]   RT_PRIM_IDs in depth-first leaf order
 //  sph     float4[n_spheres]   {c0.xyz, radius}                         16 B

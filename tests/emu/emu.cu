@@ -166,6 +166,10 @@ int emu_counts(void *p, int *n_nodes, int *n_leaf, int *n_big) { EmuScene *E = (
 int emu_download(void *p, rt_bvh_node *nodes, int32_t *leaf, int32_t *big) {
   EmuScene *E = (EmuScene *)p;
   memcpy(nodes, E->nodes.data(), sizeof(float4) * E->nodes.size());
+  for (size_t i = 0; i < E->nodes.size() / 2; i++) { // byte offsets -> indices (public rt_bvh_node contract)
+    nodes[i].escape >>= RT_NODE_SHIFT;
+    if (nodes[i].payload >= 0) nodes[i].payload >>= RT_NODE_SHIFT;
+  }
   memcpy(leaf, E->leaf_prims.data(), sizeof(int32_t) * E->leaf_prims.size());
   memcpy(big, E->big.data(), sizeof(int32_t) * E->big.size());
   return 0;
@@ -206,3 +210,5 @@ int emu_render(void *p, int W, int H, int spp_begin, int spp_count, uint64_t see
   return 0;
 }
 }
+
+#include "warpsim.inc"
