@@ -518,14 +518,14 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
 
 // ------------------------------------------------------------------ render
 typedef void (*render_kernel_t)(const RenderParams);
-static render_kernel_t pick_render_kernel(int profile, bool smem, bool count) {
-#define PICK(P, G)                                                                 \
-  return smem ? (count ? k_render<P, G, true, true> : k_render<P, G, true, false>) \
-              : (count ? k_render<P, G, false, true> : k_render<P, G, false, false>)
+static render_kernel_t pick_render_kernel(int profile, int smem, bool count) {
+#define PICK3(P, G, C) (smem == 2 ? k_render<P, G, 2, C> : (smem == 1 ? k_render<P, G, 1, C> : k_render<P, G, 0, C>))
+#define PICK(P, G) return count ? PICK3(P, G, true) : PICK3(P, G, false)
   if (profile == 0) { PICK(0, false); }
   if (profile == 1) { PICK(1, false); }
   PICK(2, true);
 #undef PICK
+#undef PICK3
 }
 
 static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, float *d_accum, cudaStream_t st,
@@ -597,8 +597,12 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
     scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat;
   }
   const size_t acc_bytes = (size_t)(block / 32) * 128 * sizeof(float);
-  const bool smem = scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin;
-  const size_t smem_bytes = acc_bytes + (smem ? scene_bytes : 0);
+  // shared-memory plan: 2 = scene + four quadrant copies of the nodes, 1 = scene, 0 = global
+  int smem = 0;
+  if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;
+  if (scene_bytes + 3 * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
+  if (const char *e = getenv("B200RT_SMEM")) smem = std::min(smem, atoi(e)); // tuning knob
+  const size_t smem_bytes = acc_bytes + (smem ? scene_bytes : 0) + (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
   render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count);
   CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

@@ -141,6 +141,17 @@ RT_HD bool hit_box(float4 lo, float4 hi, const RayPre &pre, float t_min, float t
   return tn <= tf;
 }
 
+// Same test for a node copy whose x and z planes were pre-swapped for the ray's direction
+// signs (lo = entry plane, hi = exit plane on those axes): 6 instead of 10 min/max.
+RT_HD bool hit_box_xz_sorted(float4 lo, float4 hi, const RayPre &pre, float t_min, float t_max) {
+  float x0 = RT_FMA(lo.x, pre.inv_d.x, -pre.ood.x), x1 = RT_FMA(hi.x, pre.inv_d.x, -pre.ood.x);
+  float y0 = RT_FMA(lo.y, pre.inv_d.y, -pre.ood.y), y1 = RT_FMA(hi.y, pre.inv_d.y, -pre.ood.y);
+  float z0 = RT_FMA(lo.z, pre.inv_d.z, -pre.ood.z), z1 = RT_FMA(hi.z, pre.inv_d.z, -pre.ood.z);
+  float tn = RT_FMAX(RT_FMAX(x0, z0), RT_FMAX(RT_FMIN(y0, y1), t_min));
+  float tf = RT_FMIN(RT_FMIN(x1, z1), RT_FMIN(RT_FMAX(y0, y1), t_max));
+  return tn <= tf;
+}
+
 // One primitive by RT_PRIM_ID. PROFILE selects the interval rule of static spheres.
 template <int PROFILE, bool GENERAL, bool BIG>
 RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &pre, float t_min, HitAcc &h) {

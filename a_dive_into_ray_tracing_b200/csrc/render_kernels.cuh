@@ -56,13 +56,30 @@ __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &o
   return dst;
 }
 
-template <int PROFILE, bool GENERAL, bool SMEM, bool COUNT>
+// SMEM: 0 = scene read from global memory (L1/L2); 1 = whole scene staged in shared memory;
+// 2 = as 1, with FOUR copies of the node array, one per sign combination of (d.x, d.z), whose
+// box planes are pre-swapped so that the slab test needs no min/max on those axes.
+template <int PROFILE, bool GENERAL, int SMEM, bool COUNT>
 __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevScene S = P.S;
   int off = 0;
   if (SMEM) {
-    S.nodes = (const float4 *)stage_to_smem(smem_raw, off, P.S.nodes, P.b_nodes);
+    if (SMEM == 2) { // quadrant-specialised node copies: swap bmin/bmax on x (bit 0) and z (bit 1)
+      S.nodes = (const float4 *)(smem_raw + off);
+      const int nn = P.b_nodes >> 5;
+      for (int i = threadIdx.x; i < 4 * nn; i += blockDim.x) {
+        const int q = i / nn, k = i - q * nn;
+        float4 lo = __ldg(P.S.nodes + 2 * k), hi = __ldg(P.S.nodes + 2 * k + 1);
+        if (q & 1) { const float t = lo.x; lo.x = hi.x; hi.x = t; }
+        if (q & 2) { const float t = lo.z; lo.z = hi.z; hi.z = t; }
+        float4 *dst = (float4 *)(smem_raw + off + q * P.b_nodes) + 2 * k;
+        dst[0] = lo; dst[1] = hi;
+      }
+      off += 4 * P.b_nodes;
+    } else {
+      S.nodes = (const float4 *)stage_to_smem(smem_raw, off, P.S.nodes, P.b_nodes);
+    }
     S.sph = (const float4 *)stage_to_smem(smem_raw, off, P.S.sph, P.b_sph);
     S.sph_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.sph_mat, P.b_sph_mat);
     S.sph_k = (const float *)stage_to_smem(smem_raw, off, P.S.sph_k, P.b_sph_k);
@@ -120,6 +137,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   // node fetch: 2 x LDS.128 straight from a 32-bit shared address (no generic-pointer
   // arithmetic in the loop); global path for scenes that do not fit shared memory
   const uint32_t nodes_s = SMEM ? (uint32_t)__cvta_generic_to_shared(S.nodes) : 0u;
+  uint32_t nbase = nodes_s; // + quadrant copy of the current ray (SMEM == 2)
   const char *nodes_g = (const char *)S.nodes;
 
   // start a segment: per-ray constants, the always-tested big primitives, enter at the root
@@ -134,6 +152,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
     }
     node = 0;
+    if (SMEM == 2) // sign BITS of 1/d (covers d = -0): which pre-swapped copy this ray walks
+      nbase = nodes_s + (((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 1)) * (unsigned)P.b_nodes;
   };
 
   for (;;) {
@@ -147,16 +167,17 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         if (__popc(__ballot_sync(FULL, searching)) < thr) break;
         const int at = searching ? node : 0;
         float4 lo, hi;
-        if (SMEM) {
-          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(nodes_s + at));
-          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nodes_s + at));
+        if (SMEM != 0) {
+          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(nbase + at));
+          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nbase + at));
         } else {
           lo = __ldg((const float4 *)(nodes_g + at));
           hi = __ldg((const float4 *)(nodes_g + at) + 1);
         }
         if (COUNT) cnt.box_tests += searching ? 1u : 0u;
         const int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
-        const int nxt = hit_box(lo, hi, pre, t_min, h.t) ? pay : esc; // inner: child; leaf: payload < 0
+        const bool bh = (SMEM == 2) ? hit_box_xz_sorted(lo, hi, pre, t_min, h.t) : hit_box(lo, hi, pre, t_min, h.t);
+        const int nxt = bh ? pay : esc; // inner: child; leaf: payload < 0
         if (searching) { node = nxt; resume = esc; }
       }
     }
@@ -176,63 +197,79 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     const bool pool_has = pool_next < pool_end;
     const bool done = alive && node == node_end;
     if (__ballot_sync(FULL, done || (!alive && pool_has))) {
+      // (a) rays that left the scene end their path now
+      const bool hit = done && h.id >= 0;
       if (done) {
         n_seg++;
-        if (h.id < 0) {
+        if (!hit) {
           L = L + beta * miss_radiance(P.sp, r.d);
+          atomicAdd(&acc[pix * 4 + 0], L.x);
+          atomicAdd(&acc[pix * 4 + 1], L.y);
+          atomicAdd(&acc[pix * 4 + 2], L.z);
           alive = false;
+        }
+      }
+      // (b) dead lanes take the next (pixel, sample) items of the tile pool by ballot rank
+      bool fresh_path = false;
+      const unsigned dead = __ballot_sync(FULL, !alive);
+      if (pool_has && dead) {
+        if (!alive) {
+          const int item = pool_next + __popc(dead & lt_mask);
+          if (item < pool_end) {
+            const int px = item & 31;
+            const int i = tile_x0 + (px & 7), j = tile_y0 + (px >> 3);
+            if (i < P.W && j < P.H) {
+              pix = px;
+              smp = s0 + (item >> 5);
+              pixel_index = j * P.W + i;
+              bounce = -1; // event index 0 = the camera ray
+              fresh_path = true;
+            }
+          }
+        }
+        pool_next = min(pool_end, pool_next + __popc(dead));
+      }
+      // (c) ONE Philox call per lane: the bounce event of a hit, or the camera event of a new path
+      Philox4 q;
+      q.x = q.y = q.z = q.w = 0u;
+      if (hit || fresh_path)
+        q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
+      bool fresh_ray = false;
+      if (hit) {
+        const bool cont = shade_hit<PROFILE, GENERAL>(S, P.sp, r, h, beta, L, q);
+        bounce++;
+        if (cont && bounce < P.sp.max_depth) {
+          fresh_ray = true;
         } else {
-          Philox4 q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo,
-                                    P.seed_hi);
-          const bool cont = shade_hit<PROFILE, GENERAL>(S, P.sp, r, h, beta, L, q);
-          bounce++;
-          if (!cont) {
-            alive = false; // absorbed (L is 0 for profiles 0/1) or hit a light
-          } else if (bounce >= P.sp.max_depth) {
-            alive = false;
+          if (cont) { // depth exhausted
             if (PROFILE == 2) {
               if (P.sp.flags & RT_FLAG_DEPTH_BACKGROUND) L = L + beta * P.sp.background; // obj_render.cu:78-83
               else L = P.sp.background;                                                    // main.cu:104
             } else {
               L = v3(0, 0, 0); // main.cpp:58-60, final.cu:53
             }
-          }
-        }
-        if (alive) {
-          begin_segment();
-        } else {
+          } // else: absorbed (L is 0 for profiles 0/1) or hit a light
           atomicAdd(&acc[pix * 4 + 0], L.x);
           atomicAdd(&acc[pix * 4 + 1], L.y);
           atomicAdd(&acc[pix * 4 + 2], L.z);
+          alive = false; // regenerated in the next round
           node = node_end;
         }
+      } else if (fresh_path) {
+        const int i = tile_x0 + (pix & 7), j = tile_y0 + (pix >> 3);
+        float x5 = 0.f;
+        if (PROFILE == 2 && P.cam.time1 != P.cam.time0)
+          x5 = u01(philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, 0u, 1u, P.seed_lo, P.seed_hi).x);
+        r = gen_camera_ray<PROFILE>(P.cam, P.W, P.H, i, j, u01(q.x), u01(q.y), u01(q.z), u01(q.w), x5);
+        beta = v3(1, 1, 1);
+        L = v3(0, 0, 0);
+        bounce = 0;
+        alive = true;
+        n_paths++;
+        fresh_ray = true;
       }
-      const unsigned dead = __ballot_sync(FULL, !alive);
-      if (pool_has && dead) {
-        if (!alive) {
-          const int item = pool_next + __popc(dead & lt_mask);
-          if (item < pool_end) {
-            pix = item & 31;
-            smp = s0 + (item >> 5);
-            const int i = tile_x0 + (pix & 7), j = tile_y0 + (pix >> 3);
-            if (i < P.W && j < P.H) {
-              pixel_index = j * P.W + i;
-              Philox4 q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, 0u, 0u, P.seed_lo, P.seed_hi);
-              float x5 = 0.f;
-              if (PROFILE == 2 && P.cam.time1 != P.cam.time0)
-                x5 = u01(philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, 0u, 1u, P.seed_lo, P.seed_hi).x);
-              r = gen_camera_ray<PROFILE>(P.cam, P.W, P.H, i, j, u01(q.x), u01(q.y), u01(q.z), u01(q.w), x5);
-              beta = v3(1, 1, 1);
-              L = v3(0, 0, 0);
-              bounce = 0;
-              alive = true;
-              n_paths++;
-              begin_segment();
-            }
-          }
-        }
-        pool_next = min(pool_end, pool_next + __popc(dead));
-      }
+      // (d) every lane with a new ray starts its segment together
+      if (fresh_ray) begin_segment();
       continue;
     }
     if (n_out < 32) continue; // some lanes still traversing, nothing to shade or regenerate
