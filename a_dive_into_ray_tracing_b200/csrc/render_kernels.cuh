@@ -26,6 +26,10 @@
 #ifndef RT_BLOCK_GENERAL
 #define RT_BLOCK_GENERAL 1024
 #endif
+// BVH steps between two warp votes in the search burst (1 or 2)
+#ifndef RT_STEPS_PER_VOTE
+#define RT_STEPS_PER_VOTE 2
+#endif
 #define RT_BLOCK_OF(GENERAL) ((GENERAL) ? RT_BLOCK_GENERAL : RT_BLOCK)
 #define RT_TILE_W 8
 #define RT_TILE_H 4
@@ -163,22 +167,25 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     if (ns0 > 0) {
       const int thr = max(1, (ns0 * P.frac8) >> 3);
       for (;;) {
-        const bool searching = (unsigned)node < (unsigned)node_end;
-        if (__popc(__ballot_sync(FULL, searching)) < thr) break;
-        const int at = searching ? node : 0;
-        float4 lo, hi;
-        if (SMEM != 0) {
-          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(nbase + at));
-          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nbase + at));
-        } else {
-          lo = __ldg((const float4 *)(nodes_g + at));
-          hi = __ldg((const float4 *)(nodes_g + at) + 1);
+        if (__popc(__ballot_sync(FULL, (unsigned)node < (unsigned)node_end)) < thr) break;
+#pragma unroll
+        for (int u = 0; u < RT_STEPS_PER_VOTE; u++) {
+          const bool searching = (unsigned)node < (unsigned)node_end;
+          const int at = searching ? node : 0;
+          float4 lo, hi;
+          if (SMEM != 0) {
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(nbase + at));
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nbase + at));
+          } else {
+            lo = __ldg((const float4 *)(nodes_g + at));
+            hi = __ldg((const float4 *)(nodes_g + at) + 1);
+          }
+          if (COUNT) cnt.box_tests += searching ? 1u : 0u;
+          const int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
+          const bool bh = (SMEM == 2) ? hit_box_xz_sorted(lo, hi, pre, t_min, h.t) : hit_box(lo, hi, pre, t_min, h.t);
+          const int nxt = bh ? pay : esc; // inner: child; leaf: payload < 0
+          if (searching) { node = nxt; resume = esc; }
         }
-        if (COUNT) cnt.box_tests += searching ? 1u : 0u;
-        const int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
-        const bool bh = (SMEM == 2) ? hit_box_xz_sorted(lo, hi, pre, t_min, h.t) : hit_box(lo, hi, pre, t_min, h.t);
-        const int nxt = bh ? pay : esc; // inner: child; leaf: payload < 0
-        if (searching) { node = nxt; resume = esc; }
       }
     }
     // ---- phase 2: pending primitive tests (one per lane per round)

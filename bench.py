@@ -294,7 +294,7 @@ def run_ours(args):
         n_chunks_bytes = W * H * 16
         hbm_bytes_per_frame = n_chunks_bytes * (2 * 3 + 2)  # partial write+read (<=3 chunks) + accum rw (approx.)
         roofline = {
-            "bound": "fp32_issue", "kernel": "k_render<0,false,true,false>",
+            "bound": "fp32_issue", "kernel": "k_render<0,false,2,false>",
             "achieved": seg_per_s * i_seg * 2.0 / 1e12 / world, "peak": fp32_peak, "unit": "TFLOP/s",
             "frac": seg_per_s * i_seg * 2.0 / 1e12 / world / fp32_peak if fp32_peak > 0 else None,
             "peak_source": "measured in this run by rt_measure_fp32_peak (FMA chain, 2 flops/FMA); "
