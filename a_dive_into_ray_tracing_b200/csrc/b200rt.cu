@@ -596,7 +596,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
     P.b_quad_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_quads);
     scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat;
   }
-  const size_t acc_bytes = (size_t)(block / 32) * 128 * sizeof(float);
+  const size_t acc_bytes = (size_t)(block / 32) * 256 * sizeof(float); // two 32-pixel tiles per warp
   // shared-memory plan: 2 = scene + four quadrant copies of the nodes, 1 = scene, 0 = global
   int smem = 0;
   if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float *acc = (float *)(smem_raw + off) + warp * 128; // [32 pixels][4]
+  float *acc = (float *)(smem_raw + off) + warp * 256; // [2 tiles in flight][32 pixels][4]
   __syncthreads();
 
   const unsigned FULL = 0xffffffffu;
@@ -129,8 +129,14 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   RayPre pre;
   pre.inv_d = v3(0, 0, 0); pre.ood = v3(0, 0, 0); pre.inv_a = 0.f;
   const float t_min = P.sp.t_min;
+  // Work items (tile, chunk of samples) are OVERLAPPED: when the current item's pool is
+  // drained its in-flight paths become the "old" item and the warp starts regenerating
+  // from the next item at once, so no lane idles through an item's drain tail. Two
+  // 32-pixel accumulators per warp; a lane's path remembers its accumulator in bit 5 of pix.
   int pool_next = 0, pool_end = 0; // warp-uniform
-  int work = -1, tile_x0 = 0, tile_y0 = 0, s0 = 0, chunk = 0, chunk_n = 0;
+  int tile_x0 = 0, tile_y0 = 0, s0 = 0, chunk = 0, chunk_n = 0, cur_buf = 0;
+  int old_x0 = 0, old_y0 = 0, old_chunk = 0, old_chunk_n = 0, old_buf = 0, old_inflight = 0;
+  bool have_cur = false, old_valid = false, more_work = true;
   Ray r;
   r.o = v3(0, 0, 0); r.d = v3(0, 0, 1); r.tm = 0;
   V3f beta = v3(1, 1, 1), L = v3(0, 0, 0);
@@ -201,8 +207,41 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     const unsigned m_out = __ballot_sync(FULL, node == node_end);
     const int n_out = __popc(m_out);
     if (n_out < P.batch && n_out < 32) continue;
+    // -- work-item management (warp-uniform)
+    if (pool_next >= pool_end && !old_valid) {
+      if (have_cur) { // the current item's pool is drained: it becomes the old item
+        const unsigned infl = __ballot_sync(FULL, alive);
+        old_x0 = tile_x0; old_y0 = tile_y0; old_chunk = chunk; old_chunk_n = chunk_n; old_buf = cur_buf;
+        old_inflight = __popc(infl);
+        old_valid = true; // flushed below as soon as old_inflight == 0
+        have_cur = false;
+      }
+      if (more_work) {
+        int w = 0;
+        if (lane == 0) w = atomicAdd(P.work_counter, 1);
+        w = __shfl_sync(FULL, w, 0);
+        if (w >= P.n_work) {
+          more_work = false;
+        } else {
+          const int tile = w % P.n_tiles;
+          chunk = w / P.n_tiles;
+          tile_x0 = (tile % P.tiles_x) * RT_TILE_W;
+          tile_y0 = (tile / P.tiles_x) * RT_TILE_H;
+          s0 = P.spp_begin + chunk * P.chunk_spp;
+          chunk_n = min(P.chunk_spp, P.spp_count - chunk * P.chunk_spp);
+          pool_next = 0;
+          pool_end = chunk_n * 32;
+          cur_buf = old_buf ^ 1;
+          have_cur = true;
+          float *a = acc + cur_buf * 128 + lane * 4;
+          a[0] = 0.f; a[1] = 0.f; a[2] = 0.f; a[3] = 0.f;
+          __syncwarp();
+        }
+      }
+    }
     const bool pool_has = pool_next < pool_end;
     const bool done = alive && node == node_end;
+    bool ended = false; // this lane's path ended in this round
     if (__ballot_sync(FULL, done || (!alive && pool_has))) {
       // (a) rays that left the scene end their path now
       const bool hit = done && h.id >= 0;
@@ -214,10 +253,15 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           atomicAdd(&acc[pix * 4 + 1], L.y);
           atomicAdd(&acc[pix * 4 + 2], L.z);
           alive = false;
+          ended = true;
         }
       }
-      // (b) dead lanes take the next (pixel, sample) items of the tile pool by ballot rank
+      // (b) one Philox call for the bounce event of every hit lane
+      Philox4 q;
+      q.x = q.y = q.z = q.w = 0u;
+      // dead lanes take the next (pixel, sample) items of the current pool by ballot rank
       bool fresh_path = false;
+      int old_pix = pix;
       const unsigned dead = __ballot_sync(FULL, !alive);
       if (pool_has && dead) {
         if (!alive) {
@@ -226,7 +270,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
             const int px = item & 31;
             const int i = tile_x0 + (px & 7), j = tile_y0 + (px >> 3);
             if (i < P.W && j < P.H) {
-              pix = px;
+              pix = px | (cur_buf << 5);
               smp = s0 + (item >> 5);
               pixel_index = j * P.W + i;
               bounce = -1; // event index 0 = the camera ray
@@ -237,8 +281,6 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         pool_next = min(pool_end, pool_next + __popc(dead));
       }
       // (c) ONE Philox call per lane: the bounce event of a hit, or the camera event of a new path
-      Philox4 q;
-      q.x = q.y = q.z = q.w = 0u;
       if (hit || fresh_path)
         q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
       bool fresh_ray = false;
@@ -260,10 +302,12 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           atomicAdd(&acc[pix * 4 + 1], L.y);
           atomicAdd(&acc[pix * 4 + 2], L.z);
           alive = false; // regenerated in the next round
+          ended = true;
           node = node_end;
         }
       } else if (fresh_path) {
-        const int i = tile_x0 + (pix & 7), j = tile_y0 + (pix >> 3);
+        const int px = pix & 31;
+        const int i = tile_x0 + (px & 7), j = tile_y0 + (px >> 3);
         float x5 = 0.f;
         if (PROFILE == 2 && P.cam.time1 != P.cam.time0)
           x5 = u01(philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, 0u, 1u, P.seed_lo, P.seed_hi).x);
@@ -277,33 +321,21 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       }
       // (d) every lane with a new ray starts its segment together
       if (fresh_ray) begin_segment();
-      continue;
+      // paths of the old item that ended in this round (their pix was captured before (b))
+      if (old_valid) old_inflight -= __popc(__ballot_sync(FULL, ended && ((old_pix >> 5) == old_buf)));
     }
-    if (n_out < 32) continue; // some lanes still traversing, nothing to shade or regenerate
-    // ---- the tile's pool is drained and every path has ended: flush, fetch the next tile
-    __syncwarp();
-    if (work >= 0) { // lane <-> pixel
-      const int i = tile_x0 + (lane & 7), j = tile_y0 + (lane >> 3);
+    // -- retire the old item once its last path has ended: lane <-> pixel, coalesced float4
+    if (old_valid && old_inflight == 0) {
+      __syncwarp();
+      const int i = old_x0 + (lane & 7), j = old_y0 + (lane >> 3);
       if (i < P.W && j < P.H) {
-        float4 v = make_float4(acc[lane * 4 + 0], acc[lane * 4 + 1], acc[lane * 4 + 2], (float)chunk_n);
-        P.partial[(size_t)chunk * ((size_t)P.W * P.H) + (size_t)j * P.W + i] = v;
+        const float *a = acc + old_buf * 128 + lane * 4;
+        P.partial[(size_t)old_chunk * ((size_t)P.W * P.H) + (size_t)j * P.W + i] =
+            make_float4(a[0], a[1], a[2], (float)old_chunk_n);
       }
+      old_valid = false;
     }
-    int w = 0;
-    if (lane == 0) w = atomicAdd(P.work_counter, 1);
-    w = __shfl_sync(FULL, w, 0);
-    if (w >= P.n_work) break;
-    work = w;
-    const int tile = w % P.n_tiles;
-    chunk = w / P.n_tiles;
-    tile_x0 = (tile % P.tiles_x) * RT_TILE_W;
-    tile_y0 = (tile / P.tiles_x) * RT_TILE_H;
-    s0 = P.spp_begin + chunk * P.chunk_spp;
-    chunk_n = min(P.chunk_spp, P.spp_count - chunk * P.chunk_spp);
-    pool_next = 0;
-    pool_end = chunk_n * 32;
-    acc[lane * 4 + 0] = 0.f; acc[lane * 4 + 1] = 0.f; acc[lane * 4 + 2] = 0.f; acc[lane * 4 + 3] = 0.f;
-    __syncwarp();
+    if (!have_cur && !old_valid && !more_work) break;
   }
   // statistics: one atomic per warp
   unsigned long long a = n_paths, b = n_seg, c = cnt.box_tests, d = cnt.prim_tests;
