@@ -176,6 +176,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of k_render per launch, from the committed
+    `ncu --set full` capture of this kernel (profiles/r1e_k_render_raw.csv); None if absent."""
+    import csv
+    try:
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1e_k_render_raw.csv"))))
+        d, u = dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
+        mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        return sum(float(d[k]) * mult[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------ our arm
 def run_ours(args):
     import torch
@@ -302,7 +315,7 @@ def run_ours(args):
             "model": {"lane_instr_per_segment": i_seg, "box_tests_per_segment": n_box,
                       "prim_tests_per_segment": n_prim, "hits_per_segment": h_bar,
                       "formula": "19*box + 16*prim + 150*hit + 40 (SURVEY.md 8d), 2 flop per lane-instruction"},
-            "traffic": None,
+            "traffic": ncu_traffic_bytes(),
             "hbm": {"bound": "hbm", "achieved": hbm_bytes_per_frame / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": hbm_bytes_per_frame / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                     "note": "framebuffer traffic only; the scene (~60 KB) lives in shared memory: not HBM-bound",
