@@ -57,6 +57,81 @@ __global__ void k_bitonic_smem(unsigned long long *a, int n_pad, int k_begin, in
   }
   for (int i = threadIdx.x; i < tile; i += blockDim.x) a[base + i] = s_keys[i];
 }
+// ---- LSD radix sort of (30-bit Morton code, primitive) pairs: 8 passes of 4-bit digits,
+// stable, multi-block. Per pass: per-block digit histograms -> exclusive scan over
+// [digit][block] -> stable scatter (rank inside a 256-item round from __match_any_sync,
+// across warps from a 16 x 8 shared table, across rounds from running per-digit bases).
+// Input pairs arrive ordered by primitive index, so the stable result equals sorting the
+// unique 64-bit keys code << 32 | primitive (what the bitonic fallback sorts).
+#define RSORT_THREADS 256
+#define RSORT_ITEMS 16
+#define RSORT_TILE (RSORT_THREADS * RSORT_ITEMS)
+__global__ void k_radix_split(const unsigned long long *keys64, unsigned *codes, int *gids, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { codes[i] = (unsigned)(keys64[i] >> 32); gids[i] = (int)(keys64[i] & 0xffffffffull); }
+}
+__global__ void k_radix_join(const unsigned *codes, const int *gids, unsigned long long *keys64, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys64[i] = ((unsigned long long)codes[i] << 32) | (unsigned)gids[i];
+}
+__global__ void __launch_bounds__(RSORT_THREADS) k_radix_hist(const unsigned *keys, int n, int shift, int *hist, int nblocks) {
+  __shared__ int cnt[16];
+  if (threadIdx.x < 16) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * RSORT_TILE;
+  for (int r = 0; r < RSORT_ITEMS; r++) {
+    int i = base + r * RSORT_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 15u], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) hist[threadIdx.x * nblocks + blockIdx.x] = cnt[threadIdx.x];
+}
+__global__ void __launch_bounds__(1024) k_radix_scan(int *hist, int total) { // in-place exclusive scan, one block
+  __shared__ int part[1024];
+  const int per = (total + 1023) / 1024;
+  const int b = threadIdx.x * per, e = min(b + per, total);
+  int s = 0;
+  for (int i = b; i < e; i++) s += hist[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { int acc = 0; for (int i = 0; i < 1024; i++) { int t = part[i]; part[i] = acc; acc += t; } }
+  __syncthreads();
+  int acc = part[threadIdx.x];
+  for (int i = b; i < e; i++) { int t = hist[i]; hist[i] = acc; acc += t; }
+}
+__global__ void __launch_bounds__(RSORT_THREADS) k_radix_scatter(const unsigned *keys_in, const int *vals_in, unsigned *keys_out,
+                                                             int *vals_out, int n, int shift, const int *offs, int nblocks) {
+  __shared__ int run[16], tot[16], wcnt[RSORT_THREADS / 32][17];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 16) run[threadIdx.x] = offs[threadIdx.x * nblocks + blockIdx.x];
+  const int base = blockIdx.x * RSORT_TILE;
+  for (int r = 0; r < RSORT_ITEMS; r++) {
+    if (threadIdx.x < (RSORT_THREADS / 32) * 17) (&wcnt[0][0])[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = base + r * RSORT_THREADS + threadIdx.x;
+    const bool valid = i < n;
+    unsigned key = 0;
+    int val = 0, d = 16;
+    if (valid) { key = keys_in[i]; val = vals_in[i]; d = (int)((key >> shift) & 15u); }
+    const unsigned same = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(same & ((1u << lane) - 1u));
+    if (rank == 0) wcnt[warp][d] = __popc(same);
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      int acc = 0;
+      for (int w = 0; w < RSORT_THREADS / 32; w++) { int t = wcnt[w][threadIdx.x]; wcnt[w][threadIdx.x] = acc; acc += t; }
+      tot[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (valid) {
+      const int pos = run[d] + wcnt[warp][d] + rank;
+      keys_out[pos] = key;
+      vals_out[pos] = val;
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) run[threadIdx.x] += tot[threadIdx.x];
+  }
+}
 __global__ void k_karras(BuildArrays B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B.n_small - 1) body_karras(B, i);
@@ -401,22 +476,54 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     B.packed = (float4 *)ctx->d_nodes.p;
     k_morton<<<(n_pad + TB - 1) / TB, TB, 0, st>>>(B, final_round);
     ctx->launches++;
-    // bitonic sort of the unique 64-bit keys: steps with j < TILE run in shared memory
-    const int SORT_THREADS = 512, TILE = 2 * SORT_THREADS;
-    if (n_pad <= TILE) {
-      k_bitonic_smem<<<1, n_pad / 2, sizeof(unsigned long long) * (size_t)n_pad, st>>>(B.keys, n_pad, 2, n_pad, 1);
-      ctx->launches++;
+    const char *sort_env = getenv("B200RT_SORT");
+    const bool use_bitonic = sort_env && !strcmp(sort_env, "bitonic"); // verification path (unique 64-bit keys)
+    if (!use_bitonic) {
+      // radix sort of (code, primitive) pairs, 8 x 4-bit passes, ping-pong buffers
+      DevBuf r_k0, r_k1, r_v0, r_v1, r_hist;
+      DevBuf *rt[] = {&r_k0, &r_k1, &r_v0, &r_v1, &r_hist};
+      auto rfree = [&]() { for (DevBuf *b : rt) dev_free(*b); };
+      const int nb = (nsm + RSORT_TILE - 1) / RSORT_TILE;
+      int rc_ = dev_reserve(ctx, r_k0, sizeof(unsigned) * (size_t)nsm);
+      if (!rc_) rc_ = dev_reserve(ctx, r_k1, sizeof(unsigned) * (size_t)nsm);
+      if (!rc_) rc_ = dev_reserve(ctx, r_v0, sizeof(int) * (size_t)nsm);
+      if (!rc_) rc_ = dev_reserve(ctx, r_v1, sizeof(int) * (size_t)nsm);
+      if (!rc_) rc_ = dev_reserve(ctx, r_hist, sizeof(int) * 16 * (size_t)nb);
+      if (rc_) { rfree(); cleanup(); return rc_; }
+      unsigned *k0 = (unsigned *)r_k0.p, *k1 = (unsigned *)r_k1.p;
+      int *v0 = (int *)r_v0.p, *v1 = (int *)r_v1.p, *hist = (int *)r_hist.p;
+      k_radix_split<<<(nsm + TB - 1) / TB, TB, 0, st>>>(B.keys, k0, v0, nsm);
+      for (int pass = 0; pass < 8; pass++) {
+        k_radix_hist<<<nb, RSORT_THREADS, 0, st>>>(k0, nsm, 4 * pass, hist, nb);
+        k_radix_scan<<<1, 1024, 0, st>>>(hist, 16 * nb);
+        k_radix_scatter<<<nb, RSORT_THREADS, 0, st>>>(k0, v0, k1, v1, nsm, 4 * pass, hist, nb);
+        std::swap(k0, k1);
+        std::swap(v0, v1);
+      }
+      k_radix_join<<<(nsm + TB - 1) / TB, TB, 0, st>>>(k0, v0, B.keys, nsm);
+      ctx->launches += 26;
+      cudaError_t e_ = cudaGetLastError();
+      if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(st);
+      rfree();
+      if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RT_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(e_)); }
     } else {
-      k_bitonic_smem<<<n_pad / TILE, SORT_THREADS, sizeof(unsigned long long) * TILE, st>>>(B.keys, n_pad, 2, TILE, 1);
-      ctx->launches++;
-      for (int k = 2 * TILE; k <= n_pad; k <<= 1) {
-        int j = k >> 1;
-        for (; j >= TILE; j >>= 1) {
-          k_bitonic<<<(n_pad + TB - 1) / TB, TB, 0, st>>>(B.keys, n_pad, j, k);
+    // bitonic sort of the unique 64-bit keys: steps with j < TILE run in shared memory
+      const int SORT_THREADS = 512, TILE = 2 * SORT_THREADS;
+      if (n_pad <= TILE) {
+        k_bitonic_smem<<<1, n_pad / 2, sizeof(unsigned long long) * (size_t)n_pad, st>>>(B.keys, n_pad, 2, n_pad, 1);
+        ctx->launches++;
+      } else {
+        k_bitonic_smem<<<n_pad / TILE, SORT_THREADS, sizeof(unsigned long long) * TILE, st>>>(B.keys, n_pad, 2, TILE, 1);
+        ctx->launches++;
+        for (int k = 2 * TILE; k <= n_pad; k <<= 1) {
+          int j = k >> 1;
+          for (; j >= TILE; j >>= 1) {
+            k_bitonic<<<(n_pad + TB - 1) / TB, TB, 0, st>>>(B.keys, n_pad, j, k);
+            ctx->launches++;
+          }
+          k_bitonic_smem<<<n_pad / TILE, SORT_THREADS, sizeof(unsigned long long) * TILE, st>>>(B.keys, n_pad, k, k, j);
           ctx->launches++;
         }
-        k_bitonic_smem<<<n_pad / TILE, SORT_THREADS, sizeof(unsigned long long) * TILE, st>>>(B.keys, n_pad, k, k, j);
-        ctx->launches++;
       }
     }
     if (nsm > 1) {

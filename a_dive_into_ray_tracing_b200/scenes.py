@@ -342,3 +342,34 @@ def obj_room(obj_path=None, width=800, height=800, subdivisions=2):
     sc.flags = RT_FLAG_FLIP_NORMALS | RT_FLAG_DEPTH_BACKGROUND
     sc.profile = RT_PROFILE_NEXT_WEEK
     return sc
+
+
+def sphere_field(n_side=100, seed=1984, width=600, height=400):
+    """Scaling-study generator (SURVEY.md §8d "fallback generator"): the weekend scene's law
+    (main.cpp:92-116) on an n_side x n_side grid -> ~n_side^2 small spheres + ground + 3 big
+    ones; camera pulled back proportionally. Profile 0."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    half = n_side // 2
+    rows = [[0, -1000, 0, 1000, 0, 0.5, 0.5, 0.5, 0, 0, 0, 0]]
+    for a in range(-half, n_side - half):
+        for b in range(-half, n_side - half):
+            choose = rng.random()
+            c = (a + 0.9 * rng.random(), 0.2, b + 0.9 * rng.random())
+            if np.hypot(c[0] - 4, c[2]) <= 0.9:
+                continue
+            if choose < 0.8:
+                alb = rng.random(3) * rng.random(3)
+                rows.append([*c, 0.2, 0, *alb, 0, 0, 0, 0])
+            elif choose < 0.95:
+                rows.append([*c, 0.2, 1, *(0.5 + 0.5 * rng.random(3)), 0.5 * rng.random(), 0, 0, 0])
+            else:
+                rows.append([*c, 0.2, 2, 0, 0, 0, 1.5, 0, 0, 0])
+    rows.append([0, 1, 0, 1.0, 2, 0, 0, 0, 1.5, 0, 0, 0])
+    rows.append([-4, 1, 0, 1.0, 0, 0.4, 0.2, 0.1, 0, 0, 0, 0])
+    rows.append([4, 1, 0, 1.0, 1, 0.7, 0.6, 0.5, 0.0, 0, 0, 0])
+    sc = scene_from_rows(np.array(rows, np.float64), "sphere_field_%d" % n_side)
+    s = n_side / 22.0
+    sc.camera = camera_from_lookat((13 * s, 2 * s, 3 * s), (0, 0, 0), (0, 1, 0), 20.0, width / height, 0.1,
+                                   10.0 * s)
+    sc.profile = RT_PROFILE_WEEKEND_CPU
+    return sc

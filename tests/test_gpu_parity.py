@@ -298,3 +298,79 @@ def test_render_into_torch_tensor_on_torch_stream():
         s.synchronize()
         assert e0.elapsed_time(e1) > 0.05  # the kernel really ran on THAT stream
         np.testing.assert_array_equal(acc2.cpu().numpy(), ref)
+
+
+def test_large_scene_global_memory_path(l1_64):
+    """~10^4 spheres: the scene no longer fits shared memory (k_render SMEM=0 variant, nodes
+    through L1/L2), the sort runs multi-block. Closest hits: BVH == brute force == oracle;
+    the rendered frame agrees with the oracle statistically."""
+    W, H = 120, 80
+    sc = scenes.sphere_field(100, width=W, height=H)
+    assert sc.n_prims > 9000
+    with capi.Context(profile=0, seed=3) as ctx:
+        ctx.upload(sc).build_accel(1)
+        nodes, leaf, big = ctx.accel()
+        check_packed_bvh(sc, nodes, leaf, big)
+        rays = D.primary_rays(sc.camera, W, H, 0, lens=(0.2, 0.1))
+        ia, ta = ctx.trace_closest(rays, use_accel=True)
+        ib, tb = ctx.trace_closest(rays, use_accel=False)
+        np.testing.assert_array_equal(ia, ib)
+        np.testing.assert_array_equal(ta, tb)
+        io, to, _ = l1_64.closest_hit(sc, 0, rays)
+        assert (ia != io).sum() <= 2
+        same = (ia == io) & (io >= 0)
+        assert (np.abs(ta[same] - to[same]) / to[same]).max() < 1e-5
+        spp, K = 32, 4
+        batches = []
+        for k in range(K):
+            ctx.clear()
+            ctx.render(W, H, spp // K, spp_begin=k * (spp // K))
+            a = ctx.accum().astype(np.float64)
+            batches.append(a[..., :3] / a[..., 3:4])
+        st = ctx.stats()
+    assert st["smem_bytes"] < 40000  # only the accumulators: the scene stayed in global memory
+    mu_a, var_mean_a = SU.batch_variance(batches)
+    r, r2, nseg = l1_64.render_parallel(sc, 0, W, H, spp, seed=5, use_ref_bvh=True)
+    mu_b, var_b = SU.mean_var(r, r2, spp)
+    ok, d, b = SU.three_sigma_check(mu_a, var_mean_a, 1, mu_b, var_b, spp)
+    assert ok, (d, b)
+    assert abs(st["segments"] / st["paths"] - nseg / (W * H * spp)) < 0.05 * nseg / (W * H * spp)
+
+
+def test_multi_primitive_leaves_give_identical_hits(hits_primary, monkeypatch):
+    """Leaf collapsing (K primitives per leaf) changes the tree, never the answer."""
+    sc = scenes.weekend(400, 225)
+    ref = None
+    for K in ("1", "2", "4", "8"):
+        monkeypatch.setenv("B200RT_MAX_LEAF", K)
+        with capi.Context(profile=0) as ctx:
+            ctx.upload(sc).build_accel(1)
+            nodes, leaf, big = ctx.accel()
+            check_packed_bvh(sc, nodes, leaf, big, max_leaf=int(K))
+            ids, ts = ctx.trace_closest(hits_primary["rays"], use_accel=True)
+            ctx.render(96, 54, 8)
+            img = ctx.accum()
+        np.testing.assert_array_equal(ids, hits_primary["ids"])
+        if ref is None:
+            ref = (ts, img, len(nodes))
+        else:
+            np.testing.assert_array_equal(ts, ref[0])
+            np.testing.assert_allclose(img, ref[1], rtol=1e-5, atol=1e-5)  # same paths; fp32 ties aside
+            assert len(nodes) < ref[2]
+
+
+def test_radix_sort_equals_bitonic_reference(monkeypatch):
+    """The LSD radix sort of (Morton code, primitive) pairs yields exactly the order of the
+    bitonic sort of the unique 64-bit keys: identical trees (single- and multi-block sizes)."""
+    for sc in (scenes.weekend(64, 36), scenes.obj_room(width=32, height=32, subdivisions=3),
+               scenes.sphere_field(100, width=64, height=36)):
+        built = []
+        for mode in ("radix", "bitonic"):
+            monkeypatch.setenv("B200RT_SORT", mode)
+            with capi.Context(profile=sc.profile) as ctx:
+                ctx.upload(sc).build_accel(1)
+                built.append(ctx.accel())
+        (n0, l0_, b0), (n1, l1_, b1) = built
+        np.testing.assert_array_equal(l0_, l1_)
+        np.testing.assert_array_equal(b0, b1)
+        assert n0.tobytes() == n1.tobytes()
