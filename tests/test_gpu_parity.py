@@ -374,3 +374,27 @@ def test_radix_sort_equals_bitonic_reference(monkeypatch):
         np.testing.assert_array_equal(l0_, l1_)
         np.testing.assert_array_equal(b0, b1)
         assert n0.tobytes() == n1.tobytes()
+
+
+def test_converged_image_vs_reference_gallery_matched_spp(golden_dir):
+    """Config 2 at MATCHED spp (1200x800, 500 spp) against the reference's own published
+    render of it (gallery/final.png, 8-bit, 4x4 box-downsampled fixture): PSNR >= 40 dB and
+    within 1.5 dB of the Monte-Carlo floor (two renders of ours with different seeds),
+    per-channel mean |delta| <= 3 sigma of the estimator (sigma from the two-seed spread)."""
+    ref = np.load(golden_dir + "/gallery_final_300x200.npy").astype(np.float64) / 4.0 / 255.0
+    W, H, spp = 1200, 800, 500
+    imgs = []
+    for seed in (1984, 7):
+        with capi.Context(profile=0, seed=seed) as ctx:
+            ctx.upload(scenes.weekend(W, H)).build_accel(1)
+            ctx.render(W, H, spp)
+            _, rgb = ctx.resolve(want_linear=False)
+        imgs.append(rgb.astype(np.float64).reshape(200, 4, 300, 4, 3).mean((1, 3)) / 255.0)
+    p_ref = SU.psnr(imgs[0], ref)
+    p_floor = SU.psnr(imgs[0], imgs[1])
+    assert p_ref >= 40.0, (p_ref, p_floor)
+    assert p_ref >= p_floor - 1.5, (p_ref, p_floor)
+    sigma = np.abs(imgs[0] - imgs[1]).reshape(-1, 3).mean(0)  # E|a-b| = 1.13 sigma_pixel for two equal estimators
+    d = np.abs(imgs[0] - ref).reshape(-1, 3).mean(0)
+    assert np.all(d <= 3.0 * sigma + 0.5 / 255.0), (d, sigma)  # + half an 8-bit level of quantisation
+    assert np.all(np.abs(imgs[0].mean((0, 1)) - ref.mean((0, 1))) < 2.0 / 255.0)

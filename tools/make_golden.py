@@ -14,6 +14,7 @@ reference sources are present.
   weekend_refvsref.json    reference-vs-reference PSNR floor (two seeds)
   gallery_final_75x50.npy  the reference's gallery/final.png (1200x800, its 500-spp
                            config-2 image) box-downsampled 16x16, uint8->float mean
+  gallery_final_300x200.npy  the same image box-downsampled 4x4 (uint16 = 4 x mean level)
 """
 import json
 import os
@@ -113,6 +114,9 @@ def main():
     assert im.shape == (800, 1200, 3)
     ds = im.reshape(50, 16, 75, 16, 3).mean((1, 3)) / 255.0
     np.save(os.path.join(G, "gallery_final_75x50.npy"), ds.astype(np.float32))
+    # 4x4 box-downsampled copy (sum of 16 8-bit values / 4, exact in uint16) for the matched-spp PSNR test
+    ds4 = im.reshape(200, 4, 300, 4, 3).mean((1, 3))
+    np.save(os.path.join(G, "gallery_final_300x200.npy"), np.round(ds4 * 4).astype(np.uint16))
     meta["gallery"] = {"shape": [50, 75, 3], "mean_rgb": ds.mean((0, 1)).tolist(),
                        "note": "top row first, gamma-space [0,1]"}
     with open(os.path.join(G, "weekend_meta.json"), "w") as fh:
