@@ -247,3 +247,18 @@ def write_ppm(path, rgb8, binary=True):
         with open(path, "w") as fh:
             fh.write("P3\n%d %d\n255\n" % (W, H))
             np.savetxt(fh, rgb8.reshape(-1, 3), fmt="%d")
+
+
+def write_png(path, rgb8):
+    """8-bit RGB PNG (zlib-compressed); rgb8 is [H][W][3], top row first."""
+    import struct
+    import zlib
+    H, W = rgb8.shape[:2]
+    raw = b"".join(b"\x00" + np.ascontiguousarray(rgb8[j], np.uint8).tobytes() for j in range(H))
+
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+    with open(path, "wb") as fh:
+        fh.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, 2, 0, 0, 0)) +
+                 chunk(b"IDAT", zlib.compress(raw, 6)) + chunk(b"IEND", b""))

@@ -41,3 +41,7 @@ void rtx_host_get(rt_sphere *s, rt_triangle *t, rt_quad *q, rt_material *m, rt_c
   if (c) *c = g_cam;
 }
 }
+
+extern "C" int rtx_host_write_png(const char *path, const unsigned char *rgb, int w, int h) {
+  return rtx::write_png_file(path, rgb, w, h) ? 0 : 1;
+}

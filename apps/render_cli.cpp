@@ -3,7 +3,7 @@
 // the C ABI and writes a P3 PPM on stdout / timing on stderr exactly like
 // rt_in_one_weekend/main.cpp:292-360 and accelerated-rt-cuda/final.cu:155-246.
 //   render_cli [--scene weekend|next_week|obj] [--obj file.obj] [--width W] [--height H]
-//              [--spp N] [--seed S] [--device D] [--binary]
+//              [--spp N] [--seed S] [--device D] [--binary | --png]   (image on stdout)
 #include <chrono>
 #include <cstring>
 #include <iostream>
@@ -14,7 +14,7 @@ int main(int argc, char **argv) {
   std::string scene = "weekend", obj;
   int W = 1200, H = 800, spp = 500, device = 0;
   unsigned long long seed = 1984;
-  bool binary = false;
+  bool binary = false, png = false;
   for (int i = 1; i < argc; i++) {
     auto is = [&](const char *f) { return !strcmp(argv[i], f) && i + 1 < argc; };
     if (is("--scene")) scene = argv[++i];
@@ -25,6 +25,7 @@ int main(int argc, char **argv) {
     else if (is("--seed")) seed = strtoull(argv[++i], nullptr, 10);
     else if (is("--device")) device = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--binary")) binary = true;
+    else if (!strcmp(argv[i], "--png")) png = true;
     else { std::cerr << "unknown argument " << argv[i] << "\n"; return 2; }
   }
   try {
@@ -71,7 +72,8 @@ int main(int argc, char **argv) {
     rt_stats_t st = r.stats();
     std::cerr << "took " << secs << " seconds. (" << st.segments / 1e6 / (st.ms_render * 1e-3) << " Mpath-bounces/s, BVH "
               << st.n_nodes << " nodes built in " << st.ms_build << " ms)\n";
-    if (binary) im.write_ppm_binary(std::cout);
+    if (png) im.write_png(std::cout);
+    else if (binary) im.write_ppm_binary(std::cout);
     else im.write_ppm(std::cout);
   } catch (const std::exception &e) {
     std::cerr << "error: " << e.what() << "\n";

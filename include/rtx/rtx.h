@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../rt_capi.h"
+#include "image_io.h"
 
 namespace rtx {
 
@@ -455,7 +456,11 @@ public:
 
 // read_triangles — triangles/cuda/include/triangle.h:217-300: `v`, `vn`, `f a/b/c` x3; the
 // face is emitted with vertex indices [6],[3],[0] and normal indices [8],[5],[2] of the
-// flattened index list (reversed winding).
+// flattened index list (reversed winding). Beyond the reference's parser (which only
+// accepts triangles written as a/b/c or a//c): `v`, `v/vt`, `v//vn`, `v/vt/vn` corners,
+// negative (relative) indices, polygons (fan triangulation, each triangle then reversed
+// like the reference does) and faces without normals (the geometric normal of the
+// REVERSED triangle stands in for the vertex normals, so orientation is well defined).
 inline void read_triangles(const std::string &filename, std::vector<shared_ptr<hittable>> &out, shared_ptr<material> mat,
                            double scale = 1.0) {
   std::ifstream in(filename);
@@ -470,16 +475,25 @@ inline void read_triangles(const std::string &filename, std::vector<shared_ptr<h
     if (type == "vn") { ls >> x >> y >> z; vns.push_back(vec3(x, y, z)); }
     else if (type == "v") { ls >> x >> y >> z; vs.push_back(vec3(x, y, z)); }
     else if (type == "f") {
-      std::vector<int> idx;
+      std::vector<int> vi, ni;
       std::string sec;
       while (ls >> sec) {
+        int idx[3] = {0, 0, 0}, k = 0;
         std::istringstream ss(sec);
         std::string num;
-        while (std::getline(ss, num, '/')) idx.push_back(num.empty() ? -1 : std::stoi(num) - 1);
+        while (k < 3 && std::getline(ss, num, '/')) { idx[k++] = num.empty() ? 0 : std::stoi(num); }
+        auto fix = [](int i, size_t n) { return i > 0 ? i - 1 : (i < 0 ? (int)n + i : -1); };
+        vi.push_back(fix(idx[0], vs.size()));
+        ni.push_back(fix(idx[2], vns.size()));
       }
-      if (idx.size() < 9) continue;
-      out.push_back(make_shared<triangle>(vs.at(idx[6]) * scale, vs.at(idx[3]) * scale, vs.at(idx[0]) * scale,
-                                          vns.at(idx[8]), vns.at(idx[5]), vns.at(idx[2]), mat));
+      for (size_t k = 1; k + 1 < vi.size(); k++) { // fan: (0, k, k+1)
+        const int a = 0, b = (int)k, c = (int)k + 1;
+        const vec3 &p0 = vs.at(vi[c]), &p1 = vs.at(vi[b]), &p2 = vs.at(vi[a]); // reversed winding
+        vec3 n0, n1, n2;
+        if (ni[a] >= 0 && ni[b] >= 0 && ni[c] >= 0) { n0 = vns.at(ni[c]); n1 = vns.at(ni[b]); n2 = vns.at(ni[a]); }
+        else { n0 = n1 = n2 = -cross(p1 - p0, p2 - p0); } // keeps the reversed triangle's own orientation
+        out.push_back(make_shared<triangle>(p0 * scale, p1 * scale, p2 * scale, n0, n1, n2, mat));
+      }
     }
   }
 }
@@ -504,6 +518,7 @@ struct image8 {
     out << "P3\n" << width << ' ' << height << "\n255\n";
     for (size_t i = 0; i + 2 < rgb.size(); i += 3) out << (int)rgb[i] << ' ' << (int)rgb[i + 1] << ' ' << (int)rgb[i + 2] << '\n';
   }
+  void write_png(std::ostream &out) const { rtx::write_png(out, rgb.data(), width, height); }
   void write_ppm_binary(std::ostream &out) const {
     out << "P6\n" << width << ' ' << height << "\n255\n";
     out.write((const char *)rgb.data(), (std::streamsize)rgb.size());

@@ -107,3 +107,45 @@ def test_render_cli_writes_the_reference_style_ppm(tmp_path):
         ctx.render(W, H, spp)
         _, rgb = ctx.resolve(want_linear=False)
     np.testing.assert_array_equal(img, rgb.astype(np.int32))
+
+
+def test_obj_reader_variants(host, tmp_path):
+    """Beyond the reference's parser: v/vt/vn corners, negative indices, polygons (fan) and
+    faces without normals load to the same triangles as the plain a//n triangle form."""
+    v = ["v 0 0 0", "v 1 0 0", "v 1 1 0", "v 0 1 0", "v 0.5 0.5 1"]
+    vn = ["vn 0 0 -1", "vn 0 0 -1", "vn 0 0 -1", "vn 0 0 -1", "vn 0 0 1"]
+    vt = ["vt 0 0", "vt 1 0"]
+    fancy = v + vn + vt + ["f 1/1/1 2/2/2 3/1/3 4/2/4",   # quad with texture coordinates
+                           "f -5//-5 -4//-4 -1//-1",        # negative indices
+                           "f 2 3 5"]                        # no normals
+    plain = v + vn + ["f 1//1 2//2 3//3", "f 1//1 3//3 4//4", "f 1//1 2//2 5//5"]
+    a = tmp_path / "fancy.obj"
+    b = tmp_path / "plain.obj"
+    a.write_text("\n".join(fancy) + "\n")
+    b.write_text("\n".join(plain) + "\n")
+    _, ta, _, _, _, _ = host(2, obj=str(a).encode())
+    _, tb, _, _, _, _ = host(2, obj=str(b).encode())
+    assert len(ta) == 4 and len(tb) == 3
+    for f in ("v0", "v1", "v2", "normal"):
+        np.testing.assert_array_equal(ta[f][:3], tb[f])
+    # the normal-less face keeps the (reversed) triangle's own orientation
+    n = ta["normal"][3].astype(np.float64)
+    e1, e2 = ta["v1"][3] - ta["v0"][3], ta["v2"][3] - ta["v0"][3]
+    assert np.dot(np.cross(e1, e2), n) > 0
+
+
+def test_png_writers(tmp_path):
+    from PIL import Image
+    from a_dive_into_ray_tracing_b200 import capi
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "apps"), "-s", "../build/librtx_host.so"])
+    L = C.CDLL(os.path.join(ROOT, "build", "librtx_host.so"))
+    rng = np.random.Generator(np.random.Philox(3))
+    img = rng.integers(0, 256, (37, 301, 3), dtype=np.uint8)  # > 65535 raw bytes: several stored blocks
+    p1, p2 = str(tmp_path / "a.png"), str(tmp_path / "b.png")
+    assert L.rtx_host_write_png(p1.encode(), img.ctypes.data_as(C.c_void_p), 301, 37) == 0
+    capi.write_png(p2, img)
+    for p in (p1, p2):
+        np.testing.assert_array_equal(np.asarray(Image.open(p).convert("RGB")), img)
+    p3 = str(tmp_path / "c.ppm")
+    capi.write_ppm(p3, img, binary=True)
+    np.testing.assert_array_equal(np.asarray(Image.open(p3).convert("RGB")), img)
