@@ -212,3 +212,14 @@ int emu_render(void *p, int W, int H, int spp_begin, int spp_count, uint64_t see
 }
 
 #include "warpsim.inc"
+
+extern "C" void emu_philox(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned *out) {
+  Philox4 q = philox4x32_10(c0, c1, c2, c3, k0, k1);
+  out[0] = q.x; out[1] = q.y; out[2] = q.z; out[3] = q.w;
+}
+extern "C" void emu_samplers(float u1, float u2, float u3, float *out9) {
+  float x, y;
+  sample_unit_disk(u1, u2, &x, &y);
+  V3f a = sample_unit_vector(u1, u2), b = sample_unit_ball(u1, u2, u3);
+  out9[0] = x; out9[1] = y; out9[2] = a.x; out9[3] = a.y; out9[4] = a.z; out9[5] = b.x; out9[6] = b.y; out9[7] = b.z; out9[8] = 0;
+}
