@@ -140,9 +140,13 @@ __global__ void k_fit(BuildArrays B, int rotate) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B.n_small) body_fit(B, i, rotate);
 }
-__global__ void k_pack(BuildArrays B) {
+__global__ void k_order(BuildArrays B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 2 * B.n_small - 1) body_pack(B, i);
+  if (i < B.n_small - 1) body_order(B, i);
+}
+__global__ void k_pack(BuildArrays B, int quadrant) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 2 * B.n_small - 1) body_pack(B, i, quadrant);
 }
 
 // ------------------------------------------------------------------ context
@@ -383,8 +387,8 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   B.tris = (const rt_triangle *)ctx->d_raw_tri.p;
   B.quads = (const rt_quad *)ctx->d_raw_quad.p;
   B.thickness = (ctx->sp.flags & RT_FLAG_FLIP_NORMALS) ? 0.01f : 0.1f; // THICKNESS of the two trees
-  DevBuf t_lo, t_hi, t_flag, t_bounds, t_small, t_keys, t_left, t_right, t_parent, t_nflag, t_size, t_lcnt, t_nlo, t_nhi;
-  DevBuf *temps[] = {&t_lo, &t_hi, &t_flag, &t_bounds, &t_small, &t_keys, &t_left, &t_right, &t_parent, &t_nflag, &t_size, &t_lcnt, &t_nlo, &t_nhi};
+  DevBuf t_lo, t_hi, t_flag, t_bounds, t_small, t_keys, t_left, t_right, t_parent, t_nflag, t_size, t_lcnt, t_nlo, t_nhi, t_swap;
+  DevBuf *temps[] = {&t_swap, &t_lo, &t_hi, &t_flag, &t_bounds, &t_small, &t_keys, &t_left, &t_right, &t_parent, &t_nflag, &t_size, &t_lcnt, &t_nlo, &t_nhi};
   auto cleanup = [&]() { for (DevBuf *b : temps) dev_free(*b); };
 #define CKB(call)                                                                                  \
   do {                                                                                             \
@@ -458,14 +462,18 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     RSV(t_left, sizeof(int) * (size_t)nsm); RSV(t_right, sizeof(int) * (size_t)nsm);
     RSV(t_parent, sizeof(int) * (size_t)n_nodes); RSV(t_nflag, sizeof(int) * (size_t)nsm);
     RSV(t_size, sizeof(int) * (size_t)n_nodes); RSV(t_lcnt, sizeof(int) * (size_t)n_nodes);
+    RSV(t_swap, sizeof(int) * (size_t)nsm);
     { int rc = dev_reserve(ctx, ctx->d_leaf_prims, sizeof(int32_t) * (size_t)nsm); if (rc) { cleanup(); return rc; } }
     RSV(t_nlo, sizeof(float4) * (size_t)n_nodes); RSV(t_nhi, sizeof(float4) * (size_t)n_nodes);
-    { int rc = dev_reserve(ctx, ctx->d_nodes, sizeof(float4) * 2 * (size_t)n_nodes); if (rc) { cleanup(); return rc; } }
+    // four packed copies, one per ray-direction quadrant (own front-to-back visiting order)
+    { int rc = dev_reserve(ctx, ctx->d_nodes, 4 * sizeof(float4) * 2 * (size_t)n_nodes); if (rc) { cleanup(); return rc; } }
     B.small_gid = (const int *)t_small.p;
     B.keys = (unsigned long long *)t_keys.p;
     B.left = (int *)t_left.p; B.right = (int *)t_right.p; B.parent = (int *)t_parent.p;
     B.flag = (int *)t_nflag.p; B.size = (int *)t_size.p; B.lcnt = (int *)t_lcnt.p;
     B.leaf_prims = (int32_t *)ctx->d_leaf_prims.p;
+    B.swapmask = (int *)t_swap.p;
+    B.packed_stride = 2 * n_nodes;
     {
       const char *e = getenv("B200RT_MAX_LEAF"); // tuning knob (leaf size)
       int ml = e ? atoi(e) : 1; // while-while traversal: single-primitive leaves measured fastest
@@ -536,8 +544,9 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
       k_fit<<<(nsm + TB - 1) / TB, TB, 0, st>>>(B, (quality > 0 && r < rounds - 1) ? 1 : 0);
       ctx->launches++;
     }
-    k_pack<<<(n_nodes + TB - 1) / TB, TB, 0, st>>>(B);
-    ctx->launches++;
+    if (nsm > 1) k_order<<<(nsm - 1 + TB - 1) / TB, TB, 0, st>>>(B);
+    for (int q = 0; q < 4; q++) k_pack<<<(n_nodes + TB - 1) / TB, TB, 0, st>>>(B, q);
+    ctx->launches += 5;
     CKB(cudaGetLastError());
     int kept = 0; // nodes that survive leaf collapsing = kept size of the root (build node 0)
     CKB(cudaMemcpyAsync(&kept, B.size, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -554,6 +563,7 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   ctx->S.leaf_prims = (const int32_t *)ctx->d_leaf_prims.p;
   ctx->n_leaf_prims = nsm;
   ctx->S.n_nodes = n_nodes;
+  ctx->S.node_stride = nsm > 0 ? (2 * nsm - 1) * 32 : 0;
   ctx->stats.n_nodes = n_nodes;
   ctx->stats.n_big_prims = n_big;
   ctx->have_accel = true;

@@ -59,6 +59,8 @@ struct BuildArrays {
   int *lcnt;                 // [2*n_small-1] primitives (build leaves) in subtree
   int max_leaf;              // subtrees with <= max_leaf primitives become ONE leaf node (1..8)
   int32_t *leaf_prims;       // [n_small] RT_PRIM_IDs in depth-first leaf order
+  int *swapmask;             // [n_small-1] bit q: in quadrant q the RIGHT child is visited first
+  int packed_stride;         // float4 elements between two quadrant copies of the packed nodes
   float4 *nbox_lo, *nbox_hi; // [2*n_small-1]
   float4 *packed;            // [2*(2*n_small-1)] output nodes
 };
@@ -271,6 +273,25 @@ RT_HD void body_fit(const BuildArrays &B, int leaf, int rotate) {
   }
 }
 
+// ---- kernel 6b: front-to-back child order per ray-direction quadrant. Quadrant q = sign
+// bits of (d.x, d.z) (bit 0: d.x < 0, bit 1: d.z < 0). Children are ordered along the axis (x
+// or z) on which their box centres differ most: the child the ray meets first comes first, so
+// hits shrink t_max early and later subtrees are culled by the slab test.
+RT_HD void body_order(const BuildArrays &B, int p) {
+  const int l = B.left[p], r = B.right[p];
+  const float4 llo = B.nbox_lo[l], lhi = B.nbox_hi[l], rlo = B.nbox_lo[r], rhi = B.nbox_hi[r];
+  const float dx = (rlo.x + rhi.x) - (llo.x + lhi.x), dz = (rlo.z + rhi.z) - (llo.z + lhi.z);
+  int mask = 0;
+  if (fabsf(dx) >= fabsf(dz)) { // left is the low-x child iff dx > 0
+    const bool left_low = dx >= 0.f;
+    for (int q = 0; q < 4; q++) { const bool neg = q & 1; if (left_low == neg) mask |= 1 << q; }
+  } else {
+    const bool left_low = dz >= 0.f;
+    for (int q = 0; q < 4; q++) { const bool neg = (q >> 1) & 1; if (left_low == neg) mask |= 1 << q; }
+  }
+  B.swapmask[p] = mask;
+}
+
 // ---- kernel 7: depth-first threaded layout + 32-byte packing. A build node `v` is
 // emitted unless it lies strictly inside a collapsed subtree (an ancestor holds
 // <= max_leaf primitives and became a multi-primitive leaf). Its position = number of
@@ -278,16 +299,19 @@ RT_HD void body_fit(const BuildArrays &B, int leaf, int rotate) {
 // kept subtree size. Leaves reference leaf_prims[first .. first+count): payload =
 // ~(first << 3 | count-1). Boxes are padded by a few ulps so that the FP32 slab test
 // stays conservative.
-RT_HD void body_pack(const BuildArrays &B, int v) {
+RT_HD void body_pack(const BuildArrays &B, int v, int quadrant) {
   const int n = B.n_small;
   int pos = 0, lpos = 0, cur = v;
   for (int p = B.parent[cur]; p >= 0; p = B.parent[cur]) {
     pos += 1;
-    if (B.right[p] == cur) { pos += B.size[B.left[p]]; lpos += B.lcnt[B.left[p]]; }
+    const bool is_right = B.right[p] == cur;
+    const bool right_first = (B.swapmask[p] >> quadrant) & 1;
+    if (is_right != right_first) pos += B.size[is_right ? B.left[p] : B.right[p]]; // visited second in this quadrant
+    if (is_right) lpos += B.lcnt[B.left[p]];                                       // leaf order stays canonical
     cur = p;
   }
   const bool build_leaf = v >= n - 1;
-  if (build_leaf) B.leaf_prims[lpos] = gid_to_prim_id(B, (int)(B.keys[v - (n - 1)] & 0xffffffffull));
+  if (build_leaf && quadrant == 0) B.leaf_prims[lpos] = gid_to_prim_id(B, (int)(B.keys[v - (n - 1)] & 0xffffffffull));
   const int par = B.parent[v];
   if (par >= 0 && B.lcnt[par] <= B.max_leaf) return; // inside a collapsed subtree
   float4 lo = B.nbox_lo[v], hi = B.nbox_hi[v];
@@ -302,6 +326,7 @@ RT_HD void body_pack(const BuildArrays &B, int v) {
   // arithmetic; rt_accel_download converts them back to indices
   lo.w = RT_I2F(escape << RT_NODE_SHIFT);
   hi.w = RT_I2F(payload >= 0 ? (payload << RT_NODE_SHIFT) : payload);
-  B.packed[2 * pos] = lo;
-  B.packed[2 * pos + 1] = hi;
+  float4 *dst = B.packed + (size_t)quadrant * B.packed_stride;
+  dst[2 * pos] = lo;
+  dst[2 * pos + 1] = hi;
 }

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       const int nn = P.b_nodes >> 5;
       for (int i = threadIdx.x; i < 4 * nn; i += blockDim.x) {
         const int q = i / nn, k = i - q * nn;
-        float4 lo = __ldg(P.S.nodes + 2 * k), hi = __ldg(P.S.nodes + 2 * k + 1);
+        const float4 *src = P.S.nodes + q * (P.S.node_stride >> 4) + 2 * k; // quadrant q's own visiting order
+        float4 lo = __ldg(src), hi = __ldg(src + 1);
         if (q & 1) { const float t = lo.x; lo.x = hi.x; hi.x = t; }
         if (q & 2) { const float t = lo.z; lo.z = hi.z; hi.z = t; }
         float4 *dst = (float4 *)(smem_raw + off + q * P.b_nodes) + 2 * k;
@@ -149,6 +150,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   const uint32_t nodes_s = SMEM ? (uint32_t)__cvta_generic_to_shared(S.nodes) : 0u;
   uint32_t nbase = nodes_s; // + quadrant copy of the current ray (SMEM == 2)
   const char *nodes_g = (const char *)S.nodes;
+  const char *nodes_q = nodes_g; // SMEM == 0: the current ray's quadrant copy in global memory
 
   // start a segment: per-ray constants, the always-tested big primitives, enter at the root
   auto begin_segment = [&]() {
@@ -162,8 +164,11 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
     }
     node = 0;
-    if (SMEM == 2) // sign BITS of 1/d (covers d = -0): which pre-swapped copy this ray walks
-      nbase = nodes_s + (((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 1)) * (unsigned)P.b_nodes;
+    // sign BITS of 1/d (covers d = -0): which quadrant copy (own child order; in shared memory also
+    // pre-swapped planes) this ray walks
+    const unsigned quadrant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 1);
+    if (SMEM == 2) nbase = nodes_s + quadrant * (unsigned)P.b_nodes;
+    if (SMEM == 0) nodes_q = nodes_g + quadrant * (unsigned)S.node_stride;
   };
 
   for (;;) {
@@ -183,8 +188,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
             asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(nbase + at));
             asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nbase + at));
           } else {
-            lo = __ldg((const float4 *)(nodes_g + at));
-            hi = __ldg((const float4 *)(nodes_g + at) + 1);
+            lo = __ldg((const float4 *)(nodes_q + at));
+            hi = __ldg((const float4 *)(nodes_q + at) + 1);
           }
           if (COUNT) cnt.box_tests += searching ? 1u : 0u;
           const int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);

@@ -94,6 +94,7 @@ struct DevScene {
   const int32_t *leaf_prims; // RT_PRIM_IDs in depth-first leaf order (leaves hold ranges of it)
   int n_nodes, n_spheres, n_tris, n_quads, n_mats, n_big;
   int any_moving;
+  int node_stride; // bytes between the four quadrant-ordered copies of `nodes` (copy 0 first)
 };
 
 struct DevCamera {

@@ -50,8 +50,9 @@ def check_packed_bvh(sc, nodes, leaf_prims, big, max_leaf=8):
     enc = ~pay[leaves]
     first, count = enc >> 3, (enc & 7) + 1
     assert np.all(count >= 1) and np.all(count <= max_leaf)
-    # leaves tile leaf_prims in depth-first order: each primitive in exactly one leaf
-    order = np.argsort(np.where(leaves)[0])
+    # leaves tile leaf_prims (canonical leaf order; the nodes themselves are laid out in the
+    # quadrant's front-to-back visiting order): each primitive in exactly one leaf
+    order = np.argsort(first)
     assert np.array_equal(first[order], np.concatenate([[0], np.cumsum(count[order])[:-1]]))
     assert int(count.sum()) == n_small
     n_leaves = int(leaves.sum())

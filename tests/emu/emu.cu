@@ -46,7 +46,7 @@ static void bind(EmuScene &E, const rt_scene_desc *sc) {
 }
 
 // serial replay of rt_accel_build (csrc/b200rt.cu) with the same kernel bodies
-static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_frac, int big_rounds, int shuffle, int max_leaf) {
+static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_frac, int big_rounds, int shuffle, int max_leaf, int quadrant = 0) {
   const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, n = ns + nt + nq;
   E.nodes.clear(); E.big.clear(); E.leaf_prims.clear(); E.sph_is_big.assign(std::max(ns, 1), 0);
   if (n == 0) return;
@@ -105,7 +105,11 @@ static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_f
       for (int i = 0; i < nsm; i++) if (!seen[i]) body_fit(B, i, (quality > 0 && r < rounds - 1) ? 1 : 0);
     }
   }
-  for (int v = 0; v < n_nodes; v++) body_pack(B, v);
+  std::vector<int> swapmask(std::max(nsm - 1, 1), 0);
+  B.swapmask = swapmask.data();
+  B.packed_stride = 2 * n_nodes;
+  for (int i = 0; i < nsm - 1; i++) body_order(B, i);
+  for (int v = 0; v < n_nodes; v++) body_pack(B, v, quadrant);
   E.nodes.resize(2 * (size_t)size[0]); // kept nodes after leaf collapsing
 }
 
