@@ -691,6 +691,8 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
     const char *e = getenv("B200RT_BATCH"), *f = getenv("B200RT_FRAC8"); // tuning knobs
     P.batch = e ? atoi(e) : 24;
     P.frac8 = f ? atoi(f) : 5;
+    const char *lm = getenv("B200RT_LEAFMIN");
+    P.leaf_min = lm ? atoi(lm) : 1; // measured: 1..5 within 0.5 %, larger values slower
     P.batch = std::max(1, std::min(P.batch, 32));
     P.frac8 = std::max(0, std::min(P.frac8, 8));
   }

@@ -45,6 +45,7 @@ struct RenderParams {
   unsigned long long *stats;     // paths, segments, box tests, prim tests
   uint32_t seed_lo, seed_hi;
   int batch;  // shade/regenerate when this many lanes are DONE or DEAD (warp-voted scheduler)
+  int leaf_min; // run the pending primitive tests when this many lanes wait (or nobody searches)
   int frac8;  // a BVH burst ends when fewer than frac8/8 of its entry lanes are still searching
   // bytes of each array staged to shared memory (all multiples of 16)
   int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big, b_leaf_prims;
@@ -200,7 +201,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       }
     }
     // ---- phase 2: pending primitive tests (one per lane per round)
-    if (__ballot_sync(FULL, node < 0)) {
+    const unsigned m_leaf = __ballot_sync(FULL, node < 0);
+    if (m_leaf && (__popc(m_leaf) >= P.leaf_min || !__ballot_sync(FULL, (unsigned)node < (unsigned)node_end))) {
       if (node < 0) {
         const int enc = ~node;
         if (COUNT) cnt.prim_tests++;

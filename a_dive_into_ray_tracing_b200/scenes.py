@@ -373,3 +373,74 @@ def sphere_field(n_side=100, seed=1984, width=600, height=400):
                                    10.0 * s)
     sc.profile = RT_PROFILE_WEEKEND_CPU
     return sc
+
+
+def _rot_y_f32(pts, angle_deg):
+    f = np.float32
+    rad = np.deg2rad(np.float64(angle_deg))
+    c, s = f(np.cos(rad)), f(np.sin(rad))
+    p = np.asarray(pts, f)
+    return np.stack([(c * p[..., 0] + s * p[..., 2]).astype(f), p[..., 1], (-s * p[..., 0] + c * p[..., 2]).astype(f)], -1)
+
+
+def box_as_triangles(p0, p1, angle_deg, offset, material):
+    """translate(rotate_y(box(p0,p1), angle), offset) — rt_next_week/cuda/box.h:41-58 with
+    main.cu:269-275: the six rects, rotated, are no longer axis aligned and become two
+    triangles each; the face normal is the rect's nominal +axis normal (never flipped in the
+    rt_next_week tree), rotated. Same construction as include/rtx/rtx.h aa_rect::flatten."""
+    f = np.float32
+    sides = [(2, p0[0], p1[0], p0[1], p1[1], p1[2]), (2, p0[0], p1[0], p0[1], p1[1], p0[2]),
+             (1, p0[0], p1[0], p0[2], p1[2], p1[1]), (1, p0[0], p1[0], p0[2], p1[2], p0[1]),
+             (0, p0[1], p1[1], p0[2], p1[2], p1[0]), (0, p0[1], p1[1], p0[2], p1[2], p0[0])]
+    out = []
+    for axis, a0, a1, b0, b1, k in sides:
+        ia, ib = (1 if axis == 0 else 0), (1 if axis == 2 else 2)
+        corners = np.zeros((4, 3), f)
+        for q, (a, b) in enumerate(((a0, b0), (a1, b0), (a1, b1), (a0, b1))):
+            corners[q, axis], corners[q, ia], corners[q, ib] = k, a, b
+        w = (_rot_y_f32(corners, angle_deg) + np.asarray(offset, f)).astype(f)
+        n = np.zeros(3, f)
+        n[axis] = 1
+        nw = _rot_y_f32(n, angle_deg)
+        for t in ((0, 1, 2), (0, 2, 3)):
+            out.append(triangle_record(w[t[0]], w[t[1]], w[t[2]], -nw, -nw, -nw, material))
+    return out
+
+
+def cornell_box(width=600, height=600):
+    """rt_next_week/cuda/main.cu:252-281,436-443: Cornell box with two rotated boxes, one
+    area light, black background; profile 2 (rt_next_week tree: normals never flip)."""
+    mats = [_mat(RT_MAT_LAMBERTIAN, (.65, .05, .05)), _mat(RT_MAT_LAMBERTIAN, (.73, .73, .73)),
+            _mat(RT_MAT_LAMBERTIAN, (.12, .45, .15)), _mat(RT_MAT_DIFFUSE_LIGHT, (15, 15, 15))]
+    red, white, green, light = 0, 1, 2, 3
+    quads = []
+
+    def quad(axis, a0, a1, b0, b1, k, m):
+        q = np.zeros((), QUAD_DT)
+        q["axis"], q["a0"], q["a1"], q["b0"], q["b1"], q["k"], q["material"] = axis, a0, a1, b0, b1, k, m
+        quads.append(q)
+
+    quad(0, 0, 555, 0, 555, 555, green)
+    quad(0, 0, 555, 0, 555, 0, red)
+    quad(1, 213, 343, 227, 332, 554, light)
+    quad(1, 0, 555, 0, 555, 0, white)
+    quad(1, 0, 555, 0, 555, 555, white)
+    quad(2, 0, 555, 0, 555, 555, white)
+    tris = box_as_triangles((0, 0, 0), (165, 330, 165), 15, (265, 0, 295), white)
+    tris += box_as_triangles((0, 0, 0), (165, 165, 165), -18, (130, 0, 65), white)
+    # materials in first-use order as the C++ flattening registers them: green, red, light, white
+    order = [green, red, light, white]
+    remap = {m: i for i, m in enumerate(order)}
+    for q in quads:
+        q["material"] = remap[int(q["material"])]
+    for t in tris:
+        t["material"] = remap[int(t["material"])]
+    sc = Scene(quads=np.array(quads, QUAD_DT), triangles=np.array(tris, TRIANGLE_DT),
+               materials=np.array([mats[m] for m in order], MATERIAL_DT), name="cornell_box")
+    sc.camera = camera_from_lookat((278, 278, -800), (278, 278, 0), (0, 1, 0), 40.0,
+                                   np.float32(width) / np.float32(height), 0.0, 800.0, 0.0, 1.0, dtype=np.float32)
+    sc.background = (0.0, 0.0, 0.0)
+    sc.sky_gradient = 0
+    sc.t_min = 1e-3
+    sc.profile = RT_PROFILE_NEXT_WEEK
+    return sc

@@ -21,6 +21,11 @@ int rtx_host_build(int which, unsigned seed, double aspect, const char *obj_path
     root->flatten(g_flat, transform());
     g_cam = camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.05,
                    (point3(13, 2, 3) - point3(0, 0, 0)).length(), 0.0, 1.0, true).describe();
+  } else if (which == 3) { // main.cu:436-443
+    hittable *root = cornell_box();
+    root->flatten(g_flat, transform());
+    g_cam = camera(point3(278, 278, -800), point3(278, 278, 0), vec3(0, 1, 0), 40, aspect, 0.0,
+                   (point3(278, 278, -800) - point3(278, 278, 0)).length(), 0.0, 1.0, true).describe();
   } else {
     hittable *root = obj_model(obj_path);
     root->flatten(g_flat, transform());

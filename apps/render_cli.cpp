@@ -2,7 +2,7 @@
 // builds a scene with the reference's own scene-description classes, renders it through
 // the C ABI and writes a P3 PPM on stdout / timing on stderr exactly like
 // rt_in_one_weekend/main.cpp:292-360 and accelerated-rt-cuda/final.cu:155-246.
-//   render_cli [--scene weekend|next_week|obj] [--obj file.obj] [--width W] [--height H]
+//   render_cli [--scene weekend|next_week|cornell|obj] [--obj file.obj] [--width W] [--height H]
 //              [--spp N] [--seed S] [--device D] [--binary | --png]   (image on stdout)
 #include <chrono>
 #include <cstring>
@@ -52,9 +52,16 @@ int main(int argc, char **argv) {
       opt.background = color(0, 0, 0);
       opt.t_min = 0.00001;
       opt.flags = RT_FLAG_FLIP_NORMALS | RT_FLAG_DEPTH_BACKGROUND;
+    } else if (scene == "cornell") { // main.cu:436-443
+      root = cornell_box();
+      opt.profile = RT_PROFILE_NEXT_WEEK;
+      opt.sky_gradient = false;
+      opt.background = color(0, 0, 0);
     } else { std::cerr << "unknown scene " << scene << "\n"; return 2; }
     camera cam = scene == "weekend"
                      ? camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.1, 10.0)
+                 : scene == "cornell"
+                     ? camera(point3(278, 278, -800), point3(278, 278, 0), vec3(0, 1, 0), 40, aspect, 0.0, 800.0, 0.0, 1.0, true)
                  : scene == "next_week"
                      ? camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.05,
                               (point3(13, 2, 3) - point3(0, 0, 0)).length(), 0.0, 1.0, true)

@@ -11,6 +11,7 @@
 #include "aarect.h"
 #include "triangle.h"
 #include "bvh.h"
+#include "box.h"
 
 // rt_in_one_weekend/main.cpp:86-131, statement for statement. g++ evaluates the
 // arguments of `point3 center(a + 0.9*random_double(), 0.2, b + 0.9*random_double())`
@@ -111,5 +112,29 @@ inline hittable *obj_model(const std::string &obj_path) {
   read_triangles(obj_path, tris, gold, 2.5);
   for (auto &t : tris) ret->add(make_shared<translate>(make_shared<rotate_y>(t, 30), vec3(0, 1.5, 0)));
   return new bvh_node(*ret, 0.0, 1.0);
+}
+
+// rt_next_week/cuda/main.cu:252-281 (cornell_box), in its raw-pointer style
+inline hittable *cornell_box() {
+  static hittable *ret[8];
+  auto red = new lambertian(color(.65, .05, .05));
+  auto white = new lambertian(color(.73, .73, .73));
+  auto green = new lambertian(color(.12, .45, .15));
+  auto light = new diffuse_light(color(15, 15, 15));
+  ret[0] = new yz_rect(0, 555, 0, 555, 555, green);
+  ret[1] = new yz_rect(0, 555, 0, 555, 0, red);
+  ret[2] = new xz_rect(213, 343, 227, 332, 554, light);
+  ret[3] = new xz_rect(0, 555, 0, 555, 0, white);
+  ret[4] = new xz_rect(0, 555, 0, 555, 555, white);
+  ret[5] = new xy_rect(0, 555, 0, 555, 555, white);
+  hittable *box1 = new box(point3(0, 0, 0), point3(165, 330, 165), white);
+  box1 = new rotate_y(box1, 15);
+  box1 = new translate(box1, vec3(265, 0, 295));
+  hittable *box2 = new box(point3(0, 0, 0), point3(165, 165, 165), white);
+  box2 = new rotate_y(box2, -18);
+  box2 = new translate(box2, vec3(130, 0, 65));
+  ret[6] = box1;
+  ret[7] = box2;
+  return new bvh_node(ret, 0, 8, 0.0f, 1.0f);
 }
 #endif

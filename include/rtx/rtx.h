@@ -322,8 +322,28 @@ public:
   aa_rect(int axis_, double a0_, double a1_, double b0_, double b1_, double k_, shared_ptr<material> m)
       : axis(axis_), a0(a0_), a1(a1_), b0(b0_), b1(b1_), k(k_), mp(m) {}
   void flatten(flat_scene &out, const transform &xf) const override {
-    if (xf.s != 0 || xf.c != 1 || xf.scale != 1) throw std::invalid_argument("rotated/scaled rect: not an axis-aligned rect");
-    int ia = (axis == 0) ? 1 : 0, ib = (axis == 2) ? 1 : 2;
+    const int ia = (axis == 0) ? 1 : 0, ib = (axis == 2) ? 1 : 2;
+    if (xf.s != 0 || xf.c != 1 || xf.scale != 1) {
+      // a rotated rect (rotate_y(box(...)) in the Cornell box, main.cu:269-275) is no longer
+      // axis aligned: emit it as two triangles whose face normal is the rect's nominal
+      // (+axis, never flipped: rt_next_week/cuda/hittable.h:29) normal, rotated
+      float c[4][3], w[4][3], n[3] = {0, 0, 0}, nw[3];
+      const double aa[4] = {a0, a1, a1, a0}, bb[4] = {b0, b0, b1, b1};
+      for (int q = 0; q < 4; q++) { c[q][axis] = (float)k; c[q][ia] = (float)aa[q]; c[q][ib] = (float)bb[q]; xf.apply(c[q], w[q]); }
+      n[axis] = 1.0f;
+      xf.rotate(n, nw);
+      const int m = out.add_material(mp.get());
+      const int tri[2][3] = {{0, 1, 2}, {0, 2, 3}};
+      for (int t = 0; t < 2; t++) {
+        rt_triangle r = {};
+        float vn[3] = {-nw[0], -nw[1], -nw[2]}; // triangle.h:24: the face normal agrees with MINUS the vertex normals
+        for (int q = 0; q < 3; q++) { r.v0[q] = w[tri[t][0]][q]; r.v1[q] = w[tri[t][1]][q]; r.v2[q] = w[tri[t][2]][q]; }
+        triangle_face_normal(r.v0, r.v1, r.v2, vn, vn, vn, r.normal);
+        r.material = m;
+        out.triangles.push_back(r);
+      }
+      return;
+    }
     rt_quad q = {};
     q.axis = axis;
     q.a0 = (float)(a0 + xf.offset[ia]); q.a1 = (float)(a1 + xf.offset[ia]);
@@ -350,6 +370,29 @@ class yz_rect : public aa_rect {
 public:
   yz_rect(double y0, double y1, double z0, double z1, double k, shared_ptr<material> m) : aa_rect(0, y0, y1, z0, z1, k, m) {}
   yz_rect(double y0, double y1, double z0, double z1, double k, material *m) : aa_rect(0, y0, y1, z0, z1, k, borrow(m)) {}
+};
+
+// box(p0, p1, material) — rt_next_week/cuda/box.h:41-58: six rects in the reference's order
+class box : public hittable {
+public:
+  box(const point3 &p0, const point3 &p1, shared_ptr<material> m) : box_min(p0), box_max(p1) { build(m); }
+  box(const point3 &p0, const point3 &p1, material *m) : box_min(p0), box_max(p1) { build(borrow(m)); }
+  void flatten(flat_scene &out, const transform &xf) const override {
+    for (const auto &s : sides) s->flatten(out, xf);
+  }
+  point3 box_min, box_max;
+  std::vector<shared_ptr<hittable>> sides;
+
+private:
+  void build(shared_ptr<material> m) {
+    const point3 &p0 = box_min, &p1 = box_max;
+    sides.push_back(make_shared<xy_rect>(p0.x(), p1.x(), p0.y(), p1.y(), p1.z(), m));
+    sides.push_back(make_shared<xy_rect>(p0.x(), p1.x(), p0.y(), p1.y(), p0.z(), m));
+    sides.push_back(make_shared<xz_rect>(p0.x(), p1.x(), p0.z(), p1.z(), p1.y(), m));
+    sides.push_back(make_shared<xz_rect>(p0.x(), p1.x(), p0.z(), p1.z(), p0.y(), m));
+    sides.push_back(make_shared<yz_rect>(p0.y(), p1.y(), p0.z(), p1.z(), p1.x(), m));
+    sides.push_back(make_shared<yz_rect>(p0.y(), p1.y(), p0.z(), p1.z(), p0.x(), m));
+  }
 };
 
 class hittable_list : public hittable {

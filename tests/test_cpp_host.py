@@ -149,3 +149,23 @@ def test_png_writers(tmp_path):
     p3 = str(tmp_path / "c.ppm")
     capi.write_ppm(p3, img, binary=True)
     np.testing.assert_array_equal(np.asarray(Image.open(p3).convert("RGB")), img)
+
+
+def test_cornell_box_boxes_and_rotations(host):
+    """box (box.h:41-58) + rotate_y + translate (main.cu:269-275): C++ and Python flatten the
+    Cornell box to the same rects / triangles; rotated box sides keep their nominal normals."""
+    s, t, q, m, cam, accel = host(3, aspect=1.0)
+    ref = scenes.cornell_box(600, 600)
+    assert accel and len(s) == 0 and len(q) == 6 and len(t) == 24 and len(m) == 4
+    for f in ("axis", "a0", "a1", "b0", "b1", "k", "material"):
+        np.testing.assert_array_equal(q[f], ref.quads[f])
+    np.testing.assert_array_equal(m["type"], ref.materials["type"])
+    np.testing.assert_allclose(m["albedo"], ref.materials["albedo"], rtol=1e-7)
+    for f in ("v0", "v1", "v2"):
+        np.testing.assert_allclose(t[f], ref.triangles[f], rtol=0, atol=1e-4)
+    np.testing.assert_allclose(t["normal"], ref.triangles["normal"], rtol=2e-6, atol=0.5)
+    np.testing.assert_array_equal(t["material"], ref.triangles["material"])
+    # first side of box1 = xy_rect at z = 165 rotated by 15 degrees: normal (sin15, 0, cos15)
+    n = t["normal"][0] / np.linalg.norm(t["normal"][0])
+    np.testing.assert_allclose(n, [np.sin(np.deg2rad(15)), 0, np.cos(np.deg2rad(15))], atol=1e-5)
+    np.testing.assert_allclose(np.array(cam.origin[:]), [278, 278, -800])

@@ -64,7 +64,8 @@ def test_emulated_profiles_vs_l1(l1_32):
     """profiles 1 (final.cu) and 2 (next-week, obj room): emulated device code vs the
     float restatement of the CUDA trees, statistically."""
     cases = [(scenes.final_cu(60, 40), 60, 40, 48), (scenes.next_week(60, 40), 60, 40, 48),
-             (scenes.obj_room(width=40, height=40, subdivisions=1), 40, 40, 96)]
+             (scenes.obj_room(width=40, height=40, subdivisions=1), 40, 40, 96),
+             (scenes.cornell_box(40, 40), 40, 40, 96)]
     for sc, W, H, spp in cases:
         e = Emu(sc, quality=1)
         s, s2, st = e.render(W, H, spp, seed=7)

@@ -122,7 +122,8 @@ def test_render_vs_reference_golden(render_c1):
 def test_render_matches_oracle_all_profiles(l1_32, l1_64):
     cases = [(scenes.weekend(60, 40), l1_64, 60, 40, 64), (scenes.final_cu(60, 40), l1_32, 60, 40, 64),
              (scenes.next_week(60, 40), l1_32, 60, 40, 64),
-             (scenes.obj_room(width=40, height=40, subdivisions=1), l1_32, 40, 40, 128)]
+             (scenes.obj_room(width=40, height=40, subdivisions=1), l1_32, 40, 40, 128),
+             (scenes.cornell_box(40, 40), l1_32, 40, 40, 128)]
     for sc, orc, W, H, spp in cases:
         K = 8
         with capi.Context(profile=sc.profile, seed=7) as ctx:
