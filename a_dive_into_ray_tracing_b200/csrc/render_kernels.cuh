@@ -70,21 +70,30 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   DevScene S = P.S;
   int off = 0;
   if (SMEM) {
-    if (SMEM == 2) { // quadrant-specialised node copies: swap bmin/bmax on x (bit 0) and z (bit 1)
+    // Nodes go to shared memory as STRUCTURE OF ARRAYS: all {bmin, escape} first, then all
+    // {bmax, payload}, with links rewritten to 16-byte units. In the 32-byte AoS layout every
+    // LDS.128 of a warp touches only half of the 32 banks (ncu: the shared-memory data pipe was
+    // 90 % busy, 8.9 wavefronts per LDS.128); SoA spreads the 16-byte slots over all banks.
+    // SMEM == 2: four quadrant copies (own visiting order), bmin/bmax pre-swapped on x (bit 0)
+    // and z (bit 1) for the ray direction signs.
+    {
       S.nodes = (const float4 *)(smem_raw + off);
       const int nn = P.b_nodes >> 5;
-      for (int i = threadIdx.x; i < 4 * nn; i += blockDim.x) {
+      const int copies = SMEM == 2 ? 4 : 1;
+      for (int i = threadIdx.x; i < copies * nn; i += blockDim.x) {
         const int q = i / nn, k = i - q * nn;
-        const float4 *src = P.S.nodes + q * (P.S.node_stride >> 4) + 2 * k; // quadrant q's own visiting order
+        const float4 *src = P.S.nodes + q * (P.S.node_stride >> 4) + 2 * k;
         float4 lo = __ldg(src), hi = __ldg(src + 1);
         if (q & 1) { const float t = lo.x; lo.x = hi.x; hi.x = t; }
         if (q & 2) { const float t = lo.z; lo.z = hi.z; hi.z = t; }
-        float4 *dst = (float4 *)(smem_raw + off + q * P.b_nodes) + 2 * k;
-        dst[0] = lo; dst[1] = hi;
+        lo.w = RT_I2F(RT_F2I(lo.w) >> 1);
+        const int pay = RT_F2I(hi.w);
+        hi.w = RT_I2F(pay >= 0 ? (pay >> 1) : pay);
+        float4 *dst = (float4 *)(smem_raw + off + q * P.b_nodes);
+        dst[k] = lo;
+        dst[nn + k] = hi;
       }
-      off += 4 * P.b_nodes;
-    } else {
-      S.nodes = (const float4 *)stage_to_smem(smem_raw, off, P.S.nodes, P.b_nodes);
+      off += copies * P.b_nodes;
     }
     S.sph = (const float4 *)stage_to_smem(smem_raw, off, P.S.sph, P.b_sph);
     S.sph_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.sph_mat, P.b_sph_mat);
@@ -123,7 +132,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   //   node == node_end       traversal finished (DONE if alive, else DEAD)
   //   node < 0               LEAF: a hit leaf is pending, node = its payload
   //                          ~(first << 3 | count-1) into leaf_prims; `resume` = where to go on
-  const int node_end = S.n_nodes << RT_NODE_SHIFT;
+  const int node_end = S.n_nodes << (SMEM ? RT_NODE_SHIFT - 1 : RT_NODE_SHIFT); // shared copies: 16-byte units
+  const unsigned hi_off = (unsigned)S.n_nodes << 4;                               // {bmax, payload} array follows
   bool alive = false;
   int node = node_end, resume = 0;
   HitAcc h;
@@ -187,7 +197,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           float4 lo, hi;
           if (SMEM != 0) {
             asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(nbase + at));
-            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+16];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nbase + at));
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nbase + hi_off + at));
           } else {
             lo = __ldg((const float4 *)(nodes_q + at));
             hi = __ldg((const float4 *)(nodes_q + at) + 1);
