@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
 
   // start a segment: per-ray constants, the always-tested big primitives, enter at the root
   auto begin_segment = [&]() {
-    pre = ray_precompute(r);
+    pre = ray_precompute_fast(r);
     h.t = INFINITY; h.id = -1;
     for (int i = 0; i < S.n_big; i++) {
       const int32_t id = S.big[i];

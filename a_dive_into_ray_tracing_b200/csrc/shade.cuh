@@ -127,20 +127,27 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
     return false;
   }
   V3f dir, att;
-  if (mtype == RT_MAT_LAMBERTIAN) {
-    if (PROFILE == 0) {
-      dir = n + sample_unit_vector(u1, u2);
-      if (dot(dir, dir) < 1e-16f) dir = n; // degenerate direction guard (material.h:24-26)
-      att = xyz(m0);
-    } else {
-      dir = n + sample_unit_ball(u1, u2, u3);
-      att = (PROFILE == 2) ? material_color(m0, m1, p) : xyz(m0);
+  if (mtype != RT_MAT_DIELECTRIC) {
+    // lambertian and metal (94 % of the hits) share the random direction: one uniform unit
+    // vector, scaled into the unit ball where the reference samples the ball — computed once,
+    // outside the per-material branches, so the warp runs the transcendental code a single time
+    V3f v = sample_unit_vector(u1, u2);
+    if (!(PROFILE == 0 && mtype == RT_MAT_LAMBERTIAN)) {
+#ifdef __CUDA_ARCH__
+      v = exp2f(__log2f(u3) * (1.0f / 3.0f)) * v; // cbrt(u3): radius of a uniform point in the ball
+#else
+      v = cbrtf(u3) * v;
+#endif
     }
-  } else if (mtype == RT_MAT_METAL) {
-    V3f refl = reflect(normalize(r.d), n);
-    dir = madd(refl, m1.w, sample_unit_ball(u1, u2, u3));
     att = (PROFILE == 2) ? material_color(m0, m1, p) : xyz(m0);
-    if (!(dot(dir, n) > 0.0f)) return false; // absorbed (adds nothing in any profile)
+    if (mtype == RT_MAT_LAMBERTIAN) {
+      dir = n + v;
+      if (PROFILE == 0 && dot(dir, dir) < 1e-16f) dir = n; // degenerate direction guard (material.h:24-26)
+    } else {
+      V3f refl = reflect(normalize(r.d), n);
+      dir = madd(refl, m1.w, v);
+      if (!(dot(dir, n) > 0.0f)) return false; // absorbed (adds nothing in any profile)
+    }
   } else { // dielectric
     att = v3(1.f, 1.f, 1.f);
     const float ir = m1.w;
