@@ -178,10 +178,10 @@ class ClockSampler:
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of k_render per launch, from the committed
-    `ncu --set full` capture of this kernel (profiles/r1g_k_render_raw.csv); None if absent."""
+    `ncu --set full` capture of this kernel (profiles/r1h_k_render_raw.csv); None if absent."""
     import csv
     try:
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1g_k_render_raw.csv"))))
+        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1h_k_render_raw.csv"))))
         d, u = dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         return sum(float(d[k]) * mult[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
