@@ -19,9 +19,14 @@ struct RayPre {
   float inv_a; // 1/(d.d)
 };
 
+// A direction component of (+-)0 would make  b/d - o/d  = inf - inf = NaN for planes on the
+// same side of the origin, and the NaN-dropping min/max would then lose the slab's far
+// plane: nudge such components to +-1e-20 (1/d = +-1e20 stays finite and keeps the sign of b - o).
+RT_HD float rt_safe_dir(float d) { return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d; }
+
 RT_HD RayPre ray_precompute(const Ray &r) {
   RayPre p;
-  p.inv_d = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+  p.inv_d = v3(1.0f / rt_safe_dir(r.d.x), 1.0f / rt_safe_dir(r.d.y), 1.0f / rt_safe_dir(r.d.z));
   p.ood = v3(r.o.x * p.inv_d.x, r.o.y * p.inv_d.y, r.o.z * p.inv_d.z);
   p.inv_a = 1.0f / dot(r.d, r.d);
   return p;
@@ -33,7 +38,8 @@ RT_HD RayPre ray_precompute(const Ray &r) {
 RT_HD RayPre ray_precompute_fast(const Ray &r) {
 #ifdef __CUDA_ARCH__
   RayPre p;
-  p.inv_d = v3(__fdividef(1.0f, r.d.x), __fdividef(1.0f, r.d.y), __fdividef(1.0f, r.d.z));
+  p.inv_d = v3(__fdividef(1.0f, rt_safe_dir(r.d.x)), __fdividef(1.0f, rt_safe_dir(r.d.y)),
+               __fdividef(1.0f, rt_safe_dir(r.d.z)));
   p.ood = v3(r.o.x * p.inv_d.x, r.o.y * p.inv_d.y, r.o.z * p.inv_d.z);
   p.inv_a = __fdividef(1.0f, dot(r.d, r.d));
   return p;
@@ -145,8 +151,8 @@ RT_HD void hit_quad(float4 q0, float4 q1, const Ray &r, float t_min, HitAcc &h, 
   h.t = t; h.id = id;
 }
 
-// Slab test against a packed node box (closed interval; NaNs from 0*inf are dropped
-// by fminf/fmaxf, which keeps the test conservative).
+// Slab test against a packed node box (closed interval). 1/d is finite (rt_safe_dir), so the
+// only NaN left is 0 * huge - 0 * huge = 0 handled exactly; fminf/fmaxf would drop any other.
 RT_HD bool hit_box(float4 lo, float4 hi, const RayPre &pre, float t_min, float t_max) {
   float x0 = RT_FMA(lo.x, pre.inv_d.x, -pre.ood.x), x1 = RT_FMA(hi.x, pre.inv_d.x, -pre.ood.x);
   float y0 = RT_FMA(lo.y, pre.inv_d.y, -pre.ood.y), y1 = RT_FMA(hi.y, pre.inv_d.y, -pre.ood.y);
