@@ -292,6 +292,8 @@ def run_ours(args):
         cctx.render(W, H, 4)
         cs = cctx.stats()
         fp32_peak = cctx.measure_fp32_peak()
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        sm_mhz_max = (clocks or {}).get("sm_max_mhz") or 1965.0
         cctx.close()
         n_box = cs["box_tests"] / cs["segments"]
         n_prim = cs["prim_tests"] / cs["segments"]
@@ -316,6 +318,14 @@ def run_ours(args):
                       "prim_tests_per_segment": n_prim, "hits_per_segment": h_bar,
                       "formula": "19*box + 16*prim + 150*hit + 40 (SURVEY.md 8d), 2 flop per lane-instruction"},
             "traffic": ncu_traffic_bytes(),
+            "smem": {"bound": "shared_memory", "unit": "GB/s",
+                     "achieved": seg_per_s * (32.0 * n_box + 16.0 * n_prim + 32.0 * h_bar) / 1e9 / world,
+                     "peak": 128.0 * sm_count * sm_mhz_max * 1e6 / 1e9,
+                     "frac": seg_per_s * (32.0 * n_box + 16.0 * n_prim + 32.0 * h_bar) / 1e9 / world /
+                             (128.0 * sm_count * sm_mhz_max * 1e6 / 1e9),
+                     "model": "B_seg = 32 B/node x box tests + 16 B x sphere tests + 32 B material per hit "
+                              "(SURVEY.md 8d); peak = nominal 128 B/clk/SM x SMs x max SM clock; ncu r1h: the "
+                              "shared-memory data pipe runs at 80 % of its wavefront peak"},
             "hbm": {"bound": "hbm", "achieved": hbm_bytes_per_frame / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": hbm_bytes_per_frame / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                     "note": "framebuffer traffic only; the scene (~60 KB) lives in shared memory: not HBM-bound",
