@@ -169,10 +169,11 @@ struct rt_ctx {
   std::vector<rt_material> mats;
   rt_scene_desc desc;
   bool general = false;
+  bool ext = false; // media or noise/image textures: the extended kernel variant
   // device scene
-  std::vector<DevBuf *> owned;
   DevBuf d_nodes, d_sph, d_sph_k, d_sph_mv, d_sph_t0, d_tri, d_tri_n, d_quad, d_sph_mat, d_tri_mat, d_quad_mat, d_mats, d_big,
-      d_leaf_prims, d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad;
+      d_leaf_prims, d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad, d_media, d_perlin_vec, d_perlin_perm, d_image_bytes,
+      d_images;
   DevScene S;
   DevCamera cam;
   ShadeParams sp;
@@ -269,7 +270,8 @@ void rt_destroy(rt_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf *all[] = {&ctx->d_nodes, &ctx->d_sph, &ctx->d_sph_k, &ctx->d_sph_mv, &ctx->d_sph_t0, &ctx->d_tri, &ctx->d_tri_n, &ctx->d_quad,
                    &ctx->d_sph_mat, &ctx->d_tri_mat, &ctx->d_quad_mat, &ctx->d_mats, &ctx->d_big, &ctx->d_leaf_prims, &ctx->d_sph_is_big,
-                   &ctx->d_raw_sph, &ctx->d_raw_tri, &ctx->d_raw_quad, &ctx->d_accum, &ctx->d_partial, &ctx->d_counter,
+                   &ctx->d_raw_sph, &ctx->d_raw_tri, &ctx->d_raw_quad, &ctx->d_media, &ctx->d_perlin_vec,
+                   &ctx->d_perlin_perm, &ctx->d_image_bytes, &ctx->d_images, &ctx->d_accum, &ctx->d_partial, &ctx->d_counter,
                    &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts};
   for (DevBuf *b : all) dev_free(*b);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -305,7 +307,11 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   ctx->desc.triangles = ctx->tris.data();
   ctx->desc.quads = ctx->quads.data();
   ctx->desc.materials = ctx->mats.data();
+  ctx->desc.media = nullptr; ctx->desc.perlin = nullptr; ctx->desc.images = nullptr; // flattened below, not kept
   ctx->general = (profile == RT_PROFILE_NEXT_WEEK);
+  ctx->ext = sc->n_media > 0;
+  for (int i = 0; i < sc->n_materials; i++)
+    if (sc->materials[i].texture >= RT_TEX_NOISE || sc->materials[i].type == RT_MAT_ISOTROPIC) ctx->ext = true;
 
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, nm = sc->n_materials;
@@ -315,6 +321,14 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   UP(d_sph, F.sph); UP(d_sph_k, F.sph_k); UP(d_sph_mv, F.sph_mv); UP(d_sph_t0, F.sph_t0); UP(d_tri, F.tri); UP(d_tri_n, F.tri_n); UP(d_quad, F.quad);
   UP(d_sph_mat, F.sph_mat); UP(d_tri_mat, F.tri_mat); UP(d_quad_mat, F.quad_mat); UP(d_mats, F.mats);
   UP(d_raw_sph, ctx->spheres); UP(d_raw_tri, ctx->tris); UP(d_raw_quad, ctx->quads);
+  UP(d_media, F.media); UP(d_perlin_vec, F.perlin_vec); UP(d_perlin_perm, F.perlin_perm); UP(d_image_bytes, F.image_bytes);
+  std::vector<DevImage> dimg((size_t)sc->n_images);
+  for (int i = 0; i < sc->n_images; i++) {
+    dimg[i].rgb = (const uint8_t *)ctx->d_image_bytes.p + F.image_offset[i];
+    dimg[i].width = sc->images[i].width;
+    dimg[i].height = sc->images[i].height;
+  }
+  UP(d_images, dimg);
 #undef UP
   std::vector<uint8_t> nobig(std::max(ns, 1), 0);
   if ((rc = dev_upload(ctx, ctx->d_sph_is_big, nobig.data(), nobig.size()))) return rc;
@@ -337,6 +351,11 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   S.mats = (const float4 *)ctx->d_mats.p;
   S.big = (const int32_t *)ctx->d_big.p;
   S.leaf_prims = (const int32_t *)ctx->d_leaf_prims.p;
+  S.media = (const float4 *)ctx->d_media.p;
+  S.perlin_vec = (const float4 *)ctx->d_perlin_vec.p;
+  S.perlin_perm = (const uint8_t *)ctx->d_perlin_perm.p;
+  S.images = (const DevImage *)ctx->d_images.p;
+  S.n_media = sc->n_media; S.n_perlin = sc->n_perlin; S.n_images = sc->n_images;
   S.n_nodes = 0; S.n_big = 0;
   S.n_spheres = ns; S.n_tris = nt; S.n_quads = nq; S.n_mats = nm;
   S.any_moving = any_moving ? 1 : 0;
@@ -635,12 +654,14 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
 
 // ------------------------------------------------------------------ render
 typedef void (*render_kernel_t)(const RenderParams);
-static render_kernel_t pick_render_kernel(int profile, int smem, bool count) {
-#define PICK3(P, G, C) (smem == 2 ? k_render<P, G, 2, C> : (smem == 1 ? k_render<P, G, 1, C> : k_render<P, G, 0, C>))
-#define PICK(P, G) return count ? PICK3(P, G, true) : PICK3(P, G, false)
-  if (profile == 0) { PICK(0, false); }
-  if (profile == 1) { PICK(1, false); }
-  PICK(2, true);
+static render_kernel_t pick_render_kernel(int profile, int smem, bool count, bool ext) {
+#define PICK3(P, G, C, E) \
+  (smem == 2 ? k_render<P, G, 2, C, E> : (smem == 1 ? k_render<P, G, 1, C, E> : k_render<P, G, 0, C, E>))
+#define PICK(P, G, E) return count ? PICK3(P, G, true, E) : PICK3(P, G, false, E)
+  if (profile == 0) { PICK(0, false, false); }
+  if (profile == 1) { PICK(1, false, false); }
+  if (ext) { PICK(2, true, true); }
+  PICK(2, true, false);
 #undef PICK
 #undef PICK3
 }
@@ -723,7 +744,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   if (const char *e = getenv("B200RT_SMEM")) smem = std::min(smem, atoi(e)); // tuning knob
   const size_t smem_bytes = acc_bytes + (smem ? scene_bytes : 0) + (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
-  render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count);
+  render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext);
   CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, (const void *)kern));

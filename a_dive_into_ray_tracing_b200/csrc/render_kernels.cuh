@@ -64,7 +64,8 @@ __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &o
 // SMEM: 0 = scene read from global memory (L1/L2); 1 = whole scene staged in shared memory;
 // 2 = as 1, with FOUR copies of the node array, one per sign combination of (d.x, d.z), whose
 // box planes are pre-swapped so that the slab test needs no min/max on those axes.
-template <int PROFILE, bool GENERAL, int SMEM, bool COUNT>
+// EXT: media + noise/image textures (rt_next_week scenes 3-8), profile 2 only.
+template <int PROFILE, bool GENERAL, int SMEM, bool COUNT, bool EXT>
 __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevScene S = P.S;
@@ -174,6 +175,9 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       if (is_sphere) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
       else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
     }
+    // participating media: a sampled scatter event becomes the initial closest hit
+    if (EXT && S.n_media)
+      apply_media(S, r, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, P.seed_lo, P.seed_hi, h);
     node = 0;
     // sign BITS of 1/d (covers d = -0): which quadrant copy (own child order; in shared memory also
     // pre-swapped planes) this ray walks
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
       bool fresh_ray = false;
       if (hit) {
-        const bool cont = shade_hit<PROFILE, GENERAL>(S, P.sp, r, h, beta, L, q);
+        const bool cont = shade_hit<PROFILE, GENERAL, EXT>(S, P.sp, r, h, beta, L, q);
         bounce++;
         if (cont && bounce < P.sp.max_depth) {
           fresh_ray = true;

@@ -77,6 +77,15 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 //  *_mat   int32 per primitive material index
 //  mats    float4[2*n_mats]    {albedo.rgb, as_float(type | texture<<8)} {albedo2.rgb, param}
 //  big     int32[n_big]        RT_PRIM_IDs tested for every ray before traversal
+//  media   float4[4*n_media]   {p0.xyz, as_float(shape)} {p1.xyz, -1/density} {offset.xyz, as_float(material)}
+//                              {sin_y, cos_y, 0, 0}            (global memory; not in the BVH)
+//  perlin_vec float4[256*n_perlin], perlin_perm uint8[768*n_perlin] (x, y, z tables)
+//  images  DevImage[n_images]  8-bit RGB rows, top row first
+struct DevImage {
+  const uint8_t *rgb;
+  int width, height;
+};
+
 struct DevScene {
   const float4 *nodes;
   const float4 *sph;
@@ -95,6 +104,11 @@ struct DevScene {
   int n_nodes, n_spheres, n_tris, n_quads, n_mats, n_big;
   int any_moving;
   int node_stride; // bytes between the four quadrant-ordered copies of `nodes` (copy 0 first)
+  const float4 *media;
+  const float4 *perlin_vec;
+  const uint8_t *perlin_perm;
+  const DevImage *images;
+  int n_media, n_perlin, n_images;
 };
 
 struct DevCamera {

@@ -14,6 +14,9 @@ struct HostFlat {
   std::vector<float4> sph, sph_mv, tri, tri_n, quad, mats;
   std::vector<float> sph_t0, sph_k;
   std::vector<int32_t> sph_mat, tri_mat, quad_mat;
+  std::vector<float4> media, perlin_vec;
+  std::vector<uint8_t> perlin_perm, image_bytes;
+  std::vector<size_t> image_offset; // into image_bytes, per image
   bool any_moving = false;
 };
 
@@ -57,10 +60,35 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
   }
   for (int i = 0; i < sc->n_materials; i++) {
     const rt_material &m = sc->materials[i];
-    if (m.type < 0 || m.type > 3) FAIL("material %d: type", i);
-    if (profile != RT_PROFILE_NEXT_WEEK && (m.type == RT_MAT_DIFFUSE_LIGHT || m.texture != RT_TEX_SOLID))
-      FAIL("material %d: lights/textures need profile 2", i);
+    if (m.type < 0 || m.type > RT_MAT_ISOTROPIC) FAIL("material %d: type", i);
+    if (m.texture < 0 || m.texture > RT_TEX_IMAGE) FAIL("material %d: texture", i);
+    if (profile != RT_PROFILE_NEXT_WEEK && (m.type >= RT_MAT_DIFFUSE_LIGHT || m.texture != RT_TEX_SOLID))
+      FAIL("material %d: lights/textures/phase functions need profile 2", i);
+    if (m.texture == RT_TEX_NOISE && !(m.albedo2[1] >= 0.f && (int)m.albedo2[1] < sc->n_perlin))
+      FAIL("material %d: perlin table index", i);
+    if (m.texture == RT_TEX_IMAGE && !(m.albedo2[0] >= 0.f && (int)m.albedo2[0] < sc->n_images))
+      FAIL("material %d: image index", i);
   }
+  if (sc->n_media < 0 || sc->n_perlin < 0 || sc->n_images < 0) FAIL("negative count");
+  if ((sc->n_media && !sc->media) || (sc->n_perlin && !sc->perlin) || (sc->n_images && !sc->images))
+    FAIL("null array with non-zero count");
+  if (sc->n_media && profile != RT_PROFILE_NEXT_WEEK) FAIL("media need profile 2");
+  for (int i = 0; i < sc->n_media; i++) {
+    const rt_medium &m = sc->media[i];
+    if (m.shape < 0 || m.shape > 1) FAIL("medium %d: shape", i);
+    if (!(m.density > 0.f)) FAIL("medium %d: density must be positive", i);
+    if (m.material < 0 || m.material >= sc->n_materials || sc->materials[m.material].type != RT_MAT_ISOTROPIC)
+      FAIL("medium %d: material must be an isotropic phase function", i);
+    if (m.shape == 0 && !(m.p1[0] > 0.f)) FAIL("medium %d: radius", i);
+  }
+  for (int i = 0; i < sc->n_perlin; i++)
+    for (int k = 0; k < 256; k++) {
+      const rt_perlin &p = sc->perlin[i];
+      if ((unsigned)p.perm_x[k] > 255u || (unsigned)p.perm_y[k] > 255u || (unsigned)p.perm_z[k] > 255u)
+        FAIL("perlin table %d: permutation entry out of range", i);
+    }
+  for (int i = 0; i < sc->n_images; i++)
+    if (sc->images[i].width < 1 || sc->images[i].height < 1 || !sc->images[i].rgb) FAIL("image %d: empty", i);
   if (profile != RT_PROFILE_NEXT_WEEK && (sc->n_triangles || sc->n_quads || any_moving))
     FAIL("triangles, rects and moving spheres need profile 2 (next-week / triangles trees)");
 
@@ -111,6 +139,28 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
     const rt_material &m = sc->materials[i];
     mats[2 * (size_t)i] = make_float4(m.albedo[0], m.albedo[1], m.albedo[2], RT_I2F(m.type | (m.texture << 8)));
     mats[2 * (size_t)i + 1] = make_float4(m.albedo2[0], m.albedo2[1], m.albedo2[2], m.param);
+  }
+  F.media.clear(); F.perlin_vec.clear(); F.perlin_perm.clear(); F.image_bytes.clear(); F.image_offset.clear();
+  for (int i = 0; i < sc->n_media; i++) {
+    const rt_medium &m = sc->media[i];
+    F.media.push_back(make_float4(m.p0[0], m.p0[1], m.p0[2], RT_I2F(m.shape)));
+    F.media.push_back(make_float4(m.p1[0], m.p1[1], m.p1[2], -1.0f / m.density));
+    F.media.push_back(make_float4(m.offset[0], m.offset[1], m.offset[2], RT_I2F(m.material)));
+    F.media.push_back(make_float4(m.shape == 1 ? m.sin_y : 0.f, m.shape == 1 ? m.cos_y : 1.f, 0.f, 0.f));
+  }
+  for (int i = 0; i < sc->n_perlin; i++) {
+    const rt_perlin &p = sc->perlin[i];
+    for (int k = 0; k < 256; k++) F.perlin_vec.push_back(make_float4(p.ranvec[k][0], p.ranvec[k][1], p.ranvec[k][2], 0.f));
+    for (int k = 0; k < 256; k++) F.perlin_perm.push_back((uint8_t)p.perm_x[k]);
+    for (int k = 0; k < 256; k++) F.perlin_perm.push_back((uint8_t)p.perm_y[k]);
+    for (int k = 0; k < 256; k++) F.perlin_perm.push_back((uint8_t)p.perm_z[k]);
+  }
+  for (int i = 0; i < sc->n_images; i++) {
+    const rt_image &im = sc->images[i];
+    F.image_offset.push_back(F.image_bytes.size());
+    const size_t bytes = (size_t)im.width * im.height * 3;
+    F.image_bytes.insert(F.image_bytes.end(), im.rgb, im.rgb + bytes);
+    while (F.image_bytes.size() & 15) F.image_bytes.push_back(0);
   }
   F.any_moving = any_moving;
   return RT_OK;

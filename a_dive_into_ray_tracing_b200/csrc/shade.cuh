@@ -11,6 +11,10 @@
 //   diffuse_light        rt_next_week/cuda/material.h:157-176
 //   checker_texture      rt_next_week/cuda/texture.h:33-53
 //   sky                  main.cpp:80-82, final.cu:46-49
+//   noise_texture/perlin rt_next_week/cuda/texture.h:55-75, perlin.h:29-72,103-122
+//   image_texture        rt_next_week/cuda/texture.h:77-124; sphere uv sphere.h:28-40, rect uv aarect.h:52-53
+//   isotropic            rt_next_week/cuda/material.h:178-195
+//   constant_medium      rt_next_week/cuda/constant_medium.h:36-73 (apply_media below)
 // Sampling is rejection-free with identical distributions (philox.cuh).
 #pragma once
 #include "intersect.cuh"
@@ -74,20 +78,151 @@ RT_HD float rt_fast_sin(float x) {
 #endif
 }
 
-RT_HD V3f material_color(float4 m0, float4 m1, V3f p) {
+// ---- rarely used texture kinds live in out-of-line functions so that the render kernel's
+// register allocation is not shaped by them.
+#ifdef __CUDA_ARCH__
+#define RT_COLD __device__ __noinline__
+#else
+#define RT_COLD static inline
+#endif
+
+// perlin::noise with the trilinear Hermite interpolation of perlin.h:29-56,103-122
+RT_COLD float perlin_noise(const float4 *__restrict__ vec, const uint8_t *__restrict__ perm, V3f p) {
+  const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+  const float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+  const float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+  const int i = (int)fx, j = (int)fy, k = (int)fz;
+  float accum = 0.0f;
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const int di = c >> 2, dj = (c >> 1) & 1, dk = c & 1;
+    const int h = perm[(i + di) & 255] ^ perm[256 + ((j + dj) & 255)] ^ perm[512 + ((k + dk) & 255)];
+    const float4 g = vec[h];
+    const float d = RT_FMA(g.z, w - (float)dk, RT_FMA(g.y, v - (float)dj, g.x * (u - (float)di)));
+    accum += (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww) * d;
+  }
+  return accum;
+}
+
+// Textures that need more than the hit point's checker parity: noise (perlin::turb, depth 7,
+// perlin.h:58-70) and image lookups with the primitive's (u, v).
+RT_COLD V3f texture_ext(const DevScene &S, float4 m0, float4 m1, V3f p, V3f outward, int32_t prim) {
+  const int tex = (RT_F2I(m0.w) >> 8) & 0xff;
+  if (tex == RT_TEX_NOISE) {
+    const int table = (int)m1.y;
+    const float4 *vec = S.perlin_vec + 256 * table;
+    const uint8_t *perm = S.perlin_perm + 768 * table;
+    const float scale = m1.x;
+    V3f q = scale * p;
+    float accum = 0.0f, weight = 1.0f;
+    for (int i = 0; i < 7; i++) {
+      accum = RT_FMA(weight, perlin_noise(vec, perm, q), accum);
+      weight *= 0.5f;
+      q = 2.0f * q;
+    }
+    const float val = 0.5f * (1.0f + sinf(RT_FMA(scale, p.z, 10.0f * fabsf(accum))));
+    return val * xyz(m0);
+  }
+  // image: (u, v) of the primitive
+  float u = 0.0f, v = 0.0f;
+  const int type = RT_PRIM_TYPE_OF(prim), idx = RT_PRIM_INDEX_OF(prim);
+  if (type == RT_PRIM_SPHERE) { // sphere.h:28-40
+    const float pi = 3.1415926535897932385f;
+    const float theta = acosf(RT_FMIN(1.0f, RT_FMAX(-1.0f, -outward.y)));
+    const float phi = atan2f(-outward.z, outward.x) + pi;
+    u = phi / (2.0f * pi);
+    v = theta / pi;
+  } else if (type == RT_PRIM_QUAD) { // aarect.h:52-53
+    const float4 q0 = S.quad[2 * idx], q1 = S.quad[2 * idx + 1];
+    const int ax = RT_F2I(q0.w);
+    const float a = ax == 0 ? p.y : p.x, b = ax == 2 ? p.y : p.z;
+    u = (a - q0.y) / (q0.z - q0.y);
+    v = (b - q1.x) / (q1.y - q1.x);
+  }
+  const DevImage im = S.images[(int)m1.x];
+  u = RT_FMIN(RT_FMAX(u, 0.0f), 1.0f);
+  v = 1.0f - RT_FMIN(RT_FMAX(v, 0.0f), 1.0f);
+  int i = (int)(u * (float)im.width), j = (int)(v * (float)im.height);
+  if (i >= im.width) i = im.width - 1;
+  if (j >= im.height) j = im.height - 1;
+  i = (i + im.width / 2 + im.width / 3) % im.width; // texture.h:110 ("try to shift the map")
+  const uint8_t *px = im.rgb + ((size_t)j * im.width + i) * 3;
+  const float cs = 1.0f / 255.0f;
+  return v3(cs * (float)px[0], cs * (float)px[1], cs * (float)px[2]);
+}
+
+// EXT: the scene uses noise / image textures or media (a separate kernel instantiation, so that
+// scenes without them keep the leaner code).
+template <bool EXT>
+RT_HD V3f material_color(const DevScene &S, float4 m0, float4 m1, V3f p, V3f outward, int32_t prim) {
   int tex = (RT_F2I(m0.w) >> 8) & 0xff;
   if (tex == RT_TEX_CHECKER) {
     float sines = rt_fast_sin(10.0f * p.x) * rt_fast_sin(10.0f * p.y) * rt_fast_sin(10.0f * p.z);
     if (sines < 0.0f) return xyz(m1); // odd
+  } else if (EXT && tex >= RT_TEX_NOISE) {
+    return texture_ext(S, m0, m1, p, outward, prim);
   }
   return xyz(m0);
+}
+
+// constant_medium::hit for every medium of the scene, at the START of a segment: the
+// free-flight distance is sampled up front and the scatter event, if it falls inside the
+// boundary, becomes the segment's initial closest hit — surfaces found nearer by the traversal
+// replace it, which is exactly "closest of surfaces and media" and also shortens the
+// traversal. Entry/exit over the whole line, entry clamped to 0 (constant_medium.h:42-56);
+// distance = -1/density * log(u) (:60-61). Deviations from the reference: the event
+// must lie before the closest surface (the reference ignores t_max) and scattering continues
+// from the scatter point (the reference restarts at the boundary entry point, :66).
+// Random numbers: Philox stream 2 + m/4 of (pixel, sample, segment).
+RT_COLD void apply_media(const DevScene &S, const Ray &r, uint32_t pixel, uint32_t smp, uint32_t segment,
+                         uint32_t seed_lo, uint32_t seed_hi, HitAcc &h) {
+  const float len = RT_SQRT(dot(r.d, r.d));
+  Philox4 q = {0u, 0u, 0u, 0u};
+  for (int m = 0; m < S.n_media; m++) {
+    if ((m & 3) == 0) q = philox4x32_10(pixel, smp, segment, 2u + (uint32_t)(m >> 2), seed_lo, seed_hi);
+    const uint32_t word = (m & 3) == 0 ? q.x : ((m & 3) == 1 ? q.y : ((m & 3) == 2 ? q.z : q.w));
+    const float4 a0 = S.media[4 * m], a1 = S.media[4 * m + 1];
+    float t1, t2;
+    if (RT_F2I(a0.w) == 0) {
+      const V3f oc = r.o - xyz(a0);
+      const float a = dot(r.d, r.d), hb = dot(oc, r.d), c = RT_FMA(-a1.x, a1.x, dot(oc, oc));
+      const float disc = RT_FMA(hb, hb, -a * c);
+      if (!(disc > 0.0f)) continue;
+      const float sq = RT_SQRT(disc);
+      t1 = (-hb - sq) / a;
+      t2 = (-hb + sq) / a;
+    } else {
+      const float4 a2 = S.media[4 * m + 2], a3 = S.media[4 * m + 3];
+      const V3f o = r.o - xyz(a2);
+      const float sn = a3.x, cs = a3.y;
+      const float ol[3] = {cs * o.x - sn * o.z, o.y, sn * o.x + cs * o.z};
+      const float dl[3] = {cs * r.d.x - sn * r.d.z, r.d.y, sn * r.d.x + cs * r.d.z};
+      const float lo[3] = {a0.x, a0.y, a0.z}, hi[3] = {a1.x, a1.y, a1.z};
+      t1 = -INFINITY; t2 = INFINITY;
+      bool miss = false;
+      for (int k = 0; k < 3; k++) {
+        if (dl[k] == 0.0f) { miss = miss || ol[k] < lo[k] || ol[k] > hi[k]; continue; }
+        const float ta = (lo[k] - ol[k]) / dl[k], tb = (hi[k] - ol[k]) / dl[k];
+        t1 = RT_FMAX(t1, RT_FMIN(ta, tb));
+        t2 = RT_FMIN(t2, RT_FMAX(ta, tb));
+      }
+      if (miss || !(t1 < t2)) continue;
+    }
+    t1 = RT_FMAX(t1, 0.0f);
+    // u in (0, 1]: log(0) cannot occur
+    const float u = (float)((word >> 8) + 1u) * (1.0f / 16777216.0f);
+    const float hit_distance = a1.w * logf(u);
+    if (hit_distance > (t2 - t1) * len) continue;
+    const float t = t1 + hit_distance / len;
+    if (t < h.t) { h.t = t; h.id = RT_PRIM_ID(RT_PRIM_MEDIUM, m); }
+  }
 }
 
 // Surface interaction at an accepted hit. Updates the ray (origin = hit point,
 // new direction), the throughput `beta` and (profile 2) the radiance `L`.
 // Returns true when the path continues.
 //   rnd: the four random words of this bounce.
-template <int PROFILE, bool GENERAL>
+template <int PROFILE, bool GENERAL, bool EXT = false>
 RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const HitAcc &h, V3f &beta, V3f &L,
                      Philox4 rnd) {
   const V3f p = madd(r.o, h.t, r.d);
@@ -107,10 +242,13 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
   } else if (type == RT_PRIM_TRIANGLE) {
     outward = xyz(S.tri_n[idx]);
     mat = S.tri_mat[idx];
-  } else {
+  } else if (!EXT || type == RT_PRIM_QUAD) {
     int ax = RT_F2I(S.quad[2 * idx].w);
     outward = v3(ax == 0 ? 1.f : 0.f, ax == 1 ? 1.f : 0.f, ax == 2 ? 1.f : 0.f);
     mat = S.quad_mat[idx];
+  } else { // scatter event inside a constant_medium: normal is arbitrary (constant_medium.h:69)
+    outward = v3(1.f, 0.f, 0.f);
+    mat = RT_F2I(S.media[4 * idx + 2].w);
   }
   const float dn_out = dot(r.d, outward);
   const bool front_face = dn_out < 0.0f;
@@ -123,7 +261,7 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
   const float u1 = u01(rnd.x), u2 = u01(rnd.y), u3 = u01(rnd.z);
 
   if (PROFILE == 2 && mtype == RT_MAT_DIFFUSE_LIGHT) {
-    L = L + beta * material_color(m0, m1, p); // emitted; never scatters
+    L = L + beta * material_color<EXT>(S, m0, m1, p, outward, h.id); // emitted; never scatters
     return false;
   }
   V3f dir, att;
@@ -139,10 +277,12 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
       v = cbrtf(u3) * v;
 #endif
     }
-    att = (PROFILE == 2) ? material_color(m0, m1, p) : xyz(m0);
+    att = (PROFILE == 2) ? material_color<EXT>(S, m0, m1, p, outward, h.id) : xyz(m0);
     if (mtype == RT_MAT_LAMBERTIAN) {
       dir = n + v;
       if (PROFILE == 0 && dot(dir, dir) < 1e-16f) dir = n; // degenerate direction guard (material.h:24-26)
+    } else if (EXT && mtype == RT_MAT_ISOTROPIC) {
+      dir = v; // random_in_unit_sphere (material.h:187-188)
     } else {
       V3f refl = reflect(normalize(r.d), n);
       dir = madd(refl, m1.w, v);

@@ -15,9 +15,9 @@ RT_FLAG_FLIP_NORMALS = 1
 RT_FLAG_DEPTH_BACKGROUND = 2
 RT_FLAG_COUNTERS = 4
 
-RT_PRIM_SPHERE, RT_PRIM_TRIANGLE, RT_PRIM_QUAD = 0, 1, 2
-RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT = 0, 1, 2, 3
-RT_TEX_SOLID, RT_TEX_CHECKER = 0, 1
+RT_PRIM_SPHERE, RT_PRIM_TRIANGLE, RT_PRIM_QUAD, RT_PRIM_MEDIUM = 0, 1, 2, 3
+RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 0, 1, 2, 3, 4
+RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_NOISE, RT_TEX_IMAGE = 0, 1, 2, 3
 
 
 def prim_id(ptype, index):
@@ -46,10 +46,17 @@ MATERIAL_DT = np.dtype(
     [("type", "<i4"), ("texture", "<i4"), ("albedo", "<f4", 3), ("param", "<f4"), ("albedo2", "<f4", 3),
      ("reserved", "<f4")]
 )
+PERLIN_DT = np.dtype([("ranvec", "<f4", (256, 3)), ("perm_x", "<i4", 256), ("perm_y", "<i4", 256),
+                      ("perm_z", "<i4", 256)])
+MEDIUM_DT = np.dtype(
+    [("shape", "<i4"), ("p0", "<f4", 3), ("p1", "<f4", 3), ("sin_y", "<f4"), ("cos_y", "<f4"), ("offset", "<f4", 3),
+     ("density", "<f4"), ("material", "<i4")]
+)
 BVH_NODE_DT = np.dtype([("bmin", "<f4", 3), ("escape", "<i4"), ("bmax", "<f4", 3), ("payload", "<i4")])
 
 assert SPHERE_DT.itemsize == 48 and TRIANGLE_DT.itemsize == 52 and QUAD_DT.itemsize == 28
 assert MATERIAL_DT.itemsize == 40 and BVH_NODE_DT.itemsize == 32
+assert PERLIN_DT.itemsize == 6144 and MEDIUM_DT.itemsize == 56
 
 
 class RtConfig(C.Structure):
@@ -70,7 +77,14 @@ class RtSceneDesc(C.Structure):
                 ("n_materials", C.c_int32), ("materials", C.c_void_p),
                 ("camera", RtCamera),
                 ("background", C.c_float * 3), ("sky_gradient", C.c_int32), ("t_min", C.c_float),
-                ("max_depth", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32)]
+                ("max_depth", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+                ("n_media", C.c_int32), ("media", C.c_void_p),
+                ("n_perlin", C.c_int32), ("perlin", C.c_void_p),
+                ("n_images", C.c_int32), ("images", C.c_void_p)]
+
+
+class RtImage(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("rgb", C.c_void_p)]
 
 
 class RtStats(C.Structure):
@@ -136,7 +150,13 @@ class Scene:
 
     def __init__(self, spheres=None, triangles=None, quads=None, materials=None, camera=None,
                  background=(0.0, 0.0, 0.0), sky_gradient=1, t_min=1e-3, max_depth=50, flags=0, name="",
-                 profile=RT_PROFILE_WEEKEND_CPU):
+                 profile=RT_PROFILE_WEEKEND_CPU, media=None, perlin=None, images=None):
+        self.media = np.ascontiguousarray(media if media is not None else np.zeros(0, MEDIUM_DT))
+        self.perlin = np.ascontiguousarray(perlin if perlin is not None else np.zeros(0, PERLIN_DT))
+        # image textures: list of uint8 arrays [h][w][3], row 0 = top
+        self.images = [np.ascontiguousarray(im, np.uint8) for im in (images or [])]
+        assert self.media.dtype == MEDIUM_DT and self.perlin.dtype == PERLIN_DT
+        assert all(im.ndim == 3 and im.shape[2] == 3 for im in self.images)
         self.spheres = np.ascontiguousarray(spheres if spheres is not None else np.zeros(0, SPHERE_DT))
         self.triangles = np.ascontiguousarray(triangles if triangles is not None else np.zeros(0, TRIANGLE_DT))
         self.quads = np.ascontiguousarray(quads if quads is not None else np.zeros(0, QUAD_DT))
@@ -172,12 +192,24 @@ class Scene:
         d.t_min = self.t_min
         d.max_depth = self.max_depth
         d.flags = self.flags
+        d.n_media = len(self.media)
+        d.media = self.media.ctypes.data if len(self.media) else None
+        d.n_perlin = len(self.perlin)
+        d.perlin = self.perlin.ctypes.data if len(self.perlin) else None
+        d.n_images = len(self.images)
+        if self.images:
+            arr = (RtImage * len(self.images))()
+            for k, im in enumerate(self.images):
+                arr[k].width, arr[k].height, arr[k].rgb = im.shape[1], im.shape[0], im.ctypes.data
+            d._images = arr
+            d.images = C.addressof(arr)
         d._keepalive = self
         return d
 
     def with_camera(self, camera):
         s = Scene(self.spheres, self.triangles, self.quads, self.materials, camera, self.background,
-                  self.sky_gradient, self.t_min, self.max_depth, self.flags, self.name, self.profile)
+                  self.sky_gradient, self.t_min, self.max_depth, self.flags, self.name, self.profile,
+                  self.media, self.perlin, self.images)
         return s
 
 

@@ -13,10 +13,10 @@ import os
 
 import numpy as np
 
-from .ctypes_defs import (MATERIAL_DT, QUAD_DT, RT_FLAG_DEPTH_BACKGROUND, RT_FLAG_FLIP_NORMALS,
-                          RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_LAMBERTIAN, RT_MAT_METAL,
+from .ctypes_defs import (MATERIAL_DT, MEDIUM_DT, PERLIN_DT, QUAD_DT, RT_FLAG_DEPTH_BACKGROUND, RT_FLAG_FLIP_NORMALS,
+                          RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC, RT_MAT_LAMBERTIAN, RT_MAT_METAL,
                           RT_PROFILE_FINAL_CU, RT_PROFILE_NEXT_WEEK, RT_PROFILE_WEEKEND_CPU, RT_TEX_CHECKER,
-                          RT_TEX_SOLID, SPHERE_DT, TRIANGLE_DT, Scene, camera_from_lookat)
+                          RT_TEX_IMAGE, RT_TEX_NOISE, RT_TEX_SOLID, SPHERE_DT, TRIANGLE_DT, Scene, camera_from_lookat)
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -444,3 +444,174 @@ def cornell_box(width=600, height=600):
     sc.t_min = 1e-3
     sc.profile = RT_PROFILE_NEXT_WEEK
     return sc
+
+
+# ------------------------------------------------------------------ rt_next_week scenes 3-8
+def make_perlin(seed=1984):
+    """One `perlin` object — rt_next_week/cuda/perlin.h:9-19: 256 gradient vectors
+    random_vec3(-1, 1) (not normalised in this tree) and three permutations produced by
+    perlin_generate_perm/permute (:76-100: for i = n-1..1 swap p[i], p[random_int(n)])."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    t = np.zeros((), PERLIN_DT)
+    t["ranvec"] = rng.uniform(-1.0, 1.0, (256, 3)).astype(np.float32)
+    for name in ("perm_x", "perm_y", "perm_z"):
+        perm = np.arange(256, dtype=np.int32)
+        for i in range(255, 0, -1):
+            target = min(255, int(rng.random() * 256.0))
+            perm[i], perm[target] = perm[target], perm[i]
+        t[name] = perm
+    return t
+
+
+def procedural_earth(width=512, height=256, seed=7):
+    """Stand-in for earthmap.jpeg (a binary asset of the reference that is not redistributed
+    here): an equirectangular map with blue oceans, green/brown continents and white caps,
+    uint8 [h][w][3], row 0 = top (north)."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    lon = (np.arange(width) + 0.5) / width * 2 * np.pi
+    lat = (0.5 - (np.arange(height) + 0.5) / height) * np.pi
+    lo, la = np.meshgrid(lon, lat)
+    x, y, z = np.cos(la) * np.cos(lo), np.sin(la), np.cos(la) * np.sin(lo)
+    f = np.zeros_like(x)
+    for octave in range(5):
+        for _ in range(4):
+            k = rng.normal(size=3)
+            k *= (2.0 ** octave) * 1.5 / np.linalg.norm(k)
+            f += np.sin(k[0] * x + k[1] * y + k[2] * z + rng.uniform(0, 2 * np.pi)) / (2.0 ** octave)
+    img = np.zeros((height, width, 3), np.float64)
+    land = f > 0.35
+    img[~land] = (0.05, 0.15, 0.45)
+    h = np.clip((f - 0.35) / 1.5, 0, 1)[..., None]
+    img = np.where(land[..., None], (1 - h) * np.array((0.15, 0.45, 0.12)) + h * np.array((0.45, 0.35, 0.2)), img)
+    img[np.abs(la) > 1.25] = (0.92, 0.94, 0.96)
+    return (np.clip(img, 0, 1) * 255.0 + 0.5).astype(np.uint8)
+
+
+def _quad(axis, a0, a1, b0, b1, k, m):
+    q = np.zeros((), QUAD_DT)
+    q["axis"], q["a0"], q["a1"], q["b0"], q["b1"], q["k"], q["material"] = axis, a0, a1, b0, b1, k, m
+    return q
+
+
+def _medium_sphere(center, radius, density, material):
+    m = np.zeros((), MEDIUM_DT)
+    m["shape"], m["p0"], m["p1"], m["cos_y"], m["density"], m["material"] = 0, center, (radius, 0, 0), 1.0, density, material
+    return m
+
+
+def _medium_box(p0, p1, angle_deg, offset, density, material):
+    """constant_medium(translate(rotate_y(box(p0, p1), angle), offset), density, colour)"""
+    m = np.zeros((), MEDIUM_DT)
+    rad = np.deg2rad(np.float64(angle_deg))
+    m["shape"], m["p0"], m["p1"], m["offset"], m["density"], m["material"] = 1, p0, p1, offset, density, material
+    m["sin_y"], m["cos_y"] = np.float32(np.sin(rad)), np.float32(np.cos(rad))
+    return m
+
+
+def _nw_camera(sc, lookfrom, lookat, vfov, width, height, aperture=0.0):
+    lookfrom = np.asarray(lookfrom, np.float32)
+    d = lookfrom - np.asarray(lookat, np.float32)
+    focus = np.sqrt(np.dot(d, d), dtype=np.float32)  # main.cu:462
+    sc.camera = camera_from_lookat(lookfrom, lookat, (0, 1, 0), vfov, np.float32(width) / np.float32(height), aperture,
+                                   focus, 0.0, 1.0, dtype=np.float32)
+    sc.sky_gradient = 0
+    sc.t_min = 1e-3
+    sc.profile = RT_PROFILE_NEXT_WEEK
+    return sc
+
+
+def two_perlin_spheres(width=600, height=400, seed=1984):
+    """rt_next_week/cuda/main.cu:212-222,417-422: noise_texture(4) on the ground and a ball."""
+    mats = [_mat(RT_MAT_LAMBERTIAN, (1, 1, 1), texture=RT_TEX_NOISE, albedo2=(4.0, 0, 0))]
+    spheres = [_sphere((0, -1000, 0), 1000, 0), _sphere((0, 2, 0), 2, 0)]
+    sc = Scene(spheres=np.array(spheres, SPHERE_DT), materials=np.array(mats, MATERIAL_DT),
+               perlin=np.array([make_perlin(seed)], PERLIN_DT), name="two_perlin_spheres")
+    sc.background = (0.70, 0.80, 1.00)
+    return _nw_camera(sc, (13, 2, 3), (0, 0, 0), 20.0, width, height)
+
+
+def earth(width=600, height=400, image=None):
+    """rt_next_week/cuda/main.cu:224-232,423-426: one sphere with an image_texture."""
+    mats = [_mat(RT_MAT_LAMBERTIAN, (1, 1, 1), texture=RT_TEX_IMAGE, albedo2=(0, 0, 0))]
+    sc = Scene(spheres=np.array([_sphere((0, 0, 0), 2, 0)], SPHERE_DT), materials=np.array(mats, MATERIAL_DT),
+               images=[procedural_earth() if image is None else image], name="earth")
+    sc.background = (0.70, 0.80, 1.00)
+    return _nw_camera(sc, (13, 2, 3), (0, 0, 0), 40.0, width, height)
+
+
+def simple_light(width=600, height=400, seed=1984):
+    """rt_next_week/cuda/main.cu:234-250,428-434: perlin spheres lit by a rect and a sphere light."""
+    mats = [_mat(RT_MAT_LAMBERTIAN, (1, 1, 1), texture=RT_TEX_NOISE, albedo2=(4.0, 0, 0)),
+            _mat(RT_MAT_DIFFUSE_LIGHT, (4, 4, 4)), _mat(RT_MAT_DIFFUSE_LIGHT, (6, 4, 4))]
+    spheres = [_sphere((0, -1000, 0), 1000, 0), _sphere((0, 2, 0), 2, 0), _sphere((0, 6, 0), 1.5, 2)]
+    quads = [_quad(2, 3, 5, 1, 2, -2, 1)]
+    sc = Scene(spheres=np.array(spheres, SPHERE_DT), quads=np.array(quads, QUAD_DT), materials=np.array(mats, MATERIAL_DT),
+               perlin=np.array([make_perlin(seed)], PERLIN_DT), name="simple_light")
+    sc.background = (0.0, 0.0, 0.0)
+    return _nw_camera(sc, (26, 3, 6), (0, 2, 0), 20.0, width, height)
+
+
+def cornell_smoke(width=600, height=600):
+    """rt_next_week/cuda/main.cu:283-310,445-451: the Cornell room with the two boxes replaced by
+    constant media (density 0.01; black and white smoke)."""
+    mats = [_mat(RT_MAT_LAMBERTIAN, (.12, .45, .15)), _mat(RT_MAT_LAMBERTIAN, (.65, .05, .05)),
+            _mat(RT_MAT_DIFFUSE_LIGHT, (15, 15, 15)), _mat(RT_MAT_LAMBERTIAN, (.73, .73, .73)),
+            _mat(RT_MAT_ISOTROPIC, (0, 0, 0)), _mat(RT_MAT_ISOTROPIC, (1, 1, 1))]
+    green, red, light, white = 0, 1, 2, 3
+    quads = [_quad(0, 0, 555, 0, 555, 555, green), _quad(0, 0, 555, 0, 555, 0, red),
+             _quad(1, 213, 343, 227, 332, 554, light), _quad(1, 0, 555, 0, 555, 0, white),
+             _quad(1, 0, 555, 0, 555, 555, white), _quad(2, 0, 555, 0, 555, 555, white)]
+    media = [_medium_box((0, 0, 0), (165, 330, 165), 15, (265, 0, 295), 0.01, 4),
+             _medium_box((0, 0, 0), (165, 165, 165), -18, (130, 0, 65), 0.01, 5)]
+    sc = Scene(quads=np.array(quads, QUAD_DT), materials=np.array(mats, MATERIAL_DT), media=np.array(media, MEDIUM_DT),
+               name="cornell_smoke")
+    sc.background = (0.0, 0.0, 0.0)
+    return _nw_camera(sc, (278, 278, -800), (278, 278, 0), 40.0, width, height)
+
+
+def box_as_quads(p0, p1, material):
+    """box(p0, p1) — rt_next_week/cuda/box.h:41-58: six axis-aligned rects."""
+    return [_quad(2, p0[0], p1[0], p0[1], p1[1], p1[2], material), _quad(2, p0[0], p1[0], p0[1], p1[1], p0[2], material),
+            _quad(1, p0[0], p1[0], p0[2], p1[2], p1[1], material), _quad(1, p0[0], p1[0], p0[2], p1[2], p0[1], material),
+            _quad(0, p0[1], p1[1], p0[2], p1[2], p1[0], material), _quad(0, p0[1], p1[1], p0[2], p1[2], p0[0], material)]
+
+
+def next_week_final(width=800, height=800, seed=1984, image=None):
+    """rt_next_week/cuda/main.cu:312-383,453-459 — the tree's default scene: 400 ground boxes, an
+    area light, a moving sphere, glass and metal balls, a blue subsurface ball (dielectric
+    boundary + dense medium), thin global fog, an image-textured and a perlin ball, and a
+    rotated, translated cluster of 1000 small spheres."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    f = np.float32
+    mats = [_mat(RT_MAT_LAMBERTIAN, (0.48, 0.83, 0.53)),  # 0 ground
+            _mat(RT_MAT_DIFFUSE_LIGHT, (7, 7, 7)),          # 1 light
+            _mat(RT_MAT_LAMBERTIAN, (0.7, 0.3, 0.1)),       # 2 moving sphere
+            _mat(RT_MAT_DIELECTRIC, param=1.5),             # 3 glass
+            _mat(RT_MAT_METAL, (0.8, 0.8, 0.9), 1.0),       # 4 metal
+            _mat(RT_MAT_ISOTROPIC, (0.2, 0.4, 0.9)),        # 5 blue medium
+            _mat(RT_MAT_ISOTROPIC, (1, 1, 1)),              # 6 fog
+            _mat(RT_MAT_LAMBERTIAN, (1, 1, 1), texture=RT_TEX_IMAGE, albedo2=(0, 0, 0)),    # 7 earth
+            _mat(RT_MAT_LAMBERTIAN, (1, 1, 1), texture=RT_TEX_NOISE, albedo2=(0.1, 0, 0)),  # 8 perlin
+            _mat(RT_MAT_LAMBERTIAN, (.73, .73, .73))]       # 9 white
+    quads = []
+    for i in range(20):
+        for j in range(20):
+            w = f(100.0)
+            x0, z0 = f(-1000.0) + f(i) * w, f(-1000.0) + f(j) * w
+            y1 = f(1.0 + 100.0 * rng.random())
+            quads += box_as_quads((x0, 0.0, z0), (x0 + w, y1, z0 + w), 0)
+    quads.append(_quad(1, 123, 423, 147, 412, 554, 1))
+    spheres = [_sphere((400, 400, 200), 50, 2, c1=(430, 400, 200), t0=0.0, t1=1.0),
+               _sphere((260, 150, 45), 50, 3), _sphere((0, 150, 145), 50, 4),
+               _sphere((360, 150, 145), 70, 3),
+               _sphere((400, 200, 400), 100, 7), _sphere((220, 280, 300), 80, 8)]
+    media = [_medium_sphere((360, 150, 145), 70, 0.2, 5), _medium_sphere((0, 0, 0), 5000, 0.0001, 6)]
+    # cluster: translate(rotate_y(bvh(1000 spheres in [0,165)^3, r = 10), 15), (-100, 270, 395))
+    centres = rng.uniform(0.0, 165.0, (1000, 3)).astype(f)
+    centres = (_rot_y_f32(centres, 15) + np.array((-100, 270, 395), f)).astype(f)
+    spheres += [_sphere(tuple(c), 10, 9) for c in centres]
+    sc = Scene(spheres=np.array(spheres, SPHERE_DT), quads=np.array(quads, QUAD_DT), materials=np.array(mats, MATERIAL_DT),
+               media=np.array(media, MEDIUM_DT), perlin=np.array([make_perlin(seed)], PERLIN_DT),
+               images=[procedural_earth() if image is None else image], name="next_week_final")
+    sc.background = (0.0, 0.0, 0.0)
+    return _nw_camera(sc, (478, 278, -600), (278, 278, 0), 40.0, width, height)

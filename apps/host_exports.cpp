@@ -26,6 +26,20 @@ int rtx_host_build(int which, unsigned seed, double aspect, const char *obj_path
     root->flatten(g_flat, transform());
     g_cam = camera(point3(278, 278, -800), point3(278, 278, 0), vec3(0, 1, 0), 40, aspect, 0.0,
                    (point3(278, 278, -800) - point3(278, 278, 0)).length(), 0.0, 1.0, true).describe();
+  } else if (which >= 4 && which <= 8) { // main.cu:417-459: perlin, earth, simple_light, cornell_smoke, final
+    static std::vector<unsigned char> map;
+    map = procedural_earth(64, 32);
+    hittable *root = which == 4 ? two_perlin_spheres()
+                     : which == 5 ? earth(map.data(), 64, 32)
+                     : which == 6 ? simple_light()
+                     : which == 7 ? cornell_smoke()
+                                  : rt_next_week_final_scene(map.data(), 64, 32);
+    root->flatten(g_flat, transform());
+    const point3 from = which == 6 ? point3(26, 3, 6) : which == 7 ? point3(278, 278, -800)
+                        : which == 8 ? point3(478, 278, -600) : point3(13, 2, 3);
+    const point3 at = which == 6 ? point3(0, 2, 0) : which >= 7 ? point3(278, 278, 0) : point3(0, 0, 0);
+    g_cam = camera(from, at, vec3(0, 1, 0), (which == 4 || which == 6) ? 20 : 40, aspect, 0.0, (from - at).length(), 0.0,
+                   1.0, true).describe();
   } else {
     hittable *root = obj_model(obj_path);
     root->flatten(g_flat, transform());
@@ -37,6 +51,17 @@ int rtx_host_build(int which, unsigned seed, double aspect, const char *obj_path
 void rtx_host_counts(int *n) {
   n[0] = (int)g_flat.spheres.size(); n[1] = (int)g_flat.triangles.size();
   n[2] = (int)g_flat.quads.size(); n[3] = (int)g_flat.materials.size(); n[4] = g_flat.wants_accel;
+}
+// n[0..2] = media, perlin tables, images; dims = (w, h) per image
+void rtx_host_counts2(int *n, int *dims) {
+  n[0] = (int)g_flat.media.size(); n[1] = (int)g_flat.perlin_tables.size(); n[2] = (int)g_flat.images.size();
+  for (size_t i = 0; i < g_flat.images.size() && dims; i++) { dims[2 * i] = g_flat.images[i].width; dims[2 * i + 1] = g_flat.images[i].height; }
+}
+void rtx_host_get2(rt_medium *m, rt_perlin *p, unsigned char **image_bytes) {
+  if (m) memcpy(m, g_flat.media.data(), sizeof(rt_medium) * g_flat.media.size());
+  if (p) memcpy(p, g_flat.perlin_tables.data(), sizeof(rt_perlin) * g_flat.perlin_tables.size());
+  for (size_t i = 0; i < g_flat.images.size() && image_bytes; i++)
+    memcpy(image_bytes[i], g_flat.images[i].rgb, (size_t)g_flat.images[i].width * g_flat.images[i].height * 3);
 }
 void rtx_host_get(rt_sphere *s, rt_triangle *t, rt_quad *q, rt_material *m, rt_camera *c) {
   if (s) memcpy(s, g_flat.spheres.data(), sizeof(rt_sphere) * g_flat.spheres.size());

@@ -2,8 +2,9 @@
 // builds a scene with the reference's own scene-description classes, renders it through
 // the C ABI and writes a P3 PPM on stdout / timing on stderr exactly like
 // rt_in_one_weekend/main.cpp:292-360 and accelerated-rt-cuda/final.cu:155-246.
-//   render_cli [--scene weekend|next_week|cornell|obj] [--obj file.obj] [--width W] [--height H]
-//              [--spp N] [--seed S] [--device D] [--binary | --png]   (image on stdout)
+//   render_cli [--scene weekend|next_week|perlin|earth|light|cornell|smoke|final|obj] [--obj file.obj]
+//              [--image map.ppm] [--width W] [--height H] [--spp N] [--seed S] [--device D]
+//              [--binary | --png]   (image on stdout; scene numbers 1-8 of rt_next_week/cuda/main.cu:402-459)
 #include <chrono>
 #include <cstring>
 #include <iostream>
@@ -11,7 +12,7 @@
 #include "scenes.h"
 
 int main(int argc, char **argv) {
-  std::string scene = "weekend", obj;
+  std::string scene = "weekend", obj, image;
   int W = 1200, H = 800, spp = 500, device = 0;
   unsigned long long seed = 1984;
   bool binary = false, png = false;
@@ -19,6 +20,7 @@ int main(int argc, char **argv) {
     auto is = [&](const char *f) { return !strcmp(argv[i], f) && i + 1 < argc; };
     if (is("--scene")) scene = argv[++i];
     else if (is("--obj")) obj = argv[++i];
+    else if (is("--image")) image = argv[++i];
     else if (is("--width")) W = atoi(argv[++i]);
     else if (is("--height")) H = atoi(argv[++i]);
     else if (is("--spp")) spp = atoi(argv[++i]);
@@ -57,11 +59,38 @@ int main(int argc, char **argv) {
       opt.profile = RT_PROFILE_NEXT_WEEK;
       opt.sky_gradient = false;
       opt.background = color(0, 0, 0);
+    } else if (scene == "perlin" || scene == "earth" || scene == "light" || scene == "smoke" || scene == "final") {
+      opt.profile = RT_PROFILE_NEXT_WEEK; // main.cu:417-459
+      opt.sky_gradient = false;
+      const bool sky = scene == "perlin" || scene == "earth";
+      opt.background = sky ? color(0.70, 0.80, 1.00) : color(0, 0, 0);
+      static std::vector<unsigned char> map;
+      int mw = 512, mh = 256;
+      if (scene == "earth" || scene == "final") {
+        if (!image.empty()) {
+          image_texture file(image.c_str());
+          if (file.data.empty()) { std::cerr << "cannot read " << image << " (binary or ASCII PPM expected)\n"; return 2; }
+          map = file.data; mw = file.width; mh = file.height;
+        } else {
+          map = procedural_earth(mw, mh);
+        }
+      }
+      root = scene == "perlin" ? two_perlin_spheres()
+             : scene == "earth" ? earth(map.data(), mw, mh)
+             : scene == "light" ? simple_light()
+             : scene == "smoke" ? cornell_smoke()
+                                : rt_next_week_final_scene(map.data(), mw, mh);
     } else { std::cerr << "unknown scene " << scene << "\n"; return 2; }
+    auto nw_cam = [&](point3 from, point3 at, double vfov) {
+      return camera(from, at, vec3(0, 1, 0), vfov, aspect, 0.0, (from - at).length(), 0.0, 1.0, true);
+    };
     camera cam = scene == "weekend"
                      ? camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.1, 10.0)
-                 : scene == "cornell"
-                     ? camera(point3(278, 278, -800), point3(278, 278, 0), vec3(0, 1, 0), 40, aspect, 0.0, 800.0, 0.0, 1.0, true)
+                 : (scene == "cornell" || scene == "smoke") ? nw_cam(point3(278, 278, -800), point3(278, 278, 0), 40)
+                 : scene == "perlin" ? nw_cam(point3(13, 2, 3), point3(0, 0, 0), 20)
+                 : scene == "earth" ? nw_cam(point3(13, 2, 3), point3(0, 0, 0), 40)
+                 : scene == "light" ? nw_cam(point3(26, 3, 6), point3(0, 2, 0), 20)
+                 : scene == "final" ? nw_cam(point3(478, 278, -600), point3(278, 278, 0), 40)
                  : scene == "next_week"
                      ? camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.05,
                               (point3(13, 2, 3) - point3(0, 0, 0)).length(), 0.0, 1.0, true)
@@ -71,7 +100,7 @@ int main(int argc, char **argv) {
     r.set_scene(*root, cam);
     std::cerr << "Rendering a " << W << "x" << H << " image with " << spp << " samples per pixel ("
               << r.flat.spheres.size() << " spheres, " << r.flat.triangles.size() << " triangles, " << r.flat.quads.size()
-              << " rects)\n";
+              << " rects, " << r.flat.media.size() << " media)\n";
     auto t0 = std::chrono::steady_clock::now();
     r.render(W, H, spp);
     image8 im = r.resolve();

@@ -137,4 +137,132 @@ inline hittable *cornell_box() {
   ret[7] = box2;
   return new bvh_node(ret, 0, 8, 0.0f, 1.0f);
 }
+
+// Stand-in for the reference's earthmap.jpeg (a binary asset that is not redistributed): an
+// equirectangular map with oceans, continents and polar caps. [h][w][3] bytes, top row first.
+inline std::vector<unsigned char> procedural_earth(int w = 512, int h = 256) {
+  std::vector<unsigned char> img((size_t)w * h * 3);
+  const double waves[6][4] = {{1.5, 0.7, -0.4, 0.3}, {-0.8, 1.9, 1.1, 1.7}, {2.6, -1.2, 2.2, 4.1},
+                              {-3.1, 2.4, -2.9, 0.9}, {5.3, 4.1, -3.7, 2.6}, {-6.2, -5.5, 6.8, 5.2}};
+  for (int j = 0; j < h; j++)
+    for (int i = 0; i < w; i++) {
+      const double lon = (i + 0.5) / w * 2 * pi, lat = (0.5 - (j + 0.5) / h) * pi;
+      const double x = std::cos(lat) * std::cos(lon), y = std::sin(lat), z = std::cos(lat) * std::sin(lon);
+      double f = 0;
+      for (int k = 0; k < 6; k++)
+        f += std::sin(waves[k][0] * x + waves[k][1] * y + waves[k][2] * z + waves[k][3]) / (1 + k / 2);
+      double c[3] = {0.05, 0.15, 0.45};
+      if (f > 0.35) {
+        const double t = std::min(1.0, (f - 0.35) / 1.5);
+        c[0] = (1 - t) * 0.15 + t * 0.45; c[1] = (1 - t) * 0.45 + t * 0.35; c[2] = (1 - t) * 0.12 + t * 0.2;
+      }
+      if (std::fabs(lat) > 1.25) { c[0] = 0.92; c[1] = 0.94; c[2] = 0.96; }
+      for (int a = 0; a < 3; a++) img[((size_t)j * w + i) * 3 + a] = (unsigned char)(c[a] * 255.0 + 0.5);
+    }
+  return img;
+}
+
+// rt_next_week/cuda/main.cu:212-222
+inline hittable *two_perlin_spheres() {
+  auto perlin_texture = new noise_texture(4);
+  static hittable *ret[2];
+  ret[0] = new sphere(point3(0, -1000, 0), 1000, new lambertian(perlin_texture));
+  ret[1] = new sphere(point3(0, 2, 0), 2, new lambertian(perlin_texture));
+  return new bvh_node(ret, 0, 2, 0.0f, 1.0f);
+}
+
+// rt_next_week/cuda/main.cu:224-232
+inline hittable *earth(unsigned char *data, int w, int h) {
+  auto earth_texture = new image_texture(data, w, h);
+  auto earth_surface = new lambertian(earth_texture);
+  static hittable *ret[1];
+  ret[0] = new sphere(point3(0, 0, 0), 2, earth_surface);
+  return new bvh_node(ret, 0, 1, 0.0f, 1.0f);
+}
+
+// rt_next_week/cuda/main.cu:234-250
+inline hittable *simple_light() {
+  auto perlin_texture = new noise_texture(4);
+  static hittable *ret[4];
+  ret[0] = new sphere(point3(0, -1000, 0), 1000, new lambertian(perlin_texture));
+  ret[1] = new sphere(point3(0, 2, 0), 2, new lambertian(perlin_texture));
+  auto diff_light = new diffuse_light(color(4, 4, 4));
+  ret[2] = new xy_rect(3, 5, 1, 2, -2, diff_light);
+  auto diff_light2 = new diffuse_light(color(6, 4, 4));
+  ret[3] = new sphere(point3(0, 6, 0), 1.5, diff_light2);
+  return new bvh_node(ret, 0, 4, 0.0f, 1.0f);
+}
+
+// rt_next_week/cuda/main.cu:283-310
+inline hittable *cornell_smoke() {
+  static hittable *ret[8];
+  auto red = new lambertian(color(.65, .05, .05));
+  auto white = new lambertian(color(.73, .73, .73));
+  auto green = new lambertian(color(.12, .45, .15));
+  auto light = new diffuse_light(color(15, 15, 15));
+  ret[0] = new yz_rect(0, 555, 0, 555, 555, green);
+  ret[1] = new yz_rect(0, 555, 0, 555, 0, red);
+  ret[2] = new xz_rect(213, 343, 227, 332, 554, light);
+  ret[3] = new xz_rect(0, 555, 0, 555, 0, white);
+  ret[4] = new xz_rect(0, 555, 0, 555, 555, white);
+  ret[5] = new xy_rect(0, 555, 0, 555, 555, white);
+  hittable *box1 = new box(point3(0, 0, 0), point3(165, 330, 165), white);
+  box1 = new rotate_y(box1, 15);
+  box1 = new translate(box1, vec3(265, 0, 295));
+  box1 = new constant_medium(box1, 0.01, color(0, 0, 0));
+  hittable *box2 = new box(point3(0, 0, 0), point3(165, 165, 165), white);
+  box2 = new rotate_y(box2, -18);
+  box2 = new translate(box2, vec3(130, 0, 65));
+  box2 = new constant_medium(box2, 0.01, color(1, 1, 1));
+  ret[6] = box1;
+  ret[7] = box2;
+  return new bvh_node(ret, 0, 8, 0.0f, 1.0f);
+}
+
+// rt_next_week/cuda/main.cu:312-383 — the tree's default scene
+inline hittable *rt_next_week_final_scene(unsigned char *data, int w, int h) {
+  const int boxes_per_side = 20;
+  const int num_obj = boxes_per_side * boxes_per_side + 10;
+  static std::vector<hittable *> ret;
+  ret.assign(num_obj, nullptr);
+  auto ground = new lambertian(color(0.48, 0.83, 0.53));
+  int index = 0;
+  for (int i = 0; i < boxes_per_side; i++) {
+    for (int j = 0; j < boxes_per_side; j++) {
+      float bw = 100.0;
+      float x0 = -1000.0f + i * bw;
+      float z0 = -1000.0f + j * bw;
+      float y0 = 0.0;
+      float x1 = x0 + bw;
+      float y1 = (float)random_double(1, 101);
+      float z1 = z0 + bw;
+      ret[index++] = new box(point3(x0, y0, z0), point3(x1, y1, z1), ground);
+    }
+  }
+  auto light = new diffuse_light(color(7, 7, 7));
+  ret[index++] = new xz_rect(123, 423, 147, 412, 554, light);
+  auto center1 = point3(400, 400, 200);
+  auto center2 = center1 + vec3(30, 0, 0);
+  auto moving_sphere_material = new lambertian(color(0.7, 0.3, 0.1));
+  ret[index++] = new moving_sphere(center1, center2, 0, 1, 50, moving_sphere_material);
+  ret[index++] = new sphere(point3(260, 150, 45), 50, new dielectric(1.5));
+  ret[index++] = new sphere(point3(0, 150, 145), 50, new metal(color(0.8, 0.8, 0.9), 1.0));
+  auto sphere_dielectric_2 = new sphere(point3(360, 150, 145), 70, new dielectric(1.5));
+  ret[index++] = sphere_dielectric_2;
+  ret[index++] = new constant_medium(sphere_dielectric_2, 0.2, color(0.2, 0.4, 0.9));
+  auto fog = new sphere(point3(0, 0, 0), 5000, new dielectric(1.5));
+  ret[index++] = new constant_medium(fog, 0.0001, color(1, 1, 1));
+  auto earth_texture = new image_texture(data, w, h);
+  auto earth_surface = new lambertian(earth_texture);
+  ret[index++] = new sphere(point3(400, 200, 400), 100, earth_surface);
+  auto pertext = new noise_texture(0.1);
+  ret[index++] = new sphere(point3(220, 280, 300), 80, new lambertian(pertext));
+  auto white = new lambertian(color(.73, .73, .73));
+  const int ns = 1000;
+  static hittable *cluster[ns];
+  for (int j = 0; j < ns; j++)
+    cluster[j] = new sphere(point3(random_double(0, 165), random_double(0, 165), random_double(0, 165)), 10, white);
+  ret[index++] = new translate(new rotate_y(new bvh_node(cluster, 0, ns, 0, 1), 15), vec3(-100, 270, 395));
+  return new bvh_node(ret.data(), 0, index, 0.0, 1.0);
+}
 #endif

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RT_CAPI_VERSION 1
+#define RT_CAPI_VERSION 2
 
 typedef struct rt_ctx rt_ctx;
 
@@ -69,7 +69,12 @@ typedef enum rt_profile {
 #define RT_FLAG_DEPTH_BACKGROUND 2u  /* obj_render.cu:78-83: depth exhausted -> unwound background */
 #define RT_FLAG_COUNTERS 4u          /* maintain node/prim test counters (slower kernel variant) */
 
-typedef enum rt_prim_type { RT_PRIM_SPHERE = 0, RT_PRIM_TRIANGLE = 1, RT_PRIM_QUAD = 2 } rt_prim_type;
+typedef enum rt_prim_type {
+  RT_PRIM_SPHERE = 0,
+  RT_PRIM_TRIANGLE = 1,
+  RT_PRIM_QUAD = 2,
+  RT_PRIM_MEDIUM = 3 /* constant_medium: never returned by rt_trace_closest (stochastic) */
+} rt_prim_type;
 /* primitive id returned by rt_trace_closest: (type << 28) | index-within-type; -1 = miss */
 #define RT_PRIM_ID(type, index) ((int32_t)(((uint32_t)(type) << 28) | (uint32_t)(index)))
 #define RT_PRIM_TYPE_OF(id) ((int)(((uint32_t)(id)) >> 28))
@@ -79,10 +84,16 @@ typedef enum rt_material_type {
   RT_MAT_LAMBERTIAN = 0,
   RT_MAT_METAL = 1,
   RT_MAT_DIELECTRIC = 2,
-  RT_MAT_DIFFUSE_LIGHT = 3
+  RT_MAT_DIFFUSE_LIGHT = 3,
+  RT_MAT_ISOTROPIC = 4 /* phase function of a constant_medium (rt_next_week/cuda/material.h:178-195) */
 } rt_material_type;
 
-typedef enum rt_texture_type { RT_TEX_SOLID = 0, RT_TEX_CHECKER = 1 } rt_texture_type;
+typedef enum rt_texture_type {
+  RT_TEX_SOLID = 0,
+  RT_TEX_CHECKER = 1,
+  RT_TEX_NOISE = 2, /* noise_texture (texture.h:55-75): albedo * 0.5 (1 + sin(scale z + 10 turb(scale p))) */
+  RT_TEX_IMAGE = 3  /* image_texture (texture.h:77-124) looked up with the primitive's (u, v) */
+} rt_texture_type;
 
 typedef struct rt_config {
   int32_t device;   /* CUDA device ordinal */
@@ -123,11 +134,37 @@ typedef struct rt_quad {
 typedef struct rt_material {
   int32_t type;      /* rt_material_type */
   int32_t texture;   /* rt_texture_type (albedo / emit) */
-  float albedo[3];   /* solid colour, or checker `even` (texture.h:33-53) */
+  float albedo[3];   /* solid colour, checker `even` (texture.h:33-53), noise tint (reference: 1,1,1) */
   float param;       /* metal: fuzz (already clamped to <=1); dielectric: index */
-  float albedo2[3];  /* checker `odd` */
+  float albedo2[3];  /* checker `odd`; noise: {scale, perlin table index, -}; image: {image index, -, -} */
   float reserved;
 } rt_material;
+
+/* perlin (rt_next_week/cuda/perlin.h:9-19,76-100): the 256 random gradient vectors and the three
+ * permutation tables of one `perlin` object, generated by the host. */
+typedef struct rt_perlin {
+  float ranvec[256][3];
+  int32_t perm_x[256], perm_y[256], perm_z[256];
+} rt_perlin;
+
+/* image_texture data (texture.h:83-88): 3 bytes per pixel, row 0 = top. */
+typedef struct rt_image {
+  int32_t width, height;
+  const uint8_t *rgb;
+} rt_image;
+
+/* constant_medium (rt_next_week/cuda/constant_medium.h:10-33) over a convex boundary:
+ * shape 0 = sphere(center = p0, radius = p1[0]); shape 1 = box(p0, p1) rotated about y by the
+ * angle with (sin_y, cos_y) and then translated by `offset` (box.h + hittable.h rotate_y/translate,
+ * main.cu:297-305). material must be RT_MAT_ISOTROPIC. */
+typedef struct rt_medium {
+  int32_t shape;
+  float p0[3], p1[3];
+  float sin_y, cos_y;
+  float offset[3];
+  float density;
+  int32_t material;
+} rt_medium;
 
 /* camera as its constructor leaves it (camera.h:8-45; rt_next_week/cuda/camera.h:25-61) */
 typedef struct rt_camera {
@@ -152,6 +189,10 @@ typedef struct rt_scene_desc {
   int32_t max_depth;   /* 50 */
   uint32_t flags;      /* RT_FLAG_FLIP_NORMALS | RT_FLAG_DEPTH_BACKGROUND */
   uint32_t reserved;
+  /* version 2: participating media and procedural / image textures (profile 2 only) */
+  int32_t n_media;     const rt_medium *media;
+  int32_t n_perlin;    const rt_perlin *perlin;
+  int32_t n_images;    const rt_image *images;
 } rt_scene_desc;
 
 /* 32-byte packed BVH node as downloaded by rt_accel_download (device layout).

@@ -8,8 +8,11 @@
 //   sphere, moving_sphere, triangle, xy/xz/yz_rect   sphere.h:10-11, moving_sphere.h:12-15,
 //                             triangles/cuda/include/triangle.h:17-20, aarect.h:15-17,70-72,126-128
 //   translate, rotate_y, bvh_node   rt_next_week/cuda/hittable.h:49-190, bvh.h:45-46
-//   lambertian, metal, dielectric, diffuse_light, solid_color, checker_texture
-//                             material.h:9-97, rt_next_week/cuda/material.h:27-176, texture.h:13-53
+//   lambertian, metal, dielectric, diffuse_light, isotropic, solid_color, checker_texture,
+//   noise_texture (+ perlin), image_texture
+//                             material.h:9-97, rt_next_week/cuda/material.h:27-195, texture.h:13-124,
+//                             perlin.h:6-125
+//   constant_medium           rt_next_week/cuda/constant_medium.h:10-33 (sphere or box boundary)
 // These are DESCRIPTION objects only: nothing here intersects rays. `flatten()` turns an
 // object graph into the plain-C rt_scene_desc (include/rt_capi.h) that the GPU core
 // consumes; instances (translate / rotate_y) are baked into the vertices, and a
@@ -89,17 +92,20 @@ inline vec3 unit_vector(vec3 v) { return v / v.length(); }
 inline std::ostream &operator<<(std::ostream &o, const vec3 &v) { return o << v.e[0] << ' ' << v.e[1] << ' ' << v.e[2]; }
 
 // ---------------------------------------------------------------- textures, materials
+class flat_scene;
 class abstract_texture {
 public:
   virtual ~abstract_texture() {}
-  virtual bool describe(rt_material &m, bool second) const = 0;
+  // fills the texture fields of `m`; `second` = the checker's odd colour slot. Tables and images
+  // are registered in `fs`.
+  virtual bool describe(rt_material &m, bool second, flat_scene &fs) const = 0;
 };
 class solid_color : public abstract_texture {
 public:
   solid_color() {}
   solid_color(color c) : color_value(c) {}
   solid_color(double r, double g, double b) : color_value(r, g, b) {}
-  bool describe(rt_material &m, bool second) const override {
+  bool describe(rt_material &m, bool second, flat_scene &) const override {
     float *dst = second ? m.albedo2 : m.albedo;
     for (int a = 0; a < 3; a++) dst[a] = (float)color_value[a];
     return true;
@@ -110,27 +116,85 @@ class checker_texture : public abstract_texture {
 public:
   checker_texture(color c1, color c2) : even(make_shared<solid_color>(c1)), odd(make_shared<solid_color>(c2)) {}
   checker_texture(shared_ptr<abstract_texture> e, shared_ptr<abstract_texture> o) : even(e), odd(o) {}
-  bool describe(rt_material &m, bool) const override {
+  checker_texture(abstract_texture *e, abstract_texture *o) : even(borrow(e)), odd(borrow(o)) {}
+  bool describe(rt_material &m, bool, flat_scene &fs) const override {
     m.texture = RT_TEX_CHECKER;
-    return even->describe(m, false) && odd->describe(m, true);
+    return even->describe(m, false, fs) && odd->describe(m, true, fs);
   }
   shared_ptr<abstract_texture> even, odd;
+};
+// perlin.h:9-19,76-100: 256 gradient vectors random_vec3(-1,1) and three permutation tables
+// (for i = n-1..1: swap p[i], p[random_int(n)]), drawn from the host generator.
+class perlin {
+public:
+  perlin() {
+    for (int i = 0; i < 256; i++)
+      for (int a = 0; a < 3; a++) table.ranvec[i][a] = (float)random_double(-1, 1);
+    int32_t *perms[3] = {table.perm_x, table.perm_y, table.perm_z};
+    for (int32_t *p : perms) {
+      for (int i = 0; i < 256; i++) p[i] = i;
+      for (int i = 255; i > 0; i--) {
+        int target = (int)(random_double() * 256.0);
+        if (target > 255) target = 255;
+        int32_t tmp = p[i]; p[i] = p[target]; p[target] = tmp;
+      }
+    }
+  }
+  rt_perlin table;
+};
+class noise_texture : public abstract_texture {
+public:
+  noise_texture() {}
+  noise_texture(double sc, void * /*curandState*, unused*/ = nullptr) : scale(sc) {}
+  bool describe(rt_material &m, bool second, flat_scene &fs) const override;
+  perlin noise;
+  double scale = 1;
+};
+// image_texture(data, w, h) as in rt_next_week/cuda/texture.h:83-88 (the bytes are copied), or
+// from a binary/ASCII PPM file. A missing image gives the reference's debug cyan (:94-96).
+class image_texture : public abstract_texture {
+public:
+  image_texture() {}
+  image_texture(const unsigned char *d, int w, int h) : width(w), height(h) {
+    if (d && w > 0 && h > 0) data.assign(d, d + (size_t)w * h * 3);
+  }
+  explicit image_texture(const char *filename) {
+    std::ifstream in(filename, std::ios::binary);
+    std::string magic;
+    int maxv = 0;
+    if (!(in >> magic) || (magic != "P6" && magic != "P3")) return;
+    auto skip = [&]() { while (in >> std::ws && in.peek() == '#') { std::string l; std::getline(in, l); } };
+    skip(); in >> width; skip(); in >> height; skip(); in >> maxv;
+    if (!in || width < 1 || height < 1 || maxv < 1 || maxv > 255) { width = height = 0; return; }
+    data.resize((size_t)width * height * 3);
+    if (magic == "P6") {
+      in.get();
+      in.read((char *)data.data(), (std::streamsize)data.size());
+    } else {
+      for (auto &b : data) { int v = 0; in >> v; b = (unsigned char)v; }
+    }
+    if (!in) { data.clear(); width = height = 0; }
+    else if (maxv != 255) for (auto &b : data) b = (unsigned char)((int)b * 255 / maxv);
+  }
+  bool describe(rt_material &m, bool second, flat_scene &fs) const override;
+  std::vector<unsigned char> data;
+  int width = 0, height = 0;
 };
 
 class material {
 public:
   virtual ~material() {}
-  virtual rt_material describe() const = 0;
+  virtual rt_material describe(flat_scene &fs) const = 0;
 };
 class lambertian : public material {
 public:
   lambertian(const color &a) : albedo(make_shared<solid_color>(a)) {}
   lambertian(shared_ptr<abstract_texture> a) : albedo(a) {}
   lambertian(abstract_texture *a) : albedo(borrow(a)) {}
-  rt_material describe() const override {
+  rt_material describe(flat_scene &fs) const override {
     rt_material m = {};
     m.type = RT_MAT_LAMBERTIAN;
-    albedo->describe(m, false);
+    albedo->describe(m, false, fs);
     return m;
   }
   shared_ptr<abstract_texture> albedo;
@@ -138,7 +202,7 @@ public:
 class metal : public material {
 public:
   metal(const color &a, double f) : albedo(a), fuzz(f < 1 ? f : 1) {}
-  rt_material describe() const override {
+  rt_material describe(flat_scene &) const override {
     rt_material m = {};
     m.type = RT_MAT_METAL;
     for (int a = 0; a < 3; a++) m.albedo[a] = (float)albedo[a];
@@ -151,7 +215,7 @@ public:
 class dielectric : public material {
 public:
   dielectric(double index_of_refraction) : ir(index_of_refraction) {}
-  rt_material describe() const override {
+  rt_material describe(flat_scene &) const override {
     rt_material m = {};
     m.type = RT_MAT_DIELECTRIC;
     m.param = (float)ir;
@@ -163,13 +227,28 @@ class diffuse_light : public material {
 public:
   diffuse_light(color c) : emit(make_shared<solid_color>(c)) {}
   diffuse_light(shared_ptr<abstract_texture> a) : emit(a) {}
-  rt_material describe() const override {
+  diffuse_light(abstract_texture *a) : emit(borrow(a)) {}
+  rt_material describe(flat_scene &fs) const override {
     rt_material m = {};
     m.type = RT_MAT_DIFFUSE_LIGHT;
-    emit->describe(m, false);
+    emit->describe(m, false, fs);
     return m;
   }
   shared_ptr<abstract_texture> emit;
+};
+// phase function of a constant_medium (rt_next_week/cuda/material.h:178-195)
+class isotropic : public material {
+public:
+  isotropic(color c) : albedo(make_shared<solid_color>(c)) {}
+  isotropic(shared_ptr<abstract_texture> a) : albedo(a) {}
+  isotropic(abstract_texture *a) : albedo(borrow(a)) {}
+  rt_material describe(flat_scene &fs) const override {
+    rt_material m = {};
+    m.type = RT_MAT_ISOTROPIC;
+    albedo->describe(m, false, fs);
+    return m;
+  }
+  shared_ptr<abstract_texture> albedo;
 };
 
 // ---------------------------------------------------------------- flattening
@@ -213,24 +292,69 @@ public:
   std::vector<rt_triangle> triangles;
   std::vector<rt_quad> quads;
   std::vector<rt_material> materials;
+  std::vector<rt_medium> media;
+  std::vector<rt_perlin> perlin_tables;
+  std::vector<rt_image> images; // rgb pointers stay owned by the image_texture objects
   bool wants_accel = false;
   int add_material(const material *m) {
     if (!m) throw std::invalid_argument("primitive without material");
     for (size_t i = 0; i < seen.size(); i++)
       if (seen[i] == m) return (int)i;
     seen.push_back(m);
-    materials.push_back(m->describe());
+    rt_material d = m->describe(*this); // may register tables / images
+    materials.push_back(d);
     return (int)materials.size() - 1;
+  }
+  int add_perlin(const perlin *p) {
+    for (size_t i = 0; i < seen_perlin.size(); i++)
+      if (seen_perlin[i] == p) return (int)i;
+    seen_perlin.push_back(p);
+    perlin_tables.push_back(p->table);
+    return (int)perlin_tables.size() - 1;
+  }
+  int add_image(const image_texture *t) {
+    for (size_t i = 0; i < seen_images.size(); i++)
+      if (seen_images[i] == t) return (int)i;
+    seen_images.push_back(t);
+    rt_image im = {t->width, t->height, t->data.data()};
+    images.push_back(im);
+    return (int)images.size() - 1;
   }
 
 private:
   std::vector<const material *> seen;
+  std::vector<const perlin *> seen_perlin;
+  std::vector<const image_texture *> seen_images;
 };
+
+inline bool noise_texture::describe(rt_material &m, bool second, flat_scene &fs) const {
+  if (second) return false; // only solid colours nest inside a checker
+  m.texture = RT_TEX_NOISE;
+  m.albedo[0] = m.albedo[1] = m.albedo[2] = 1.0f; // color(1,1,1) * ... texture.h:68
+  m.albedo2[0] = (float)scale;
+  m.albedo2[1] = (float)fs.add_perlin(&noise);
+  return true;
+}
+inline bool image_texture::describe(rt_material &m, bool second, flat_scene &fs) const {
+  if (second) return false;
+  if (data.empty()) { // texture.h:94-96
+    m.texture = RT_TEX_SOLID;
+    m.albedo[0] = 0.0f; m.albedo[1] = 1.0f; m.albedo[2] = 1.0f;
+    return true;
+  }
+  m.texture = RT_TEX_IMAGE;
+  m.albedo[0] = m.albedo[1] = m.albedo[2] = 1.0f;
+  m.albedo2[0] = (float)fs.add_image(this);
+  return true;
+}
 
 class hittable {
 public:
   virtual ~hittable() {}
   virtual void flatten(flat_scene &out, const transform &xf) const = 0;
+  // shape of this object as the boundary of a constant_medium (sphere or box, possibly under
+  // rotate_y / translate); false = unsupported
+  virtual bool as_medium_boundary(rt_medium &, const transform &) const { return false; }
 };
 
 // triangle ctor — triangles/cuda/include/triangle.h:17-53 in float arithmetic
@@ -262,6 +386,15 @@ public:
     s.material = out.add_material(mat_ptr.get());
     s.time0 = 0; s.time1 = 1; s.moving = 0;
     out.spheres.push_back(s);
+  }
+  bool as_medium_boundary(rt_medium &m, const transform &xf) const override {
+    m.shape = 0;
+    float c[3] = {(float)center[0], (float)center[1], (float)center[2]};
+    xf.apply(c, m.p0);
+    m.p1[0] = (float)(std::fabs(radius) * xf.scale); m.p1[1] = m.p1[2] = 0;
+    m.sin_y = 0; m.cos_y = 1;
+    m.offset[0] = m.offset[1] = m.offset[2] = 0;
+    return true;
   }
   point3 center;
   double radius = 0;
@@ -380,6 +513,16 @@ public:
   void flatten(flat_scene &out, const transform &xf) const override {
     for (const auto &s : sides) s->flatten(out, xf);
   }
+  bool as_medium_boundary(rt_medium &m, const transform &xf) const override {
+    m.shape = 1;
+    for (int a = 0; a < 3; a++) {
+      m.p0[a] = (float)(box_min[a] * xf.scale);
+      m.p1[a] = (float)(box_max[a] * xf.scale);
+      m.offset[a] = (float)xf.offset[a];
+    }
+    m.sin_y = (float)xf.s; m.cos_y = (float)xf.c;
+    return true;
+  }
   point3 box_min, box_max;
   std::vector<shared_ptr<hittable>> sides;
 
@@ -413,6 +556,9 @@ public:
   translate(shared_ptr<hittable> p, const vec3 &d) : ptr(p), offset(d) {}
   translate(hittable *p, const vec3 &d) : ptr(borrow(p)), offset(d) {}
   void flatten(flat_scene &out, const transform &xf) const override { ptr->flatten(out, xf.then_translate(offset)); }
+  bool as_medium_boundary(rt_medium &m, const transform &xf) const override {
+    return ptr->as_medium_boundary(m, xf.then_translate(offset));
+  }
   shared_ptr<hittable> ptr;
   vec3 offset;
 };
@@ -421,8 +567,35 @@ public:
   rotate_y(shared_ptr<hittable> p, double angle_deg) : ptr(p), angle(angle_deg) {}
   rotate_y(hittable *p, double angle_deg) : ptr(borrow(p)), angle(angle_deg) {}
   void flatten(flat_scene &out, const transform &xf) const override { ptr->flatten(out, xf.then_rotate_y(angle)); }
+  bool as_medium_boundary(rt_medium &m, const transform &xf) const override {
+    return ptr->as_medium_boundary(m, xf.then_rotate_y(angle));
+  }
   shared_ptr<hittable> ptr;
   double angle;
+};
+// constant_medium(boundary, density, colour | texture) — constant_medium.h:10-33. The boundary
+// must be convex: a sphere or a box, directly or under rotate_y / translate.
+class constant_medium : public hittable {
+public:
+  constant_medium(shared_ptr<hittable> b, double d, shared_ptr<abstract_texture> a)
+      : boundary(b), density(d), phase_function(make_shared<isotropic>(a)) {}
+  constant_medium(shared_ptr<hittable> b, double d, color c)
+      : boundary(b), density(d), phase_function(make_shared<isotropic>(c)) {}
+  constant_medium(hittable *b, double d, abstract_texture *a)
+      : boundary(borrow(b)), density(d), phase_function(make_shared<isotropic>(a)) {}
+  constant_medium(hittable *b, double d, color c)
+      : boundary(borrow(b)), density(d), phase_function(make_shared<isotropic>(c)) {}
+  void flatten(flat_scene &out, const transform &xf) const override {
+    rt_medium m = {};
+    if (!boundary || !boundary->as_medium_boundary(m, xf))
+      throw std::invalid_argument("constant_medium: the boundary must be a sphere or a box");
+    m.density = (float)density;
+    m.material = out.add_material(phase_function.get());
+    out.media.push_back(m);
+  }
+  shared_ptr<hittable> boundary;
+  double density;
+  shared_ptr<material> phase_function;
 };
 // bvh_node(list, start, end, time0, time1[, rng]) — bvh.h:45-46: a request for an
 // acceleration structure over the range; the device builds one LBVH over everything.
@@ -588,6 +761,9 @@ public:
     d.n_triangles = (int)fs.triangles.size(); d.triangles = fs.triangles.data();
     d.n_quads = (int)fs.quads.size(); d.quads = fs.quads.data();
     d.n_materials = (int)fs.materials.size(); d.materials = fs.materials.data();
+    d.n_media = (int)fs.media.size(); d.media = fs.media.data();
+    d.n_perlin = (int)fs.perlin_tables.size(); d.perlin = fs.perlin_tables.data();
+    d.n_images = (int)fs.images.size(); d.images = fs.images.data();
     d.camera = cam.describe();
     for (int a = 0; a < 3; a++) d.background[a] = (float)o.background[a];
     d.sky_gradient = o.sky_gradient ? 1 : 0;

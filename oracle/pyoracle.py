@@ -56,6 +56,12 @@ class L1:
         self._quant = getattr(self.lib, p + "quantise")
         self._quant.restype = None
         self._quant.argtypes = [C.c_int, _vp, C.c_int, _vp]
+        self._tex = getattr(self.lib, p + "tex_value_at")
+        self._tex.restype = None
+        self._tex.argtypes = [C.POINTER(RtSceneDesc), C.c_int, C.c_int, _vp, _vp]
+        self._suv = getattr(self.lib, p + "sphere_uv_at")
+        self._suv.restype = None
+        self._suv.argtypes = [C.c_int, _vp, _vp]
         self.lib.orc_srand.argtypes = [C.c_uint]
 
     def srand(self, seed):
@@ -128,6 +134,20 @@ class L1:
         ok = self._scatter(C.byref(d), profile, material, d_in.ctypes.data, n.ctypes.data, seed, int(libc_rand),
                            out.ctypes.data, att.ctypes.data)
         return ok, out, att
+
+    def tex_value(self, scene, material, uvp):
+        """texture value at rows (u, v, px, py, pz)"""
+        uvp = np.ascontiguousarray(uvp, np.float64).reshape(-1, 5)
+        out = np.zeros((len(uvp), 3))
+        d = scene.desc()
+        self._tex(C.byref(d), material, len(uvp), uvp.ctypes.data, out.ctypes.data)
+        return out
+
+    def sphere_uv(self, normals):
+        n = np.ascontiguousarray(normals, np.float64).reshape(-1, 3)
+        out = np.zeros((len(n), 2))
+        self._suv(len(n), n.ctypes.data, out.ctypes.data)
+        return out
 
     def quantise(self, profile, sum3, spp):
         sum3 = np.ascontiguousarray(sum3, np.float64)

@@ -30,6 +30,8 @@
 #define FMAX fmax
 #define POW pow
 #define SIN sin
+#define LOG log
+#define FLOOR floor
 #define ACOS acos
 #define ATAN2 atan2
 #define INFINITY_R ((double)INFINITY)
@@ -44,6 +46,8 @@
 #undef FMAX
 #undef POW
 #undef SIN
+#undef LOG
+#undef FLOOR
 #undef ACOS
 #undef ATAN2
 #undef INFINITY_R
@@ -58,10 +62,12 @@
 #define FMAX fmaxf
 #define POW powf
 #define SIN sinf
+#define LOG logf
+#define FLOOR floorf
 #define ACOS acosf
 #define ATAN2 atan2f
 #define INFINITY_R ((float)INFINITY)
 #include "rt_oracle_impl.h"
 
 void orc_srand(unsigned seed) { srand(seed); }
-int orc_version(void) { return 1; }
+int orc_version(void) { return 2; }

@@ -403,12 +403,57 @@ static int FN(ref_bvh_hit)(FN(World) *w, const FN(RefBvh) *b, const FN(Ray) *r, 
 }
 
 /* ---- textures & materials ---- */
-/* texture.h:13-53 */
-static V3 FN(tex_value)(const rt_material *m, V3 p) {
+/* perlin::noise + trilinear_interp — rt_next_week/cuda/perlin.h:29-56,103-122 */
+static REAL FN(perlin_noise)(const rt_perlin *pn, V3 p) {
+  REAL fx = FLOOR(p.x), fy = FLOOR(p.y), fz = FLOOR(p.z);
+  REAL u = p.x - fx, v = p.y - fy, w = p.z - fz;
+  REAL uu = u * u * ((REAL)3 - (REAL)2 * u), vv = v * v * ((REAL)3 - (REAL)2 * v), ww = w * w * ((REAL)3 - (REAL)2 * w);
+  int i = (int)fx, j = (int)fy, k = (int)fz;
+  REAL accum = 0;
+  for (int di = 0; di < 2; di++)
+    for (int dj = 0; dj < 2; dj++)
+      for (int dk = 0; dk < 2; dk++) {
+        const float *c = pn->ranvec[pn->perm_x[(i + di) & 255] ^ pn->perm_y[(j + dj) & 255] ^ pn->perm_z[(k + dk) & 255]];
+        V3 weight_v = FN(v)(u - (REAL)di, v - (REAL)dj, w - (REAL)dk);
+        accum += ((REAL)di * uu + (REAL)(1 - di) * ((REAL)1 - uu)) * ((REAL)dj * vv + (REAL)(1 - dj) * ((REAL)1 - vv)) *
+                 ((REAL)dk * ww + (REAL)(1 - dk) * ((REAL)1 - ww)) * FN(dot)(FN(from3f)(c), weight_v);
+      }
+  return accum;
+}
+/* perlin::turb — perlin.h:58-70 (depth 7) */
+static REAL FN(perlin_turb)(const rt_perlin *pn, V3 p) {
+  REAL accum = 0, weight = 1;
+  for (int i = 0; i < 7; i++) {
+    accum += weight * FN(perlin_noise)(pn, p);
+    weight *= (REAL)0.5;
+    p = FN(scale)((REAL)2, p);
+  }
+  return FABS(accum);
+}
+/* texture.h:13-53 (solid, checker), :55-75 (noise), :77-124 (image, with its map shift :110) */
+static V3 FN(tex_value)(const rt_scene_desc *sc, const rt_material *m, REAL u, REAL v, V3 p) {
   if (m->texture == RT_TEX_CHECKER) {
     REAL sines = SIN((REAL)10 * p.x) * SIN((REAL)10 * p.y) * SIN((REAL)10 * p.z);
     if (sines < 0) return FN(from3f)(m->albedo2); /* odd */
     return FN(from3f)(m->albedo);                  /* even */
+  }
+  if (m->texture == RT_TEX_NOISE) {
+    REAL sc_ = (REAL)m->albedo2[0];
+    const rt_perlin *pn = &sc->perlin[(int)m->albedo2[1]];
+    REAL val = (REAL)0.5 * ((REAL)1 + SIN(sc_ * p.z + (REAL)10 * FN(perlin_turb)(pn, FN(scale)(sc_, p))));
+    return FN(scale)(val, FN(from3f)(m->albedo));
+  }
+  if (m->texture == RT_TEX_IMAGE) {
+    const rt_image *im = &sc->images[(int)m->albedo2[0]];
+    u = u < 0 ? 0 : (u > 1 ? 1 : u);
+    v = (REAL)1 - (v < 0 ? 0 : (v > 1 ? 1 : v));
+    int i = (int)(u * (REAL)im->width), j = (int)(v * (REAL)im->height);
+    if (i >= im->width) i = im->width - 1;
+    if (j >= im->height) j = im->height - 1;
+    i = (i + im->width / 2 + im->width / 3) % im->width;
+    const uint8_t *px = im->rgb + ((size_t)j * im->width + i) * 3;
+    const REAL cs = (REAL)1 / (REAL)255;
+    return FN(v)(cs * (REAL)px[0], cs * (REAL)px[1], cs * (REAL)px[2]);
   }
   return FN(from3f)(m->albedo);
 }
@@ -456,14 +501,14 @@ static int FN(scatter)(const FN(World) *w, const rt_material *m, const FN(Ray) *
       /* accelerated-rt-cuda/material.h:36-44; rt_next_week/cuda/material.h:43-52 */
       V3 target = FN(add)(FN(add)(rec->p, rec->normal), FN(random_in_unit_sphere)(rng));
       out->d = FN(sub)(target, rec->p);
-      *atten = (w->profile == 2) ? FN(tex_value)(m, rec->p) : FN(from3f)(m->albedo);
+      *atten = (w->profile == 2) ? FN(tex_value)(w->sc, m, rec->u, rec->v, rec->p) : FN(from3f)(m->albedo);
     }
     return 1;
   case RT_MAT_METAL: {
     /* material.h:40-49; accelerated-rt-cuda/material.h:58-71 */
     V3 reflected = FN(reflect)(FN(unit)(rin->d), rec->normal);
     out->d = FN(add)(reflected, FN(scale)((REAL)m->param, FN(random_in_unit_sphere)(rng)));
-    *atten = (w->profile == 2) ? FN(tex_value)(m, rec->p) : FN(from3f)(m->albedo);
+    *atten = (w->profile == 2) ? FN(tex_value)(w->sc, m, rec->u, rec->v, rec->p) : FN(from3f)(m->albedo);
     return FN(dot)(out->d, rec->normal) > 0;
   }
   case RT_MAT_DIELECTRIC: {
@@ -501,19 +546,86 @@ static int FN(scatter)(const FN(World) *w, const rt_material *m, const FN(Ray) *
     }
     return 1;
   }
+  case RT_MAT_ISOTROPIC: /* rt_next_week/cuda/material.h:183-191 */
+    out->d = FN(random_in_unit_sphere)(rng);
+    *atten = FN(tex_value)(w->sc, m, rec->u, rec->v, rec->p);
+    return 1;
   default: /* diffuse_light: rt_next_week/cuda/material.h:163-167 */
     return 0;
   }
 }
 /* rt_next_week/cuda/material.h:34-36,169-172 */
-static V3 FN(emitted)(const rt_material *m, V3 p) {
-  if (m->type == RT_MAT_DIFFUSE_LIGHT) return FN(tex_value)(m, p);
+static V3 FN(emitted)(const rt_scene_desc *sc, const rt_material *m, REAL u, REAL v, V3 p) {
+  if (m->type == RT_MAT_DIFFUSE_LIGHT) return FN(tex_value)(sc, m, u, v, p);
   return FN(v)(0, 0, 0);
 }
 
 static int FN(world_hit)(FN(World) *w, const FN(RefBvh) *bvh, const FN(Ray) *r, REAL t_min, REAL t_max, FN(Hit) *rec) {
   if (bvh) return FN(ref_bvh_hit)(w, bvh, r, t_min, t_max, rec);
   return FN(list_hit)(w, r, t_min, t_max, rec);
+}
+
+/* constant_medium::hit — rt_next_week/cuda/constant_medium.h:36-73 over a convex boundary
+ * (sphere, or box under rotate_y + translate: box.h, hittable.h). Entry/exit of the whole line,
+ * entry clamped to 0 (:54-56), free-flight distance -1/density * log(rnd) (:60-61).
+ * Two deliberate deviations, both following the book text the reference tree was written from
+ * (RTNW "Volumes"): the scatter event must lie before the closest surface found (the reference
+ * ignores t_max, so a medium visited after a nearer surface overrides it, depending on BVH
+ * order), and the scattered ray leaves from the scatter point r.at(t) (the reference uses
+ * r.at(rec1.t), the boundary entry point, :66). */
+static int FN(medium_hit)(const FN(World) *w, int idx, const FN(Ray) *r, REAL t_max, FN(Hit) *h, FN(Rng) *rng) {
+  const rt_medium *m = &w->sc->media[idx];
+  REAL t1, t2;
+  if (m->shape == 0) {
+    V3 oc = FN(sub)(r->o, FN(from3f)(m->p0));
+    REAL radius = (REAL)m->p1[0];
+    REAL a = FN(len2)(r->d), hb = FN(dot)(oc, r->d), c = FN(len2)(oc) - radius * radius;
+    REAL disc = hb * hb - a * c;
+    if (!(disc > 0)) return 0;
+    t1 = (-hb - SQRT(disc)) / a;
+    t2 = (-hb + SQRT(disc)) / a;
+  } else {
+    /* translate::hit then rotate_y::hit move the ray into the box frame (hittable.h) */
+    V3 o = FN(sub)(r->o, FN(from3f)(m->offset)), d = r->d;
+    REAL sn = (REAL)m->sin_y, cs = (REAL)m->cos_y;
+    V3 ol = FN(v)(cs * o.x - sn * o.z, o.y, sn * o.x + cs * o.z);
+    V3 dl = FN(v)(cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z);
+    t1 = -INFINITY_R; t2 = INFINITY_R;
+    for (int a = 0; a < 3; a++) {
+      REAL oa = FN(comp)(ol, a), da = FN(comp)(dl, a), lo = (REAL)m->p0[a], hi = (REAL)m->p1[a];
+      if (da == 0) { if (oa < lo || oa > hi) return 0; continue; }
+      REAL ta = (lo - oa) / da, tb = (hi - oa) / da;
+      if (ta > tb) { REAL s_ = ta; ta = tb; tb = s_; }
+      if (ta > t1) t1 = ta;
+      if (tb < t2) t2 = tb;
+    }
+    if (!(t1 < t2)) return 0;
+  }
+  if (t1 < 0) t1 = 0;
+  REAL ray_length = FN(len)(r->d);
+  REAL inside = (t2 - t1) * ray_length;
+  REAL hit_distance = ((REAL)-1 / (REAL)m->density) * LOG(FN(rnd)(rng));
+  if (hit_distance > inside) return 0;
+  REAL t = t1 + hit_distance / ray_length;
+  if (!(t < t_max)) return 0;
+  h->t = t;
+  h->p = FN(at)(r, t);
+  h->normal = FN(v)(1, 0, 0); /* arbitrary (:69-70) */
+  h->front_face = 1;
+  h->u = h->v = 0;
+  h->material = m->material;
+  h->prim = RT_PRIM_ID(RT_PRIM_MEDIUM, idx);
+  return 1;
+}
+
+/* closest of the surfaces and the media (profile 2) */
+static int FN(scene_hit)(FN(World) *w, const FN(RefBvh) *bvh, const FN(Ray) *r, REAL t_min, FN(Hit) *rec, FN(Rng) *rng) {
+  int any = FN(world_hit)(w, bvh, r, t_min, INFINITY_R, rec);
+  REAL closest = any ? rec->t : INFINITY_R;
+  FN(Hit) tmp;
+  for (int i = 0; i < w->sc->n_media; i++)
+    if (FN(medium_hit)(w, i, r, closest, &tmp, rng)) { any = 1; closest = tmp.t; *rec = tmp; }
+  return any;
 }
 
 /* ray_color main.cpp:57-83 (profile 0, recursion unrolled forward: the product of
@@ -559,10 +671,10 @@ static V3 FN(ray_color)(FN(World) *w, const FN(RefBvh) *bvh, FN(Ray) r, FN(Rng) 
   for (i = 0; i < depth && i < 256; i++) {
     FN(Hit) rec;
     (*nseg)++;
-    if (FN(world_hit)(w, bvh, &r, t_min, INFINITY_R, &rec)) {
+    if (FN(scene_hit)(w, bvh, &r, t_min, &rec, rng)) {
       const rt_material *m = &sc->materials[rec.material];
       FN(Ray) sca; V3 att;
-      V3 em = FN(emitted)(m, rec.p);
+      V3 em = FN(emitted)(sc, m, rec.u, rec.v, rec.p);
       if (FN(scatter)(w, m, &r, &rec, &att, &sca, rng)) {
         emitted_rec[i] = em; atten_rec[i] = att; r = sca;
       } else {
@@ -759,6 +871,24 @@ int FN(scatter_one)(const rt_scene_desc *sc, int profile, int material, const do
   dir_out[0] = out.d.x; dir_out[1] = out.d.y; dir_out[2] = out.d.z;
   atten_out[0] = att.x; atten_out[1] = att.y; atten_out[2] = att.z;
   return ok;
+}
+
+/* texture value of a material at (u, v, p) through this restatement (texture parity tests) */
+void FN(tex_value_at)(const rt_scene_desc *sc, int material, int n, const double *uvp /*[n][5]*/, double *rgb /*[n][3]*/) {
+  for (int k = 0; k < n; k++) {
+    const double *q = uvp + 5 * k;
+    V3 c = FN(tex_value)(sc, &sc->materials[material], (REAL)q[0], (REAL)q[1], FN(v)((REAL)q[2], (REAL)q[3], (REAL)q[4]));
+    rgb[3 * k] = c.x; rgb[3 * k + 1] = c.y; rgb[3 * k + 2] = c.z;
+  }
+}
+
+/* sphere (u, v) of an outward unit normal — rt_next_week/cuda/sphere.h:28-40 */
+void FN(sphere_uv_at)(int n, const double *normal /*[n][3]*/, double *uv /*[n][2]*/) {
+  for (int k = 0; k < n; k++) {
+    REAL u, v;
+    FN(sphere_uv)(FN(v)((REAL)normal[3 * k], (REAL)normal[3 * k + 1], (REAL)normal[3 * k + 2]), &u, &v);
+    uv[2 * k] = u; uv[2 * k + 1] = v;
+  }
 }
 
 /* write_color color.h:14-28 (profile 0) / final.cu:91-95,227-229 (profiles 1, 2;

@@ -20,6 +20,7 @@ struct EmuScene {
   std::vector<float4> nodes;
   std::vector<int32_t> big, leaf_prims;
   std::vector<uint8_t> sph_is_big;
+  std::vector<DevImage> images;
   DevScene S;
   DevCamera cam;
   ShadeParams sp;
@@ -36,6 +37,14 @@ static void bind(EmuScene &E, const rt_scene_desc *sc) {
   S.n_nodes = (int)E.nodes.size() / 2; S.n_big = (int)E.big.size();
   S.n_spheres = sc->n_spheres; S.n_tris = sc->n_triangles; S.n_quads = sc->n_quads; S.n_mats = sc->n_materials;
   S.any_moving = E.F.any_moving;
+  E.images.resize((size_t)sc->n_images);
+  for (int i = 0; i < sc->n_images; i++) {
+    E.images[i].rgb = E.F.image_bytes.data() + E.F.image_offset[i];
+    E.images[i].width = sc->images[i].width; E.images[i].height = sc->images[i].height;
+  }
+  S.media = E.F.media.data(); S.perlin_vec = E.F.perlin_vec.data(); S.perlin_perm = E.F.perlin_perm.data();
+  S.images = E.images.data();
+  S.n_media = sc->n_media; S.n_perlin = sc->n_perlin; S.n_images = sc->n_images;
   const rt_camera &c = sc->camera;
   E.cam.origin = v3_from(c.origin); E.cam.llc = v3_from(c.lower_left_corner);
   E.cam.horizontal = v3_from(c.horizontal); E.cam.vertical = v3_from(c.vertical);
@@ -132,11 +141,15 @@ static void render_t(EmuScene *E, int W, int H, int spp_begin, int spp_count, ui
         int bounce = 0;
         npath++;
         for (;;) {
-          HitAcc h = trace_closest<PROFILE, GENERAL, true>(E->S, r, E->sp.t_min, INFINITY, &cnt);
+          HitAcc hm;
+          hm.t = INFINITY; hm.id = -1;
+          if (GENERAL && E->S.n_media) apply_media(E->S, r, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, k0, k1, hm);
+          HitAcc h = trace_closest<PROFILE, GENERAL, true>(E->S, r, E->sp.t_min, hm.t, &cnt);
+          if (h.id < 0) h = hm;
           nseg++;
           if (h.id < 0) { L = L + beta * miss_radiance(E->sp, r.d); break; }
           Philox4 qq = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, k0, k1);
-          bool cont = shade_hit<PROFILE, GENERAL>(E->S, E->sp, r, h, beta, L, qq);
+          bool cont = shade_hit<PROFILE, GENERAL, GENERAL>(E->S, E->sp, r, h, beta, L, qq);
           bounce++;
           if (!cont) break;
           if (bounce >= E->sp.max_depth) {
@@ -213,6 +226,17 @@ int emu_render(void *p, int W, int H, int spp_begin, int spp_count, uint64_t see
   else render_t<2, true>(E, W, H, spp_begin, spp_count, seed, j0, j1, sum, sumsq, stats);
   return 0;
 }
+}
+
+// material colour at a hit point through the device code (material_color -> texture_ext)
+extern "C" void emu_texture(void *p_, int material, int n, const int32_t *prim, const float *p /*[n][3]*/,
+                            const float *outward /*[n][3]*/, float *rgb /*[n][3]*/) {
+  EmuScene *E = (EmuScene *)p_;
+  const float4 m0 = E->S.mats[2 * material], m1 = E->S.mats[2 * material + 1];
+  for (int k = 0; k < n; k++) {
+    V3f c = material_color<true>(E->S, m0, m1, v3_from(p + 3 * k), v3_from(outward + 3 * k), prim[k]);
+    rgb[3 * k] = c.x; rgb[3 * k + 1] = c.y; rgb[3 * k + 2] = c.z;
+  }
 }
 
 #include "warpsim.inc"

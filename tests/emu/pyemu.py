@@ -67,6 +67,17 @@ class Emu:
                            cnt.ctypes.data)
         return ids, ts, cnt
 
+    def texture(self, material, prim, p, outward):
+        """material colour at hit points p of primitives `prim` with outward normals (device code)"""
+        p = np.ascontiguousarray(p, np.float32).reshape(-1, 3)
+        outward = np.ascontiguousarray(outward, np.float32).reshape(-1, 3)
+        prim = np.ascontiguousarray(np.broadcast_to(np.asarray(prim, np.int32), (len(p),)))
+        out = np.zeros((len(p), 3), np.float32)
+        self.lib.emu_texture.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]
+        self.lib.emu_texture(self.h, material, len(p), prim.ctypes.data, p.ctypes.data, outward.ctypes.data,
+                             out.ctypes.data)
+        return out
+
     def render(self, W, H, spp, spp_begin=0, seed=1984, rows=None, threads=None):
         from concurrent.futures import ThreadPoolExecutor
         s = np.zeros((H, W, 3), np.float64)

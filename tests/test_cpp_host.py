@@ -169,3 +169,107 @@ def test_cornell_box_boxes_and_rotations(host):
     n = t["normal"][0] / np.linalg.norm(t["normal"][0])
     np.testing.assert_allclose(n, [np.sin(np.deg2rad(15)), 0, np.cos(np.deg2rad(15))], atol=1e-5)
     np.testing.assert_allclose(np.array(cam.origin[:]), [278, 278, -800])
+
+
+def _host_extras():
+    L = C.CDLL(os.path.join(ROOT, "build", "librtx_host.so"))
+    n = np.zeros(3, np.int32)
+    dims = np.zeros(16, np.int32)
+    L.rtx_host_counts2.argtypes = [_vp, _vp]
+    L.rtx_host_get2.argtypes = [_vp, _vp, _vp]
+    L.rtx_host_counts2(n.ctypes.data, dims.ctypes.data)
+    media = np.zeros(n[0], D.MEDIUM_DT)
+    perlin = np.zeros(n[1], D.PERLIN_DT)
+    images = [np.zeros((dims[2 * i + 1], dims[2 * i], 3), np.uint8) for i in range(n[2])]
+    ptrs = (C.c_void_p * max(len(images), 1))(*[im.ctypes.data for im in images])
+    L.rtx_host_get2(media.ctypes.data, perlin.ctypes.data, C.addressof(ptrs))
+    return media, perlin, images
+
+
+def test_next_week_scenes_3_to_8_cpp_equals_python(host):
+    """noise_texture / image_texture / isotropic / constant_medium of include/rtx flatten to the
+    same description as the Python scenes (main.cu:212-383)."""
+    # 4: two perlin spheres — two lambertians sharing one noise texture -> one table
+    s, t, q, m, cam, accel = host(4, seed=3)
+    media, perlin, images = _host_extras()
+    ref = scenes.two_perlin_spheres(600, 400)
+    assert len(s) == 2 and len(m) == 2 and len(perlin) == 1 and len(media) == 0 and not images
+    assert np.all(m["texture"] == D.RT_TEX_NOISE) and np.all(m["albedo2"][:, 0] == 4.0) and np.all(m["albedo2"][:, 1] == 0.0)
+    np.testing.assert_array_equal(s["center0"], ref.spheres["center0"])
+    for name in ("perm_x", "perm_y", "perm_z"):
+        assert sorted(perlin[name][0].tolist()) == list(range(256))
+    assert np.abs(perlin["ranvec"]).max() <= 1.0 and perlin["ranvec"].std() > 0.4
+    # 5: earth — the image bytes travel intact
+    s, t, q, m, cam, accel = host(5)
+    media, perlin, images = _host_extras()
+    assert len(images) == 1 and images[0].shape == (32, 64, 3) and m["texture"][0] == D.RT_TEX_IMAGE
+    assert images[0].std() > 10  # not blank
+    # 6: simple_light
+    s, t, q, m, cam, accel = host(6)
+    ref = scenes.simple_light(600, 400)
+    assert len(s) == 3 and len(q) == 1
+    np.testing.assert_array_equal(m[s["material"]]["type"], ref.materials[ref.spheres["material"]]["type"])
+    np.testing.assert_array_equal(m[q["material"]]["albedo"], [[4, 4, 4]])
+    np.testing.assert_allclose(np.array(cam.origin[:]), [26, 3, 6])
+    # 7: cornell_smoke — rotated + translated boxes become oriented media
+    s, t, q, m, cam, accel = host(7, aspect=1.0)
+    media, perlin, images = _host_extras()
+    ref = scenes.cornell_smoke(600, 600)
+    assert len(q) == 6 and len(t) == 0 and len(media) == 2
+    for f in ("shape", "p0", "p1", "offset", "density"):
+        np.testing.assert_array_equal(media[f], ref.media[f])
+    np.testing.assert_allclose(media["sin_y"], ref.media["sin_y"], atol=1e-7)
+    np.testing.assert_allclose(media["cos_y"], ref.media["cos_y"], atol=1e-7)
+    np.testing.assert_array_equal(m[media["material"]]["type"], [D.RT_MAT_ISOTROPIC] * 2)
+    np.testing.assert_array_equal(m[media["material"]]["albedo"], [[0, 0, 0], [1, 1, 1]])
+    # 8: the final scene — counts and the fixed objects
+    s, t, q, m, cam, accel = host(8, seed=5, aspect=1.0)
+    media, perlin, images = _host_extras()
+    ref = scenes.next_week_final(800, 800)
+    assert len(q) == 400 * 6 + 1 == len(ref.quads) and len(s) == 6 + 1000 == len(ref.spheres)
+    assert len(media) == 2 and len(perlin) == 1 and len(images) == 1
+    np.testing.assert_array_equal(s["center0"][:6], ref.spheres["center0"][:6])
+    np.testing.assert_array_equal(s["radius"][:6], ref.spheres["radius"][:6])
+    assert s["moving"][0] == 1 and tuple(s["center1"][0]) == (430, 400, 200)
+    np.testing.assert_array_equal(media["p0"], ref.media["p0"])
+    np.testing.assert_array_equal(media["p1"], ref.media["p1"])
+    np.testing.assert_allclose(media["density"], [0.2, 0.0001])
+    # the cluster: rotated by 15 degrees and moved to (-100, 270, 395): inside the transformed cube
+    c = s["center0"][6:].astype(np.float64) - [-100, 270, 395]
+    ang = np.deg2rad(15)
+    local = np.stack([np.cos(ang) * c[:, 0] - np.sin(ang) * c[:, 2], c[:, 1], np.sin(ang) * c[:, 0] + np.cos(ang) * c[:, 2]], 1)
+    assert local.min() > -1e-3 and local.max() < 165 + 1e-3
+    # boxes: heights in [1, 101), footprint 100 x 100
+    tops = q["k"][(q["axis"] == 1)][:-1].reshape(400, 2)[:, 0]
+    assert tops.min() >= 1 and tops.max() < 101
+
+
+def test_constant_medium_rejects_unsupported_boundaries(tmp_path):
+    src = tmp_path / "bad.cpp"
+    src.write_text('#include "constant_medium.h"\n#include "aarect.h"\nint main() {\n'
+                   '  auto m = new lambertian(color(1, 1, 1));\n'
+                   '  hittable *r = new xy_rect(0, 1, 0, 1, 0, m);\n'
+                   '  hittable *cm = new constant_medium(r, 0.1, color(1, 1, 1));\n'
+                   '  flat_scene fs;\n'
+                   '  try { cm->flatten(fs, transform()); } catch (const std::invalid_argument &) { return 0; }\n'
+                   '  return 1;\n}\n')
+    exe = tmp_path / "bad"
+    subprocess.check_call(["g++", "-std=c++17", "-I", os.path.join(ROOT, "include", "rtx"), "-I",
+                           os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+@pytest.mark.gpu
+def test_render_cli_final_scene(tmp_path):
+    """the rt_next_week tree's default scene through the C++ host program"""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "apps"), "-s"])
+    out = tmp_path / "final.ppm"
+    with open(out, "wb") as f:
+        p = subprocess.run([os.path.join(ROOT, "build", "render_cli"), "--scene", "final", "--width", "120", "--height",
+                            "120", "--spp", "64", "--binary"], stdout=f, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    assert "2 media" in p.stderr and "1006 spheres" in p.stderr
+    raw = out.read_bytes()
+    assert raw.startswith(b"P6\n120 120\n255\n")
+    img = np.frombuffer(raw[len(b"P6\n120 120\n255\n"):], np.uint8).reshape(120, 120, 3)
+    assert 20 < img.mean() < 200 and img.std() > 10

@@ -20,7 +20,15 @@ CONFIGS = [
      lambda: scenes.obj_room(width=800, height=800, subdivisions=3), 800, 800, 1500),
     ("C4 next_week 1200x800 1000spp", lambda: scenes.next_week(1200, 800), 1200, 800, 1000),
     ("C5 weekend 3840x2160 5000spp", lambda: scenes.weekend(3840, 2160), 3840, 2160, 5000),
+    # rt_next_week/cuda/main.cu:453-459,507-510: the tree's default scene at its default size
+    ("N8 next_week_final 800x800 5000spp", lambda: scenes.next_week_final(800, 800), 800, 800, 5000),
+    ("N7 cornell_smoke 600x600 1000spp", lambda: scenes.cornell_smoke(600, 600), 600, 600, 1000),
+    ("N6 cornell_box 600x600 1000spp", lambda: scenes.cornell_box(600, 600), 600, 600, 1000),
+    ("N3 two_perlin_spheres 1200x800 500spp", lambda: scenes.two_perlin_spheres(1200, 800), 1200, 800, 500),
 ]
+only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+if only:
+    CONFIGS = [c for c in CONFIGS if any(c[0].startswith(o) for o in only[0].split(","))]
 out = []
 for name, mk, W, H, spp in CONFIGS:
     if quick:
