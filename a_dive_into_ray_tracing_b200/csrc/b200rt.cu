@@ -312,6 +312,7 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   ctx->ext = sc->n_media > 0;
   for (int i = 0; i < sc->n_materials; i++)
     if (sc->materials[i].texture >= RT_TEX_NOISE || sc->materials[i].type == RT_MAT_ISOTROPIC) ctx->ext = true;
+  if (const char *e = getenv("B200RT_EXT")) ctx->ext = ctx->ext || (ctx->general && atoi(e) != 0); // measurement knob
 
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, nm = sc->n_materials;

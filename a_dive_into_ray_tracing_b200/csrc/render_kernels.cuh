@@ -177,7 +177,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     }
     // participating media: a sampled scatter event becomes the initial closest hit
     if (EXT && S.n_media)
-      apply_media(S, r, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, P.seed_lo, P.seed_hi, h);
+      h = apply_media(S.media, S.n_media, r.o, r.d, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, P.seed_lo,
+                      P.seed_hi, h);
     node = 0;
     // sign BITS of 1/d (covers d = -0): which quadrant copy (own child order; in shared memory also
     // pre-swapped planes) this ray walks

@@ -106,12 +106,16 @@ RT_COLD float perlin_noise(const float4 *__restrict__ vec, const uint8_t *__rest
 
 // Textures that need more than the hit point's checker parity: noise (perlin::turb, depth 7,
 // perlin.h:58-70) and image lookups with the primitive's (u, v).
-RT_COLD V3f texture_ext(const DevScene &S, float4 m0, float4 m1, V3f p, V3f outward, int32_t prim) {
+// (Everything is passed and returned BY VALUE: handing the kernel's DevScene / hit record to an
+// out-of-line function by reference would pin them in local memory for the whole kernel.)
+RT_COLD V3f texture_ext(const float4 *__restrict__ perlin_vec, const uint8_t *__restrict__ perlin_perm,
+                        const DevImage *__restrict__ images, const float4 *__restrict__ quads, float4 m0, float4 m1,
+                        V3f p, V3f outward, int32_t prim) {
   const int tex = (RT_F2I(m0.w) >> 8) & 0xff;
   if (tex == RT_TEX_NOISE) {
     const int table = (int)m1.y;
-    const float4 *vec = S.perlin_vec + 256 * table;
-    const uint8_t *perm = S.perlin_perm + 768 * table;
+    const float4 *vec = perlin_vec + 256 * table;
+    const uint8_t *perm = perlin_perm + 768 * table;
     const float scale = m1.x;
     V3f q = scale * p;
     float accum = 0.0f, weight = 1.0f;
@@ -133,13 +137,13 @@ RT_COLD V3f texture_ext(const DevScene &S, float4 m0, float4 m1, V3f p, V3f outw
     u = phi / (2.0f * pi);
     v = theta / pi;
   } else if (type == RT_PRIM_QUAD) { // aarect.h:52-53
-    const float4 q0 = S.quad[2 * idx], q1 = S.quad[2 * idx + 1];
+    const float4 q0 = quads[2 * idx], q1 = quads[2 * idx + 1];
     const int ax = RT_F2I(q0.w);
     const float a = ax == 0 ? p.y : p.x, b = ax == 2 ? p.y : p.z;
     u = (a - q0.y) / (q0.z - q0.y);
     v = (b - q1.x) / (q1.y - q1.x);
   }
-  const DevImage im = S.images[(int)m1.x];
+  const DevImage im = images[(int)m1.x];
   u = RT_FMIN(RT_FMAX(u, 0.0f), 1.0f);
   v = 1.0f - RT_FMIN(RT_FMAX(v, 0.0f), 1.0f);
   int i = (int)(u * (float)im.width), j = (int)(v * (float)im.height);
@@ -160,7 +164,7 @@ RT_HD V3f material_color(const DevScene &S, float4 m0, float4 m1, V3f p, V3f out
     float sines = rt_fast_sin(10.0f * p.x) * rt_fast_sin(10.0f * p.y) * rt_fast_sin(10.0f * p.z);
     if (sines < 0.0f) return xyz(m1); // odd
   } else if (EXT && tex >= RT_TEX_NOISE) {
-    return texture_ext(S, m0, m1, p, outward, prim);
+    return texture_ext(S.perlin_vec, S.perlin_perm, S.images, S.quad, m0, m1, p, outward, prim);
   }
   return xyz(m0);
 }
@@ -174,29 +178,29 @@ RT_HD V3f material_color(const DevScene &S, float4 m0, float4 m1, V3f p, V3f out
 // must lie before the closest surface (the reference ignores t_max) and scattering continues
 // from the scatter point (the reference restarts at the boundary entry point, :66).
 // Random numbers: Philox stream 2 + m/4 of (pixel, sample, segment).
-RT_COLD void apply_media(const DevScene &S, const Ray &r, uint32_t pixel, uint32_t smp, uint32_t segment,
-                         uint32_t seed_lo, uint32_t seed_hi, HitAcc &h) {
-  const float len = RT_SQRT(dot(r.d, r.d));
+RT_COLD HitAcc apply_media(const float4 *__restrict__ media, int n_media, V3f ro, V3f rd, uint32_t pixel, uint32_t smp,
+                           uint32_t segment, uint32_t seed_lo, uint32_t seed_hi, HitAcc h) {
+  const float len = RT_SQRT(dot(rd, rd));
   Philox4 q = {0u, 0u, 0u, 0u};
-  for (int m = 0; m < S.n_media; m++) {
+  for (int m = 0; m < n_media; m++) {
     if ((m & 3) == 0) q = philox4x32_10(pixel, smp, segment, 2u + (uint32_t)(m >> 2), seed_lo, seed_hi);
     const uint32_t word = (m & 3) == 0 ? q.x : ((m & 3) == 1 ? q.y : ((m & 3) == 2 ? q.z : q.w));
-    const float4 a0 = S.media[4 * m], a1 = S.media[4 * m + 1];
+    const float4 a0 = media[4 * m], a1 = media[4 * m + 1];
     float t1, t2;
     if (RT_F2I(a0.w) == 0) {
-      const V3f oc = r.o - xyz(a0);
-      const float a = dot(r.d, r.d), hb = dot(oc, r.d), c = RT_FMA(-a1.x, a1.x, dot(oc, oc));
+      const V3f oc = ro - xyz(a0);
+      const float a = dot(rd, rd), hb = dot(oc, rd), c = RT_FMA(-a1.x, a1.x, dot(oc, oc));
       const float disc = RT_FMA(hb, hb, -a * c);
       if (!(disc > 0.0f)) continue;
       const float sq = RT_SQRT(disc);
       t1 = (-hb - sq) / a;
       t2 = (-hb + sq) / a;
     } else {
-      const float4 a2 = S.media[4 * m + 2], a3 = S.media[4 * m + 3];
-      const V3f o = r.o - xyz(a2);
+      const float4 a2 = media[4 * m + 2], a3 = media[4 * m + 3];
+      const V3f o = ro - xyz(a2);
       const float sn = a3.x, cs = a3.y;
       const float ol[3] = {cs * o.x - sn * o.z, o.y, sn * o.x + cs * o.z};
-      const float dl[3] = {cs * r.d.x - sn * r.d.z, r.d.y, sn * r.d.x + cs * r.d.z};
+      const float dl[3] = {cs * rd.x - sn * rd.z, rd.y, sn * rd.x + cs * rd.z};
       const float lo[3] = {a0.x, a0.y, a0.z}, hi[3] = {a1.x, a1.y, a1.z};
       t1 = -INFINITY; t2 = INFINITY;
       bool miss = false;
@@ -216,6 +220,7 @@ RT_COLD void apply_media(const DevScene &S, const Ray &r, uint32_t pixel, uint32
     const float t = t1 + hit_distance / len;
     if (t < h.t) { h.t = t; h.id = RT_PRIM_ID(RT_PRIM_MEDIUM, m); }
   }
+  return h;
 }
 
 // Surface interaction at an accepted hit. Updates the ray (origin = hit point,

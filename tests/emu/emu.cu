@@ -143,7 +143,8 @@ static void render_t(EmuScene *E, int W, int H, int spp_begin, int spp_count, ui
         for (;;) {
           HitAcc hm;
           hm.t = INFINITY; hm.id = -1;
-          if (GENERAL && E->S.n_media) apply_media(E->S, r, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, k0, k1, hm);
+          if (GENERAL && E->S.n_media)
+            hm = apply_media(E->S.media, E->S.n_media, r.o, r.d, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, k0, k1, hm);
           HitAcc h = trace_closest<PROFILE, GENERAL, true>(E->S, r, E->sp.t_min, hm.t, &cnt);
           if (h.id < 0) h = hm;
           nseg++;
