@@ -743,6 +743,13 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;
   if (scene_bytes + 3 * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
   if (const char *e = getenv("B200RT_SMEM")) smem = std::min(smem, atoi(e)); // tuning knob
+  if (smem == 0) {
+    // Global-memory node path: the four quadrant-ordered copies pay while they stay cache
+    // resident (measured: neutral up to 164 k nodes, one copy +14 % at 655 k nodes = 84 MB of copies).
+    bool one_copy = 4 * (size_t)P.b_nodes > ((size_t)48 << 20);
+    if (const char *e = getenv("B200RT_ONECOPY")) one_copy = atoi(e) != 0; // measurement knob
+    if (one_copy) P.S.node_stride = 0;
+  }
   const size_t smem_bytes = acc_bytes + (smem ? scene_bytes : 0) + (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
   render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext);
