@@ -615,3 +615,45 @@ def next_week_final(width=800, height=800, seed=1984, image=None):
                images=[procedural_earth() if image is None else image], name="next_week_final")
     sc.background = (0.0, 0.0, 0.0)
     return _nw_camera(sc, (478, 278, -600), (278, 278, 0), 40.0, width, height)
+
+
+# ------------------------------------------------------------------ text scene files
+def load_scene_file(path, width=None, height=None):
+    """Parse a text scene file (format: include/rtx/scene_file.h) with the C++ host layer
+    (build/librtx_host.so — g++ only, no CUDA) and return the flattened Scene plus the file's
+    default (width, height, spp)."""
+    import ctypes as C
+    import subprocess
+
+    from .ctypes_defs import RtCamera
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-C", os.path.join(root, "apps"), "-s", "../build/librtx_host.so"])
+    L = C.CDLL(os.path.join(root, "build", "librtx_host.so"))
+    vp = C.c_void_p
+    L.rtx_host_load_scene_file.argtypes = [C.c_char_p, C.c_int, C.c_int, vp, vp, C.c_char_p, C.c_int]
+    L.rtx_host_counts.argtypes = [vp]
+    L.rtx_host_get.argtypes = [vp, vp, vp, vp, vp]
+    L.rtx_host_counts2.argtypes = [vp, vp]
+    L.rtx_host_get2.argtypes = [vp, vp, vp]
+    opts = np.zeros(8, np.int32)
+    fopts = np.zeros(4, np.float32)
+    err = C.create_string_buffer(512)
+    if L.rtx_host_load_scene_file(os.fsencode(path), width or 0, height or 0, opts.ctypes.data, fopts.ctypes.data, err, 512):
+        raise ValueError(err.value.decode())
+    n = np.zeros(5, np.int32)
+    L.rtx_host_counts(n.ctypes.data)
+    sph, tri = np.zeros(n[0], SPHERE_DT), np.zeros(n[1], TRIANGLE_DT)
+    quad, mats = np.zeros(n[2], QUAD_DT), np.zeros(n[3], MATERIAL_DT)
+    cam = RtCamera()
+    L.rtx_host_get(sph.ctypes.data, tri.ctypes.data, quad.ctypes.data, mats.ctypes.data, C.addressof(cam))
+    n2 = np.zeros(3, np.int32)
+    dims = np.zeros(64, np.int32)
+    L.rtx_host_counts2(n2.ctypes.data, dims.ctypes.data)
+    media, perlin = np.zeros(n2[0], MEDIUM_DT), np.zeros(n2[1], PERLIN_DT)
+    images = [np.zeros((dims[2 * i + 1], dims[2 * i], 3), np.uint8) for i in range(n2[2])]
+    ptrs = (C.c_void_p * max(len(images), 1))(*[im.ctypes.data for im in images])
+    L.rtx_host_get2(media.ctypes.data, perlin.ctypes.data, C.addressof(ptrs))
+    sc = Scene(spheres=sph, triangles=tri, quads=quad, materials=mats, camera=cam, background=tuple(fopts[:3]),
+               sky_gradient=int(opts[1]), t_min=float(fopts[3]), max_depth=int(opts[2]), flags=int(opts[3]),
+               name=os.path.basename(path), profile=int(opts[0]), media=media, perlin=perlin, images=images)
+    return sc, (int(opts[4]), int(opts[5]), int(opts[6]))

@@ -2,6 +2,7 @@
 // scene with the rtx classes, flatten it, hand the flattened arrays back. No CUDA here.
 #include <cstring>
 #include "scenes.h"
+#include "scene_file.h"
 
 static flat_scene g_flat;
 static rt_camera g_cam;
@@ -74,4 +75,27 @@ void rtx_host_get(rt_sphere *s, rt_triangle *t, rt_quad *q, rt_material *m, rt_c
 
 extern "C" int rtx_host_write_png(const char *path, const unsigned char *rgb, int w, int h) {
   return rtx::write_png_file(path, rgb, w, h) ? 0 : 1;
+}
+
+// Parse + flatten a text scene file (include/rtx/scene_file.h). opts: profile, sky_gradient, max_depth,
+// flags, width, height, spp; fopts: background rgb, t_min. Returns 0, or 1 with the message in err.
+extern "C" int rtx_host_load_scene_file(const char *path, int width, int height, int *opts, float *fopts, char *err,
+                                        int errcap) {
+  try {
+    scene_file sf = load_scene_file(path);
+    g_flat = flat_scene();
+    static scene_file keep; // the flattened image pointers refer to textures owned by the scene
+    keep = sf;
+    keep.world.flatten(g_flat, transform());
+    const int w = width > 0 ? width : keep.width, h = height > 0 ? height : keep.height;
+    g_cam = keep.make_camera(w, h).describe();
+    opts[0] = keep.opt.profile; opts[1] = keep.opt.sky_gradient ? 1 : 0; opts[2] = keep.opt.max_depth;
+    opts[3] = (int)keep.opt.flags; opts[4] = w; opts[5] = h; opts[6] = keep.spp;
+    for (int a = 0; a < 3; a++) fopts[a] = (float)keep.opt.background[a];
+    fopts[3] = (float)keep.opt.t_min;
+    return 0;
+  } catch (const std::exception &e) {
+    snprintf(err, errcap, "%s", e.what());
+    return 1;
+  }
 }

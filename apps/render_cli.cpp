@@ -5,16 +5,19 @@
 //   render_cli [--scene weekend|next_week|perlin|earth|light|cornell|smoke|final|obj] [--obj file.obj]
 //              [--image map.ppm] [--width W] [--height H] [--spp N] [--seed S] [--device D]
 //              [--binary | --png]   (image on stdout; scene numbers 1-8 of rt_next_week/cuda/main.cu:402-459)
+//   render_cli --scene-file FILE.scene [--width W --height H --spp N ...]   (include/rtx/scene_file.h)
 #include <chrono>
 #include <cstring>
 #include <iostream>
 
 #include "scenes.h"
+#include "scene_file.h"
 
 int main(int argc, char **argv) {
-  std::string scene = "weekend", obj, image;
-  int W = 1200, H = 800, spp = 500, device = 0;
+  std::string scene = "weekend", obj, image, scene_path;
+  int W = 0, H = 0, spp = 0, device = 0;
   unsigned long long seed = 1984;
+  bool have_seed = false;
   bool binary = false, png = false;
   for (int i = 1; i < argc; i++) {
     auto is = [&](const char *f) { return !strcmp(argv[i], f) && i + 1 < argc; };
@@ -24,7 +27,8 @@ int main(int argc, char **argv) {
     else if (is("--width")) W = atoi(argv[++i]);
     else if (is("--height")) H = atoi(argv[++i]);
     else if (is("--spp")) spp = atoi(argv[++i]);
-    else if (is("--seed")) seed = strtoull(argv[++i], nullptr, 10);
+    else if (is("--seed")) { seed = strtoull(argv[++i], nullptr, 10); have_seed = true; }
+    else if (is("--scene-file")) scene_path = argv[++i];
     else if (is("--device")) device = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--binary")) binary = true;
     else if (!strcmp(argv[i], "--png")) png = true;
@@ -32,13 +36,28 @@ int main(int argc, char **argv) {
   }
   try {
     render_options opt;
+    scene_file sf;
+    if (!scene_path.empty()) {
+      sf = load_scene_file(scene_path);
+      opt = sf.opt;
+      if (!W) W = sf.width;
+      if (!H) H = sf.height;
+      if (!spp) spp = sf.spp;
+      if (!have_seed) seed = sf.opt.seed;
+      scene = "file";
+    }
+    if (!W) W = 1200;
+    if (!H) H = 800;
+    if (!spp) spp = 500;
     opt.device = device;
     opt.seed = seed;
     const double aspect = double(W) / H;
     hittable_list world;
     hittable *root = nullptr;
     std::vector<hittable *> d_list(22 * 22 + 1 + 3 + 1);
-    if (scene == "weekend") { // main.cpp:292-311
+    if (scene == "file") {
+      root = &sf.world;
+    } else if (scene == "weekend") { // main.cpp:292-311
       world = random_scene();
       root = &world;
     } else if (scene == "next_week") { // main.cu:402-407,462-465
@@ -84,7 +103,8 @@ int main(int argc, char **argv) {
     auto nw_cam = [&](point3 from, point3 at, double vfov) {
       return camera(from, at, vec3(0, 1, 0), vfov, aspect, 0.0, (from - at).length(), 0.0, 1.0, true);
     };
-    camera cam = scene == "weekend"
+    camera cam = scene == "file" ? sf.make_camera(W, H)
+                 : scene == "weekend"
                      ? camera(point3(13, 2, 3), point3(0, 0, 0), vec3(0, 1, 0), 20, aspect, 0.1, 10.0)
                  : (scene == "cornell" || scene == "smoke") ? nw_cam(point3(278, 278, -800), point3(278, 278, 0), 40)
                  : scene == "perlin" ? nw_cam(point3(13, 2, 3), point3(0, 0, 0), 20)

@@ -127,25 +127,44 @@ public:
 // (for i = n-1..1: swap p[i], p[random_int(n)]), drawn from the host generator.
 class perlin {
 public:
-  perlin() {
+  perlin() { fill([]() { return random_double(); }); }
+  // tables from a private generator (SplitMix64): independent of the global rand() stream
+  explicit perlin(uint64_t seed) {
+    uint64_t state = seed;
+    fill([&state]() {
+      uint64_t z = (state += 0x9E3779B97F4A7C15ull);
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+      z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+      z ^= z >> 31;
+      return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+    });
+  }
+  rt_perlin table;
+
+private:
+  template <class Rnd> void fill(Rnd rnd) {
     for (int i = 0; i < 256; i++)
-      for (int a = 0; a < 3; a++) table.ranvec[i][a] = (float)random_double(-1, 1);
+      for (int a = 0; a < 3; a++) table.ranvec[i][a] = (float)(-1.0 + 2.0 * rnd());
     int32_t *perms[3] = {table.perm_x, table.perm_y, table.perm_z};
     for (int32_t *p : perms) {
       for (int i = 0; i < 256; i++) p[i] = i;
       for (int i = 255; i > 0; i--) {
-        int target = (int)(random_double() * 256.0);
+        int target = (int)(rnd() * 256.0);
         if (target > 255) target = 255;
         int32_t tmp = p[i]; p[i] = p[target]; p[target] = tmp;
       }
     }
   }
-  rt_perlin table;
 };
 class noise_texture : public abstract_texture {
 public:
   noise_texture() {}
   noise_texture(double sc, void * /*curandState*, unused*/ = nullptr) : scale(sc) {}
+  static shared_ptr<noise_texture> seeded(double sc, uint64_t seed) {
+    auto t = make_shared<noise_texture>(sc);
+    t->noise = perlin(seed);
+    return t;
+  }
   bool describe(rt_material &m, bool second, flat_scene &fs) const override;
   perlin noise;
   double scale = 1;

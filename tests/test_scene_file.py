@@ -1,0 +1,127 @@
+"""Text scene files (include/rtx/scene_file.h; SURVEY.md §8f rank 3 "scene file instead of
+compiled-in scenes"): the C++ parser builds the reference's own classes, which flatten to the same
+description as the hand-written scenes; errors carry file:line; the device code renders a scene
+using every statement the same as the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from a_dive_into_ray_tracing_b200 import ctypes_defs as D
+from a_dive_into_ray_tracing_b200 import scenes
+from tests import stats_util as SU
+from tests.emu.pyemu import Emu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCENES = os.path.join(ROOT, "scenes")
+
+
+def test_cornell_smoke_file_equals_compiled_scene():
+    sc, (w, h, spp) = scenes.load_scene_file(os.path.join(SCENES, "cornell_smoke.scene"))
+    ref = scenes.cornell_smoke(600, 600)
+    assert (w, h, spp) == (600, 600, 200) and sc.profile == 2 and sc.sky_gradient == 0
+    for f in ("axis", "a0", "a1", "b0", "b1", "k"):
+        np.testing.assert_array_equal(sc.quads[f], ref.quads[f])
+    np.testing.assert_array_equal(sc.materials[sc.quads["material"]]["albedo"], ref.materials[ref.quads["material"]]["albedo"])
+    for f in ("shape", "p0", "p1", "offset", "density"):
+        np.testing.assert_array_equal(sc.media[f], ref.media[f])
+    np.testing.assert_allclose(sc.media["sin_y"], ref.media["sin_y"], atol=1e-7)
+    np.testing.assert_array_equal(sc.materials[sc.media["material"]]["albedo"], [[0, 0, 0], [1, 1, 1]])
+    for f in ("origin", "lower_left_corner", "horizontal", "vertical"):
+        np.testing.assert_allclose(np.array(getattr(sc.camera, f)[:]), np.array(getattr(ref.camera, f)[:]), rtol=1e-6)
+
+
+def test_weekend_profile_file_and_camera_override():
+    sc, dims = scenes.load_scene_file(os.path.join(SCENES, "three_spheres.scene"))
+    assert sc.profile == 0 and sc.sky_gradient == 1 and dims == (400, 225, 100)
+    np.testing.assert_array_equal(sc.spheres["radius"], np.array([100, 0.5, 0.5, -0.45, 0.5], np.float32))
+    assert sc.spheres["material"][2] == sc.spheres["material"][3]  # the two glass spheres share one material
+    assert len(sc.materials) == 4
+    ref = D.camera_from_lookat((-2, 2, 1), (0, 0, -1), (0, 1, 0), 20.0, 400 / 225, 0.1, 3.4, dtype=np.float64)
+    for f in ("origin", "lower_left_corner", "horizontal", "vertical", "u", "v"):
+        np.testing.assert_array_equal(np.array(getattr(sc.camera, f)[:]), np.array(getattr(ref, f)[:]))
+    # a caller-chosen frame changes the aspect ratio of the camera
+    sc2, dims2 = scenes.load_scene_file(os.path.join(SCENES, "three_spheres.scene"), width=300, height=300)
+    assert dims2[:2] == (300, 300)
+    assert abs(np.linalg.norm(sc2.camera.horizontal[:]) / np.linalg.norm(sc2.camera.vertical[:]) - 1.0) < 1e-6
+
+
+def test_obj_and_image_statements(tmp_path):
+    obj = tmp_path / "mesh.obj"
+    scenes.make_blob_mesh(str(obj), subdivisions=1)
+    img = scenes.procedural_earth(16, 8)
+    with open(tmp_path / "map.ppm", "wb") as f:
+        f.write(b"P6\n# a comment\n16 8\n255\n" + img.tobytes())
+    (tmp_path / "s.scene").write_text(
+        "profile next_week\nimage 64 64 4\ncamera lookfrom 0 0 9 lookat 0 0 0 vfov 40\nbackground 0.5 0.5 0.5\n"
+        "flags flip_normals depth_background\ntmin 0.00001\n"
+        "material gold metal 1 0.84 0 0.5\nmaterial map lambertian image map.ppm\n"
+        "obj mesh.obj gold scale 2.5 rotate_y 30 translate 0 1.5 0\nsphere 3 0 0 1 map\n")
+    sc, _ = scenes.load_scene_file(str(tmp_path / "s.scene"))
+    ntri = len(scenes.read_obj_triangles(str(obj))[0])
+    assert len(sc.triangles) == ntri and len(sc.images) == 1
+    np.testing.assert_array_equal(sc.images[0], img)
+    assert sc.flags == D.RT_FLAG_FLIP_NORMALS | D.RT_FLAG_DEPTH_BACKGROUND and abs(sc.t_min - 1e-5) < 1e-12
+    # the same placement as the compiled obj_room scene: scale 2.5, rotate 30 degrees, lift 1.5
+    ref = scenes.obj_room(str(obj), 64, 64)
+    np.testing.assert_allclose(sc.triangles["v0"], ref.triangles["v0"][:ntri], atol=2e-6)
+    np.testing.assert_allclose(sc.triangles["normal"], ref.triangles["normal"][:ntri], atol=2e-5)
+
+
+@pytest.mark.parametrize("text,needle", [
+    ("camera lookfrom 0 0 1 lookat 0 0 0 vfov 40\nsphere 0 0 0 1 nope\n", ":2: unknown material 'nope'"),
+    ("camera lookfrom 0 0 1 lookat 0 0 0 vfov 40\nsphere 0 0 zero 1 m\n", ":2: expected a number"),
+    ("camera lookfrom 0 0 1 lookat 0 0 0 vfov 40\nteapot 1 2 3\n", ":2: unknown statement 'teapot'"),
+    ("material m lambertian 1 1 1\nsphere 0 0 0 1 m\n", "no camera statement"),
+    ("camera lookfrom 0 0 1 vfov 40\n", ":1: camera needs lookfrom, lookat and vfov"),
+    ("camera lookfrom 0 0 1 lookat 0 0 0 vfov 40\nmaterial m metal 1 1 1\n", ":2: missing fuzz"),
+    ("camera lookfrom 0 0 1 lookat 0 0 0 vfov 40\nmaterial m lambertian 1 1 1\nsphere 0 0 0 1 m extra\n", ":3: unexpected 'extra'"),
+    ("camera lookfrom 0 0 1 lookat 0 0 0 vfov 40\nmedium sphere 0 0 0 1 0 1 1 1\n", ":2: medium density must be positive"),
+    ("camera lookfrom 0 0 1 lookat 0 0 0 vfov 40\nmaterial i lambertian image missing.ppm\n", ":2: cannot read image"),
+])
+def test_errors_name_file_and_line(tmp_path, text, needle):
+    p = tmp_path / "bad.scene"
+    p.write_text(text)
+    with pytest.raises(ValueError) as e:
+        scenes.load_scene_file(str(p))
+    assert needle in str(e.value) and "bad.scene" in str(e.value)
+
+
+def test_showcase_scene_device_code_vs_oracle(l1_32):
+    """every statement kind in one scene: emulated device code vs the restatement"""
+    W, H, spp = 48, 30, 128
+    sc, _ = scenes.load_scene_file(os.path.join(SCENES, "showcase.scene"), W, H)
+    assert len(sc.media) == 2 and len(sc.perlin) == 1 and sc.spheres["moving"].sum() == 1
+    s, s2, st = Emu(sc, quality=1).render(W, H, spp, seed=7)
+    r, r2, nseg = l1_32.render_parallel(sc, 2, W, H, spp, seed=5)
+    mu_a, var_a = SU.mean_var(s, s2, spp)
+    mu_b, var_b = SU.mean_var(r, r2, spp)
+    ok, d, b = SU.three_sigma_check(mu_a, var_a, spp, mu_b, var_b, spp)
+    assert ok, (d, b)
+    z = SU.zscores(mu_a, var_a, spp, mu_b, var_b, spp)
+    assert abs(z.mean()) < 0.15 and 0.8 < z.std() < 1.25, (z.mean(), z.std())
+
+
+@pytest.mark.gpu
+def test_render_cli_scene_file_equals_python_binding(tmp_path):
+    """render_cli --scene-file == loading the same file through the Python binding (same seed)"""
+    from a_dive_into_ray_tracing_b200 import capi
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "apps"), "-s"])
+    path = os.path.join(SCENES, "showcase.scene")
+    W, H, spp = 96, 60, 16
+    out = tmp_path / "o.ppm"
+    with open(out, "wb") as f:
+        p = subprocess.run([os.path.join(ROOT, "build", "render_cli"), "--scene-file", path, "--width", str(W), "--height",
+                            str(H), "--spp", str(spp), "--binary"], stdout=f, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert p.returncode == 0, p.stderr
+    raw = out.read_bytes()
+    head = b"P6\n%d %d\n255\n" % (W, H)
+    img = np.frombuffer(raw[len(head):], np.uint8).reshape(H, W, 3)
+    sc, _ = scenes.load_scene_file(path, W, H)
+    with capi.Context(profile=sc.profile, seed=7) as ctx:  # the file says `seed 7`
+        ctx.upload(sc).build_accel(1)
+        ctx.render(W, H, spp)
+        _, rgb = ctx.resolve(want_linear=False)
+    np.testing.assert_array_equal(img, rgb)
+    assert img.std() > 10
