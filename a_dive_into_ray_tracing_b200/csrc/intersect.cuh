@@ -67,21 +67,33 @@ RT_HD bool accept_root(float root, float t_min, bool closed, const HitAcc &h, in
 // closest approach and l = g - q d the perpendicular from the ray to the centre,
 //   disc = r^2 - |l|^2,   roots = q -/+ sqrt(disc/(d.d)).
 // (|l| <= r whenever there is a hit, so no large numbers are subtracted.)
+// Shared root-selection logic, written without branches (predicate arithmetic only): in the
+// render kernel a handful of lanes run this while the rest of the warp waits, so every
+// divergent side costs a full warp instruction (ncu r1h: the branchy version averaged 5-9
+// active lanes). r1 <= r2 are the two roots; `valid` = the discriminant test passed.
+RT_HD void take_sphere_roots(bool valid, float r1, float r2, bool closed, float t_min, HitAcc &h, int32_t id) {
+  const bool tie_wins = closed ? (id > h.id) : (id < h.id);
+  const bool lo1 = closed ? (r1 >= t_min) : (r1 > t_min);
+  const bool lo2 = closed ? (r2 >= t_min) : (r2 > t_min);
+  const bool ok1 = lo1 & ((r1 < h.t) | ((r1 == h.t) & tie_wins));
+  // the near root was inside the interval (so the reference stops there) even if it lost a tie
+  const bool in1 = lo1 & (closed ? (r1 <= h.t) : (r1 < h.t));
+  const bool ok2 = (!in1) & lo2 & ((r2 < h.t) | ((r2 == h.t) & tie_wins));
+  const bool take = valid & (ok1 | ok2);
+  const float t = ok1 ? r1 : r2;
+  h.t = take ? t : h.t;
+  h.id = take ? id : h.id;
+}
+
 RT_HD void hit_sphere(float4 s, V3f center, bool closed, const Ray &r, const RayPre &pre, float t_min, HitAcc &h,
                       int32_t id) {
   V3f g = center - r.o;
   float q = dot(g, r.d) * pre.inv_a;
   V3f l = madd(g, -q, r.d);
   float disc = RT_FMA(s.w, s.w, -dot(l, l));
-  if (closed ? (disc < 0.0f) : !(disc > 0.0f)) return;
-  float sq = RT_SQRT(disc * pre.inv_a);
-  float root = q - sq;
-  if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; return; }
-  // the near root failed its range test: the reference then tries the far root
-  bool near_in_range = closed ? (root >= t_min && root <= h.t) : (root > t_min && root < h.t);
-  if (near_in_range) return; // it was in range but lost a tie: the far root cannot win either
-  root = q + sq;
-  if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; }
+  const bool valid = closed ? (disc >= 0.0f) : (disc > 0.0f);
+  float sq = RT_SQRT(RT_FMAX(disc, 0.0f) * pre.inv_a);
+  take_sphere_roots(valid, q - sq, q + sq, closed, t_min, h, id);
 }
 
 // Oversized spheres (the r = 1000 ground, always-tested "big" list). With |c - o| ~ 1e3
@@ -98,17 +110,12 @@ RT_HD void hit_sphere_big(float4 s, float K, bool closed, const Ray &r, const Ra
   const float a = dot(r.d, r.d);
   const float bp = dot(c, r.d) - dot(r.o, r.d);
   const float disc = RT_FMA(bp, bp, -a * f);
-  if (closed ? (disc < 0.0f) : !(disc > 0.0f)) return;
-  const float sq = RT_SQRT(disc);
+  const bool valid = closed ? (disc >= 0.0f) : (disc > 0.0f);
+  const float sq = RT_SQRT(RT_FMAX(disc, 0.0f));
   const float s1 = bp + (bp >= 0.0f ? sq : -sq);
   const float ta = (s1 != 0.0f) ? f / s1 : 0.0f;
   const float tb = s1 * pre.inv_a;
-  float root = RT_FMIN(ta, tb);
-  if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; return; }
-  bool near_in_range = closed ? (root >= t_min && root <= h.t) : (root > t_min && root < h.t);
-  if (near_in_range) return;
-  root = RT_FMAX(ta, tb);
-  if (accept_root(root, t_min, closed, h, id)) { h.t = root; h.id = id; }
+  take_sphere_roots(valid, RT_FMIN(ta, tb), RT_FMAX(ta, tb), closed, t_min, h, id);
 }
 
 // moving_sphere::center — moving_sphere.h:34-36. mv = {c1-c0, 1/(time1-time0)}.

@@ -49,6 +49,9 @@ struct RenderParams {
   int frac8;  // a BVH burst ends when fewer than frac8/8 of its entry lanes are still searching
   // bytes of each array staged to shared memory (all multiples of 16)
   int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big, b_leaf_prims;
+  // sphere-only kernels with single-primitive leaves: the staged leaf payloads name the sphere
+  // directly (~(sphere << 3)) and the sphere array sits at this byte offset of the shared copy
+  int direct_leaf, off_sph;
 };
 
 __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &off, const void *src, int bytes) {
@@ -88,7 +91,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         if (q & 1) { const float t = lo.x; lo.x = hi.x; hi.x = t; }
         if (q & 2) { const float t = lo.z; lo.z = hi.z; hi.z = t; }
         lo.w = RT_I2F(RT_F2I(lo.w) >> 1);
-        const int pay = RT_F2I(hi.w);
+        int pay = RT_F2I(hi.w);
+        if (!GENERAL && P.direct_leaf && pay < 0) pay = ~(__ldg(P.S.leaf_prims + ((~pay) >> 3)) << 3);
         hi.w = RT_I2F(pay >= 0 ? (pay >> 1) : pay);
         float4 *dst = (float4 *)(smem_raw + off + q * P.b_nodes);
         dst[k] = lo;
@@ -221,8 +225,18 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       if (node < 0) {
         const int enc = ~node;
         if (COUNT) cnt.prim_tests++;
-        hit_prim<PROFILE, GENERAL, false>(S, S.leaf_prims[enc >> 3], r, pre, t_min, h);
-        node = (enc & 7) ? node - 7 : resume; // next primitive of the leaf (first+1, count-1) or go on
+        if (!GENERAL && SMEM != 0 && P.direct_leaf) {
+          // single-sphere leaf named by the payload itself: one LDS.128 from a 32-bit shared address
+          const int id = enc >> 3;
+          float4 s4;
+          asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w)
+              : "r"(nodes_s + (unsigned)P.off_sph + ((unsigned)id << 4)));
+          hit_sphere(s4, xyz(s4), PROFILE == 0, r, pre, t_min, h, id);
+          node = resume;
+        } else {
+          hit_prim<PROFILE, GENERAL, false>(S, S.leaf_prims[enc >> 3], r, pre, t_min, h);
+          node = (enc & 7) ? node - 7 : resume; // next primitive of the leaf (first+1, count-1) or go on
+        }
       }
     }
     // ---- phase 3: shade + regenerate once enough lanes are out of the traversal
