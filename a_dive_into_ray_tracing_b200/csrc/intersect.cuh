@@ -113,7 +113,7 @@ RT_HD void hit_sphere_big(float4 s, float K, bool closed, const Ray &r, const Ra
   const bool valid = closed ? (disc >= 0.0f) : (disc > 0.0f);
   const float sq = RT_SQRT(RT_FMAX(disc, 0.0f));
   const float s1 = bp + (bp >= 0.0f ? sq : -sq);
-  const float ta = (s1 != 0.0f) ? f / s1 : 0.0f;
+  const float ta = (s1 != 0.0f) ? RT_FDIV(f, s1) : 0.0f;
   const float tb = s1 * pre.inv_a;
   take_sphere_roots(valid, RT_FMIN(ta, tb), RT_FMAX(ta, tb), closed, t_min, h, id);
 }
@@ -133,7 +133,7 @@ RT_HD void hit_triangle(float4 pl, float4 e0, float4 e1, float4 e2, const Ray &r
   V3f n = xyz(pl);
   float nd = dot(n, r.d);
   if (fabsf(nd) < 0.01f) return;
-  float t = (pl.w - dot(n, r.o)) / nd;
+  float t = RT_FDIV(pl.w - dot(n, r.o), nd);
   if (t < 0.0f) return;
   if (!accept_root(t, t_min, true, h, id)) return;
   V3f p = madd(r.o, t, r.d);
@@ -148,7 +148,7 @@ RT_HD void hit_quad(float4 q0, float4 q1, const Ray &r, float t_min, HitAcc &h, 
   int ax = RT_F2I(q0.w);
   float oa = ax == 0 ? r.o.x : (ax == 1 ? r.o.y : r.o.z);
   float da = ax == 0 ? r.d.x : (ax == 1 ? r.d.y : r.d.z);
-  float t = (q0.x - oa) / da;
+  float t = RT_FDIV(q0.x - oa, da);
   if (!accept_root(t, t_min, true, h, id)) return;
   // in-plane coordinates: axis 0 -> (y,z), 1 -> (x,z), 2 -> (x,y)
   float o1 = ax == 0 ? r.o.y : r.o.x, d1 = ax == 0 ? r.d.y : r.d.x;

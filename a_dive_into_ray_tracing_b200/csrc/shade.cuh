@@ -33,11 +33,11 @@ RT_HD Ray gen_camera_ray(const DevCamera &cam, int W, int H, int i, int j, float
                          float x5) {
   float s, t;
   if (PROFILE == 0) { // main.cpp:278-279
-    s = ((float)i + x1) / (float)(W - 1);
-    t = ((float)j + x2) / (float)(H - 1);
+    s = RT_FDIV((float)i + x1, (float)(W - 1));
+    t = RT_FDIV((float)j + x2, (float)(H - 1));
   } else { // final.cu:85-86
-    s = ((float)i + x1) / (float)W;
-    t = ((float)j + x2) / (float)H;
+    s = RT_FDIV((float)i + x1, (float)W);
+    t = RT_FDIV((float)j + x2, (float)H);
   }
   V3f offset = v3(0.f, 0.f, 0.f);
   if (cam.lens_radius > 0.0f) {
@@ -64,7 +64,7 @@ RT_HD V3f sky_color(V3f d) {
 RT_HD V3f reflect(V3f v, V3f n) { return madd(v, -2.0f * dot(v, n), n); }
 
 RT_HD float schlick5(float cosine, float ref_idx) {
-  float r0 = (1.0f - ref_idx) / (1.0f + ref_idx);
+  float r0 = RT_FDIV(1.0f - ref_idx, 1.0f + ref_idx);
   r0 = r0 * r0;
   float m = 1.0f - cosine, m2 = m * m;
   return RT_FMA(1.0f - r0, m2 * m2 * m, r0);
@@ -242,7 +242,7 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
       float4 mv = S.sph_mv[idx];
       if (mv.w != 0.0f) c = sphere_center_at(s, mv, S.sph_t0[idx], r.tm);
     }
-    outward = (1.0f / s.w) * (p - c); // (p - center) / radius
+    outward = RT_FDIV(1.0f, s.w) * (p - c); // (p - center) / radius
     mat = S.sph_mat[idx];
   } else if (type == RT_PRIM_TRIANGLE) {
     outward = xyz(S.tri_n[idx]);
@@ -277,7 +277,11 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
     V3f v = sample_unit_vector(u1, u2);
     if (!(PROFILE == 0 && mtype == RT_MAT_LAMBERTIAN)) {
 #ifdef __CUDA_ARCH__
-      v = exp2f(__log2f(u3) * (1.0f / 3.0f)) * v; // cbrt(u3): radius of a uniform point in the ball
+      {
+        float rad; // cbrt(u3) = 2^(log2(u3)/3): radius of a uniform point in the ball (u3 = 0 -> 0)
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(__log2f(u3) * (1.0f / 3.0f)));
+        v = rad * v;
+      }
 #else
       v = cbrtf(u3) * v;
 #endif
@@ -297,7 +301,7 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
     att = v3(1.f, 1.f, 1.f);
     const float ir = m1.w;
     if (PROFILE == 0) {
-      float ratio = front_face ? (1.0f / ir) : ir;
+      float ratio = front_face ? RT_FDIV(1.0f, ir) : ir;
       V3f ud = normalize(r.d);
       float cos_theta = RT_FMIN(-dot(ud, n), 1.0f);
       float sin_theta = RT_SQRT(RT_FMAX(0.0f, RT_FMA(-cos_theta, cos_theta, 1.0f)));
@@ -320,7 +324,7 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
         cosine = dn * inv_len;
         cosine = RT_SQRT(RT_FMAX(0.0f, 1.0f - ir * ir * (1.0f - cosine * cosine)));
       } else {
-        on = n; ni_over_nt = 1.0f / ir;
+        on = n; ni_over_nt = RT_FDIV(1.0f, ir);
         cosine = -dn * inv_len;
       }
       V3f uv = inv_len * r.d;
