@@ -753,6 +753,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   const size_t smem_bytes = acc_bytes + (smem ? scene_bytes : 0) + (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
   // staging order in k_render: node copies first, then the sphere array
   P.off_sph = (smem == 2 ? 4 : 1) * P.b_nodes;
+  P.hi_off = S.n_nodes << 4;
   P.direct_leaf = (!ctx->general && smem != 0 && ctx->max_leaf == 1) ? 1 : 0;
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
   render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext);

@@ -26,9 +26,11 @@
 #ifndef RT_BLOCK_GENERAL
 #define RT_BLOCK_GENERAL 1024
 #endif
-// BVH steps between two warp votes in the search burst (1 or 2)
+// BVH steps between two warp votes in the search burst. Measured (B200, after the r1i instruction
+// diet): sphere-only kernel 2/3/4 steps -> 78.2/76.8/77.5 ms (config 2); general kernel
+// 173/171/167 ms (config 3, 150 spp).
 #ifndef RT_STEPS_PER_VOTE
-#define RT_STEPS_PER_VOTE 2
+#define RT_STEPS_PER_VOTE(GENERAL) ((GENERAL) ? 4 : 3)
 #endif
 #define RT_BLOCK_OF(GENERAL) ((GENERAL) ? RT_BLOCK_GENERAL : RT_BLOCK)
 #define RT_TILE_W 8
@@ -52,6 +54,7 @@ struct RenderParams {
   // sphere-only kernels with single-primitive leaves: the staged leaf payloads name the sphere
   // directly (~(sphere << 3)) and the sphere array sits at this byte offset of the shared copy
   int direct_leaf, off_sph;
+  int hi_off; // bytes from a node's {bmin, escape} slot to its {bmax, payload} slot in the shared copies
 };
 
 __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &off, const void *src, int bytes) {
@@ -73,9 +76,13 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevScene S = P.S;
   int off = 0;
+  // 32-bit shared-window address of the staged node copies (they start the dynamic segment)
+  const uint32_t nodes_s = SMEM ? (uint32_t)__cvta_generic_to_shared(smem_raw) : 0u;
   if (SMEM) {
     // Nodes go to shared memory as STRUCTURE OF ARRAYS: all {bmin, escape} first, then all
-    // {bmax, payload}, with links rewritten to 16-byte units. In the 32-byte AoS layout every
+    // {bmax, payload}, with links rewritten to ABSOLUTE 32-bit shared addresses of the target's
+    // {bmin, escape} slot in the same copy (0 = traversal finished), so that a BVH step needs no
+    // address arithmetic: LDS [node] and LDS [node + hi_off]. In the 32-byte AoS layout every
     // LDS.128 of a warp touches only half of the 32 banks (ncu: the shared-memory data pipe was
     // 90 % busy, 8.9 wavefronts per LDS.128); SoA spreads the 16-byte slots over all banks.
     // SMEM == 2: four quadrant copies (own visiting order), bmin/bmax pre-swapped on x (bit 0)
@@ -90,10 +97,12 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         float4 lo = __ldg(src), hi = __ldg(src + 1);
         if (q & 1) { const float t = lo.x; lo.x = hi.x; hi.x = t; }
         if (q & 2) { const float t = lo.z; lo.z = hi.z; hi.z = t; }
-        lo.w = RT_I2F(RT_F2I(lo.w) >> 1);
+        const int base_q = (int)nodes_s + q * P.b_nodes;
+        const int esc = RT_F2I(lo.w) >> 1; // 16-byte-slot offset within the copy
+        lo.w = RT_I2F(esc == (nn << 4) ? 0 : base_q + esc);
         int pay = RT_F2I(hi.w);
         if (!GENERAL && P.direct_leaf && pay < 0) pay = ~(__ldg(P.S.leaf_prims + ((~pay) >> 3)) << 3);
-        hi.w = RT_I2F(pay >= 0 ? (pay >> 1) : pay);
+        hi.w = RT_I2F(pay >= 0 ? base_q + (pay >> 1) : pay);
         float4 *dst = (float4 *)(smem_raw + off + q * P.b_nodes);
         dst[k] = lo;
         dst[nn + k] = hi;
@@ -133,12 +142,13 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   // regenerates once `batch` lanes are DONE/DEAD (or nobody is traversing) while the
   // remaining lanes keep their traversal state in registers.
   // Encoding: `alive` (the lane owns a path) and `node`:
-  //   0 <= node < node_end   SEARCH: byte offset of the next BVH node
-  //   node == node_end       traversal finished (DONE if alive, else DEAD)
-  //   node < 0               LEAF: a hit leaf is pending, node = its payload
-  //                          ~(first << 3 | count-1) into leaf_prims; `resume` = where to go on
-  const int node_end = S.n_nodes << (SMEM ? RT_NODE_SHIFT - 1 : RT_NODE_SHIFT); // shared copies: 16-byte units
-  const unsigned hi_off = (unsigned)S.n_nodes << 4;                               // {bmax, payload} array follows
+  //   SEARCH   the next BVH node: its shared address (> 0; shared copies) or its byte offset
+  //            in [0, node_end) (global path)
+  //   node == node_end   traversal finished (DONE if alive, else DEAD); 0 for the shared copies
+  //   node < 0           LEAF: a hit leaf is pending, node = its payload
+  //                      ~(first << 3 | count-1) into leaf_prims; `resume` = where to go on
+  const int node_end = SMEM ? 0 : (S.n_nodes << RT_NODE_SHIFT);
+#define RT_SEARCHING(n) (SMEM ? ((n) > 0) : ((unsigned)(n) < (unsigned)node_end))
   bool alive = false;
   int node = node_end, resume = 0;
   HitAcc h;
@@ -163,8 +173,6 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   cnt.box_tests = 0; cnt.prim_tests = 0;
   // node fetch: 2 x LDS.128 straight from a 32-bit shared address (no generic-pointer
   // arithmetic in the loop); global path for scenes that do not fit shared memory
-  const uint32_t nodes_s = SMEM ? (uint32_t)__cvta_generic_to_shared(S.nodes) : 0u;
-  uint32_t nbase = nodes_s; // + quadrant copy of the current ray (SMEM == 2)
   const char *nodes_g = (const char *)S.nodes;
   const char *nodes_q = nodes_g; // SMEM == 0: the current ray's quadrant copy in global memory
 
@@ -183,30 +191,34 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     if (EXT && S.n_media)
       h = apply_media(S.media, S.n_media, r.o, r.d, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, P.seed_lo,
                       P.seed_hi, h);
-    node = 0;
     // sign BITS of 1/d (covers d = -0): which quadrant copy (own child order; in shared memory also
     // pre-swapped planes) this ray walks
     const unsigned quadrant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 1);
-    if (SMEM == 2) nbase = nodes_s + quadrant * (unsigned)P.b_nodes;
-    if (SMEM == 0) nodes_q = nodes_g + quadrant * (unsigned)S.node_stride;
+    if (SMEM == 0) {
+      node = 0;
+      nodes_q = nodes_g + quadrant * (unsigned)S.node_stride;
+    } else { // the root's shared address in this ray's copy (no nodes: finished at once)
+      node = S.n_nodes ? (int)(nodes_s + (SMEM == 2 ? quadrant * (unsigned)P.b_nodes : 0u)) : 0;
+    }
   };
 
   for (;;) {
     // ---- phase 1: a burst of BVH steps (branch-free body: lanes that are not searching
     // fetch node 0 and discard the result)
-    const int ns0 = __popc(__ballot_sync(FULL, (unsigned)node < (unsigned)node_end));
+    const int ns0 = __popc(__ballot_sync(FULL, RT_SEARCHING(node)));
     if (ns0 > 0) {
       const int thr = max(1, (ns0 * P.frac8) >> 3);
       for (;;) {
-        if (__popc(__ballot_sync(FULL, (unsigned)node < (unsigned)node_end)) < thr) break;
+        if (__popc(__ballot_sync(FULL, RT_SEARCHING(node))) < thr) break;
 #pragma unroll
-        for (int u = 0; u < RT_STEPS_PER_VOTE; u++) {
-          const bool searching = (unsigned)node < (unsigned)node_end;
-          const int at = searching ? node : 0;
+        for (int u = 0; u < RT_STEPS_PER_VOTE(GENERAL); u++) {
+          const bool searching = RT_SEARCHING(node);
+          // lanes that are not searching fetch the first node and discard the result
+          const int at = searching ? node : (SMEM ? (int)nodes_s : 0);
           float4 lo, hi;
           if (SMEM != 0) {
-            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(nbase + at));
-            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(nbase + hi_off + at));
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(at));
+            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(at + P.hi_off));
           } else {
             lo = __ldg((const float4 *)(nodes_q + at));
             hi = __ldg((const float4 *)(nodes_q + at) + 1);
@@ -221,7 +233,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     }
     // ---- phase 2: pending primitive tests (one per lane per round)
     const unsigned m_leaf = __ballot_sync(FULL, node < 0);
-    if (m_leaf && (__popc(m_leaf) >= P.leaf_min || !__ballot_sync(FULL, (unsigned)node < (unsigned)node_end))) {
+    if (m_leaf && (__popc(m_leaf) >= P.leaf_min || !__ballot_sync(FULL, RT_SEARCHING(node)))) {
       if (node < 0) {
         const int enc = ~node;
         if (COUNT) cnt.prim_tests++;
