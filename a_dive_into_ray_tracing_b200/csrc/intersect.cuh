@@ -38,10 +38,9 @@ RT_HD RayPre ray_precompute(const Ray &r) {
 RT_HD RayPre ray_precompute_fast(const Ray &r) {
 #ifdef __CUDA_ARCH__
   RayPre p;
-  p.inv_d = v3(__fdividef(1.0f, rt_safe_dir(r.d.x)), __fdividef(1.0f, rt_safe_dir(r.d.y)),
-               __fdividef(1.0f, rt_safe_dir(r.d.z)));
+  p.inv_d = v3(rt_rcp_approx(rt_safe_dir(r.d.x)), rt_rcp_approx(rt_safe_dir(r.d.y)), rt_rcp_approx(rt_safe_dir(r.d.z)));
   p.ood = v3(r.o.x * p.inv_d.x, r.o.y * p.inv_d.y, r.o.z * p.inv_d.z);
-  p.inv_a = __fdividef(1.0f, dot(r.d, r.d));
+  p.inv_a = rt_rcp_approx(dot(r.d, r.d));
   return p;
 #else
   return ray_precompute(r);

@@ -37,7 +37,13 @@ static __device__ __forceinline__ float rt_sqrt_approx(float x) {
 #define RT_MULHI(a, b) __umulhi((a), (b))
 // fast division (MUFU.RCP + multiply, <= 2 ulp) for quantities whose parity bound is 1e-5 relative
 // or statistical: the IEEE sequence costs ~12 instructions and a slow-path branch per use
-#define RT_FDIV(a, b) __fdividef((a), (b))
+// (rcp.approx.ftz is ONE MUFU; __fdividef adds a denormal-rescue sequence of 4 instructions)
+static __device__ __forceinline__ float rt_rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#define RT_FDIV(a, b) ((a) * rt_rcp_approx(b))
 #else
 static inline int rt_host_f2i(float x) { int i; memcpy(&i, &x, 4); return i; }
 static inline float rt_host_i2f(int i) { float x; memcpy(&x, &i, 4); return x; }
