@@ -178,10 +178,12 @@ class ClockSampler:
 
 def ncu_traffic_bytes():
     """dram__bytes_read.sum + dram__bytes_write.sum of k_render per launch, from the committed
-    `ncu --set full` capture of this kernel (profiles/r1h_k_render_raw.csv); None if absent."""
+    newest `ncu --set full` capture of this kernel (profiles/r1*_k_render_raw.csv); None if absent."""
     import csv
+    import glob
     try:
-        rows = list(csv.reader(open(os.path.join(ROOT, "profiles", "r1h_k_render_raw.csv"))))
+        newest = sorted(glob.glob(os.path.join(ROOT, "profiles", "r1*_k_render_raw.csv")))[-1]
+        rows = list(csv.reader(open(newest)))
         d, u = dict(zip(rows[0], rows[2])), dict(zip(rows[0], rows[1]))
         mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         return sum(float(d[k]) * mult[u[k]] for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
@@ -324,8 +326,8 @@ def run_ours(args):
                      "frac": seg_per_s * (32.0 * n_box + 16.0 * n_prim + 32.0 * h_bar) / 1e9 / world /
                              (128.0 * sm_count * sm_mhz_max * 1e6 / 1e9),
                      "model": "B_seg = 32 B/node x box tests + 16 B x sphere tests + 32 B material per hit "
-                              "(SURVEY.md 8d); peak = nominal 128 B/clk/SM x SMs x max SM clock; ncu r1h: the "
-                              "shared-memory data pipe runs at 80 % of its wavefront peak"},
+                              "(SURVEY.md 8d); peak = nominal 128 B/clk/SM x SMs x max SM clock; ncu (profiles/): "
+                              "the shared-memory data pipe runs at ~80 % of its wavefront peak"},
             "hbm": {"bound": "hbm", "achieved": hbm_bytes_per_frame / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak,
                     "unit": "GB/s", "frac": hbm_bytes_per_frame / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
                     "note": "framebuffer traffic only; the scene (~60 KB) lives in shared memory: not HBM-bound",
@@ -365,10 +367,17 @@ def run_ours(args):
 
 def main():
     args = parse()
+    # The contract is ONE JSON line on stdout. Libraries write there too (NCCL prints its version
+    # banner on fd 1): point fd 1 at stderr while working and hand the real stdout to print().
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
