@@ -100,3 +100,59 @@ def test_gpu_builder_and_traversal(seed, n_sph, n_tri, n_quad, cluster, dup, max
             assert np.all(a[..., 3] == 4) and np.all(np.isfinite(a))
     finally:
         os.environ.pop("B200RT_MAX_LEAF", None)
+
+
+# ---------------------------------------------------------------- white furnace with media
+def furnace_scene(seed, n_sph, n_tri, n_quad, n_media):
+    """Random geometry whose every interaction conserves energy exactly (white lambertian, glass,
+    white isotropic media) under a uniform white background: every pixel must come out as 1 -
+    any lost or invented path (NaN direction, missed surface, wrong medium interval) shows."""
+    from a_dive_into_ray_tracing_b200.scenes import _medium_box, _medium_sphere
+    sc, _ = random_scene(seed, n_sph, n_tri, n_quad, cluster=False, dup=False)
+    rng = np.random.Generator(np.random.Philox(seed + 77))
+    mats = np.zeros(4, MATERIAL_DT)
+    mats["type"] = [D.RT_MAT_LAMBERTIAN, D.RT_MAT_DIELECTRIC, D.RT_MAT_LAMBERTIAN, D.RT_MAT_ISOTROPIC]
+    mats["albedo"] = 1.0
+    mats["param"] = [0, 1.5, 0, 0]
+    media = []
+    for _ in range(n_media):
+        c = rng.normal(size=3) * 3.0
+        if rng.random() < 0.5:
+            media.append(_medium_sphere(tuple(c), 0.3 + 2.0 * rng.random(), 0.05 + 3.0 * rng.random(), 3))
+        else:
+            ext = 0.3 + 2.5 * rng.random(3)
+            media.append(_medium_box(tuple(-ext), tuple(ext), float(rng.uniform(-180, 180)), tuple(c),
+                                     0.05 + 3.0 * rng.random(), 3))
+    sc2 = Scene(spheres=sc.spheres, triangles=sc.triangles, quads=sc.quads, materials=mats,
+                media=np.array(media, D.MEDIUM_DT) if media else None, profile=D.RT_PROFILE_NEXT_WEEK, sky_gradient=0,
+                background=(1.0, 1.0, 1.0), t_min=1e-3, max_depth=50, name="furnace",
+                flags=D.RT_FLAG_FLIP_NORMALS if seed & 1 else 0)
+    sc2.spheres["moving"] = 0  # (a moving sphere can swallow a ray origin between two bounces: still energy-neutral, but keep the scene static)
+    sc2.camera = sc.camera
+    return sc2
+
+
+furnace_args = dict(seed=st.integers(0, 10 ** 6), n_sph=st.integers(0, 30), n_tri=st.integers(0, 20),
+                    n_quad=st.integers(0, 8), n_media=st.integers(0, 5))
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(**furnace_args)
+def test_emulated_white_furnace(seed, n_sph, n_tri, n_quad, n_media):
+    from tests.emu.pyemu import Emu
+    sc = furnace_scene(seed, n_sph, n_tri, n_quad, n_media)
+    s, _, st_ = Emu(sc, quality=1).render(24, 24, 4, seed=seed)
+    np.testing.assert_allclose(s / 4, 1.0, atol=2e-5)
+
+
+@pytest.mark.gpu
+@settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@given(**furnace_args)
+def test_gpu_white_furnace(seed, n_sph, n_tri, n_quad, n_media):
+    from a_dive_into_ray_tracing_b200 import capi
+    sc = furnace_scene(seed, n_sph, n_tri, n_quad, n_media)
+    with capi.Context(profile=2, seed=seed) as ctx:
+        ctx.upload(sc).build_accel(1)
+        ctx.render(48, 48, 8)
+        lin, _ = ctx.resolve()
+    np.testing.assert_allclose(lin, 1.0, atol=2e-5)
