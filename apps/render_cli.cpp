@@ -5,17 +5,20 @@
 //   render_cli [--scene weekend|next_week|perlin|earth|light|cornell|smoke|final|obj] [--obj file.obj]
 //              [--image map.ppm] [--width W] [--height H] [--spp N] [--seed S] [--device D]
 //              [--binary | --png]   (image on stdout; scene numbers 1-8 of rt_next_week/cuda/main.cu:402-459)
+//              [--gpus N]  sample split over N devices, one host thread and one context per device,
+//                          frames summed on the host (the NCCL variant is dist.py)
 //   render_cli --scene-file FILE.scene [--width W --height H --spp N ...]   (include/rtx/scene_file.h)
 #include <chrono>
 #include <cstring>
 #include <iostream>
+#include <thread>
 
 #include "scenes.h"
 #include "scene_file.h"
 
 int main(int argc, char **argv) {
   std::string scene = "weekend", obj, image, scene_path;
-  int W = 0, H = 0, spp = 0, device = 0;
+  int W = 0, H = 0, spp = 0, device = 0, gpus = 1;
   unsigned long long seed = 1984;
   bool have_seed = false;
   bool binary = false, png = false;
@@ -30,6 +33,7 @@ int main(int argc, char **argv) {
     else if (is("--seed")) { seed = strtoull(argv[++i], nullptr, 10); have_seed = true; }
     else if (is("--scene-file")) scene_path = argv[++i];
     else if (is("--device")) device = atoi(argv[++i]);
+    else if (is("--gpus")) gpus = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--binary")) binary = true;
     else if (!strcmp(argv[i], "--png")) png = true;
     else { std::cerr << "unknown argument " << argv[i] << "\n"; return 2; }
@@ -121,11 +125,42 @@ int main(int argc, char **argv) {
     std::cerr << "Rendering a " << W << "x" << H << " image with " << spp << " samples per pixel ("
               << r.flat.spheres.size() << " spheres, " << r.flat.triangles.size() << " triangles, " << r.flat.quads.size()
               << " rects, " << r.flat.media.size() << " media)\n";
+    // further devices: the same scene, each its own context; device g renders the global sample
+    // indices [g*spp/G, (g+1)*spp/G) (counter-based RNG: the image does not depend on G)
+    if (gpus < 1 || device + gpus > rt_device_count()) throw std::runtime_error("--gpus: not that many CUDA devices");
+    std::vector<std::unique_ptr<renderer>> more;
+    for (int g = 1; g < gpus; g++) {
+      render_options og = opt;
+      og.device = device + g;
+      more.emplace_back(new renderer(og));
+      more.back()->set_scene(*root, cam);
+    }
+    auto share = [&](int g) { return std::make_pair((int)((long long)spp * g / gpus), (int)((long long)spp * (g + 1) / gpus)); };
     auto t0 = std::chrono::steady_clock::now();
-    r.render(W, H, spp);
+    {
+      std::vector<std::thread> workers;
+      std::vector<std::string> errors(gpus);
+      for (int g = 1; g < gpus; g++)
+        workers.emplace_back([&, g]() {
+          try { more[g - 1]->render(W, H, share(g).second - share(g).first, share(g).first); }
+          catch (const std::exception &e) { errors[g] = e.what(); }
+        });
+      r.render(W, H, share(0).second - share(0).first, share(0).first);
+      for (auto &w : workers) w.join();
+      for (auto &e : errors) if (!e.empty()) throw std::runtime_error(e);
+    }
+    if (gpus > 1) { // combine: sum of the float4 frames (fixed device order -> deterministic)
+      std::vector<float> sum = r.accum_download();
+      for (auto &m : more) {
+        std::vector<float> f = m->accum_download();
+        for (size_t k = 0; k < sum.size(); k++) sum[k] += f[k];
+      }
+      r.accum_upload(W, H, sum);
+    }
     image8 im = r.resolve();
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     rt_stats_t st = r.stats();
+    for (auto &m : more) { rt_stats_t sg = m->stats(); st.segments += sg.segments; st.ms_render = std::max(st.ms_render, sg.ms_render); }
     std::cerr << "took " << secs << " seconds. (" << st.segments / 1e6 / (st.ms_render * 1e-3) << " Mpath-bounces/s, BVH "
               << st.n_nodes << " nodes built in " << st.ms_build << " ms)\n";
     if (png) im.write_png(std::cout);

@@ -807,6 +807,17 @@ public:
     check(rt_resolve(ctx, nullptr, im.rgb.data()));
     return im;
   }
+  // accumulation frame (float4 per pixel: sum R, G, B and the sample count) — checkpoints, and the
+  // host-side combine of a multi-GPU sample split
+  std::vector<float> accum_download() {
+    std::vector<float> f((size_t)W * H * 4);
+    check(rt_accum_download(ctx, f.data(), f.size()));
+    return f;
+  }
+  void accum_upload(int width, int height, const std::vector<float> &f) {
+    W = width; H = height;
+    check(rt_accum_upload(ctx, width, height, f.data(), f.size()));
+  }
   rt_stats_t stats() { rt_stats_t s; check(rt_stats(ctx, &s)); return s; }
   rt_ctx *handle() { return ctx; }
   flat_scene flat;
