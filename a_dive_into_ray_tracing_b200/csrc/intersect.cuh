@@ -129,32 +129,39 @@ RT_HD V3f sphere_center_at(float4 s, float4 mv, float time0, float tm) {
 // m_e = cross(N^, edge), k_e = m_e.vert the edge test is m_e.p - k_e >= 0.
 RT_HD void hit_triangle(float4 pl, float4 e0, float4 e1, float4 e2, const Ray &r, float t_min, HitAcc &h,
                         int32_t id) {
-  V3f n = xyz(pl);
-  float nd = dot(n, r.d);
-  if (fabsf(nd) < 0.01f) return;
-  float t = RT_FDIV(pl.w - dot(n, r.o), nd);
-  if (t < 0.0f) return;
-  if (!accept_root(t, t_min, true, h, id)) return;
-  V3f p = madd(r.o, t, r.d);
-  if (dot(xyz(e0), p) - e0.w < 0.0f) return;
-  if (dot(xyz(e1), p) - e1.w < 0.0f) return;
-  if (dot(xyz(e2), p) - e2.w < 0.0f) return;
-  h.t = t; h.id = id;
+  // branch-free: a rejected candidate leaves NaN/inf in t or p, and every comparison below is
+  // written so that NaN fails it
+  const V3f n = xyz(pl);
+  const float nd = dot(n, r.d);
+  const float t = RT_FDIV(pl.w - dot(n, r.o), nd);
+  bool ok = (fabsf(nd) >= 0.01f) & (t >= 0.0f) & accept_root(t, t_min, true, h, id);
+  const V3f p = madd(r.o, t, r.d);
+  ok = ok & (dot(xyz(e0), p) - e0.w >= 0.0f) & (dot(xyz(e1), p) - e1.w >= 0.0f) & (dot(xyz(e2), p) - e2.w >= 0.0f);
+  h.t = ok ? t : h.t;
+  h.id = ok ? id : h.id;
 }
 
 // Axis-aligned rectangle: q0 = {k, a0, a1, as_float(axis)}, q1 = {b0, b1, -, -}.
-RT_HD void hit_quad(float4 q0, float4 q1, const Ray &r, float t_min, HitAcc &h, int32_t id) {
-  int ax = RT_F2I(q0.w);
-  float oa = ax == 0 ? r.o.x : (ax == 1 ? r.o.y : r.o.z);
-  float da = ax == 0 ? r.d.x : (ax == 1 ? r.d.y : r.d.z);
-  float t = RT_FDIV(q0.x - oa, da);
-  if (!accept_root(t, t_min, true, h, id)) return;
-  // in-plane coordinates: axis 0 -> (y,z), 1 -> (x,z), 2 -> (x,y)
-  float o1 = ax == 0 ? r.o.y : r.o.x, d1 = ax == 0 ? r.d.y : r.d.x;
-  float o2 = ax == 2 ? r.o.y : r.o.z, d2 = ax == 2 ? r.d.y : r.d.z;
-  float a = RT_FMA(t, d1, o1), b = RT_FMA(t, d2, o2);
-  if (a < q0.y || a > q0.z || b < q1.x || b > q1.y) return;
-  h.t = t; h.id = id;
+// t = (k - o_axis) / d_axis with the ray's precomputed reciprocal (the subtraction comes first: a
+// ray leaving this very plane gets t = 0 exactly). The axis is switched on, not selected by
+// arithmetic: for the always-tested walls it is uniform across the warp.
+RT_HD void hit_quad(float4 q0, float4 q1, const Ray &r, const RayPre &pre, float t_min, HitAcc &h, int32_t id) {
+  const int ax = RT_F2I(q0.w);
+  float t, a, b; // in-plane coordinates: axis 0 -> (y,z), 1 -> (x,z), 2 -> (x,y)
+  if (ax == 0) {
+    t = (q0.x - r.o.x) * pre.inv_d.x;
+    a = RT_FMA(t, r.d.y, r.o.y); b = RT_FMA(t, r.d.z, r.o.z);
+  } else if (ax == 1) {
+    t = (q0.x - r.o.y) * pre.inv_d.y;
+    a = RT_FMA(t, r.d.x, r.o.x); b = RT_FMA(t, r.d.z, r.o.z);
+  } else {
+    t = (q0.x - r.o.z) * pre.inv_d.z;
+    a = RT_FMA(t, r.d.x, r.o.x); b = RT_FMA(t, r.d.y, r.o.y);
+  }
+  const bool inside = (a >= q0.y) & (a <= q0.z) & (b >= q1.x) & (b <= q1.y);
+  const bool take = inside & accept_root(t, t_min, true, h, id);
+  h.t = take ? t : h.t;
+  h.id = take ? id : h.id;
 }
 
 // Slab test against a packed node box (closed interval). 1/d is finite (rt_safe_dir), so the
@@ -205,7 +212,7 @@ RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &p
     hit_triangle(t[0], t[1], t[2], t[3], r, t_min, h, id);
   } else {
     const float4 *q = S.quad + 2 * idx;
-    hit_quad(q[0], q[1], r, t_min, h, id);
+    hit_quad(q[0], q[1], r, pre, t_min, h, id);
   }
 }
 
