@@ -75,3 +75,9 @@ def test_product_never_touches_the_oracle():
                 txt = open(os.path.join(base, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "liboracle" not in txt and "libref_l0" not in txt, f
                 assert "libemu" not in txt and "tests.emu" not in txt, f
+
+
+def test_graft_entry_build_runs():
+    """the driver's "does it build" entry point (kept in step with the ABI version)"""
+    import __graft_entry__ as g
+    g.build()
