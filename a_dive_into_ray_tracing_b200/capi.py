@@ -26,7 +26,7 @@ STATUS = {0: "RT_OK", 1: "RT_ERR_INVALID", 2: "RT_ERR_CUDA", 3: "RT_ERR_STATE", 
 SYMBOLS = ["rt_version", "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_scene_upload",
            "rt_accel_build", "rt_accel_download", "rt_trace_closest", "rt_render", "rt_render_device",
            "rt_accum_clear", "rt_accum_download", "rt_accum_upload", "rt_accum_device_ptr", "rt_resolve",
-           "rt_resolve_device", "rt_stats", "rt_stats_reset", "rt_sync", "rt_measure_fp32_peak"]
+           "rt_resolve_device", "rt_render_aov", "rt_stats", "rt_stats_reset", "rt_sync", "rt_measure_fp32_peak"]
 
 
 class RtError(RuntimeError):
@@ -84,6 +84,8 @@ def load_library():
     L.rt_accum_device_ptr.argtypes = [_vp]
     L.rt_resolve.restype = C.c_int
     L.rt_resolve.argtypes = [_vp, _vp, _vp]
+    L.rt_render_aov.restype = C.c_int
+    L.rt_render_aov.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp]
     L.rt_resolve_device.restype = C.c_int
     L.rt_resolve_device.argtypes = [_vp, C.c_int, C.c_int, _vp, _vp, _vp, _vp]
     L.rt_stats.restype = C.c_int
@@ -217,6 +219,12 @@ class Context:
         self._ck(self.lib.rt_resolve_device(self.h, W, H, d_accum_ptr, lin.ctypes.data if want_linear else None,
                                             rgb.ctypes.data if want_rgb8 else None, self._stream(stream_ptr)))
         return lin, rgb
+
+    def render_aov(self, W, H, spp=1):
+        """first-hit feature buffers [H][W][8]: albedo rgb, normal xyz, t, hit fraction (bottom row first)"""
+        out = np.empty((H, W, 8), np.float32)
+        self._ck(self.lib.rt_render_aov(self.h, W, H, spp, out.ctypes.data))
+        return out
 
     def stats(self):
         s = RtStats()

@@ -831,6 +831,33 @@ int rt_accum_upload(rt_ctx *ctx, int width, int height, const float *rgba, size_
   return RT_OK;
 }
 
+int rt_render_aov(rt_ctx *ctx, int width, int height, int spp, float *aov) {
+  if (!ctx || !aov || width < 2 || height < 2 || spp < 1) return RT_ERR_INVALID;
+  if (!ctx->have_scene) return fail(ctx, RT_ERR_STATE, "rt_render_aov before rt_scene_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (!ctx->have_accel) {
+    int rc = rt_accel_build(ctx, 1);
+    if (rc) return rc;
+  }
+  const size_t n_pix = (size_t)width * height;
+  int rc = dev_reserve(ctx, ctx->d_linear, sizeof(float) * 8 * n_pix);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const unsigned grid = (unsigned)((n_pix + 127) / 128);
+  const uint32_t k0 = (uint32_t)(ctx->cfg.seed & 0xffffffffu), k1 = (uint32_t)(ctx->cfg.seed >> 32);
+  float *out = (float *)ctx->d_linear.p;
+  switch (ctx->cfg.profile) {
+  case 0: k_aov<0, false><<<grid, 128, 0, st>>>(ctx->S, ctx->cam, ctx->sp, width, height, spp, k0, k1, out); break;
+  case 1: k_aov<1, false><<<grid, 128, 0, st>>>(ctx->S, ctx->cam, ctx->sp, width, height, spp, k0, k1, out); break;
+  default: k_aov<2, true><<<grid, 128, 0, st>>>(ctx->S, ctx->cam, ctx->sp, width, height, spp, k0, k1, out); break;
+  }
+  ctx->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(aov, out, sizeof(float) * 8 * n_pix, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RT_OK;
+}
+
 void *rt_accum_device_ptr(rt_ctx *ctx) { return ctx ? ctx->d_accum.p : nullptr; }
 
 int rt_resolve_device(rt_ctx *ctx, int width, int height, const float *d_accum, float *linear_rgb, uint8_t *rgb8,

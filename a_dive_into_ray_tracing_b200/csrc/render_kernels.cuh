@@ -434,6 +434,41 @@ __global__ void k_resolve(const float4 *__restrict__ accum, int W, int H, int pr
   }
 }
 
+// Denoiser feature buffers: one thread per pixel, `spp` camera samples with the same Philox camera
+// streams as k_render (event 0, streams 0 and 1), first SURFACE hit only (media are ignored).
+// out: float[H*W][8] = albedo.rgb, normal.xyz, t, hit fraction.
+template <int PROFILE, bool GENERAL>
+RT_HD void aov_pixel(const DevScene &S, const DevCamera &cam, const ShadeParams &sp, int W, int H, int spp, uint32_t seed_lo,
+                     uint32_t seed_hi, int p, float *out) {
+  const int i = p % W, j = p / W;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int smp = 0; smp < spp; smp++) {
+    const Philox4 q = philox4x32_10((uint32_t)p, (uint32_t)smp, 0u, 0u, seed_lo, seed_hi);
+    float x5 = 0.f;
+    if (PROFILE == 2 && cam.time1 != cam.time0) x5 = u01(philox4x32_10((uint32_t)p, (uint32_t)smp, 0u, 1u, seed_lo, seed_hi).x);
+    const Ray r = gen_camera_ray<PROFILE>(cam, W, H, i, j, u01(q.x), u01(q.y), u01(q.z), u01(q.w), x5);
+    const HitAcc h = trace_closest<PROFILE, GENERAL, false>(S, r, sp.t_min, INFINITY, nullptr);
+    V3f albedo, normal = v3(0, 0, 0);
+    if (h.id >= 0) {
+      first_hit_features<PROFILE, GENERAL>(S, sp, r, h, albedo, normal);
+      acc[6] += h.t; acc[7] += 1.0f;
+    } else {
+      albedo = miss_radiance(sp, r.d);
+    }
+    acc[0] += albedo.x; acc[1] += albedo.y; acc[2] += albedo.z;
+    acc[3] += normal.x; acc[4] += normal.y; acc[5] += normal.z;
+  }
+  const float inv = 1.0f / (float)spp;
+  for (int k = 0; k < 8; k++) out[8 * (size_t)p + k] = acc[k] * inv;
+}
+
+template <int PROFILE, bool GENERAL>
+__global__ void k_aov(const DevScene S, const DevCamera cam, const ShadeParams sp, int W, int H, int spp, uint32_t seed_lo,
+                      uint32_t seed_hi, float *__restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < W * H) aov_pixel<PROFILE, GENERAL>(S, cam, sp, W, H, spp, seed_lo, seed_hi, p, out);
+}
+
 template <int PROFILE, bool GENERAL>
 __global__ void k_trace_closest(const DevScene S, const uint8_t *__restrict__ sphere_is_big,
                                 const float4 *__restrict__ rays, int n, float t_min, float t_max, int use_accel,

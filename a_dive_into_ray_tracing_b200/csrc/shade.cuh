@@ -223,16 +223,11 @@ RT_COLD HitAcc apply_media(const float4 *__restrict__ media, int n_media, V3f ro
   return h;
 }
 
-// Surface interaction at an accepted hit. Updates the ray (origin = hit point,
-// new direction), the throughput `beta` and (profile 2) the radiance `L`.
-// Returns true when the path continues.
-//   rnd: the four random words of this bounce.
-template <int PROFILE, bool GENERAL, bool EXT = false>
-RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const HitAcc &h, V3f &beta, V3f &L,
-                     Philox4 rnd) {
-  const V3f p = madd(r.o, h.t, r.d);
-  V3f outward;
-  int mat;
+// Outward (nominal) normal and material of the primitive hit at p = r.at(h.t):
+// sphere (p - c)/r (sphere.h:57), triangle unit face normal (triangle.h:49), rect +axis
+// (aarect.h:54), medium arbitrary (constant_medium.h:69).
+template <bool GENERAL, bool EXT>
+RT_HD void surface_at(const DevScene &S, const Ray &r, const HitAcc &h, V3f p, V3f &outward, int &mat) {
   int type = GENERAL ? RT_PRIM_TYPE_OF(h.id) : RT_PRIM_SPHERE;
   int idx = GENERAL ? RT_PRIM_INDEX_OF(h.id) : h.id;
   if (type == RT_PRIM_SPHERE) {
@@ -255,6 +250,39 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
     outward = v3(1.f, 0.f, 0.f);
     mat = RT_F2I(S.media[4 * idx + 2].w);
   }
+}
+
+// First-hit features of a camera ray for denoisers (rt_render_aov): albedo = the texture colour the
+// integrator would multiply by (1 for glass, emission clamped to 1 for lights), normal = the
+// shading normal (facing the ray where the profile flips it), t = the ray parameter.
+template <int PROFILE, bool GENERAL>
+RT_HD void first_hit_features(const DevScene &S, const ShadeParams &sp, const Ray &r, const HitAcc &h, V3f &albedo,
+                              V3f &normal) {
+  const V3f p = madd(r.o, h.t, r.d);
+  V3f outward;
+  int mat;
+  surface_at<GENERAL, GENERAL>(S, r, h, p, outward, mat);
+  normal = outward;
+  if (PROFILE == 0 || (PROFILE == 2 && (sp.flags & RT_FLAG_FLIP_NORMALS)))
+    if (!(dot(r.d, outward) < 0.0f)) normal = -outward;
+  const float4 m0 = S.mats[2 * mat], m1 = S.mats[2 * mat + 1];
+  const int mtype = RT_F2I(m0.w) & 0xff;
+  if (mtype == RT_MAT_DIELECTRIC) albedo = v3(1.f, 1.f, 1.f);
+  else albedo = (PROFILE == 2) ? material_color<GENERAL>(S, m0, m1, p, outward, h.id) : xyz(m0);
+  if (mtype == RT_MAT_DIFFUSE_LIGHT) albedo = v3(RT_FMIN(albedo.x, 1.f), RT_FMIN(albedo.y, 1.f), RT_FMIN(albedo.z, 1.f));
+}
+
+// Surface interaction at an accepted hit. Updates the ray (origin = hit point,
+// new direction), the throughput `beta` and (profile 2) the radiance `L`.
+// Returns true when the path continues.
+//   rnd: the four random words of this bounce.
+template <int PROFILE, bool GENERAL, bool EXT = false>
+RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const HitAcc &h, V3f &beta, V3f &L,
+                     Philox4 rnd) {
+  const V3f p = madd(r.o, h.t, r.d);
+  V3f outward;
+  int mat;
+  surface_at<GENERAL, EXT>(S, r, h, p, outward, mat);
   const float dn_out = dot(r.d, outward);
   const bool front_face = dn_out < 0.0f;
   V3f n = outward;

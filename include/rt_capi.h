@@ -261,6 +261,14 @@ int rt_resolve(rt_ctx *ctx, float *linear_rgb, uint8_t *rgb8);
 int rt_resolve_device(rt_ctx *ctx, int width, int height, const float *d_accum, float *linear_rgb,
                       uint8_t *rgb8, void *stream);
 
+/* Denoiser feature buffers ("denoise-ready AOVs"; the reference renders one shot and has
+ * none). Per pixel, the mean over `spp` camera samples - sample k of a pixel is the same primary ray
+ * rt_render traces - of the first SURFACE hit's albedo (the texture colour the integrator multiplies by; 1 for
+ * dielectrics; emission clamped to 1; the miss colour for rays that leave the scene), shading normal (facing
+ * the ray where the profile flips normals; 0 on a miss) and ray parameter t (0 on a miss).
+ * aov: host float[H][W][8] = albedo.rgb, normal.xyz, t, hit fraction; bottom row first. */
+int rt_render_aov(rt_ctx *ctx, int width, int height, int spp, float *aov);
+
 int rt_stats(rt_ctx *ctx, rt_stats_t *out);
 int rt_stats_reset(rt_ctx *ctx);
 int rt_sync(rt_ctx *ctx);

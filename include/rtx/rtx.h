@@ -807,6 +807,12 @@ public:
     check(rt_resolve(ctx, nullptr, im.rgb.data()));
     return im;
   }
+  // denoiser feature buffers [H][W][8]: albedo rgb, normal xyz, t, hit fraction (rt_render_aov)
+  std::vector<float> render_aov(int width, int height, int samples_per_pixel = 1) {
+    std::vector<float> f((size_t)width * height * 8);
+    check(rt_render_aov(ctx, width, height, samples_per_pixel, f.data()));
+    return f;
+  }
   // accumulation frame (float4 per pixel: sum R, G, B and the sample count) — checkpoints, and the
   // host-side combine of a multi-GPU sample split
   std::vector<float> accum_download() {

@@ -13,7 +13,7 @@
 
 #include "../../a_dive_into_ray_tracing_b200/csrc/bvh_build.cuh"
 #include "../../a_dive_into_ray_tracing_b200/csrc/scene_flatten.h"
-#include "../../a_dive_into_ray_tracing_b200/csrc/shade.cuh"
+#include "../../a_dive_into_ray_tracing_b200/csrc/render_kernels.cuh"
 
 struct EmuScene {
   HostFlat F;
@@ -238,6 +238,18 @@ extern "C" void emu_texture(void *p_, int material, int n, const int32_t *prim, 
     V3f c = material_color<true>(E->S, m0, m1, v3_from(p + 3 * k), v3_from(outward + 3 * k), prim[k]);
     rgb[3 * k] = c.x; rgb[3 * k + 1] = c.y; rgb[3 * k + 2] = c.z;
   }
+}
+
+// rt_render_aov through the same per-pixel device code (render_kernels.cuh aov_pixel)
+extern "C" int emu_aov(void *p_, int W, int H, int spp, uint64_t seed, float *out) {
+  EmuScene *E = (EmuScene *)p_;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  for (int p = 0; p < W * H; p++) {
+    if (E->profile == 0) aov_pixel<0, false>(E->S, E->cam, E->sp, W, H, spp, k0, k1, p, out);
+    else if (E->profile == 1) aov_pixel<1, false>(E->S, E->cam, E->sp, W, H, spp, k0, k1, p, out);
+    else aov_pixel<2, true>(E->S, E->cam, E->sp, W, H, spp, k0, k1, p, out);
+  }
+  return 0;
 }
 
 #include "warpsim.inc"

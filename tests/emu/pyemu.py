@@ -78,6 +78,12 @@ class Emu:
                              out.ctypes.data)
         return out
 
+    def aov(self, W, H, spp=1, seed=1984):
+        out = np.zeros((H, W, 8), np.float32)
+        self.lib.emu_aov.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_uint64, _vp]
+        self.lib.emu_aov(self.h, W, H, spp, seed, out.ctypes.data)
+        return out
+
     def render(self, W, H, spp, spp_begin=0, seed=1984, rows=None, threads=None):
         from concurrent.futures import ThreadPoolExecutor
         s = np.zeros((H, W, 3), np.float64)
