@@ -172,7 +172,7 @@ struct rt_ctx {
   bool ext = false; // media or noise/image textures: the extended kernel variant
   // device scene
   DevBuf d_nodes, d_sph, d_sph_k, d_sph_mv, d_sph_t0, d_tri, d_tri_n, d_quad, d_sph_mat, d_tri_mat, d_quad_mat, d_mats, d_big,
-      d_leaf_prims, d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad, d_media, d_perlin_vec, d_perlin_perm, d_image_bytes,
+      d_leaf_prims, d_bigq, d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad, d_media, d_perlin_vec, d_perlin_perm, d_image_bytes,
       d_images;
   DevScene S;
   DevCamera cam;
@@ -269,7 +269,7 @@ void rt_destroy(rt_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   DevBuf *all[] = {&ctx->d_nodes, &ctx->d_sph, &ctx->d_sph_k, &ctx->d_sph_mv, &ctx->d_sph_t0, &ctx->d_tri, &ctx->d_tri_n, &ctx->d_quad,
-                   &ctx->d_sph_mat, &ctx->d_tri_mat, &ctx->d_quad_mat, &ctx->d_mats, &ctx->d_big, &ctx->d_leaf_prims, &ctx->d_sph_is_big,
+                   &ctx->d_sph_mat, &ctx->d_tri_mat, &ctx->d_quad_mat, &ctx->d_mats, &ctx->d_big, &ctx->d_leaf_prims, &ctx->d_bigq, &ctx->d_sph_is_big,
                    &ctx->d_raw_sph, &ctx->d_raw_tri, &ctx->d_raw_quad, &ctx->d_media, &ctx->d_perlin_vec,
                    &ctx->d_perlin_perm, &ctx->d_image_bytes, &ctx->d_images, &ctx->d_accum, &ctx->d_partial, &ctx->d_counter,
                    &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts};
@@ -334,6 +334,7 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   std::vector<uint8_t> nobig(std::max(ns, 1), 0);
   if ((rc = dev_upload(ctx, ctx->d_sph_is_big, nobig.data(), nobig.size()))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_big, 16))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_bigq, 32))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_leaf_prims, 16))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_nodes, 32))) return rc;
 
@@ -357,7 +358,8 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   S.perlin_perm = (const uint8_t *)ctx->d_perlin_perm.p;
   S.images = (const DevImage *)ctx->d_images.p;
   S.n_media = sc->n_media; S.n_perlin = sc->n_perlin; S.n_images = sc->n_images;
-  S.n_nodes = 0; S.n_big = 0;
+  S.bigq = (const float4 *)ctx->d_bigq.p;
+  S.n_nodes = 0; S.n_big = 0; S.n_bigq = 0;
   S.n_spheres = ns; S.n_tris = nt; S.n_quads = nq; S.n_mats = nm;
   S.any_moving = any_moving ? 1 : 0;
 
@@ -395,7 +397,7 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   const int ns = ctx->S.n_spheres, nt = ctx->S.n_tris, nq = ctx->S.n_quads;
   const int n = ns + nt + nq;
   ctx->big_ids.clear();
-  ctx->S.n_nodes = 0; ctx->S.n_big = 0; ctx->n_leaf_prims = 0;
+  ctx->S.n_nodes = 0; ctx->S.n_big = 0; ctx->S.n_bigq = 0; ctx->n_leaf_prims = 0;
   ctx->stats.n_nodes = 0; ctx->stats.n_big_prims = 0;
   if (n == 0) { ctx->have_accel = true; ctx->stats.ms_build = 0; return RT_OK; }
   CK(cudaEventRecord(ctx->ev0, st));
@@ -462,13 +464,27 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   }
   const int nsm = (int)small.size();
   {
-    std::vector<int32_t> bigpad(std::max<size_t>(ctx->big_ids.size(), 4), 0);
-    std::copy(ctx->big_ids.begin(), ctx->big_ids.end(), bigpad.begin());
+    // rects go to their own decoded list (no id fetch / type dispatch in the segment start)
+    std::vector<int32_t> others;
+    std::vector<float4> bigq;
+    for (int32_t id : ctx->big_ids) {
+      if (RT_PRIM_TYPE_OF(id) != RT_PRIM_QUAD) { others.push_back(id); continue; }
+      const rt_quad &q = ctx->quads[RT_PRIM_INDEX_OF(id)];
+      bigq.push_back(make_float4(q.k, q.a0, q.a1, RT_I2F(q.axis)));
+      bigq.push_back(make_float4(q.b0, q.b1, RT_I2F(id), 0.f));
+    }
+    const int n_bigq = (int)bigq.size() / 2;
+    std::vector<int32_t> bigpad(std::max<size_t>(others.size(), 4), 0);
+    std::copy(others.begin(), others.end(), bigpad.begin());
+    bigq.resize(std::max<size_t>(bigq.size(), 2), make_float4(0, 0, 0, 0));
     int rc = dev_upload(ctx, ctx->d_big, bigpad.data(), bigpad.size() * sizeof(int32_t));
+    if (!rc) rc = dev_upload(ctx, ctx->d_bigq, bigq.data(), bigq.size() * sizeof(float4));
     if (!rc) rc = dev_upload(ctx, ctx->d_sph_is_big, sph_is_big.data(), sph_is_big.size());
     if (rc) { cleanup(); return rc; }
     ctx->S.big = (const int32_t *)ctx->d_big.p;
-    ctx->S.n_big = n_big;
+    ctx->S.n_big = (int)others.size();
+    ctx->S.bigq = (const float4 *)ctx->d_bigq.p;
+    ctx->S.n_bigq = n_bigq;
   }
   int n_nodes = nsm > 0 ? 2 * nsm - 1 : 0;
   if (nsm > 0) {
@@ -597,7 +613,7 @@ int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nod
   CK(cudaSetDevice(ctx->cfg.device));
   if (n_nodes) *n_nodes = ctx->S.n_nodes;
   if (n_leaf) *n_leaf = ctx->n_leaf_prims;
-  if (n_big) *n_big = ctx->S.n_big;
+  if (n_big) *n_big = (int)ctx->big_ids.size();
   if (nodes) {
     if (cap_nodes < ctx->S.n_nodes) return fail(ctx, RT_ERR_INVALID, "node buffer too small");
     if (ctx->S.n_nodes)
@@ -614,7 +630,7 @@ int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nod
                     cudaMemcpyDeviceToHost));
   }
   if (big_prims) {
-    if (cap_big < ctx->S.n_big) return fail(ctx, RT_ERR_INVALID, "big-primitive buffer too small");
+    if (cap_big < (int)ctx->big_ids.size()) return fail(ctx, RT_ERR_INVALID, "big-primitive buffer too small");
     std::copy(ctx->big_ids.begin(), ctx->big_ids.end(), big_prims);
   }
   return RT_OK;
@@ -634,7 +650,7 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(ctx->d_rays.p, rays, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
   DevScene S = ctx->S;
-  if (!use_accel) { S.n_nodes = 0; S.n_big = 0; }
+  if (!use_accel) { S.n_nodes = 0; S.n_big = 0; S.n_bigq = 0; }
   const int TB = 128, g = (n + TB - 1) / TB;
   const uint8_t *isbig = (const uint8_t *)ctx->d_sph_is_big.p;
   const float4 *dr = (const float4 *)ctx->d_rays.p;
@@ -725,6 +741,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   P.b_sph_k = (int)pad16(sizeof(float) * (size_t)S.n_spheres);
   P.b_mats = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_mats);
   P.b_big = (int)pad16(sizeof(int32_t) * (size_t)S.n_big);
+  P.b_bigq = ctx->general ? (int)pad16(sizeof(float4) * 2 * (size_t)S.n_bigq) : 0;
   P.b_leaf_prims = (int)pad16(sizeof(int32_t) * (size_t)ctx->n_leaf_prims);
   size_t scene_bytes = (size_t)P.b_nodes + P.b_sph + P.b_sph_k + P.b_sph_mat + P.b_mats + P.b_big + P.b_leaf_prims;
   if (ctx->general) {
@@ -735,7 +752,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
     P.b_quad = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_quads);
     P.b_tri_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_tris);
     P.b_quad_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_quads);
-    scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat;
+    scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat + P.b_bigq;
   }
   const size_t acc_bytes = (size_t)(block / 32) * 256 * sizeof(float); // two 32-pixel tiles per warp
   // shared-memory plan: 2 = scene + four quadrant copies of the nodes, 1 = scene, 0 = global

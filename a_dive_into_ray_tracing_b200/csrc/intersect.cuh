@@ -237,6 +237,13 @@ RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r, float t_min, float t
     if (is_sphere) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
     else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
   }
+  if (GENERAL) {
+    for (int i = 0; i < S.n_bigq; i++) {
+      if (COUNT) cnt->prim_tests++;
+      const float4 q0 = S.bigq[2 * i], q1 = S.bigq[2 * i + 1];
+      hit_quad(q0, q1, r, pre, t_min, h, RT_F2I(q1.z));
+    }
+  }
   int node = 0; // byte offset of the current node
   const int n_nodes = S.n_nodes << RT_NODE_SHIFT;
   int first = 0, left = 0; // pending primitives of the last hit leaf: leaf_prims[first .. first+left)

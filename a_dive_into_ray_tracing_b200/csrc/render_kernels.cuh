@@ -50,7 +50,7 @@ struct RenderParams {
   int leaf_min; // run the pending primitive tests when this many lanes wait (or nobody searches)
   int frac8;  // a BVH burst ends when fewer than frac8/8 of its entry lanes are still searching
   // bytes of each array staged to shared memory (all multiples of 16)
-  int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big, b_leaf_prims;
+  int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big, b_leaf_prims, b_bigq;
   // sphere-only kernels with single-primitive leaves: the staged leaf payloads name the sphere
   // directly (~(sphere << 3)) and the sphere array sits at this byte offset of the shared copy
   int direct_leaf, off_sph;
@@ -123,6 +123,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       S.quad = (const float4 *)stage_to_smem(smem_raw, off, P.S.quad, P.b_quad);
       S.tri_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.tri_mat, P.b_tri_mat);
       S.quad_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.quad_mat, P.b_quad_mat);
+      S.bigq = (const float4 *)stage_to_smem(smem_raw, off, P.S.bigq, P.b_bigq);
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -186,6 +187,13 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       const bool is_sphere = !GENERAL || RT_PRIM_TYPE_OF(id) == RT_PRIM_SPHERE;
       if (is_sphere) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
       else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
+    }
+    if (GENERAL) { // always-tested rects (walls): decoded records, the same address for every lane
+      for (int i = 0; i < S.n_bigq; i++) {
+        if (COUNT) cnt.prim_tests++;
+        const float4 q0 = S.bigq[2 * i], q1 = S.bigq[2 * i + 1];
+        hit_quad(q0, q1, r, pre, t_min, h, RT_F2I(q1.z));
+      }
     }
     // participating media: a sampled scatter event becomes the initial closest hit
     if (EXT && S.n_media)

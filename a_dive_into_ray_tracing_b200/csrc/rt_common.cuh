@@ -98,7 +98,9 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 //  quad    float4[2*n_quads]   {k, a0, a1, as_float(axis)} {b0, b1, 0, 0}
 //  *_mat   int32 per primitive material index
 //  mats    float4[2*n_mats]    {albedo.rgb, as_float(type | texture<<8)} {albedo2.rgb, param}
-//  big     int32[n_big]        RT_PRIM_IDs tested for every ray before traversal
+//  big     int32[n_big]        RT_PRIM_IDs tested for every ray before traversal (spheres, triangles)
+//  bigq    float4[2*n_bigq]    always-tested RECTS (room walls), decoded: {k, a0, a1, as_float(axis)}
+//                              {b0, b1, as_float(RT_PRIM_ID), 0} - no id fetch / type dispatch per ray
 //  media   float4[4*n_media]   {p0.xyz, as_float(shape)} {p1.xyz, -1/density} {offset.xyz, as_float(material)}
 //                              {sin_y, cos_y, 0, 0}            (global memory; not in the BVH)
 //  perlin_vec float4[256*n_perlin], perlin_perm uint8[768*n_perlin] (x, y, z tables)
@@ -126,6 +128,8 @@ struct DevScene {
   int n_nodes, n_spheres, n_tris, n_quads, n_mats, n_big;
   int any_moving;
   int node_stride; // bytes between the four quadrant-ordered copies of `nodes` (copy 0 first)
+  const float4 *bigq;
+  int n_bigq;
   const float4 *media;
   const float4 *perlin_vec;
   const uint8_t *perlin_perm;
