@@ -24,7 +24,7 @@ STATUS = {0: "RT_OK", 1: "RT_ERR_INVALID", 2: "RT_ERR_CUDA", 3: "RT_ERR_STATE", 
 
 # every symbol include/rt_capi.h declares
 SYMBOLS = ["rt_version", "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_scene_upload",
-           "rt_accel_build", "rt_accel_download", "rt_trace_closest", "rt_render", "rt_render_device",
+           "rt_accel_build", "rt_accel_download", "rt_trace_closest", "rt_render", "rt_render_device", "rt_render_rows_device",
            "rt_accum_clear", "rt_accum_download", "rt_accum_upload", "rt_accum_device_ptr", "rt_resolve",
            "rt_resolve_device", "rt_render_aov", "rt_stats", "rt_stats_reset", "rt_sync", "rt_measure_fp32_peak"]
 
@@ -84,6 +84,8 @@ def load_library():
     L.rt_accum_device_ptr.argtypes = [_vp]
     L.rt_resolve.restype = C.c_int
     L.rt_resolve.argtypes = [_vp, _vp, _vp]
+    L.rt_render_rows_device.restype = C.c_int
+    L.rt_render_rows_device.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp]
     L.rt_render_aov.restype = C.c_int
     L.rt_render_aov.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _vp]
     L.rt_resolve_device.restype = C.c_int
@@ -190,6 +192,11 @@ class Context:
     def render_device(self, W, H, spp_count, spp_begin, d_accum_ptr, stream_ptr=None):
         self._ck(self.lib.rt_render_device(self.h, W, H, spp_begin, spp_count, d_accum_ptr,
                                            self._stream(stream_ptr)))
+
+    def render_rows_device(self, W, H, row_begin, row_end, spp_count, spp_begin, d_accum_ptr, stream_ptr=None):
+        """rows [row_begin, row_end) only (row 0 = bottom); the rest of the frame is left untouched"""
+        self._ck(self.lib.rt_render_rows_device(self.h, W, H, row_begin, row_end, spp_begin, spp_count, d_accum_ptr,
+                                                self._stream(stream_ptr)))
 
     def clear(self):
         self._ck(self.lib.rt_accum_clear(self.h))

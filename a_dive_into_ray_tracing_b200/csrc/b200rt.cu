@@ -684,8 +684,11 @@ static render_kernel_t pick_render_kernel(int profile, int smem, bool count, boo
 }
 
 static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, float *d_accum, cudaStream_t st,
-                       bool timed) {
+                       bool timed, int y0 = 0, int y1 = -1) {
+  if (y1 < 0) y1 = H;
   if (W < 2 || H < 2 || spp_count < 0 || spp_begin < 0) return fail(ctx, RT_ERR_INVALID, "bad frame parameters");
+  if (y0 < 0 || y1 > H || y0 > y1) return fail(ctx, RT_ERR_INVALID, "bad row range");
+  if (y0 == y1) return RT_OK;
   if (!ctx->have_scene) return fail(ctx, RT_ERR_STATE, "rt_render before rt_scene_upload");
   if (!ctx->have_accel) {
     int rc = rt_accel_build(ctx, 1);
@@ -697,8 +700,9 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   memset(&P, 0, sizeof P);
   P.S = ctx->S; P.cam = ctx->cam; P.sp = ctx->sp;
   P.W = W; P.H = H;
+  P.y0 = y0; P.y1 = y1;
   P.tiles_x = (W + RT_TILE_W - 1) / RT_TILE_W;
-  P.n_tiles = P.tiles_x * ((H + RT_TILE_H - 1) / RT_TILE_H);
+  P.n_tiles = P.tiles_x * ((y1 - y0 + RT_TILE_H - 1) / RT_TILE_H);
   const int grid = ctx->sm_count;
   const int block = RT_BLOCK_OF(ctx->general);
   const int n_warps = grid * (block / 32);
@@ -781,7 +785,9 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   if (timed) CK(cudaEventRecord(ctx->ev0, st));
   kern<<<grid, block, smem_bytes, st>>>(P);
   CK(cudaGetLastError());
-  k_combine<<<(unsigned)((n_pix + 255) / 256), 256, 0, st>>>((float4 *)d_accum, P.partial, (int)n_pix, P.n_chunks);
+  const int first_px = y0 * W, n_band = (y1 - y0) * W;
+  k_combine<<<(unsigned)((n_band + 255) / 256), 256, 0, st>>>((float4 *)d_accum, P.partial, (int)n_pix, P.n_chunks, first_px,
+                                                              n_band);
   CK(cudaGetLastError());
   ctx->launches += 2;
   if (timed) CK(cudaEventRecord(ctx->ev1, st));
@@ -818,6 +824,14 @@ int rt_render_device(rt_ctx *ctx, int width, int height, int spp_begin, int spp_
   CK(cudaSetDevice(ctx->cfg.device));
   return render_into(ctx, width, height, spp_begin, spp_count, d_accum, stream ? (cudaStream_t)stream : ctx->stream,
                      false);
+}
+
+int rt_render_rows_device(rt_ctx *ctx, int width, int height, int row_begin, int row_end, int spp_begin, int spp_count,
+                          float *d_accum, void *stream) {
+  if (!ctx || !d_accum) return RT_ERR_INVALID;
+  CK(cudaSetDevice(ctx->cfg.device));
+  return render_into(ctx, width, height, spp_begin, spp_count, d_accum, stream ? (cudaStream_t)stream : ctx->stream,
+                     false, row_begin, row_end);
 }
 
 int rt_accum_clear(rt_ctx *ctx) {

@@ -41,6 +41,7 @@ struct RenderParams {
   DevCamera cam;
   ShadeParams sp;
   int W, H, tiles_x, n_tiles;
+  int y0, y1; // rows rendered by this launch: [y0, y1) (the whole frame: 0, H)
   int n_chunks, chunk_spp, spp_begin, spp_count, n_work;
   float4 *partial;               // [n_chunks][H*W]
   int *work_counter;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           const int tile = w % P.n_tiles;
           chunk = w / P.n_tiles;
           tile_x0 = (tile % P.tiles_x) * RT_TILE_W;
-          tile_y0 = (tile / P.tiles_x) * RT_TILE_H;
+          tile_y0 = P.y0 + (tile / P.tiles_x) * RT_TILE_H;
           s0 = P.spp_begin + chunk * P.chunk_spp;
           chunk_n = min(P.chunk_spp, P.spp_count - chunk * P.chunk_spp);
           pool_next = 0;
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           if (item < pool_end) {
             const int px = item & 31;
             const int i = tile_x0 + (px & 7), j = tile_y0 + (px >> 3);
-            if (i < P.W && j < P.H) {
+            if (i < P.W && j < P.y1) {
               pix = px | (cur_buf << 5);
               smp = s0 + (item >> 5);
               pixel_index = j * P.W + i;
@@ -384,7 +385,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     if (old_valid && old_inflight == 0) {
       __syncwarp();
       const int i = old_x0 + (lane & 7), j = old_y0 + (lane >> 3);
-      if (i < P.W && j < P.H) {
+      if (i < P.W && j < P.y1) {
         const float *a = acc + old_buf * 128 + lane * 4;
         P.partial[(size_t)old_chunk * ((size_t)P.W * P.H) + (size_t)j * P.W + i] =
             make_float4(a[0], a[1], a[2], (float)old_chunk_n);
@@ -407,10 +408,12 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   }
 }
 
-// accum[p] += sum over chunks (fixed order) of partial[c][p]
-__global__ void k_combine(float4 *__restrict__ accum, const float4 *__restrict__ partial, int n_pix, int n_chunks) {
+// accum[p] += sum over chunks (fixed order) of partial[c][p] for the pixels [first, first + count)
+__global__ void k_combine(float4 *__restrict__ accum, const float4 *__restrict__ partial, int n_pix, int n_chunks,
+                          int first, int count) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pix) return;
+  if (p >= count) return;
+  p += first;
   float4 a = accum[p];
   for (int c = 0; c < n_chunks; c++) {
     float4 v = __ldcs(partial + (size_t)c * n_pix + p);

@@ -17,6 +17,13 @@ def sample_range(spp, rank, world):
     return begin, end - begin
 
 
+def row_range(H, rank, world, align=4):
+    """Contiguous bands of rows (multiples of the 8x4 tile height) for the image-space split."""
+    bands = (H + align - 1) // align
+    b0, b1 = (bands * rank) // world, (bands * (rank + 1)) // world
+    return min(H, b0 * align), min(H, b1 * align)
+
+
 def reduce_frames(accum, dst=0):
     """Sum the per-rank accumulation frames onto `dst` (in place on dst)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -24,14 +31,20 @@ def reduce_frames(accum, dst=0):
     return accum
 
 
-def render_frame(ctx, W, H, spp, accum, rank=0, world=1, stream=None):
-    """Render this rank's share of `spp` samples into the CUDA tensor `accum`
-    ([H, W, 4] float32, zeroed by the caller) on the current torch stream, then
-    reduce to rank 0. No host synchronisation."""
+def render_frame(ctx, W, H, spp, accum, rank=0, world=1, stream=None, split="samples"):
+    """Render this rank's share of the frame into the CUDA tensor `accum` ([H, W, 4] float32,
+    zeroed by the caller) on the current torch stream, then reduce to rank 0. No host
+    synchronisation. split = "samples": every pixel, a share of the sample indices (the default:
+    perfectly balanced); "rows": all samples of a band of rows (latency of low-spp frames; the
+    bands' cost depends on the image content)."""
     assert accum.is_cuda and accum.dtype == torch.float32 and accum.is_contiguous()
     assert tuple(accum.shape) == (H, W, 4)
-    begin, count = sample_range(spp, rank, world)
     s = stream if stream is not None else torch.cuda.current_stream()
-    ctx.render_device(W, H, count, begin, accum.data_ptr(), s.cuda_stream)
+    if split == "rows":
+        y0, y1 = row_range(H, rank, world)
+        ctx.render_rows_device(W, H, y0, y1, spp, 0, accum.data_ptr(), s.cuda_stream)
+    else:
+        begin, count = sample_range(spp, rank, world)
+        ctx.render_device(W, H, count, begin, accum.data_ptr(), s.cuda_stream)
     reduce_frames(accum)
     return accum

@@ -248,6 +248,11 @@ int rt_render(rt_ctx *ctx, int width, int height, int spp_begin, int spp_count);
  * (cudaStream_t as void*; NULL = the context's stream). No host sync. */
 int rt_render_device(rt_ctx *ctx, int width, int height, int spp_begin, int spp_count, float *d_accum,
                      void *stream);
+/* Image-space split (SURVEY.md 8e alternative / 8f: tile split for interactive latency): as rt_render_device,
+ * but only the rows [row_begin, row_end) of the frame (row 0 = bottom) are rendered and accumulated; every
+ * other pixel of d_accum is left untouched. A pixel's samples do not depend on the split. */
+int rt_render_rows_device(rt_ctx *ctx, int width, int height, int row_begin, int row_end, int spp_begin,
+                          int spp_count, float *d_accum, void *stream);
 int rt_accum_clear(rt_ctx *ctx);
 int rt_accum_download(rt_ctx *ctx, float *rgba, size_t n_floats);     /* host <- device */
 int rt_accum_upload(rt_ctx *ctx, int width, int height, const float *rgba, size_t n_floats); /* resume */

@@ -5,7 +5,7 @@ import subprocess
 import sys
 import textwrap
 
-from a_dive_into_ray_tracing_b200.dist import sample_range
+from a_dive_into_ray_tracing_b200.dist import row_range, sample_range
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -18,6 +18,17 @@ def test_sample_range_partitions_exactly():
                 b, c = sample_range(spp, r, world)
                 seen += list(range(b, b + c))
             assert seen == list(range(spp))
+
+
+def test_row_range_partitions_exactly_on_tile_rows():
+    for H in (2, 54, 225, 800, 2160):
+        for world in (1, 2, 3, 4, 8):
+            rows = []
+            for r in range(world):
+                y0, y1 = row_range(H, r, world)
+                assert y0 % 4 == 0 and (y1 % 4 == 0 or y1 == H) and 0 <= y0 <= y1 <= H
+                rows += list(range(y0, y1))
+            assert rows == list(range(H))
 
 
 WORKER = textwrap.dedent("""
@@ -37,6 +48,15 @@ WORKER = textwrap.dedent("""
     if rank == 0:
         assert torch.all(acc[..., 3] == spp), acc[..., 3]
         assert torch.all(acc[..., 0] == spp * (spp + 1) / 2)
+    # image-space split: every rank fills its band of rows with all samples
+    from a_dive_into_ray_tracing_b200.dist import row_range
+    y0, y1 = row_range(H, rank, world)
+    img = torch.zeros(H, W, 4)
+    img[y0:y1, :, :3] = spp * (spp + 1) / 2        # stand-in for rt_render_rows_device
+    img[y0:y1, :, 3] = spp
+    reduce_frames(img)
+    if rank == 0:
+        assert torch.equal(img, acc)
         print("OK")
     dist.destroy_process_group()
 """) % ROOT

@@ -186,6 +186,32 @@ def test_determinism_and_sample_split():
     assert np.abs(outs[0] - outs[3]).mean() > 1e-3
 
 
+def test_row_band_split_equals_full_frame():
+    """rt_render_rows_device: bands [0,24) + [24,40) + [40,54) of a frame, rendered into one zeroed
+    device buffer, equal the full-frame render up to fp32 summation order (the sample chunks differ);
+    rows outside a band are not touched."""
+    import torch
+    W, H, spp = 96, 54, 32
+    sc = scenes.weekend(W, H)
+    with capi.Context(profile=0, seed=5) as ctx:
+        ctx.upload(sc).build_accel(1)
+        ctx.render(W, H, spp)
+        full = ctx.accum()
+        buf = torch.zeros(H, W, 4, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        ctx.render_rows_device(W, H, 24, 40, spp, 0, buf.data_ptr(), st)
+        torch.cuda.synchronize()
+        part = buf.cpu().numpy()
+        assert np.all(part[:24] == 0) and np.all(part[40:] == 0) and np.all(part[24:40, :, 3] == spp)
+        ctx.render_rows_device(W, H, 0, 24, spp, 0, buf.data_ptr(), st)
+        ctx.render_rows_device(W, H, 40, 54, spp, 0, buf.data_ptr(), st)
+        ctx.render_rows_device(W, H, 54, 54, spp, 0, buf.data_ptr(), st)  # empty band: no-op
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(buf.cpu().numpy(), full, rtol=2e-6, atol=1e-5)
+        with pytest.raises(capi.RtError):
+            ctx.render_rows_device(W, H, 10, 60, spp, 0, buf.data_ptr(), st)
+
+
 def test_resolve_matches_write_color(l1_64, l1_32):
     W, H = 64, 40
     for sc, orc in ((scenes.weekend(W, H), l1_64), (scenes.final_cu(W, H), l1_32)):
