@@ -197,7 +197,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from a_dive_into_ray_tracing_b200 import capi, ctypes_defs as D, scenes
-    from a_dive_into_ray_tracing_b200.dist import render_frame, sample_range
+    from a_dive_into_ray_tracing_b200.dist import render_frame
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

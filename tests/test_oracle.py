@@ -3,7 +3,6 @@ were produced by the UNMODIFIED reference (tools/make_golden.py), and — where 
 compiled reference oracle/_ref/libref_l0.so is available — bit-exact pinning of the
 restatement against it."""
 import numpy as np
-import pytest
 
 from a_dive_into_ray_tracing_b200 import ctypes_defs as D
 from a_dive_into_ray_tracing_b200 import scenes

@@ -1,10 +1,13 @@
-import sys, time, os
+"""Large-mesh scaling of the config-3 room (closed procedural mesh subdivided N times): BVH build and
+render time through the C ABI. Usage: python tools/big_mesh.py <subdivisions>   (4..7 = 5k..328k triangles)"""
+import os
+import sys
+import time
+
 sys.path.insert(0, os.getcwd())
-import numpy as np
 from a_dive_into_ray_tracing_b200 import capi, scenes
 sub = int(sys.argv[1])
 sc = scenes.obj_room(width=800, height=800, subdivisions=sub)
-t0=time.time()
 with capi.Context(profile=sc.profile, seed=1984) as ctx:
     ctx.upload(sc).build_accel(1)
     ctx.render(800, 800, 4); ctx.clear(); ctx.stats_reset()
