@@ -9,9 +9,11 @@ from a_dive_into_ray_tracing_b200 import capi, scenes  # noqa: E402
 
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 500
 which = sys.argv[2] if len(sys.argv) > 2 else "weekend"
-W, H = (1200, 800) if which != "obj_room" else (800, 800)
-sc = {"weekend": scenes.weekend, "final_cu": scenes.final_cu, "next_week": scenes.next_week}.get(
-    which, lambda w, h: scenes.obj_room(width=w, height=h))(W, H)
+W, H = (1200, 800) if which in ("weekend", "final_cu", "next_week", "two_perlin_spheres") else (800, 800)
+if which == "obj_room":
+    sc = scenes.obj_room(width=W, height=H)
+else:
+    sc = getattr(scenes, which)(W, H)  # any scene function of scenes.py taking (width, height)
 with capi.Context(profile=sc.profile, seed=1984) as ctx:
     ctx.upload(sc).build_accel(1)
     for _ in range(2):
