@@ -673,7 +673,8 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
 typedef void (*render_kernel_t)(const RenderParams);
 static render_kernel_t pick_render_kernel(int profile, int smem, bool count, bool ext) {
 #define PICK3(P, G, C, E) \
-  (smem == 2 ? k_render<P, G, 2, C, E> : (smem == 1 ? k_render<P, G, 1, C, E> : k_render<P, G, 0, C, E>))
+  (smem == 2 ? k_render<P, G, 2, C, E>                                                                  \
+             : (smem == 1 ? k_render<P, G, 1, C, E> : (smem == 3 ? k_render<P, G, 3, C, E> : k_render<P, G, 0, C, E>)))
 #define PICK(P, G, E) return count ? PICK3(P, G, true, E) : PICK3(P, G, false, E)
   if (profile == 0) { PICK(0, false, false); }
   if (profile == 1) { PICK(1, false, false); }
@@ -763,7 +764,13 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   int smem = 0;
   if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;
   if (scene_bytes + 3 * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
-  if (const char *e = getenv("B200RT_SMEM")) smem = std::min(smem, atoi(e)); // tuning knob
+  // nodes only: one node copy resident, primitives through L1/L2
+  if (smem == 0 && (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin && S.n_nodes > 0) smem = 3;
+  if (const char *e = getenv("B200RT_SMEM")) { // tuning knob: cap the plan (3 ranks between 0 and 1)
+    const int cap = atoi(e);
+    const int rank_of[4] = {0, 2, 3, 1}; // plan -> rank
+    if (rank_of[smem] > rank_of[cap < 0 || cap > 3 ? 0 : cap]) smem = cap < 0 || cap > 3 ? 0 : cap;
+  }
   if (smem == 0) {
     // Global-memory node path: the four quadrant-ordered copies pay while they stay cache
     // resident (measured: neutral up to 164 k nodes, one copy +14 % at 655 k nodes = 84 MB of copies).
@@ -771,11 +778,12 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
     if (const char *e = getenv("B200RT_ONECOPY")) one_copy = atoi(e) != 0; // measurement knob
     if (one_copy) P.S.node_stride = 0;
   }
-  const size_t smem_bytes = acc_bytes + (smem ? scene_bytes : 0) + (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
+  const size_t smem_bytes = acc_bytes + (smem == 3 ? (size_t)P.b_nodes : (smem ? scene_bytes : 0)) +
+                            (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
   // staging order in k_render: node copies first, then the sphere array
   P.off_sph = (smem == 2 ? 4 : 1) * P.b_nodes;
   P.hi_off = S.n_nodes << 4;
-  P.direct_leaf = (!ctx->general && smem != 0 && ctx->max_leaf == 1) ? 1 : 0;
+  P.direct_leaf = (!ctx->general && (smem == 1 || smem == 2) && ctx->max_leaf == 1) ? 1 : 0;
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
   render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext);
   CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));

@@ -68,7 +68,9 @@ __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &o
   return dst;
 }
 
-// SMEM: 0 = scene read from global memory (L1/L2); 1 = whole scene staged in shared memory;
+// SMEM: 3 = only the node array (one copy) staged in shared memory, primitives and materials read
+// through L1/L2 (scenes whose nodes fit but whose primitives do not);
+// 0 = scene read from global memory (L1/L2); 1 = whole scene staged in shared memory;
 // 2 = as 1, with FOUR copies of the node array, one per sign combination of (d.x, d.z), whose
 // box planes are pre-swapped so that the slab test needs no min/max on those axes.
 // EXT: media + noise/image textures (rt_next_week scenes 3-8), profile 2 only.
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       }
       off += copies * P.b_nodes;
     }
+    if (SMEM != 3) {
     S.sph = (const float4 *)stage_to_smem(smem_raw, off, P.S.sph, P.b_sph);
     S.sph_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.sph_mat, P.b_sph_mat);
     S.sph_k = (const float *)stage_to_smem(smem_raw, off, P.S.sph_k, P.b_sph_k);
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       S.tri_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.tri_mat, P.b_tri_mat);
       S.quad_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.quad_mat, P.b_quad_mat);
       S.bigq = (const float4 *)stage_to_smem(smem_raw, off, P.S.bigq, P.b_bigq);
+    }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

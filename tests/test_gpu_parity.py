@@ -364,6 +364,28 @@ def test_large_scene_global_memory_path(l1_64):
     assert abs(st["segments"] / st["paths"] - nseg / (W * H * spp)) < 0.05 * nseg / (W * H * spp)
 
 
+@pytest.mark.parametrize("name", ["weekend", "next_week", "cornell_box", "next_week_final"])
+def test_shared_memory_plans_render_the_same_image(name, monkeypatch):
+    """k_render's four residency plans (0 global, 3 nodes only, 1 scene + one node copy, 2 scene + four
+    quadrant copies) differ in where the data sits and in the node visiting order, never in a path's
+    result: frames agree to fp32 summation order."""
+    W, H, spp = 64, 48, 8
+    sc = getattr(scenes, name)(W, H)
+    frames, plans = [], []
+    for cap in ("2", "1", "3", "0"):
+        monkeypatch.setenv("B200RT_SMEM", cap)
+        with capi.Context(profile=sc.profile, seed=11) as ctx:
+            ctx.upload(sc).build_accel(1)
+            ctx.render(W, H, spp)
+            frames.append(ctx.accum())
+            plans.append(ctx.stats()["smem_bytes"])
+    assert plans[-1] < 40000  # plan 0: only the accumulators
+    if name != "next_week_final":  # (its 6 813 nodes do not fit: every cap ends in plan 0)
+        assert plans[0] >= plans[1] >= plans[2] > plans[3]
+    for f in frames[1:]:
+        np.testing.assert_allclose(f, frames[0], rtol=1e-5, atol=1e-4)
+
+
 def test_multi_primitive_leaves_give_identical_hits(hits_primary, monkeypatch):
     """Leaf collapsing (K primitives per leaf) changes the tree, never the answer."""
     sc = scenes.weekend(400, 225)
