@@ -57,18 +57,28 @@ def check_packed_bvh(sc, nodes, leaf_prims, big, max_leaf=8):
     assert int(count.sum()) == n_small
     n_leaves = int(leaves.sum())
     assert n == 2 * n_leaves - 1  # full binary tree
-    # threaded layout: depth-first preorder
-    assert np.all(esc > np.arange(n)) and np.all(esc <= n) and esc[0] == n
-    inner = ~leaves
-    assert np.all(pay[inner] == np.arange(n)[inner] + 1)  # first child follows its parent
-    assert np.all(esc[leaves] == np.arange(n)[leaves] + 1)
     lo, hi = nodes["bmin"].astype(np.float64), nodes["bmax"].astype(np.float64)
     assert np.all(lo <= hi)
-    for i in np.where(inner)[0]:
-        l = i + 1
-        r = esc[l]
-        assert r < n and esc[r] == esc[i]  # the two children tile the parent's range
+    inner = ~leaves
+    assert np.all((esc >= 0) & (esc <= n)) and np.all((pay[inner] >= 0) & (pay[inner] < n))
+    # threaded links, in ANY storage order (depth-first as built, or with the top of the tree moved
+    # to the front): the root is node 0 and escapes to n; an inner node's first child is its payload,
+    # the second child is the first child's escape, and the second child escapes where its parent does
+    assert esc[0] == n
+    seen = np.zeros(n, bool)
+    stack = [0]
+    while stack:
+        i = stack.pop()
+        assert not seen[i]
+        seen[i] = True
+        if leaves[i]:
+            continue
+        l = int(pay[i])
+        r = int(esc[l])
+        assert r < n and esc[r] == esc[i]
         assert np.all(lo[i] <= np.minimum(lo[l], lo[r]) + 1e-12) and np.all(hi[i] >= np.maximum(hi[l], hi[r]) - 1e-12)
+        stack += [l, r]
+    assert seen.all()  # every node is reachable exactly once
     for i, f, c in zip(np.where(leaves)[0], first, count):
         for pid in leaf_prims[f:f + c]:
             blo, bhi = boxes[int(pid)]
