@@ -3,6 +3,7 @@
 // `new sphere(...)/new lambertian(...)` object graph of create_world<<<1,1>>>
 // (accelerated-rt-cuda/final.cu:100-143, rt_next_week/cuda/main.cu:386-467).
 #pragma once
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <string>
@@ -40,23 +41,39 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
   if (sc->n_spheres >= (1 << 28) || sc->n_triangles >= (1 << 28) || sc->n_quads >= (1 << 28))
     FAIL("too many primitives");
   if (sc->max_depth < 1) FAIL("max_depth must be >= 1");
+  // non-finite geometry would poison the bounds / Morton codes of the builder: reject it here
+  auto finite3 = [](const float *p) { return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]); };
+  {
+    const rt_camera &c = sc->camera;
+    if (!finite3(c.origin) || !finite3(c.lower_left_corner) || !finite3(c.horizontal) || !finite3(c.vertical) ||
+        !finite3(c.u) || !finite3(c.v) || !std::isfinite(c.lens_radius) || !std::isfinite(c.time0) || !std::isfinite(c.time1))
+      FAIL("camera: non-finite field");
+    if (!finite3(sc->background) || !std::isfinite(sc->t_min)) FAIL("non-finite background / t_min");
+  }
   bool any_moving = false;
   for (int i = 0; i < sc->n_spheres; i++) {
     const rt_sphere &s = sc->spheres[i];
     if (s.material < 0 || s.material >= sc->n_materials) FAIL("sphere %d: material index", i);
+    if (!finite3(s.center0) || !finite3(s.center1) || !std::isfinite(s.radius) || !std::isfinite(s.time0) ||
+        !std::isfinite(s.time1))
+      FAIL("sphere %d: non-finite field", i);
     if (s.radius == 0.0f) FAIL("sphere %d: zero radius", i);
     if (s.moving) {
       any_moving = true;
       if (s.time1 == s.time0) FAIL("moving sphere %d: time0 == time1", i);
     }
   }
-  for (int i = 0; i < sc->n_triangles; i++)
-    if (sc->triangles[i].material < 0 || sc->triangles[i].material >= sc->n_materials)
-      FAIL("triangle %d: material index", i);
+  for (int i = 0; i < sc->n_triangles; i++) {
+    const rt_triangle &t = sc->triangles[i];
+    if (t.material < 0 || t.material >= sc->n_materials) FAIL("triangle %d: material index", i);
+    if (!finite3(t.v0) || !finite3(t.v1) || !finite3(t.v2) || !finite3(t.normal)) FAIL("triangle %d: non-finite field", i);
+  }
   for (int i = 0; i < sc->n_quads; i++) {
     const rt_quad &q = sc->quads[i];
     if (q.material < 0 || q.material >= sc->n_materials) FAIL("quad %d: material index", i);
     if (q.axis < 0 || q.axis > 2) FAIL("quad %d: axis", i);
+    if (!std::isfinite(q.a0) || !std::isfinite(q.a1) || !std::isfinite(q.b0) || !std::isfinite(q.b1) || !std::isfinite(q.k))
+      FAIL("quad %d: non-finite field", i);
   }
   for (int i = 0; i < sc->n_materials; i++) {
     const rt_material &m = sc->materials[i];
@@ -80,6 +97,9 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
     if (m.material < 0 || m.material >= sc->n_materials || sc->materials[m.material].type != RT_MAT_ISOTROPIC)
       FAIL("medium %d: material must be an isotropic phase function", i);
     if (m.shape == 0 && !(m.p1[0] > 0.f)) FAIL("medium %d: radius", i);
+    if (!finite3(m.p0) || !finite3(m.p1) || !finite3(m.offset) || !std::isfinite(m.sin_y) || !std::isfinite(m.cos_y) ||
+        !std::isfinite(m.density))
+      FAIL("medium %d: non-finite field", i);
   }
   for (int i = 0; i < sc->n_perlin; i++)
     for (int k = 0; k < 256; k++) {

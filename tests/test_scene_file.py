@@ -125,3 +125,31 @@ def test_render_cli_scene_file_equals_python_binding(tmp_path):
         _, rgb = ctx.resolve(want_linear=False)
     np.testing.assert_array_equal(img, rgb)
     assert img.std() > 10
+
+
+def test_parser_never_crashes_on_garbage(tmp_path):
+    """fuzz: random statements built from the format's vocabulary either load or raise a ValueError
+    naming the file - the C++ parser must not crash or accept trailing junk silently"""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+    words = ["profile", "next_week", "weekend", "image", "camera", "lookfrom", "lookat", "vfov", "vup", "aperture",
+             "focus", "shutter", "sky", "background", "tmin", "depth", "seed", "flags", "flip_normals", "material",
+             "m", "lambertian", "checker", "noise", "image", "metal", "dielectric", "light", "sphere",
+             "moving_sphere", "xy_rect", "xz_rect", "yz_rect", "box", "triangle", "obj", "medium", "rotate_y",
+             "translate", "scale", "0", "1", "-2.5", "1e3", "nan", "inf", "-", "#", "x.ppm", "y.obj", "0.5"]
+    line = st.lists(st.sampled_from(words), min_size=0, max_size=14).map(" ".join)
+    p = tmp_path / "fuzz.scene"
+
+    @settings(max_examples=150, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(st.lists(line, min_size=0, max_size=8))
+    def run(lines):
+        p.write_text("camera lookfrom 0 0 5 lookat 0 0 0 vfov 40\nmaterial m lambertian 0.5 0.5 0.5\n" + "\n".join(lines) + "\n")
+        try:
+            sc, dims = scenes.load_scene_file(str(p))
+        except ValueError as e:
+            assert "fuzz.scene" in str(e)
+            return
+        assert dims[0] >= 2 and dims[1] >= 2 and dims[2] >= 1
+        assert np.all(sc.spheres["material"] < len(sc.materials))
+
+    run()

@@ -148,6 +148,14 @@ def test_scene_validation_of_new_fields():
     sc.profile = D.RT_PROFILE_FINAL_CU
     with pytest.raises(ValueError):
         Emu(sc)
+    # non-finite geometry never reaches the builder
+    for field, scene_fn, arr in (("center0", scenes.weekend, "spheres"), ("k", scenes.cornell_box, "quads"),
+                                 ("v1", scenes.cornell_box, "triangles"), ("density", scenes.cornell_smoke, "media")):
+        sc = scene_fn(8, 8)
+        a = getattr(sc, arr)
+        a[field][0] = np.nan if a[field][0].ndim == 0 else np.full_like(a[field][0], np.inf)
+        with pytest.raises(ValueError, match="non-finite|density"):
+            Emu(sc)
 
 
 # ------------------------------------------------------------------------------- GPU
