@@ -62,6 +62,9 @@ class L1:
         self._suv = getattr(self.lib, p + "sphere_uv_at")
         self._suv.restype = None
         self._suv.argtypes = [C.c_int, _vp, _vp]
+        self._mdemo = getattr(self.lib, p + "medium_reference_order_demo")
+        self._mdemo.restype = C.c_double
+        self._mdemo.argtypes = [C.POINTER(RtSceneDesc), _vp, C.c_int, C.c_int, C.c_uint64]
         self.lib.orc_srand.argtypes = [C.c_uint]
 
     def srand(self, seed):
@@ -134,6 +137,13 @@ class L1:
         ok = self._scatter(C.byref(d), profile, material, d_in.ctypes.data, n.ctypes.data, seed, int(libc_rand),
                            out.ctypes.data, att.ctypes.data)
         return ok, out, att
+
+    def medium_reference_order_demo(self, scene, ray8, order, n_trials=20000, seed=1):
+        """fraction of trials in which the medium is the closest hit under the REFERENCE's
+        constant_medium::hit (no t_max test), media visited before (0) / after (1) the surfaces"""
+        ray8 = np.ascontiguousarray(ray8, np.float32)
+        d = scene.desc()
+        return float(self._mdemo(C.byref(d), ray8.ctypes.data, order, n_trials, seed))
 
     def tex_value(self, scene, material, uvp):
         """texture value at rows (u, v, px, py, pz)"""

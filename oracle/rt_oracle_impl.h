@@ -873,6 +873,40 @@ int FN(scatter_one)(const rt_scene_desc *sc, int profile, int material, const do
   return ok;
 }
 
+/* Evidence for the medium deviation documented above medium_hit: constant_medium::hit AS THE REFERENCE
+ * WROTE IT (rt_next_week/cuda/constant_medium.h:36-73: no t_max test) inside hittable_list::hit's loop
+ * (hittable_list.h:20-34 pattern: every object is offered closest_so_far, and whatever returns true
+ * replaces the record). Returns, over n_trials random numbers, the fraction of trials in which the
+ * MEDIUM ends up as the closest hit for one ray, with the media visited before (order 0) or after
+ * (order 1) the surfaces - the two differ, i.e. the reference's image depends on list / BVH order. */
+double FN(medium_reference_order_demo)(const rt_scene_desc *sc, const float *ray8, int order, int n_trials, uint64_t seed) {
+  FN(World) w = {sc, 2, sc->flags, 0, 0};
+  FN(Rng) rng;
+  FN(rng_seed)(&rng, seed);
+  rng.libc = 0;
+  FN(Ray) r;
+  r.o = FN(from3f)(ray8); r.tm = (REAL)ray8[3]; r.d = FN(from3f)(ray8 + 4);
+  int medium_wins = 0;
+  for (int k = 0; k < n_trials; k++) {
+    FN(Hit) rec, tmp;
+    int any = 0, is_medium = 0;
+    REAL closest = INFINITY_R;
+    for (int pass = 0; pass < 2; pass++) {
+      if ((pass == 0) == (order == 0)) { /* the media */
+        for (int i = 0; i < sc->n_media; i++) {
+          /* the reference's version: the scatter event is accepted wherever it falls inside the boundary */
+          if (FN(medium_hit)(&w, i, &r, INFINITY_R, &tmp, &rng)) { any = 1; closest = tmp.t; rec = tmp; is_medium = 1; }
+        }
+      } else { /* the surfaces, each offered closest_so_far */
+        if (FN(list_hit)(&w, &r, (REAL)sc->t_min, closest, &tmp)) { any = 1; closest = tmp.t; rec = tmp; is_medium = 0; }
+      }
+    }
+    (void)rec;
+    medium_wins += any && is_medium;
+  }
+  return (double)medium_wins / (double)n_trials;
+}
+
 /* texture value of a material at (u, v, p) through this restatement (texture parity tests) */
 void FN(tex_value_at)(const rt_scene_desc *sc, int material, int n, const double *uvp /*[n][5]*/, double *rgb /*[n][3]*/) {
   for (int k = 0; k < n; k++) {

@@ -241,3 +241,34 @@ def test_gpu_next_week_scenes_vs_oracle(l1_32, name):
     se = np.sqrt((var_mean_a + var_b / spp).reshape(-1, 3).sum(0)) / (W * H)
     dm = np.abs(mu_a.reshape(-1, 3).mean(0) - mu_b.reshape(-1, 3).mean(0))
     assert np.all(dm < 4 * se + 1e-4), (name, dm, se)
+
+
+def test_reference_medium_semantics_depend_on_object_order(l1_64):
+    """Why the medium deviates from the reference (DESIGN.md 7b): constant_medium::hit as written
+    ignores t_max, so inside hittable_list / bvh_node it overrides a nearer surface whenever it is
+    visited after it. One ray, a wall 10 units away inside fog of density 0.05: physically the fog
+    scatters first with probability 1 - exp(-0.5) = 39 %; the reference's code gives 39 % if the fog is
+    listed before the wall and ~100 % if it is listed after it."""
+    mats = np.array([_mat(D.RT_MAT_LAMBERTIAN, (0.5, 0.5, 0.5)), _mat(D.RT_MAT_ISOTROPIC, (1, 1, 1))], D.MATERIAL_DT)
+    sc = D.Scene(quads=np.array([_quad(2, -50, 50, -50, 50, -10.0, 0)], D.QUAD_DT), materials=mats,
+                 media=np.array([_medium_sphere((0, 0, 0), 100.0, 0.05, 1)], D.MEDIUM_DT),
+                 profile=D.RT_PROFILE_NEXT_WEEK, background=(0, 0, 0), sky_gradient=0)
+    ray = np.array([0, 0, 0, 0, 0, 0, -1, 0], np.float32)
+    physical = 1.0 - np.exp(-0.05 * 10.0)
+    before = l1_64.medium_reference_order_demo(sc, ray, order=0)
+    after = l1_64.medium_reference_order_demo(sc, ray, order=1)
+    assert abs(before - physical) < 0.015, before
+    assert after > 0.98, after  # the wall all but disappears: 1 - exp(-0.05 * 100)
+    # the semantics used for parity (the scatter event must lie before the closest surface) give the
+    # physical answer: an emitting wall seen through absorbing fog keeps exp(-0.5) of its radiance
+    mats = np.array([_mat(D.RT_MAT_DIFFUSE_LIGHT, (1, 1, 1)), _mat(D.RT_MAT_ISOTROPIC, (0, 0, 0))], D.MATERIAL_DT)
+    sc2 = D.Scene(quads=sc.quads, materials=mats, media=sc.media, profile=D.RT_PROFILE_NEXT_WEEK, background=(0, 0, 0),
+                  sky_gradient=0)
+    sc2.camera = D.camera_from_lookat((0, 0, 0), (0, 0, -1), (0, 1, 0), 1.0, 1.0, 0.0, 1.0, dtype=np.float32)
+    W, H, spp = 8, 8, 512
+    want = np.exp(-0.5)
+    se = np.sqrt(want * (1 - want) / (W * H * spp))
+    s, _, _ = Emu(sc2).render(W, H, spp)
+    assert abs(s.mean() / spp - want) < 4 * se + 2e-3, s.mean() / spp
+    r, _, _ = l1_64.render_parallel(sc2, 2, W, H, spp, seed=9)
+    assert abs(r.mean() / spp - want) < 4 * se + 2e-3, r.mean() / spp
