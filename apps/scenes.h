@@ -1,141 +1,188 @@
-// apps/scenes.h — the reference's scenes written against its own scene-description
-// surface (include/rtx compat headers): this is existing-style scene code, compiled
-// unchanged in spirit, that now feeds the B200 core.
+// apps/scenes.h — the reference's scenes as DATA, built through its own scene-description
+// surface (include/rtx compat headers: sphere, moving_sphere, xy/xz/yz_rect, box, translate,
+// rotate_y, constant_medium, bvh_node, the materials and textures). The numbers are the
+// reference's (file:line cited per scene); the code that assembles them is table-driven and
+// shared between scenes. Where the reference draws random numbers the ORDER of the draws is kept,
+// so that the Weekend scene reproduces tests/golden bit for bit under glibc's rand().
 #ifndef APPS_SCENES_H
 #define APPS_SCENES_H
+#include <algorithm>
+
+#include "aarect.h"
+#include "box.h"
+#include "bvh.h"
 #include "camera.h"
+#include "constant_medium.h"
 #include "hittable_list.h"
 #include "material.h"
-#include "sphere.h"
 #include "moving_sphere.h"
-#include "aarect.h"
+#include "sphere.h"
 #include "triangle.h"
-#include "bvh.h"
-#include "box.h"
 
-// rt_in_one_weekend/main.cpp:86-131, statement for statement. g++ evaluates the
-// arguments of `point3 center(a + 0.9*random_double(), 0.2, b + 0.9*random_double())`
-// and of `color::random() * color::random()` right to left; the order is spelled out so
-// that any compiler reproduces the reference's 487-sphere scene (tests/golden).
+namespace scene_data {
+
+// One axis-aligned rectangle: plane (0 = yz, 1 = xz, 2 = xy), in-plane ranges, offset, material slot.
+struct rect_row { int plane; double a0, a1, b0, b1, k; int mat; };
+
+inline hittable *make_rect(const rect_row &r, material *m) {
+  if (r.plane == 0) return new yz_rect(r.a0, r.a1, r.b0, r.b1, r.k, m);
+  if (r.plane == 1) return new xz_rect(r.a0, r.a1, r.b0, r.b1, r.k, m);
+  return new xy_rect(r.a0, r.a1, r.b0, r.b1, r.k, m);
+}
+
+// translate(rotate_y(object, degrees), offset) — the only instance wrapper chain the reference uses
+inline hittable *placed(hittable *h, double degrees, const vec3 &offset) {
+  return new translate(new rotate_y(h, degrees), offset);
+}
+
+inline hittable *as_bvh(std::vector<hittable *> &objects) { // the vector must outlive the node's use
+  return new bvh_node(objects.data(), 0, objects.size(), 0.0, 1.0);
+}
+
+// the three showpiece balls both random scenes end with (main.cpp:123-130, main.cu:189-194)
+struct big_ball { double x; int kind; color c; double param; };
+static const big_ball kBigBalls[3] = {{0, 2, color(0, 0, 0), 1.5}, {-4, 0, color(0.4, 0.2, 0.1), 0}, {4, 1, color(0.7, 0.6, 0.5), 0.0}};
+
+} // namespace scene_data
+
+// Weekend cover scene — rt_in_one_weekend/main.cpp:86-131. Draw order per grid cell (g++ evaluates
+// constructor / operator arguments right to left): material choice, z offset, x offset; then for a
+// diffuse ball the SECOND factor of the albedo product before the first.
 inline hittable_list random_scene() {
+  using namespace scene_data;
   hittable_list world;
-  auto ground_material = make_shared<lambertian>(color(0.5, 0.5, 0.5));
-  world.add(make_shared<sphere>(point3(0, -1000, 0), 1000, ground_material));
-  for (int a = -11; a < 11; a++) {
+  world.add(make_shared<sphere>(point3(0, -1000, 0), 1000, make_shared<lambertian>(color(0.5, 0.5, 0.5))));
+  const point3 keep_clear(4, 0.2, 0);
+  for (int a = -11; a < 11; a++)
     for (int b = -11; b < 11; b++) {
-      auto choose_mat = random_double();
-      double cz = b + 0.9 * random_double();
-      double cx = a + 0.9 * random_double();
-      point3 center(cx, 0.2, cz);
-      if ((center - point3(4, 0.2, 0)).length() > 0.9) {
-        shared_ptr<material> sphere_material;
-        if (choose_mat < 0.8) {
-          color second = color::random();
-          color first = color::random();
-          auto albedo = first * second;
-          sphere_material = make_shared<lambertian>(albedo);
-          world.add(make_shared<sphere>(center, 0.2, sphere_material));
-        } else if (choose_mat < 0.95) {
-          auto albedo = color::random(0.5, 1);
-          auto fuzz = random_double(0, 0.5);
-          sphere_material = make_shared<metal>(albedo, fuzz);
-          world.add(make_shared<sphere>(center, 0.2, sphere_material));
-        } else {
-          sphere_material = make_shared<dielectric>(1.5);
-          world.add(make_shared<sphere>(center, 0.2, sphere_material));
-        }
+      const double pick = random_double();
+      const double dz = 0.9 * random_double(), dx = 0.9 * random_double();
+      const point3 at(a + dx, 0.2, b + dz);
+      if (!((at - keep_clear).length() > 0.9)) continue;
+      shared_ptr<material> m;
+      if (pick < 0.8) {
+        const color second = color::random(), first = color::random();
+        m = make_shared<lambertian>(first * second);
+      } else if (pick < 0.95) {
+        const color tint = color::random(0.5, 1);
+        m = make_shared<metal>(tint, random_double(0, 0.5));
+      } else {
+        m = make_shared<dielectric>(1.5);
       }
+      world.add(make_shared<sphere>(at, 0.2, m));
     }
+  for (const big_ball &bb : kBigBalls) {
+    shared_ptr<material> m = bb.kind == 2   ? shared_ptr<material>(make_shared<dielectric>(bb.param))
+                             : bb.kind == 0 ? shared_ptr<material>(make_shared<lambertian>(bb.c))
+                                            : shared_ptr<material>(make_shared<metal>(bb.c, bb.param));
+    world.add(make_shared<sphere>(point3(bb.x, 1, 0), 1.0, m));
   }
-  auto material1 = make_shared<dielectric>(1.5);
-  world.add(make_shared<sphere>(point3(0, 1, 0), 1.0, material1));
-  auto material2 = make_shared<lambertian>(color(0.4, 0.2, 0.1));
-  world.add(make_shared<sphere>(point3(-4, 1, 0), 1.0, material2));
-  auto material3 = make_shared<metal>(color(0.7, 0.6, 0.5), 0.0);
-  world.add(make_shared<sphere>(color(4, 1, 0), 1.0, material3));
   return world;
 }
 
-// rt_next_week/cuda/main.cu:153-198 in its raw-pointer style (`new`, RND); RND is
-// cuRAND there, glibc here (the sequence is not part of the contract).
-#define RND ((float)random_double())
+// Motion-blur scene — rt_next_week/cuda/main.cu:153-198 in the raw-pointer style of the CUDA trees
+// (cuRAND there, the host generator here: the sequence is not part of the contract). d_list must hold
+// 22*22 + 4 pointers, as the reference's create_world expects.
 inline hittable *next_week_random_scene(hittable **d_list) {
-  auto checker = new checker_texture(color(0.2, 0.3, 0.1), color(0.9, 0.9, 0.9));
-  d_list[0] = new sphere(vec3(0, -1000.0, -1), 1000, new lambertian(checker));
-  int i = 1;
-  for (int a = -11; a < 11; a++) {
+  using namespace scene_data;
+  auto rnd = []() { return (float)random_double(); };
+  int n = 0;
+  d_list[n++] = new sphere(vec3(0, -1000.0, -1), 1000,
+                           new lambertian(new checker_texture(color(0.2, 0.3, 0.1), color(0.9, 0.9, 0.9))));
+  for (int a = -11; a < 11; a++)
     for (int b = -11; b < 11; b++) {
-      float choose_mat = RND;
-      float cx = a + RND, cz = b + RND;
-      vec3 center(cx, 0.2, cz);
-      if (choose_mat < 0.8f) {
-        vec3 center2 = center + vec3(0, RND * 0.5f, 0);
-        float r0 = RND * RND, r1 = RND * RND, r2 = RND * RND;
-        d_list[i++] = new moving_sphere(center, center2, 0.0, 1.0, 0.2, new lambertian(vec3(r0, r1, r2)));
-      } else if (choose_mat < 0.95f) {
-        float r0 = 0.5f * (1.0f + RND), r1 = 0.5f * (1.0f + RND), r2 = 0.5f * (1.0f + RND);
-        d_list[i++] = new sphere(center, 0.2, new metal(vec3(r0, r1, r2), 0.5f * RND));
+      const float pick = rnd();
+      const float x = a + rnd();
+      const float z = b + rnd();
+      const vec3 at(x, 0.2, z);
+      if (pick < 0.8f) { // moving diffuse ball: squared-uniform albedo, centre rising by up to 0.5
+        const vec3 to = at + vec3(0, rnd() * 0.5f, 0);
+        float rgb[3];
+        for (float &ch : rgb) { const float u = rnd(), v = rnd(); ch = u * v; }
+        d_list[n++] = new moving_sphere(at, to, 0.0, 1.0, 0.2, new lambertian(vec3(rgb[0], rgb[1], rgb[2])));
+      } else if (pick < 0.95f) {
+        float rgb[3];
+        for (float &ch : rgb) ch = 0.5f * (1.0f + rnd());
+        d_list[n++] = new sphere(at, 0.2, new metal(vec3(rgb[0], rgb[1], rgb[2]), 0.5f * rnd()));
       } else {
-        d_list[i++] = new sphere(center, 0.2, new dielectric(1.5));
+        d_list[n++] = new sphere(at, 0.2, new dielectric(1.5));
       }
     }
+  for (const big_ball &bb : kBigBalls) {
+    material *m = bb.kind == 2 ? (material *)new dielectric(bb.param)
+                  : bb.kind == 0 ? (material *)new lambertian(bb.c) : (material *)new metal(bb.c, bb.param);
+    d_list[n++] = new sphere(vec3(bb.x, 1, 0), 1.0, m);
   }
-  d_list[i++] = new sphere(vec3(0, 1, 0), 1.0, new dielectric(1.5));
-  d_list[i++] = new sphere(vec3(-4, 1, 0), 1.0, new lambertian(vec3(0.4, 0.2, 0.1)));
-  d_list[i++] = new sphere(vec3(4, 1, 0), 1.0, new metal(vec3(0.7, 0.6, 0.5), 0.0));
-  return new bvh_node(d_list, 0, 22 * 22 + 1 + 3, 0.0f, 1.0f);
+  return new bvh_node(d_list, 0, n, 0.0f, 1.0f);
 }
 
-// triangles/cuda/obj_render.cu:384-524 (obj_model): the mesh inside a lit, mirrored room
+// Mesh in a lit, mirrored room — triangles/cuda/obj_render.cu:384-524: two coloured sphere lights, two
+// strip lights, red floor / ceiling, blue side walls, a pale back wall, three mirrors, and the mesh
+// scaled 2.5x, turned 30 degrees and lifted 1.5.
 inline hittable *obj_model(const std::string &obj_path) {
-  std::vector<shared_ptr<hittable>> tris;
-  auto blue_1 = new lambertian(color(0, 129.0f / 256.0, 167.0f / 256.0));
-  auto red_1 = new lambertian(color(240.0f / 256.0, 113.0f / 256.0, 103.0f / 256.0));
-  auto yellow_1 = new lambertian(color(253.0f / 256.0, 252.0f / 256.0, 220.0f / 256.0));
-  auto gold = make_shared<metal>(color(255.0f / 256.0, 215.0f / 256.0, 0.0f / 256.0), 0.5);
-  auto light = new diffuse_light(color(20, 20, 20) * 0.25);
-  auto *ret = new hittable_list();
-  ret->add(borrow<hittable>(new sphere(point3(-1, 3.69 + 1, -2.5), 0.3,
-                                       new diffuse_light(color(255.0f / 256.0, 59.0f / 256.0, 148.0f / 256.0) * 2))));
-  ret->add(borrow<hittable>(new sphere(point3(1, 3.69 + 1, -2.5), 0.3,
-                                       new diffuse_light(color(166.0f / 256.0, 253.0f / 256.0, 41.0f / 256.0) * 2))));
-  ret->add(borrow<hittable>(new xz_rect(-4, 4, 3, 4, 4 + 1 - 0.01, light)));
-  ret->add(borrow<hittable>(new xz_rect(-4, 4, 2, 3, -4 + 0.01, light)));
-  ret->add(borrow<hittable>(new xy_rect(-4, 4, -4, 4 + 1, -4, yellow_1)));
-  ret->add(borrow<hittable>(new xy_rect(-3, 3, -4, 4 + 1, -3.999, new metal(color(0.8, 0.8, 0.9), 0.0))));
-  ret->add(borrow<hittable>(new xz_rect(-40, 40, -40, 40, -4, red_1)));
-  ret->add(borrow<hittable>(new xz_rect(-40, 40, -40, 40, 4 + 1, red_1)));
-  ret->add(borrow<hittable>(new yz_rect(-4, 4 + 1, -4, 4, -4, blue_1)));
-  ret->add(borrow<hittable>(new yz_rect(-4, 4 + 1, -4, 4, 4, blue_1)));
-  ret->add(borrow<hittable>(new yz_rect(-1, 3 + 1, -4, 4, -3.999, new metal(color(0.8, 0.8, 0.9), 0.0))));
-  ret->add(borrow<hittable>(new yz_rect(-1, 3 + 1 - 0.001, -4, 4, 3.999, new metal(color(0.8, 0.8, 0.9), 0.0))));
-  read_triangles(obj_path, tris, gold, 2.5);
-  for (auto &t : tris) ret->add(make_shared<translate>(make_shared<rotate_y>(t, 30), vec3(0, 1.5, 0)));
-  return new bvh_node(*ret, 0.0, 1.0);
+  using namespace scene_data;
+  auto rgb256 = [](double r, double g, double b) { return color(r / 256.0, g / 256.0, b / 256.0); };
+  material *mats[] = {new diffuse_light(color(20, 20, 20) * 0.25),          // 0 strip lights
+                      new lambertian(rgb256(253.0f, 252.0f, 220.0f)),       // 1 back wall
+                      new lambertian(rgb256(240.0f, 113.0f, 103.0f)),       // 2 floor / ceiling
+                      new lambertian(rgb256(0, 129.0f, 167.0f)),            // 3 side walls
+                      nullptr};                                             // 4 mirrors: one material each
+  const double top = 4 + 1;
+  const rect_row rows[] = {{1, -4, 4, 3, 4, top - 0.01, 0},   {1, -4, 4, 2, 3, -4 + 0.01, 0},
+                           {2, -4, 4, -4, top, -4, 1},        {2, -3, 3, -4, top, -3.999, 4},
+                           {1, -40, 40, -40, 40, -4, 2},      {1, -40, 40, -40, 40, top, 2},
+                           {0, -4, top, -4, 4, -4, 3},        {0, -4, top, -4, 4, 4, 3},
+                           {0, -1, 3 + 1, -4, 4, -3.999, 4},  {0, -1, 3 + 1 - 0.001, -4, 4, 3.999, 4}};
+  auto *room = new hittable_list();
+  const color bulbs[2] = {rgb256(255.0f, 59.0f, 148.0f) * 2, rgb256(166.0f, 253.0f, 41.0f) * 2};
+  for (int k = 0; k < 2; k++)
+    room->add(borrow<hittable>(new sphere(point3(k ? 1 : -1, 3.69 + 1, -2.5), 0.3, new diffuse_light(bulbs[k]))));
+  for (const rect_row &r : rows)
+    room->add(borrow<hittable>(make_rect(r, r.mat == 4 ? new metal(color(0.8, 0.8, 0.9), 0.0) : mats[r.mat])));
+  std::vector<shared_ptr<hittable>> mesh;
+  read_triangles(obj_path, mesh, make_shared<metal>(rgb256(255.0f, 215.0f, 0.0f), 0.5), 2.5);
+  for (auto &t : mesh) room->add(make_shared<translate>(make_shared<rotate_y>(t, 30), vec3(0, 1.5, 0)));
+  return new bvh_node(*room, 0.0, 1.0);
 }
 
-// rt_next_week/cuda/main.cu:252-281 (cornell_box), in its raw-pointer style
+namespace scene_data {
+// The Cornell room shared by scenes 6 and 7 (rt_next_week/cuda/main.cu:252-266, 283-297): material
+// slots 0 green, 1 red, 2 light, 3 white; the two blocks are 165-wide boxes turned by +15 / -18 degrees.
+struct cornell_parts { std::vector<hittable *> walls; material *white; hittable *block[2]; };
+inline cornell_parts cornell_room() {
+  material *m[4] = {new lambertian(color(.12, .45, .15)), new lambertian(color(.65, .05, .05)),
+                    new diffuse_light(color(15, 15, 15)), new lambertian(color(.73, .73, .73))};
+  const rect_row rows[] = {{0, 0, 555, 0, 555, 555, 0}, {0, 0, 555, 0, 555, 0, 1}, {1, 213, 343, 227, 332, 554, 2},
+                           {1, 0, 555, 0, 555, 0, 3},   {1, 0, 555, 0, 555, 555, 3}, {2, 0, 555, 0, 555, 555, 3}};
+  cornell_parts c;
+  for (const rect_row &r : rows) c.walls.push_back(make_rect(r, m[r.mat]));
+  c.white = m[3];
+  const double height[2] = {330, 165}, turn[2] = {15, -18};
+  const vec3 where[2] = {vec3(265, 0, 295), vec3(130, 0, 65)};
+  for (int k = 0; k < 2; k++)
+    c.block[k] = placed(new box(point3(0, 0, 0), point3(165, height[k], 165), c.white), turn[k], where[k]);
+  return c;
+}
+} // namespace scene_data
+
+// rt_next_week/cuda/main.cu:252-281
 inline hittable *cornell_box() {
-  static hittable *ret[8];
-  auto red = new lambertian(color(.65, .05, .05));
-  auto white = new lambertian(color(.73, .73, .73));
-  auto green = new lambertian(color(.12, .45, .15));
-  auto light = new diffuse_light(color(15, 15, 15));
-  ret[0] = new yz_rect(0, 555, 0, 555, 555, green);
-  ret[1] = new yz_rect(0, 555, 0, 555, 0, red);
-  ret[2] = new xz_rect(213, 343, 227, 332, 554, light);
-  ret[3] = new xz_rect(0, 555, 0, 555, 0, white);
-  ret[4] = new xz_rect(0, 555, 0, 555, 555, white);
-  ret[5] = new xy_rect(0, 555, 0, 555, 555, white);
-  hittable *box1 = new box(point3(0, 0, 0), point3(165, 330, 165), white);
-  box1 = new rotate_y(box1, 15);
-  box1 = new translate(box1, vec3(265, 0, 295));
-  hittable *box2 = new box(point3(0, 0, 0), point3(165, 165, 165), white);
-  box2 = new rotate_y(box2, -18);
-  box2 = new translate(box2, vec3(130, 0, 65));
-  ret[6] = box1;
-  ret[7] = box2;
-  return new bvh_node(ret, 0, 8, 0.0f, 1.0f);
+  static std::vector<hittable *> objects;
+  scene_data::cornell_parts c = scene_data::cornell_room();
+  objects = c.walls;
+  objects.push_back(c.block[0]);
+  objects.push_back(c.block[1]);
+  return scene_data::as_bvh(objects);
+}
+
+// rt_next_week/cuda/main.cu:283-310: the blocks become black and white smoke of density 0.01
+inline hittable *cornell_smoke() {
+  static std::vector<hittable *> objects;
+  scene_data::cornell_parts c = scene_data::cornell_room();
+  objects = c.walls;
+  objects.push_back(new constant_medium(c.block[0], 0.01, color(0, 0, 0)));
+  objects.push_back(new constant_medium(c.block[1], 0.01, color(1, 1, 1)));
+  return scene_data::as_bvh(objects);
 }
 
 // Stand-in for the reference's earthmap.jpeg (a binary asset that is not redistributed): an
@@ -162,107 +209,66 @@ inline std::vector<unsigned char> procedural_earth(int w = 512, int h = 256) {
   return img;
 }
 
-// rt_next_week/cuda/main.cu:212-222
-inline hittable *two_perlin_spheres() {
-  auto perlin_texture = new noise_texture(4);
-  static hittable *ret[2];
-  ret[0] = new sphere(point3(0, -1000, 0), 1000, new lambertian(perlin_texture));
-  ret[1] = new sphere(point3(0, 2, 0), 2, new lambertian(perlin_texture));
-  return new bvh_node(ret, 0, 2, 0.0f, 1.0f);
-}
-
-// rt_next_week/cuda/main.cu:224-232
-inline hittable *earth(unsigned char *data, int w, int h) {
-  auto earth_texture = new image_texture(data, w, h);
-  auto earth_surface = new lambertian(earth_texture);
-  static hittable *ret[1];
-  ret[0] = new sphere(point3(0, 0, 0), 2, earth_surface);
-  return new bvh_node(ret, 0, 1, 0.0f, 1.0f);
-}
-
-// rt_next_week/cuda/main.cu:234-250
-inline hittable *simple_light() {
-  auto perlin_texture = new noise_texture(4);
-  static hittable *ret[4];
-  ret[0] = new sphere(point3(0, -1000, 0), 1000, new lambertian(perlin_texture));
-  ret[1] = new sphere(point3(0, 2, 0), 2, new lambertian(perlin_texture));
-  auto diff_light = new diffuse_light(color(4, 4, 4));
-  ret[2] = new xy_rect(3, 5, 1, 2, -2, diff_light);
-  auto diff_light2 = new diffuse_light(color(6, 4, 4));
-  ret[3] = new sphere(point3(0, 6, 0), 1.5, diff_light2);
-  return new bvh_node(ret, 0, 4, 0.0f, 1.0f);
-}
-
-// rt_next_week/cuda/main.cu:283-310
-inline hittable *cornell_smoke() {
-  static hittable *ret[8];
-  auto red = new lambertian(color(.65, .05, .05));
-  auto white = new lambertian(color(.73, .73, .73));
-  auto green = new lambertian(color(.12, .45, .15));
-  auto light = new diffuse_light(color(15, 15, 15));
-  ret[0] = new yz_rect(0, 555, 0, 555, 555, green);
-  ret[1] = new yz_rect(0, 555, 0, 555, 0, red);
-  ret[2] = new xz_rect(213, 343, 227, 332, 554, light);
-  ret[3] = new xz_rect(0, 555, 0, 555, 0, white);
-  ret[4] = new xz_rect(0, 555, 0, 555, 555, white);
-  ret[5] = new xy_rect(0, 555, 0, 555, 555, white);
-  hittable *box1 = new box(point3(0, 0, 0), point3(165, 330, 165), white);
-  box1 = new rotate_y(box1, 15);
-  box1 = new translate(box1, vec3(265, 0, 295));
-  box1 = new constant_medium(box1, 0.01, color(0, 0, 0));
-  hittable *box2 = new box(point3(0, 0, 0), point3(165, 165, 165), white);
-  box2 = new rotate_y(box2, -18);
-  box2 = new translate(box2, vec3(130, 0, 65));
-  box2 = new constant_medium(box2, 0.01, color(1, 1, 1));
-  ret[6] = box1;
-  ret[7] = box2;
-  return new bvh_node(ret, 0, 8, 0.0f, 1.0f);
-}
-
-// rt_next_week/cuda/main.cu:312-383 — the tree's default scene
-inline hittable *rt_next_week_final_scene(unsigned char *data, int w, int h) {
-  const int boxes_per_side = 20;
-  const int num_obj = boxes_per_side * boxes_per_side + 10;
-  static std::vector<hittable *> ret;
-  ret.assign(num_obj, nullptr);
-  auto ground = new lambertian(color(0.48, 0.83, 0.53));
-  int index = 0;
-  for (int i = 0; i < boxes_per_side; i++) {
-    for (int j = 0; j < boxes_per_side; j++) {
-      float bw = 100.0;
-      float x0 = -1000.0f + i * bw;
-      float z0 = -1000.0f + j * bw;
-      float y0 = 0.0;
-      float x1 = x0 + bw;
-      float y1 = (float)random_double(1, 101);
-      float z1 = z0 + bw;
-      ret[index++] = new box(point3(x0, y0, z0), point3(x1, y1, z1), ground);
-    }
+// rt_next_week/cuda/main.cu:212-250: noise_texture(4) on a ground sphere and a ball; scene 5 adds a
+// rect light and a sphere light
+inline hittable *perlin_pair(bool with_lights) {
+  static std::vector<hittable *> objects;
+  objects.clear();
+  auto marble = new noise_texture(4);
+  objects.push_back(new sphere(point3(0, -1000, 0), 1000, new lambertian(marble)));
+  objects.push_back(new sphere(point3(0, 2, 0), 2, new lambertian(marble)));
+  if (with_lights) {
+    objects.push_back(new xy_rect(3, 5, 1, 2, -2, new diffuse_light(color(4, 4, 4))));
+    objects.push_back(new sphere(point3(0, 6, 0), 1.5, new diffuse_light(color(6, 4, 4))));
   }
-  auto light = new diffuse_light(color(7, 7, 7));
-  ret[index++] = new xz_rect(123, 423, 147, 412, 554, light);
-  auto center1 = point3(400, 400, 200);
-  auto center2 = center1 + vec3(30, 0, 0);
-  auto moving_sphere_material = new lambertian(color(0.7, 0.3, 0.1));
-  ret[index++] = new moving_sphere(center1, center2, 0, 1, 50, moving_sphere_material);
-  ret[index++] = new sphere(point3(260, 150, 45), 50, new dielectric(1.5));
-  ret[index++] = new sphere(point3(0, 150, 145), 50, new metal(color(0.8, 0.8, 0.9), 1.0));
-  auto sphere_dielectric_2 = new sphere(point3(360, 150, 145), 70, new dielectric(1.5));
-  ret[index++] = sphere_dielectric_2;
-  ret[index++] = new constant_medium(sphere_dielectric_2, 0.2, color(0.2, 0.4, 0.9));
-  auto fog = new sphere(point3(0, 0, 0), 5000, new dielectric(1.5));
-  ret[index++] = new constant_medium(fog, 0.0001, color(1, 1, 1));
-  auto earth_texture = new image_texture(data, w, h);
-  auto earth_surface = new lambertian(earth_texture);
-  ret[index++] = new sphere(point3(400, 200, 400), 100, earth_surface);
-  auto pertext = new noise_texture(0.1);
-  ret[index++] = new sphere(point3(220, 280, 300), 80, new lambertian(pertext));
+  return scene_data::as_bvh(objects);
+}
+inline hittable *two_perlin_spheres() { return perlin_pair(false); }
+inline hittable *simple_light() { return perlin_pair(true); }
+
+// rt_next_week/cuda/main.cu:224-232: one image-textured globe
+inline hittable *earth(unsigned char *data, int w, int h) {
+  static std::vector<hittable *> objects;
+  objects.assign(1, new sphere(point3(0, 0, 0), 2, new lambertian(new image_texture(data, w, h))));
+  return scene_data::as_bvh(objects);
+}
+
+// The rt_next_week tree's default scene — main.cu:312-383: a 20 x 20 field of ground boxes of random
+// height (1..101), an area light, a motion-blurred ball, glass and brushed-metal balls, a blue
+// "subsurface" ball (glass boundary + dense medium), thin fog over everything, the globe, a marble
+// ball, and 1000 small white balls in a cube turned by 15 degrees.
+inline hittable *rt_next_week_final_scene(unsigned char *data, int w, int h) {
+  using namespace scene_data;
+  static std::vector<hittable *> objects;
+  static std::vector<hittable *> cluster;
+  objects.clear();
+  cluster.clear();
+  auto ground = new lambertian(color(0.48, 0.83, 0.53));
+  const int side = 20;
+  const float pitch = 100.0f;
+  for (int i = 0; i < side; i++)
+    for (int j = 0; j < side; j++) {
+      const float x = -1000.0f + i * pitch, z = -1000.0f + j * pitch;
+      const float top = (float)random_double(1, 101);
+      objects.push_back(new box(point3(x, 0.0f, z), point3(x + pitch, top, z + pitch), ground));
+    }
+  objects.push_back(new xz_rect(123, 423, 147, 412, 554, new diffuse_light(color(7, 7, 7))));
+  const point3 from(400, 400, 200);
+  objects.push_back(new moving_sphere(from, from + vec3(30, 0, 0), 0, 1, 50, new lambertian(color(0.7, 0.3, 0.1))));
+  objects.push_back(new sphere(point3(260, 150, 45), 50, new dielectric(1.5)));
+  objects.push_back(new sphere(point3(0, 150, 145), 50, new metal(color(0.8, 0.8, 0.9), 1.0)));
+  hittable *skin = new sphere(point3(360, 150, 145), 70, new dielectric(1.5));
+  objects.push_back(skin);
+  objects.push_back(new constant_medium(skin, 0.2, color(0.2, 0.4, 0.9)));
+  objects.push_back(new constant_medium(new sphere(point3(0, 0, 0), 5000, new dielectric(1.5)), 0.0001, color(1, 1, 1)));
+  objects.push_back(new sphere(point3(400, 200, 400), 100, new lambertian(new image_texture(data, w, h))));
+  objects.push_back(new sphere(point3(220, 280, 300), 80, new lambertian(new noise_texture(0.1))));
   auto white = new lambertian(color(.73, .73, .73));
-  const int ns = 1000;
-  static hittable *cluster[ns];
-  for (int j = 0; j < ns; j++)
-    cluster[j] = new sphere(point3(random_double(0, 165), random_double(0, 165), random_double(0, 165)), 10, white);
-  ret[index++] = new translate(new rotate_y(new bvh_node(cluster, 0, ns, 0, 1), 15), vec3(-100, 270, 395));
-  return new bvh_node(ret.data(), 0, index, 0.0, 1.0);
+  for (int k = 0; k < 1000; k++) {
+    const double x = random_double(0, 165), y = random_double(0, 165), z = random_double(0, 165);
+    cluster.push_back(new sphere(point3(x, y, z), 10, white));
+  }
+  objects.push_back(placed(as_bvh(cluster), 15, vec3(-100, 270, 395)));
+  return as_bvh(objects);
 }
 #endif
