@@ -636,6 +636,8 @@ int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nod
   return RT_OK;
 }
 
+static int trace_through_render_kernel(rt_ctx *ctx, int n, float t_min, float t_max, cudaStream_t st);
+
 int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *prim_id,
                      float *t) {
   if (!ctx || n < 0 || (n && (!rays || !prim_id || !t))) return RT_ERR_INVALID;
@@ -656,6 +658,9 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
   const float4 *dr = (const float4 *)ctx->d_rays.p;
   int32_t *di = (int32_t *)ctx->d_ids.p;
   float *dt = (float *)ctx->d_ts.p;
+  if (use_accel == 2) { // through k_render's own scheduler and traversal (TRACE instantiation)
+    if ((rc = trace_through_render_kernel(ctx, n, t_min, t_max, st))) return rc;
+  } else
   switch (ctx->cfg.profile) {
   case 0: k_trace_closest<0, false><<<g, TB, 0, st>>>(S, isbig, dr, n, t_min, t_max, use_accel, di, dt); break;
   case 1: k_trace_closest<1, false><<<g, TB, 0, st>>>(S, isbig, dr, n, t_min, t_max, use_accel, di, dt); break;
@@ -682,6 +687,117 @@ static render_kernel_t pick_render_kernel(int profile, int smem, bool count, boo
   PICK(2, true, false);
 #undef PICK
 #undef PICK3
+}
+
+// Scheduler thresholds, the bytes of every scene array and the shared-memory residency plan of
+// k_render (shared by the render launches and the TRACE parity hook, which must run the very same
+// plan). smem: 2 = scene + four quadrant copies of the nodes, 1 = scene, 3 = nodes only, 0 = global.
+static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &smem, size_t &smem_bytes) {
+  {
+    const char *e = getenv("B200RT_BATCH"), *f = getenv("B200RT_FRAC8"); // tuning knobs (DESIGN.md)
+    P.batch = e ? atoi(e) : 24;
+    P.frac8 = f ? atoi(f) : 5;
+    const char *lm = getenv("B200RT_LEAFMIN");
+    P.leaf_min = lm ? atoi(lm) : 1; // measured: 1..5 within 0.5 %, larger values slower
+    P.batch = std::max(1, std::min(P.batch, 32));
+    P.frac8 = std::max(0, std::min(P.frac8, 8));
+  }
+  const DevScene &S = ctx->S;
+  P.b_nodes = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_nodes);
+  P.b_sph = (int)pad16(sizeof(float4) * (size_t)S.n_spheres);
+  P.b_sph_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_spheres);
+  P.b_sph_k = (int)pad16(sizeof(float) * (size_t)S.n_spheres);
+  P.b_mats = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_mats);
+  P.b_big = (int)pad16(sizeof(int32_t) * (size_t)S.n_big);
+  P.b_bigq = ctx->general ? (int)pad16(sizeof(float4) * 2 * (size_t)S.n_bigq) : 0;
+  P.b_leaf_prims = (int)pad16(sizeof(int32_t) * (size_t)ctx->n_leaf_prims);
+  size_t scene_bytes = (size_t)P.b_nodes + P.b_sph + P.b_sph_k + P.b_sph_mat + P.b_mats + P.b_big + P.b_leaf_prims;
+  if (ctx->general) {
+    P.b_sph_mv = S.any_moving ? (int)pad16(sizeof(float4) * (size_t)S.n_spheres) : 0;
+    P.b_sph_t0 = S.any_moving ? (int)pad16(sizeof(float) * (size_t)S.n_spheres) : 0;
+    P.b_tri = (int)pad16(sizeof(float4) * 4 * (size_t)S.n_tris);
+    P.b_tri_n = (int)pad16(sizeof(float4) * (size_t)S.n_tris);
+    P.b_quad = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_quads);
+    P.b_tri_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_tris);
+    P.b_quad_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_quads);
+    scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat + P.b_bigq;
+  }
+  const size_t acc_bytes = (size_t)(block / 32) * 256 * sizeof(float); // two 32-pixel tiles per warp
+  // shared-memory plan: 2 = scene + four quadrant copies of the nodes, 1 = scene, 0 = global
+  smem = 0;
+  if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;
+  if (scene_bytes + 3 * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
+  // nodes only: one node copy resident, primitives through L1/L2
+  if (smem == 0 && (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin && S.n_nodes > 0) smem = 3;
+  if (const char *e = getenv("B200RT_SMEM")) { // tuning knob: cap the plan (3 ranks between 0 and 1)
+    const int cap = atoi(e);
+    const int rank_of[4] = {0, 2, 3, 1}; // plan -> rank
+    if (rank_of[smem] > rank_of[cap < 0 || cap > 3 ? 0 : cap]) smem = cap < 0 || cap > 3 ? 0 : cap;
+  }
+  if (smem == 0) {
+    // Global-memory node path: the four quadrant-ordered copies pay while they stay cache
+    // resident (measured: neutral up to 164 k nodes, one copy +14 % at 655 k nodes = 84 MB of copies).
+    bool one_copy = 4 * (size_t)P.b_nodes > ((size_t)48 << 20);
+    if (const char *e = getenv("B200RT_ONECOPY")) one_copy = atoi(e) != 0; // measurement knob
+    if (one_copy) P.S.node_stride = 0;
+  }
+  smem_bytes = acc_bytes + (smem == 3 ? (size_t)P.b_nodes : (smem ? scene_bytes : 0)) +
+                            (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
+  // staging order in k_render: node copies first, then the sphere array
+  P.off_sph = (smem == 2 ? 4 : 1) * P.b_nodes;
+  P.hi_off = S.n_nodes << 4;
+  P.direct_leaf = (!ctx->general && (smem == 1 || smem == 2) && ctx->max_leaf == 1) ? 1 : 0;
+}
+
+static render_kernel_t pick_trace_kernel(int profile, int smem) {
+#define PICKT(P, G) \
+  return smem == 2 ? k_render<P, G, 2, false, false, true>                                              \
+                   : (smem == 1 ? k_render<P, G, 1, false, false, true>                                 \
+                                : (smem == 3 ? k_render<P, G, 3, false, false, true> : k_render<P, G, 0, false, false, true>))
+  if (profile == 0) { PICKT(0, false); }
+  if (profile == 1) { PICKT(1, false); }
+  PICKT(2, true);
+#undef PICKT
+}
+
+// rt_trace_closest(use_accel = 2): the rays in d_rays through the TRACE instantiation of k_render
+// with the same residency plan, scheduler thresholds, grid and block as a render launch.
+static int trace_through_render_kernel(rt_ctx *ctx, int n, float t_min, float t_max, cudaStream_t st) {
+  RenderParams P;
+  memset(&P, 0, sizeof P);
+  P.S = ctx->S; P.cam = ctx->cam; P.sp = ctx->sp;
+  P.sp.t_min = t_min;
+  P.W = 8; P.H = 4; P.y0 = 0; P.y1 = 4; P.tiles_x = 1;
+  P.trace_rays = (const float4 *)ctx->d_rays.p;
+  P.trace_id = (int32_t *)ctx->d_ids.p;
+  P.trace_t = (float *)ctx->d_ts.p;
+  P.trace_tmax = t_max;
+  P.n_rays = n;
+  P.trace_item = 256; // 8 "samples" of a 32-lane pool, like a render work item
+  if (const char *e = getenv("B200RT_TRACE_ITEM")) P.trace_item = std::max(1, atoi(e));
+  P.n_work = (n + P.trace_item - 1) / P.trace_item;
+  P.n_tiles = P.n_work; // item w: tile w, chunk 0
+  P.n_chunks = 1; P.chunk_spp = 1; P.spp_count = 1;
+  const int grid = ctx->sm_count, block = RT_BLOCK_OF(ctx->general);
+  int rc;
+  if ((rc = dev_reserve(ctx, ctx->d_counter, 16))) return rc;
+  if (!ctx->d_stats.p) {
+    if ((rc = dev_reserve(ctx, ctx->d_stats, 64))) return rc;
+    CK(cudaMemsetAsync(ctx->d_stats.p, 0, 64, st));
+  }
+  P.work_counter = (int *)ctx->d_counter.p;
+  P.stats = (unsigned long long *)ctx->d_stats.p;
+  int smem = 0;
+  size_t smem_bytes = 0;
+  plan_scene_residency(ctx, P, block, smem, smem_bytes);
+  render_kernel_t kern = pick_trace_kernel(ctx->cfg.profile, smem);
+  CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  CK(cudaMemsetAsync(P.work_counter, 0, 4, st));
+  kern<<<grid, block, smem_bytes, st>>>(P);
+  CK(cudaGetLastError());
+  ctx->stats.smem_bytes = (int)smem_bytes;
+  ctx->stats.smem_plan = smem;
+  return RT_OK;
 }
 
 static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, float *d_accum, cudaStream_t st,
@@ -730,60 +846,9 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   P.stats = (unsigned long long *)ctx->d_stats.p;
   P.seed_lo = (uint32_t)(ctx->cfg.seed & 0xffffffffu);
   P.seed_hi = (uint32_t)(ctx->cfg.seed >> 32);
-  {
-    const char *e = getenv("B200RT_BATCH"), *f = getenv("B200RT_FRAC8"); // tuning knobs (DESIGN.md)
-    P.batch = e ? atoi(e) : 24;
-    P.frac8 = f ? atoi(f) : 5;
-    const char *lm = getenv("B200RT_LEAFMIN");
-    P.leaf_min = lm ? atoi(lm) : 1; // measured: 1..5 within 0.5 %, larger values slower
-    P.batch = std::max(1, std::min(P.batch, 32));
-    P.frac8 = std::max(0, std::min(P.frac8, 8));
-  }
-  const DevScene &S = ctx->S;
-  P.b_nodes = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_nodes);
-  P.b_sph = (int)pad16(sizeof(float4) * (size_t)S.n_spheres);
-  P.b_sph_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_spheres);
-  P.b_sph_k = (int)pad16(sizeof(float) * (size_t)S.n_spheres);
-  P.b_mats = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_mats);
-  P.b_big = (int)pad16(sizeof(int32_t) * (size_t)S.n_big);
-  P.b_bigq = ctx->general ? (int)pad16(sizeof(float4) * 2 * (size_t)S.n_bigq) : 0;
-  P.b_leaf_prims = (int)pad16(sizeof(int32_t) * (size_t)ctx->n_leaf_prims);
-  size_t scene_bytes = (size_t)P.b_nodes + P.b_sph + P.b_sph_k + P.b_sph_mat + P.b_mats + P.b_big + P.b_leaf_prims;
-  if (ctx->general) {
-    P.b_sph_mv = S.any_moving ? (int)pad16(sizeof(float4) * (size_t)S.n_spheres) : 0;
-    P.b_sph_t0 = S.any_moving ? (int)pad16(sizeof(float) * (size_t)S.n_spheres) : 0;
-    P.b_tri = (int)pad16(sizeof(float4) * 4 * (size_t)S.n_tris);
-    P.b_tri_n = (int)pad16(sizeof(float4) * (size_t)S.n_tris);
-    P.b_quad = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_quads);
-    P.b_tri_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_tris);
-    P.b_quad_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_quads);
-    scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat + P.b_bigq;
-  }
-  const size_t acc_bytes = (size_t)(block / 32) * 256 * sizeof(float); // two 32-pixel tiles per warp
-  // shared-memory plan: 2 = scene + four quadrant copies of the nodes, 1 = scene, 0 = global
   int smem = 0;
-  if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;
-  if (scene_bytes + 3 * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
-  // nodes only: one node copy resident, primitives through L1/L2
-  if (smem == 0 && (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin && S.n_nodes > 0) smem = 3;
-  if (const char *e = getenv("B200RT_SMEM")) { // tuning knob: cap the plan (3 ranks between 0 and 1)
-    const int cap = atoi(e);
-    const int rank_of[4] = {0, 2, 3, 1}; // plan -> rank
-    if (rank_of[smem] > rank_of[cap < 0 || cap > 3 ? 0 : cap]) smem = cap < 0 || cap > 3 ? 0 : cap;
-  }
-  if (smem == 0) {
-    // Global-memory node path: the four quadrant-ordered copies pay while they stay cache
-    // resident (measured: neutral up to 164 k nodes, one copy +14 % at 655 k nodes = 84 MB of copies).
-    bool one_copy = 4 * (size_t)P.b_nodes > ((size_t)48 << 20);
-    if (const char *e = getenv("B200RT_ONECOPY")) one_copy = atoi(e) != 0; // measurement knob
-    if (one_copy) P.S.node_stride = 0;
-  }
-  const size_t smem_bytes = acc_bytes + (smem == 3 ? (size_t)P.b_nodes : (smem ? scene_bytes : 0)) +
-                            (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
-  // staging order in k_render: node copies first, then the sphere array
-  P.off_sph = (smem == 2 ? 4 : 1) * P.b_nodes;
-  P.hi_off = S.n_nodes << 4;
-  P.direct_leaf = (!ctx->general && (smem == 1 || smem == 2) && ctx->max_leaf == 1) ? 1 : 0;
+  size_t smem_bytes = 0;
+  plan_scene_residency(ctx, P, block, smem, smem_bytes);
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
   render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext);
   CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
@@ -800,6 +865,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   ctx->launches += 2;
   if (timed) CK(cudaEventRecord(ctx->ev1, st));
   ctx->stats.smem_bytes = (int)smem_bytes;
+  ctx->stats.smem_plan = smem;
   ctx->stats.block_threads = block;
   ctx->stats.grid_blocks = grid;
   ctx->stats.regs_per_thread = fa.numRegs;

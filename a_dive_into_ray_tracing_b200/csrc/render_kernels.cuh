@@ -56,6 +56,14 @@ struct RenderParams {
   // directly (~(sphere << 3)) and the sphere array sits at this byte offset of the shared copy
   int direct_leaf, off_sph;
   int hi_off; // bytes from a node's {bmin, escape} slot to its {bmax, payload} slot in the shared copies
+  // TRACE instantiation (parity hook, rt_trace_closest use_accel = 2): the pool of a work item is a
+  // run of caller-supplied rays instead of (pixel, sample) pairs; a finished traversal writes
+  // (primitive id, t) instead of being shaded
+  const float4 *trace_rays; // [n_rays][2]: {origin, time} {direction, -}
+  int32_t *trace_id;
+  float *trace_t;
+  float trace_tmax;
+  int n_rays, trace_item; // rays per work item
 };
 
 __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &off, const void *src, int bytes) {
@@ -74,7 +82,11 @@ __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &o
 // 2 = as 1, with FOUR copies of the node array, one per sign combination of (d.x, d.z), whose
 // box planes are pre-swapped so that the slab test needs no min/max on those axes.
 // EXT: media + noise/image textures (rt_next_week scenes 3-8), profile 2 only.
-template <int PROFILE, bool GENERAL, int SMEM, bool COUNT, bool EXT>
+// TRACE: the closest-hit parity hook THROUGH this kernel's own traversal: same staging, same lane
+// state machine, same warp-voted search bursts / primitive-test rounds / regeneration by ballot
+// rank, same ray_precompute_fast and quadrant copies - only the two ends differ: a new "path" is a
+// caller ray (no camera, no Philox) and a finished traversal is written out instead of shaded.
+template <int PROFILE, bool GENERAL, int SMEM, bool COUNT, bool EXT, bool TRACE = false>
 __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevScene S = P.S;
@@ -185,7 +197,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   // start a segment: per-ray constants, the always-tested big primitives, enter at the root
   auto begin_segment = [&]() {
     pre = ray_precompute_fast(r);
-    h.t = INFINITY; h.id = -1;
+    h.t = TRACE ? P.trace_tmax : INFINITY; h.id = -1;
     for (int i = 0; i < S.n_big; i++) {
       const int32_t id = S.big[i];
       if (COUNT) cnt.prim_tests++;
@@ -292,6 +304,10 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           chunk_n = min(P.chunk_spp, P.spp_count - chunk * P.chunk_spp);
           pool_next = 0;
           pool_end = chunk_n * 32;
+          if (TRACE) { // item w = the rays [w * trace_item, (w + 1) * trace_item)
+            s0 = w * P.trace_item;
+            pool_end = min(P.trace_item, P.n_rays - s0);
+          }
           cur_buf = old_buf ^ 1;
           have_cur = true;
           float *a = acc + cur_buf * 128 + lane * 4;
@@ -305,10 +321,15 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     bool ended = false; // this lane's path ended in this round
     if (__ballot_sync(FULL, done || (!alive && pool_has))) {
       // (a) rays that left the scene end their path now
-      const bool hit = done && h.id >= 0;
+      const bool hit = !TRACE && done && h.id >= 0;
       if (done) {
         n_seg++;
-        if (!hit) {
+        if (TRACE) { // the traversal's result IS the output
+          P.trace_id[pixel_index] = h.id;
+          P.trace_t[pixel_index] = h.id >= 0 ? h.t : 0.f;
+          alive = false;
+          ended = true;
+        } else if (!hit) {
           L = L + beta * miss_radiance(P.sp, r.d);
           atomicAdd(&acc[pix * 4 + 0], L.x);
           atomicAdd(&acc[pix * 4 + 1], L.y);
@@ -327,7 +348,13 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       if (pool_has && dead) {
         if (!alive) {
           const int item = pool_next + __popc(dead & lt_mask);
-          if (item < pool_end) {
+          if (TRACE) {
+            if (item < pool_end) {
+              pix = cur_buf << 5;
+              pixel_index = s0 + item; // the ray's index
+              fresh_path = true;
+            }
+          } else if (item < pool_end) {
             const int px = item & 31;
             const int i = tile_x0 + (px & 7), j = tile_y0 + (px >> 3);
             if (i < P.W && j < P.y1) {
@@ -342,7 +369,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         pool_next = min(pool_end, pool_next + __popc(dead));
       }
       // (c) ONE Philox call per lane: the bounce event of a hit, or the camera event of a new path
-      if (hit || fresh_path)
+      if (!TRACE && (hit || fresh_path))
         q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
       bool fresh_ray = false;
       if (hit) {
@@ -366,6 +393,12 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           ended = true;
           node = node_end;
         }
+      } else if (TRACE && fresh_path) {
+        const float4 ra = __ldg(P.trace_rays + 2 * (size_t)pixel_index), rb = __ldg(P.trace_rays + 2 * (size_t)pixel_index + 1);
+        r.o = v3(ra.x, ra.y, ra.z); r.tm = ra.w; r.d = v3(rb.x, rb.y, rb.z);
+        alive = true;
+        n_paths++;
+        fresh_ray = true;
       } else if (fresh_path) {
         const int px = pix & 31;
         const int i = tile_x0 + (px & 7), j = tile_y0 + (px >> 3);
@@ -389,7 +422,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     if (old_valid && old_inflight == 0) {
       __syncwarp();
       const int i = old_x0 + (lane & 7), j = old_y0 + (lane >> 3);
-      if (i < P.W && j < P.y1) {
+      if (!TRACE && i < P.W && j < P.y1) {
         const float *a = acc + old_buf * 128 + lane * 4;
         P.partial[(size_t)old_chunk * ((size_t)P.W * P.H) + (size_t)j * P.W + i] =
             make_float4(a[0], a[1], a[2], (float)old_chunk_n);

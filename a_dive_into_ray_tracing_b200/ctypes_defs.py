@@ -93,7 +93,8 @@ class RtStats(C.Structure):
                 ("ms_upload", C.c_float), ("ms_build", C.c_float), ("ms_render", C.c_float),
                 ("ms_resolve", C.c_float),
                 ("n_nodes", C.c_int32), ("n_big_prims", C.c_int32), ("smem_bytes", C.c_int32),
-                ("block_threads", C.c_int32), ("grid_blocks", C.c_int32), ("regs_per_thread", C.c_int32)]
+                ("block_threads", C.c_int32), ("grid_blocks", C.c_int32), ("regs_per_thread", C.c_int32),
+                ("smem_plan", C.c_int32), ("reserved", C.c_int32)]
 
 
 def camera_from_lookat(lookfrom, lookat, vup, vfov_deg, aspect, aperture, focus_dist, time0=0.0, time1=0.0,

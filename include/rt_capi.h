@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RT_CAPI_VERSION 2
+#define RT_CAPI_VERSION 3
 
 typedef struct rt_ctx rt_ctx;
 
@@ -216,6 +216,9 @@ typedef struct rt_stats_t {
   uint64_t kernel_launches;/* kernels of this library launched */
   float ms_upload, ms_build, ms_render, ms_resolve; /* last call of each phase (CUDA events) */
   int32_t n_nodes, n_big_prims, smem_bytes, block_threads, grid_blocks, regs_per_thread;
+  int32_t smem_plan;       /* residency plan of the last render / trace launch: 2 = scene + four node orderings in
+                            * shared memory, 1 = scene + one ordering, 3 = nodes only, 0 = everything through L1/L2 */
+  int32_t reserved;
 } rt_stats_t;
 
 int rt_version(void);
@@ -235,7 +238,11 @@ int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nod
                       int cap_leaf, int *n_leaf, int32_t *big_prims, int cap_big, int *n_big);
 
 /* rays: [n][8] floats = origin.xyz, time, direction.xyz, unused. use_accel 0 =
- * brute force over the flattened arrays, 1 = through the BVH. */
+ * brute force over the flattened arrays, 1 = through the BVH with a plain one-ray-per-thread loop,
+ * 2 = through the BVH with the RENDER KERNEL's own machinery (the TRACE instantiation of k_render: the
+ * same shared-memory residency plan and quadrant node orderings, warp-voted search bursts, hardware
+ * reciprocals in the ray setup, direct leaf payloads and regeneration by ballot rank as rt_render),
+ * so that the closest-hit parity tests cover the code that is timed. */
 int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel,
                      int32_t *prim_id, float *t);
 

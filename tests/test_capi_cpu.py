@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.SYMBOLS) == syms
     for s in syms:
         assert hasattr(lib, s), s
-    assert capi.load_library().rt_version() == 2
+    assert capi.load_library().rt_version() == 3
 
 
 def test_struct_sizes_match_header():
