@@ -86,7 +86,8 @@ RT_HD float rt_fast_sin(float x) {
 #define RT_COLD static inline
 #endif
 
-// perlin::noise with the trilinear Hermite interpolation of perlin.h:29-56,103-122
+// perlin::noise with the trilinear Hermite interpolation of perlin.h:29-56,103-122 (as the reference
+// computes it: see the note at the weight vector)
 RT_COLD float perlin_noise(const float4 *__restrict__ vec, const uint8_t *__restrict__ perm, V3f p) {
   const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
   const float u = p.x - fx, v = p.y - fy, w = p.z - fz;
@@ -98,7 +99,9 @@ RT_COLD float perlin_noise(const float4 *__restrict__ vec, const uint8_t *__rest
     const int di = c >> 2, dj = (c >> 1) & 1, dk = c & 1;
     const int h = perm[(i + di) & 255] ^ perm[256 + ((j + dj) & 255)] ^ perm[512 + ((k + dk) & 255)];
     const float4 g = vec[h];
-    const float d = RT_FMA(g.z, w - (float)dk, RT_FMA(g.y, v - (float)dj, g.x * (u - (float)di)));
+    // perlin.h:41-43 smooths u, v, w in place BEFORE trilinear_interp, so the reference's weight vector
+    // (perlin.h:111) uses the smoothed coordinates (pinned: tests/golden/cuda_ref_nw_cornell_inst.npz)
+    const float d = RT_FMA(g.z, ww - (float)dk, RT_FMA(g.y, vv - (float)dj, g.x * (uu - (float)di)));
     accum += (di ? uu : 1.0f - uu) * (dj ? vv : 1.0f - vv) * (dk ? ww : 1.0f - ww) * d;
   }
   return accum;

@@ -68,6 +68,8 @@ typedef enum rt_profile {
 #define RT_FLAG_FLIP_NORMALS 1u      /* triangles/cuda/include/hittable.h:29 (normal faces the ray) */
 #define RT_FLAG_DEPTH_BACKGROUND 2u  /* obj_render.cu:78-83: depth exhausted -> unwound background */
 #define RT_FLAG_COUNTERS 4u          /* maintain node/prim test counters (slower kernel variant) */
+#define RT_FLAG_REFERENCE_MEDIUM 8u  /* constant_medium.h:66: the scattered ray leaves from the boundary ENTRY point
+                                      * r.at(rec1.t) (entry clamped to the ray origin), not from the scatter point */
 
 typedef enum rt_prim_type {
   RT_PRIM_SPHERE = 0,

@@ -66,6 +66,69 @@ class L1:
         self._mdemo.restype = C.c_double
         self._mdemo.argtypes = [C.POINTER(RtSceneDesc), _vp, C.c_int, C.c_int, C.c_uint64]
         self.lib.orc_srand.argtypes = [C.c_uint]
+        # pinning against the reference's CUDA-tree device code (oracle/ref_cuda_harness.cu records)
+        for name, args in (("pin_hits", [C.POINTER(RtSceneDesc), C.c_int, _vp, _vp, C.c_int, C.c_double, C.c_double, _vp]),
+                           ("pin_scatter", [C.POINTER(RtSceneDesc), C.c_int, _vp, _vp, C.c_int, C.c_double, C.c_double,
+                                            C.c_uint64, _vp]),
+                           ("pin_media", [C.POINTER(RtSceneDesc), _vp, C.c_int, C.c_uint64, _vp]),
+                           ("pin_color", [C.POINTER(RtSceneDesc), C.c_int, _vp, _vp, C.c_int, C.c_uint64, _vp]),
+                           ("xorwow_kat", [C.c_uint64, C.c_int, _vp])):
+            f = getattr(self.lib, p + name)
+            f.restype = None
+            f.argtypes = args
+            setattr(self, "_" + name, f)
+
+    # records of oracle/ref_cuda_harness.cu (HHit, HScatter, HMediumHit) and orc_inst
+    PIN_HIT_DT = np.dtype([("hit", "<i4"), ("obj", "<i4"), ("t", "<f4"), ("p", "<f4", 3), ("n", "<f4", 3), ("u", "<f4"),
+                           ("v", "<f4"), ("front_face", "<i4")])
+    PIN_SCATTER_DT = np.dtype([("ok", "<i4"), ("att", "<f4", 3), ("o", "<f4", 3), ("d", "<f4", 3), ("tm", "<f4"),
+                               ("emitted", "<f4", 3), ("draws", "<i4")])
+    PIN_MEDIUM_DT = np.dtype([("hit", "<i4"), ("t", "<f4"), ("p", "<f4", 3), ("draws", "<i4")])
+    INST_DT = np.dtype([("sin_y", "<f4"), ("cos_y", "<f4"), ("offset", "<f4", 3), ("flag", "<i4")])
+
+    @staticmethod
+    def _inst_ptr(inst):
+        if inst is None:
+            return None, None
+        inst = np.ascontiguousarray(inst, L1.INST_DT)
+        return inst, inst.ctypes.data
+
+    def pin_hits(self, scene, profile, rays, t_min, t_max=3.4028234663852886e38, inst=None):
+        rays = np.ascontiguousarray(rays, np.float32)
+        out = np.zeros(len(rays), self.PIN_HIT_DT)
+        d = scene.desc()
+        keep, ip = self._inst_ptr(inst)
+        self._pin_hits(C.byref(d), profile, ip, rays.ctypes.data, len(rays), float(t_min), float(t_max), out.ctypes.data)
+        return out
+
+    def pin_scatter(self, scene, profile, rays, t_min, seed, t_max=3.4028234663852886e38, inst=None):
+        rays = np.ascontiguousarray(rays, np.float32)
+        out = np.zeros(len(rays), self.PIN_SCATTER_DT)
+        d = scene.desc()
+        keep, ip = self._inst_ptr(inst)
+        self._pin_scatter(C.byref(d), profile, ip, rays.ctypes.data, len(rays), float(t_min), float(t_max), int(seed),
+                          out.ctypes.data)
+        return out
+
+    def pin_media(self, scene, rays, seed):
+        rays = np.ascontiguousarray(rays, np.float32)
+        out = np.zeros((len(rays), len(scene.media)), self.PIN_MEDIUM_DT)
+        d = scene.desc()
+        self._pin_media(C.byref(d), rays.ctypes.data, len(rays), int(seed), out.ctypes.data)
+        return out
+
+    def pin_color(self, scene, profile, rays, seed, inst=None):
+        rays = np.ascontiguousarray(rays, np.float32)
+        out = np.zeros((len(rays), 4), np.float32)
+        d = scene.desc()
+        keep, ip = self._inst_ptr(inst)
+        self._pin_color(C.byref(d), profile, ip, rays.ctypes.data, len(rays), int(seed), out.ctypes.data)
+        return out
+
+    def xorwow_kat(self, seed, n=8):
+        out = np.zeros(n, np.float32)
+        self._xorwow_kat(int(seed), n, out.ctypes.data)
+        return out
 
     def srand(self, seed):
         self.lib.orc_srand(seed)

@@ -114,7 +114,7 @@ __device__ material *make_material(const HMat &m, abstract_texture *tex) {
 
 __global__ void k_build(HHeader H, const HSphere *sph, const HTri *tri, const HQuad *quad, const HMat *mats, const HInst *inst,
                         const HMedium *media, unsigned char **img_data, const int *img_wh, World w, curandState *rs,
-                        float *perlin_out) {
+                        float *perlin_out, float *inst_sc, float *med_sc) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   curand_init(H.seed, 0, 0, rs);
   int n_noise = 0;
@@ -155,17 +155,25 @@ __global__ void k_build(HHeader H, const HSphere *sph, const HTri *tri, const HQ
     else if (q.axis == 1) w.objs[k] = new xz_rect(q.a0, q.a1, q.b0, q.b1, q.k, w.obj_mat[k]);
     else w.objs[k] = new yz_rect(q.a0, q.a1, q.b0, q.b1, q.k, w.obj_mat[k]);
   }
-  for (int i = 0; i < k; i++)
-    if (inst[i].flag)
-      w.objs[i] = new translate(new rotate_y(w.objs[i], inst[i].angle_deg), vec3(inst[i].off[0], inst[i].off[1], inst[i].off[2]));
+  for (int i = 0; i < k; i++) {
+    inst_sc[2 * i] = 0.f; inst_sc[2 * i + 1] = 1.f;
+    if (inst[i].flag) {
+      rotate_y *ry = new rotate_y(w.objs[i], inst[i].angle_deg);
+      inst_sc[2 * i] = ry->sin_theta; inst_sc[2 * i + 1] = ry->cos_theta; // sinf / cosf as the device evaluates them
+      w.objs[i] = new translate(ry, vec3(inst[i].off[0], inst[i].off[1], inst[i].off[2]));
+    }
+  }
   for (int m = 0; m < H.n_media; m++, k++) {
     const HMedium &md = media[m];
     hittable *b;
     material *bm = new dielectric(1.5f); // the boundary's own material is never used (main.cu:297-305)
+    med_sc[2 * m] = 0.f; med_sc[2 * m + 1] = 1.f;
     if (md.shape == 0) b = new sphere(vec3(md.p0[0], md.p0[1], md.p0[2]), md.p1[0], bm);
-    else
-      b = new translate(new rotate_y(new box(vec3(md.p0[0], md.p0[1], md.p0[2]), vec3(md.p1[0], md.p1[1], md.p1[2]), bm), md.angle_deg),
-                        vec3(md.off[0], md.off[1], md.off[2]));
+    else {
+      rotate_y *ry = new rotate_y(new box(vec3(md.p0[0], md.p0[1], md.p0[2]), vec3(md.p1[0], md.p1[1], md.p1[2]), bm), md.angle_deg);
+      med_sc[2 * m] = ry->sin_theta; med_sc[2 * m + 1] = ry->cos_theta;
+      b = new translate(ry, vec3(md.off[0], md.off[1], md.off[2]));
+    }
     constant_medium *cm = new constant_medium(b, md.density, color(md.albedo[0], md.albedo[1], md.albedo[2]));
     w.objs[k] = cm;
     w.obj_mat[k] = cm->phase_function;
@@ -343,11 +351,13 @@ int main(int argc, char **argv) {
   int n_noise = 0;
   for (auto &m : mats) n_noise += m.texture == 2;
   float *d_perlin; HCK(cudaMalloc(&d_perlin, sizeof(float) * 1536 * std::max(n_noise, 1)));
+  float *d_inst_sc, *d_med_sc;
+  HCK(cudaMalloc(&d_inst_sc, sizeof(float) * 2 * std::max(n_prims, 1))); HCK(cudaMalloc(&d_med_sc, sizeof(float) * 2 * std::max(H.n_media, 1)));
   unsigned char **d_img = upload(img_ptrs);
   int *d_wh = upload(img_wh);
   HSphere *d_sph = upload(sph); HTri *d_tri = upload(tri); HQuad *d_quad = upload(quad); HMat *d_mats = upload(mats);
   HInst *d_inst = upload(inst); HMedium *d_media = upload(media); HTexQ *d_texq = upload(texq); float *d_rays = upload(rays);
-  k_build<<<1, 1>>>(H, d_sph, d_tri, d_quad, d_mats, d_inst, d_media, d_img, d_wh, w, rs, d_perlin);
+  k_build<<<1, 1>>>(H, d_sph, d_tri, d_quad, d_mats, d_inst, d_media, d_img, d_wh, w, rs, d_perlin, d_inst_sc, d_med_sc);
   HCK(cudaGetLastError()); HCK(cudaDeviceSynchronize());
 
   const int TB = 64, g = (H.n_rays + TB - 1) / TB;
@@ -376,6 +386,7 @@ int main(int argc, char **argv) {
   wr(fo, o_list, H.n_rays); wr(fo, o_bvh, H.n_rays); wr(fo, o_sc, H.n_rays); wr(fo, o_med, (size_t)H.n_rays * H.n_media);
   wr(fo, o_col, 8 * (size_t)H.n_colorrays); wr(fo, o_tex, 3 * (size_t)H.n_texq); wr(fo, d_perlin, 1536 * (size_t)n_noise);
   wr(fo, o_x, 128);
+  wr(fo, d_inst_sc, 2 * (size_t)n_prims); wr(fo, d_med_sc, 2 * (size_t)H.n_media);
   fclose(fo);
   fprintf(stderr, "ref_cuda_harness tree %d: %d objects (%d media), %d rays, %d colour rays, %d texture queries -> %s\n", TREE,
           n_objs, H.n_media, H.n_rays, H.n_colorrays, H.n_texq, argv[2]);

@@ -34,7 +34,7 @@ static inline REAL FN(comp)(V3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y :
 /* ---- RNG: splitmix64-seeded xoshiro256** (the reference uses glibc rand() on
  * the CPU, rtweekend.h:21-24, and cuRAND XORWOW on the GPU; neither sequence is
  * part of the contract — parity of images is statistical). */
-typedef struct { uint64_t s[4]; uint64_t draws; int libc; } FN(Rng);
+typedef struct { uint64_t s[4]; uint64_t draws; int libc; /* 1: glibc rand(); 2: cuRAND XORWOW replay */ uint32_t xv[5], xd; } FN(Rng);
 static inline uint64_t FN(rotl)(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
 static void FN(rng_seed)(FN(Rng) *r, uint64_t seed) {
   uint64_t z = seed;
@@ -48,6 +48,28 @@ static void FN(rng_seed)(FN(Rng) *r, uint64_t seed) {
   r->draws = 0;
   r->libc = 0;
 }
+/* cuRAND's default generator as the CUDA trees use it: curand_init(seed, 0, 0, &state) and
+ * curand_uniform (restated from the published header curand_kernel.h, CUDA 12.9:
+ * _curand_init_scratch :772-798 with subsequence = offset = 0, curand :863-874, _curand_uniform =
+ * x * 2^-32 + 2^-33, i.e. (0, 1]). Pinned by the known answers the harness records
+ * (tests/golden/cuda_ref_*.npz "xorwow"). */
+static void FN(rng_seed_xorwow)(FN(Rng) *r, uint64_t seed) {
+  uint32_t s0 = ((uint32_t)seed) ^ 0xaad26b49u, s1 = (uint32_t)(seed >> 32) ^ 0xf7dcefddu;
+  uint32_t t0 = 1099087573u * s0, t1 = 2591861531u * s1;
+  r->xd = 6615241u + t1 + t0;
+  r->xv[0] = 123456789u + t0; r->xv[1] = 362436069u ^ t0; r->xv[2] = 521288629u + t1;
+  r->xv[3] = 88675123u ^ t1; r->xv[4] = 5783321u + t0;
+  r->draws = 0;
+  r->libc = 2;
+}
+static inline float FN(xorwow_uniform)(FN(Rng) *r) {
+  uint32_t t = r->xv[0] ^ (r->xv[0] >> 2);
+  r->xv[0] = r->xv[1]; r->xv[1] = r->xv[2]; r->xv[2] = r->xv[3]; r->xv[3] = r->xv[4];
+  r->xv[4] = (r->xv[4] ^ (r->xv[4] << 4)) ^ (t ^ (t << 1));
+  r->xd += 362437u;
+  r->draws++;
+  return (float)(r->xv[4] + r->xd) * 2.3283064e-10f + (2.3283064e-10f / 2.0f);
+}
 static inline uint64_t FN(rng_next)(FN(Rng) *r) {
   uint64_t *s = r->s;
   uint64_t result = FN(rotl)(s[1] * 5, 7) * 9, t = s[1] << 17;
@@ -58,6 +80,7 @@ static inline uint64_t FN(rng_next)(FN(Rng) *r) {
 /* random_double() in [0,1) — rtweekend.h:21-24 (31 random bits there; 24/53 here) */
 static inline REAL FN(rnd)(FN(Rng) *r) {
   /* pinning mode: the reference's own generator, rtweekend.h:21-24 */
+  if (r->libc == 2) return (REAL)FN(xorwow_uniform)(r);
   if (r->libc) { r->draws++; return (REAL)(rand() / (RAND_MAX + 1.0)); }
 #if REAL_IS_FLOAT
   return (REAL)(FN(rng_next)(r) >> 40) * (REAL)(1.0 / 16777216.0);
@@ -72,7 +95,11 @@ static inline REAL FN(rnd_range)(FN(Rng) *r, REAL lo, REAL hi) { return lo + (hi
 static V3 FN(random_in_unit_sphere)(FN(Rng) *r) {
   for (;;) {
     V3 p;
-    if (r->libc) { /* g++ evaluates vec3(random_double(..) x3) (vec3.h:46-49) right to left */
+    if (r->libc == 2) { /* 2.0f * RANDVEC3 - vec3(1,1,1) (rt_next_week/cuda/material.h:11-21); nvcc evaluates left to right */
+      p.x = (REAL)2 * FN(rnd)(r) - (REAL)1;
+      p.y = (REAL)2 * FN(rnd)(r) - (REAL)1;
+      p.z = (REAL)2 * FN(rnd)(r) - (REAL)1;
+    } else if (r->libc) { /* g++ evaluates vec3(random_double(..) x3) (vec3.h:46-49) right to left */
       p.z = FN(rnd_range)(r, (REAL)-1, (REAL)1);
       p.y = FN(rnd_range)(r, (REAL)-1, (REAL)1);
       p.x = FN(rnd_range)(r, (REAL)-1, (REAL)1);
@@ -106,6 +133,10 @@ static V3 FN(random_in_unit_disk)(FN(Rng) *r) {
 /* vec3.h:114 */
 static inline V3 FN(reflect)(V3 a, V3 n) { return FN(sub)(a, FN(scale)((REAL)2 * FN(dot)(a, n), n)); }
 
+#ifndef ORC_INST_DEFINED
+#define ORC_INST_DEFINED
+typedef struct orc_inst { float sin_y, cos_y, offset[3]; int32_t flag; } orc_inst;
+#endif
 typedef struct { V3 o, d; REAL tm; } FN(Ray);
 static inline V3 FN(at)(const FN(Ray) *r, REAL t) { return FN(add)(r->o, FN(scale)(t, r->d)); }
 
@@ -124,6 +155,10 @@ typedef struct {
   uint32_t flags;
   /* statistics */
   uint64_t n_prim_tests, n_box_tests;
+  /* optional per-primitive translate(rotate_y(object, angle), offset) wrappers in RAY-TRANSFORM form
+   * (list order: spheres, triangles, quads), as the reference intersects instances */
+  const orc_inst *inst;
+  int ref_list_media; /* pinning mode: constant_medium::hit exactly as written, media last in list order */
 } FN(World);
 
 /* hittable.h:22-25 (CPU: flips), rt_next_week/cuda/hittable.h:22-30 (never flips),
@@ -245,11 +280,37 @@ static int FN(quad_hit)(FN(World) *w, int idx, const FN(Ray) *r, REAL t_min, REA
   return 1;
 }
 
-static int FN(prim_hit)(FN(World) *w, int32_t prim, const FN(Ray) *r, REAL t_min, REAL t_max, FN(Hit) *h) {
+static int FN(prim_hit_plain)(FN(World) *w, int32_t prim, const FN(Ray) *r, REAL t_min, REAL t_max, FN(Hit) *h) {
   int type = RT_PRIM_TYPE_OF(prim), idx = RT_PRIM_INDEX_OF(prim);
   if (type == RT_PRIM_SPHERE) return FN(sphere_hit)(w, idx, r, t_min, t_max, h);
   if (type == RT_PRIM_TRIANGLE) return FN(triangle_hit)(w, idx, r, t_min, t_max, h);
   return FN(quad_hit)(w, idx, r, t_min, t_max, h);
+}
+/* translate::hit (rt_next_week/cuda/hittable.h:66-79) around rotate_y::hit (:156-190): the RAY is moved
+ * into the object's frame (t is preserved: neither rescales d), the hit point and normal are moved back,
+ * and each wrapper re-applies set_face_normal with ITS ray (rotate_y: object-space ray against the
+ * world-space normal, then translate: the un-rotated moved ray - which has the last word). */
+static int FN(prim_hit)(FN(World) *w, int32_t prim, const FN(Ray) *r, REAL t_min, REAL t_max, FN(Hit) *h) {
+  if (!w->inst) return FN(prim_hit_plain)(w, prim, r, t_min, t_max, h);
+  int type = RT_PRIM_TYPE_OF(prim), idx = RT_PRIM_INDEX_OF(prim);
+  int flat = idx + (type >= RT_PRIM_TRIANGLE ? w->sc->n_spheres : 0) + (type >= RT_PRIM_QUAD ? w->sc->n_triangles : 0);
+  const orc_inst *in = &w->inst[flat];
+  if (!in->flag) return FN(prim_hit_plain)(w, prim, r, t_min, t_max, h);
+  const REAL sn = (REAL)in->sin_y, cs = (REAL)in->cos_y;
+  FN(Ray) moved = *r;
+  moved.o = FN(sub)(r->o, FN(from3f)(in->offset));
+  FN(Ray) rot = moved;
+  rot.o.x = cs * moved.o.x - sn * moved.o.z; rot.o.z = sn * moved.o.x + cs * moved.o.z;
+  rot.d.x = cs * moved.d.x - sn * moved.d.z; rot.d.z = sn * moved.d.x + cs * moved.d.z;
+  if (!FN(prim_hit_plain)(w, prim, &rot, t_min, t_max, h)) return 0;
+  V3 p = h->p, n = h->normal;
+  p.x = cs * h->p.x + sn * h->p.z; p.z = -sn * h->p.x + cs * h->p.z;
+  n.x = cs * h->normal.x + sn * h->normal.z; n.z = -sn * h->normal.x + cs * h->normal.z;
+  h->p = p;
+  FN(set_face_normal)(w, h, &rot, n);
+  h->p = FN(add)(h->p, FN(from3f)(in->offset));
+  FN(set_face_normal)(w, h, &moved, h->normal);
+  return 1;
 }
 
 /* hittable_list::hit — hittable_list.h:20-34 / accelerated-rt-cuda/hittable_list.h:22-37.
@@ -260,11 +321,11 @@ static int FN(list_hit)(FN(World) *w, const FN(Ray) *r, REAL t_min, REAL t_max, 
   REAL closest = t_max;
   const rt_scene_desc *sc = w->sc;
   for (int i = 0; i < sc->n_spheres; i++)
-    if (FN(sphere_hit)(w, i, r, t_min, closest, &tmp)) { any = 1; closest = tmp.t; *rec = tmp; }
+    if (FN(prim_hit)(w, RT_PRIM_ID(RT_PRIM_SPHERE, i), r, t_min, closest, &tmp)) { any = 1; closest = tmp.t; *rec = tmp; }
   for (int i = 0; i < sc->n_triangles; i++)
-    if (FN(triangle_hit)(w, i, r, t_min, closest, &tmp)) { any = 1; closest = tmp.t; *rec = tmp; }
+    if (FN(prim_hit)(w, RT_PRIM_ID(RT_PRIM_TRIANGLE, i), r, t_min, closest, &tmp)) { any = 1; closest = tmp.t; *rec = tmp; }
   for (int i = 0; i < sc->n_quads; i++)
-    if (FN(quad_hit)(w, i, r, t_min, closest, &tmp)) { any = 1; closest = tmp.t; *rec = tmp; }
+    if (FN(prim_hit)(w, RT_PRIM_ID(RT_PRIM_QUAD, i), r, t_min, closest, &tmp)) { any = 1; closest = tmp.t; *rec = tmp; }
   return any;
 }
 
@@ -414,7 +475,10 @@ static REAL FN(perlin_noise)(const rt_perlin *pn, V3 p) {
     for (int dj = 0; dj < 2; dj++)
       for (int dk = 0; dk < 2; dk++) {
         const float *c = pn->ranvec[pn->perm_x[(i + di) & 255] ^ pn->perm_y[(j + dj) & 255] ^ pn->perm_z[(k + dk) & 255]];
-        V3 weight_v = FN(v)(u - (REAL)di, v - (REAL)dj, w - (REAL)dk);
+        /* perlin.h:41-43 smooths u, v, w IN PLACE before calling trilinear_interp, so the reference's
+         * weight vector (perlin.h:111) is built from the SMOOTHED coordinates (the book uses the raw ones);
+         * pinned by tests/golden/cuda_ref_nw_cornell_inst.npz */
+        V3 weight_v = FN(v)(uu - (REAL)di, vv - (REAL)dj, ww - (REAL)dk);
         accum += ((REAL)di * uu + (REAL)(1 - di) * ((REAL)1 - uu)) * ((REAL)dj * vv + (REAL)(1 - dj) * ((REAL)1 - vv)) *
                  ((REAL)dk * ww + (REAL)(1 - dk) * ((REAL)1 - ww)) * FN(dot)(FN(from3f)(c), weight_v);
       }
@@ -609,8 +673,67 @@ static int FN(medium_hit)(const FN(World) *w, int idx, const FN(Ray) *r, REAL t_
   REAL t = t1 + hit_distance / ray_length;
   if (!(t < t_max)) return 0;
   h->t = t;
-  h->p = FN(at)(r, t);
+  h->p = FN(at)(r, (w->flags & RT_FLAG_REFERENCE_MEDIUM) ? t1 : t); /* constant_medium.h:66 when asked for */
   h->normal = FN(v)(1, 0, 0); /* arbitrary (:69-70) */
+  h->front_face = 1;
+  h->u = h->v = 0;
+  h->material = m->material;
+  h->prim = RT_PRIM_ID(RT_PRIM_MEDIUM, idx);
+  return 1;
+}
+
+/* constant_medium::hit EXACTLY as the reference wrote it (rt_next_week/cuda/constant_medium.h:36-85): two
+ * boundary->hit calls (-inf..inf, then rec1.t + 0.00001..inf) through the boundary's own hit function -
+ * sphere::hit (sphere.h:43-77) or translate(rotate_y(box)) with box::hit = hittable_list of six rects
+ * (box.h:40-63, list order xy(z1), xy(z0), xz(y1), xz(y0), yz(x1), yz(x0)) -, t_min / t_max IGNORED,
+ * rec.p = r.at(rec1.t). Used only to pin this file against the reference's device code
+ * (tests/test_cuda_ref_pinning.py); the product semantics are medium_hit above. */
+static int FN(ref_boundary_hit)(const rt_medium *m, const FN(Ray) *r, REAL t_min, REAL t_max, REAL *t_out) {
+  if (m->shape == 0) {
+    V3 oc = FN(sub)(r->o, FN(from3f)(m->p0));
+    REAL radius = (REAL)m->p1[0];
+    REAL a = FN(dot)(r->d, r->d), b = FN(dot)(oc, r->d), c = FN(dot)(oc, oc) - radius * radius;
+    REAL disc = b * b - a * c;
+    if (disc > 0) {
+      REAL temp = (-b - SQRT(disc)) / a;
+      if (temp < t_max && temp > t_min) { *t_out = temp; return 1; }
+      temp = (-b + SQRT(disc)) / a;
+      if (temp < t_max && temp > t_min) { *t_out = temp; return 1; }
+    }
+    return 0;
+  }
+  V3 o = FN(sub)(r->o, FN(from3f)(m->offset)), d = r->d;
+  REAL sn = (REAL)m->sin_y, cs = (REAL)m->cos_y;
+  REAL ol[3] = {cs * o.x - sn * o.z, o.y, sn * o.x + cs * o.z};
+  REAL dl[3] = {cs * d.x - sn * d.z, d.y, sn * d.x + cs * d.z};
+  int any = 0;
+  REAL closest = t_max;
+  const int axes[3] = {2, 1, 0};
+  for (int f = 0; f < 6; f++) {
+    const int ax = axes[f >> 1], ia = (ax == 0) ? 1 : 0, ib = (ax == 2) ? 1 : 2;
+    const REAL k = (f & 1) ? (REAL)m->p0[ax] : (REAL)m->p1[ax];
+    REAL t = (k - ol[ax]) / dl[ax];
+    if (t < t_min || t > closest) continue;
+    REAL a = ol[ia] + t * dl[ia], b = ol[ib] + t * dl[ib];
+    if (a < (REAL)m->p0[ia] || a > (REAL)m->p1[ia] || b < (REAL)m->p0[ib] || b > (REAL)m->p1[ib]) continue;
+    any = 1; closest = t;
+  }
+  *t_out = closest;
+  return any;
+}
+static int FN(medium_hit_ref)(const FN(World) *w, int idx, const FN(Ray) *r, FN(Hit) *h, FN(Rng) *rng) {
+  const rt_medium *m = &w->sc->media[idx];
+  REAL t1, t2;
+  if (!FN(ref_boundary_hit)(m, r, -INFINITY_R, INFINITY_R, &t1)) return 0;
+  if (!FN(ref_boundary_hit)(m, r, (REAL)((double)t1 + 0.00001), INFINITY_R, &t2)) return 0;
+  if (t1 < 0) t1 = 0;
+  const REAL ray_length = FN(len)(r->d);
+  const REAL inside = (t2 - t1) * ray_length;
+  const REAL hit_distance = ((REAL)-1 / (REAL)m->density) * LOG(FN(rnd)(rng));
+  if (hit_distance > inside) return 0;
+  h->t = t1 + hit_distance / ray_length;
+  h->p = FN(at)(r, t1);
+  h->normal = FN(v)(1, 0, 0);
   h->front_face = 1;
   h->u = h->v = 0;
   h->material = m->material;
@@ -623,6 +746,11 @@ static int FN(scene_hit)(FN(World) *w, const FN(RefBvh) *bvh, const FN(Ray) *r, 
   int any = FN(world_hit)(w, bvh, r, t_min, INFINITY_R, rec);
   REAL closest = any ? rec->t : INFINITY_R;
   FN(Hit) tmp;
+  if (w->ref_list_media) { /* pinning mode: the media as the LAST items of the reference's hittable_list */
+    for (int i = 0; i < w->sc->n_media; i++)
+      if (FN(medium_hit_ref)(w, i, r, &tmp, rng)) { any = 1; closest = tmp.t; *rec = tmp; }
+    return any;
+  }
   for (int i = 0; i < w->sc->n_media; i++)
     if (FN(medium_hit)(w, i, r, closest, &tmp, rng)) { any = 1; closest = tmp.t; *rec = tmp; }
   return any;
@@ -941,4 +1069,112 @@ void FN(quantise)(int profile, const double *sum3, int spp, int *rgb) {
       rgb[a] = q > 255 ? 255 : q;
     }
   }
+}
+
+/* ------------------------------------------------------------------ pinning against the reference's CUDA trees
+ * The records below mirror oracle/ref_cuda_harness.cu (HHit, HScatter, HMediumHit), which runs the reference's
+ * unmodified device code; tests/test_cuda_ref_pinning.py compares field by field. `obj` = flat list index
+ * (spheres, triangles, quads, then media). Random numbers: XORWOW, seed + 1 + ray index per ray. */
+#ifndef ORC_PIN_RECORDS_DEFINED
+#define ORC_PIN_RECORDS_DEFINED
+typedef struct { int32_t hit, obj; float t, p[3], n[3], u, v; int32_t front_face; } orc_pin_hit;
+typedef struct { int32_t ok; float att[3], o[3], d[3], tm, emitted[3]; int32_t draws; } orc_pin_scatter;
+typedef struct { int32_t hit; float t, p[3]; int32_t draws; } orc_pin_medium;
+#endif
+static int FN(flat_index)(const rt_scene_desc *sc, int32_t prim) {
+  int type = RT_PRIM_TYPE_OF(prim), idx = RT_PRIM_INDEX_OF(prim);
+  if (type == RT_PRIM_SPHERE) return idx;
+  if (type == RT_PRIM_TRIANGLE) return sc->n_spheres + idx;
+  if (type == RT_PRIM_QUAD) return sc->n_spheres + sc->n_triangles + idx;
+  return sc->n_spheres + sc->n_triangles + sc->n_quads + idx;
+}
+static FN(Ray) FN(ray_from8)(const float *q) {
+  FN(Ray) r;
+  r.o = FN(from3f)(q); r.tm = (REAL)q[3]; r.d = FN(from3f)(q + 4);
+  return r;
+}
+void FN(pin_hits)(const rt_scene_desc *sc, int profile, const orc_inst *inst, const float *rays, int n, double t_min,
+                  double t_max, orc_pin_hit *out) {
+  FN(World) w = {sc, profile, sc->flags, 0, 0, inst, 0};
+  for (int k = 0; k < n; k++) {
+    FN(Ray) r = FN(ray_from8)(rays + 8 * k);
+    FN(Hit) rec;
+    orc_pin_hit o;
+    memset(&o, 0, sizeof o);
+    o.obj = -1;
+    if (FN(list_hit)(&w, &r, (REAL)t_min, (t_max >= 3.0e38) ? INFINITY_R : (REAL)t_max, &rec)) {
+      o.hit = 1; o.obj = FN(flat_index)(sc, rec.prim); o.t = (float)rec.t;
+      o.p[0] = (float)rec.p.x; o.p[1] = (float)rec.p.y; o.p[2] = (float)rec.p.z;
+      o.n[0] = (float)rec.normal.x; o.n[1] = (float)rec.normal.y; o.n[2] = (float)rec.normal.z;
+      o.u = (float)rec.u; o.v = (float)rec.v; o.front_face = rec.front_face;
+    }
+    out[k] = o;
+  }
+}
+void FN(pin_scatter)(const rt_scene_desc *sc, int profile, const orc_inst *inst, const float *rays, int n, double t_min,
+                     double t_max, uint64_t seed, orc_pin_scatter *out) {
+  FN(World) w = {sc, profile, sc->flags, 0, 0, inst, 0};
+  for (int k = 0; k < n; k++) {
+    FN(Ray) r = FN(ray_from8)(rays + 8 * k);
+    FN(Rng) rng;
+    FN(rng_seed_xorwow)(&rng, seed + 1 + (uint64_t)k);
+    FN(Hit) rec;
+    orc_pin_scatter o;
+    memset(&o, 0, sizeof o);
+    o.ok = -1;
+    if (FN(list_hit)(&w, &r, (REAL)t_min, (t_max >= 3.0e38) ? INFINITY_R : (REAL)t_max, &rec)) {
+      const rt_material *m = &sc->materials[rec.material];
+      FN(Ray) sca;
+      sca.o = FN(v)(0, 0, 0); sca.d = FN(v)(0, 0, 0); sca.tm = 0;
+      V3 att = FN(v)(0, 0, 0);
+      V3 em = FN(emitted)(sc, m, rec.u, rec.v, rec.p);
+      o.ok = FN(scatter)(&w, m, &r, &rec, &att, &sca, &rng);
+      if (m->type == RT_MAT_DIFFUSE_LIGHT) { sca.o = FN(v)(0, 0, 0); sca.tm = 0; } /* the reference leaves `scattered` untouched */
+      o.att[0] = (float)att.x; o.att[1] = (float)att.y; o.att[2] = (float)att.z;
+      o.o[0] = (float)sca.o.x; o.o[1] = (float)sca.o.y; o.o[2] = (float)sca.o.z;
+      o.d[0] = (float)sca.d.x; o.d[1] = (float)sca.d.y; o.d[2] = (float)sca.d.z;
+      o.tm = (float)sca.tm;
+      o.emitted[0] = (float)em.x; o.emitted[1] = (float)em.y; o.emitted[2] = (float)em.z;
+    }
+    o.draws = (int32_t)rng.draws;
+    out[k] = o;
+  }
+}
+void FN(pin_media)(const rt_scene_desc *sc, const float *rays, int n, uint64_t seed, orc_pin_medium *out) {
+  FN(World) w = {sc, 2, sc->flags, 0, 0, NULL, 1};
+  for (int k = 0; k < n; k++) {
+    FN(Ray) r = FN(ray_from8)(rays + 8 * k);
+    for (int m = 0; m < sc->n_media; m++) {
+      FN(Rng) rng;
+      FN(rng_seed_xorwow)(&rng, seed + 1 + (uint64_t)k);
+      FN(Hit) rec;
+      orc_pin_medium o;
+      memset(&o, 0, sizeof o);
+      if (FN(medium_hit_ref)(&w, m, &r, &rec, &rng)) {
+        o.hit = 1; o.t = (float)rec.t;
+        o.p[0] = (float)rec.p.x; o.p[1] = (float)rec.p.y; o.p[2] = (float)rec.p.z;
+      }
+      o.draws = (int32_t)rng.draws;
+      out[(size_t)k * sc->n_media + m] = o;
+    }
+  }
+}
+/* get_color (main.cu:48-105 / obj_render.cu:20-86) per ray over the LIST world with the media last, each ray
+ * from its own XORWOW stream. out: [n][4] = rgb, draws. */
+void FN(pin_color)(const rt_scene_desc *sc, int profile, const orc_inst *inst, const float *rays, int n, uint64_t seed,
+                   float *out) {
+  FN(World) w = {sc, profile, sc->flags, 0, 0, inst, 1};
+  for (int k = 0; k < n; k++) {
+    FN(Ray) r = FN(ray_from8)(rays + 8 * k);
+    FN(Rng) rng;
+    FN(rng_seed_xorwow)(&rng, seed + 1 + (uint64_t)k);
+    uint64_t nseg = 0;
+    V3 c = FN(ray_color)(&w, NULL, r, &rng, &nseg);
+    out[4 * k] = (float)c.x; out[4 * k + 1] = (float)c.y; out[4 * k + 2] = (float)c.z; out[4 * k + 3] = (float)rng.draws;
+  }
+}
+void FN(xorwow_kat)(uint64_t seed, int n, float *out) {
+  FN(Rng) rng;
+  FN(rng_seed_xorwow)(&rng, seed);
+  for (int k = 0; k < n; k++) out[k] = FN(xorwow_uniform)(&rng);
 }
