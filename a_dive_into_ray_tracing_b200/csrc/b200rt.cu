@@ -144,9 +144,9 @@ __global__ void k_order(BuildArrays B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B.n_small - 1) body_order(B, i);
 }
-__global__ void k_pack(BuildArrays B, int quadrant) {
+__global__ void k_pack(BuildArrays B, int octant) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 2 * B.n_small - 1) body_pack(B, i, quadrant);
+  if (i < 2 * B.n_small - 1) body_pack(B, i, octant);
 }
 
 // ------------------------------------------------------------------ context
@@ -179,6 +179,7 @@ struct rt_ctx {
   ShadeParams sp;
   std::vector<int32_t> big_ids;
   int n_leaf_prims = 0, max_leaf = 1;
+  float root_box[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // {bmin.xyz, -, bmax.xyz, -} of the BVH root
   // frame
   int W = 0, H = 0;
   DevBuf d_accum, d_partial, d_counter, d_stats, d_linear, d_rgb8, d_rays, d_ids, d_ts;
@@ -399,6 +400,7 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   ctx->big_ids.clear();
   ctx->S.n_nodes = 0; ctx->S.n_big = 0; ctx->S.n_bigq = 0; ctx->n_leaf_prims = 0;
   ctx->stats.n_nodes = 0; ctx->stats.n_big_prims = 0;
+  memset(ctx->root_box, 0, sizeof ctx->root_box);
   if (n == 0) { ctx->have_accel = true; ctx->stats.ms_build = 0; return RT_OK; }
   CK(cudaEventRecord(ctx->ev0, st));
 
@@ -501,8 +503,8 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     RSV(t_swap, sizeof(int) * (size_t)nsm);
     { int rc = dev_reserve(ctx, ctx->d_leaf_prims, sizeof(int32_t) * (size_t)nsm); if (rc) { cleanup(); return rc; } }
     RSV(t_nlo, sizeof(float4) * (size_t)n_nodes); RSV(t_nhi, sizeof(float4) * (size_t)n_nodes);
-    // four packed copies, one per ray-direction quadrant (own front-to-back visiting order)
-    { int rc = dev_reserve(ctx, ctx->d_nodes, 4 * sizeof(float4) * 2 * (size_t)n_nodes); if (rc) { cleanup(); return rc; } }
+    // eight packed copies, one per ray-direction octant (own front-to-back visiting order)
+    { int rc = dev_reserve(ctx, ctx->d_nodes, RT_N_ORDERINGS * sizeof(float4) * 2 * (size_t)n_nodes); if (rc) { cleanup(); return rc; } }
     B.small_gid = (const int *)t_small.p;
     B.keys = (unsigned long long *)t_keys.p;
     B.left = (int *)t_left.p; B.right = (int *)t_right.p; B.parent = (int *)t_parent.p;
@@ -581,11 +583,13 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
       ctx->launches++;
     }
     if (nsm > 1) k_order<<<(nsm - 1 + TB - 1) / TB, TB, 0, st>>>(B);
-    for (int q = 0; q < 4; q++) k_pack<<<(n_nodes + TB - 1) / TB, TB, 0, st>>>(B, q);
-    ctx->launches += 5;
+    for (int q = 0; q < RT_N_ORDERINGS; q++) k_pack<<<(n_nodes + TB - 1) / TB, TB, 0, st>>>(B, q);
+    ctx->launches += 1 + RT_N_ORDERINGS;
     CKB(cudaGetLastError());
     int kept = 0; // nodes that survive leaf collapsing = kept size of the root (build node 0)
     CKB(cudaMemcpyAsync(&kept, B.size, sizeof(int), cudaMemcpyDeviceToHost, st));
+    // the root's box (record 0 of every ordering) = the frame of the render kernel's 16-bit quantised nodes
+    CKB(cudaMemcpyAsync(ctx->root_box, ctx->d_nodes.p, sizeof ctx->root_box, cudaMemcpyDeviceToHost, st));
     CKB(cudaStreamSynchronize(st));
     n_nodes = kept;
   }
@@ -691,7 +695,7 @@ static render_kernel_t pick_render_kernel(int profile, int smem, bool count, boo
 
 // Scheduler thresholds, the bytes of every scene array and the shared-memory residency plan of
 // k_render (shared by the render launches and the TRACE parity hook, which must run the very same
-// plan). smem: 2 = scene + four quadrant copies of the nodes, 1 = scene, 3 = nodes only, 0 = global.
+// plan). smem: 2 = scene + eight octant orderings of the nodes, 1 = scene + one ordering, 3 = nodes only, 0 = global.
 static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &smem, size_t &smem_bytes) {
   {
     const char *e = getenv("B200RT_BATCH"), *f = getenv("B200RT_FRAC8"); // tuning knobs
@@ -703,7 +707,15 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
     P.frac8 = std::max(0, std::min(P.frac8, 8));
   }
   const DevScene &S = ctx->S;
-  P.b_nodes = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_nodes);
+  // shared-memory node copies: 16-byte quantised records + one sentinel per copy (k_render staging loop)
+  P.b_nodes = S.n_nodes ? 16 * (S.n_nodes + 1) : 0;
+  for (int a = 0; a < 3; a++) {
+    const float lo = ctx->root_box[a], hi = ctx->root_box[4 + a];
+    const float ext = std::max(hi - lo, 1e-6f * std::max(std::max(fabsf(lo), fabsf(hi)), 1e-30f));
+    P.qbase[a] = lo;
+    P.qscale[a] = ext * (1.0f / (float)(RT_Q_MAX - 8)); // the root spans 0..RT_Q_MAX-8: room for the outward padding steps
+    P.qinv[a] = 1.0f / P.qscale[a];
+  }
   P.b_sph = (int)pad16(sizeof(float4) * (size_t)S.n_spheres);
   P.b_sph_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_spheres);
   P.b_sph_k = (int)pad16(sizeof(float) * (size_t)S.n_spheres);
@@ -723,10 +735,10 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
     scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat + P.b_bigq;
   }
   const size_t acc_bytes = (size_t)(block / 32) * 256 * sizeof(float); // two 32-pixel tiles per warp
-  // shared-memory plan: 2 = scene + four quadrant copies of the nodes, 1 = scene, 0 = global
+  // shared-memory plan: 2 = scene + eight octant orderings of the (quantised) nodes, 1 = scene, 0 = global
   smem = 0;
   if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;
-  if (scene_bytes + 3 * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
+  if (scene_bytes + (RT_N_ORDERINGS - 1) * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
   // nodes only: one node copy resident, primitives through L1/L2
   if (smem == 0 && (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin && S.n_nodes > 0) smem = 3;
   if (const char *e = getenv("B200RT_SMEM")) { // tuning knob: cap the plan (3 ranks between 0 and 1)
@@ -735,17 +747,16 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
     if (rank_of[smem] > rank_of[cap < 0 || cap > 3 ? 0 : cap]) smem = cap < 0 || cap > 3 ? 0 : cap;
   }
   if (smem == 0) {
-    // Global-memory node path: the four quadrant-ordered copies pay while they stay cache
+    // Global-memory node path: the octant-ordered copies pay while they stay cache
     // resident (measured: neutral up to 164 k nodes, one copy +14 % at 655 k nodes = 84 MB of copies).
-    bool one_copy = 4 * (size_t)P.b_nodes > ((size_t)48 << 20);
+    bool one_copy = RT_N_ORDERINGS * 32 * (size_t)S.n_nodes > ((size_t)48 << 20);
     if (const char *e = getenv("B200RT_ONECOPY")) one_copy = atoi(e) != 0; // measurement knob
     if (one_copy) P.S.node_stride = 0;
   }
   smem_bytes = acc_bytes + (smem == 3 ? (size_t)P.b_nodes : (smem ? scene_bytes : 0)) +
-                            (smem == 2 ? 3 * (size_t)P.b_nodes : 0);
+                            (smem == 2 ? (RT_N_ORDERINGS - 1) * (size_t)P.b_nodes : 0);
   // staging order in k_render: node copies first, then the sphere array
-  P.off_sph = (smem == 2 ? 4 : 1) * P.b_nodes;
-  P.hi_off = S.n_nodes << 4;
+  P.off_sph = (smem == 2 ? RT_N_ORDERINGS : 1) * P.b_nodes;
   P.direct_leaf = (!ctx->general && (smem == 1 || smem == 2) && ctx->max_leaf == 1) ? 1 : 0;
 }
 

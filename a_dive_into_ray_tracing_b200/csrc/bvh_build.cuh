@@ -59,8 +59,8 @@ struct BuildArrays {
   int *lcnt;                 // [2*n_small-1] primitives (build leaves) in subtree
   int max_leaf;              // subtrees with <= max_leaf primitives become ONE leaf node (1..8)
   int32_t *leaf_prims;       // [n_small] RT_PRIM_IDs in depth-first leaf order
-  int *swapmask;             // [n_small-1] bit q: in quadrant q the RIGHT child is visited first
-  int packed_stride;         // float4 elements between two quadrant copies of the packed nodes
+  int *swapmask;             // [n_small-1] bit o: in octant o the RIGHT child is visited first
+  int packed_stride;         // float4 elements between two octant orderings of the packed nodes
   float4 *nbox_lo, *nbox_hi; // [2*n_small-1]
   float4 *packed;            // [2*(2*n_small-1)] output nodes
 };
@@ -273,22 +273,21 @@ RT_HD void body_fit(const BuildArrays &B, int leaf, int rotate) {
   }
 }
 
-// ---- kernel 6b: front-to-back child order per ray-direction quadrant. Quadrant q = sign
-// bits of (d.x, d.z) (bit 0: d.x < 0, bit 1: d.z < 0). Children are ordered along the axis (x
-// or z) on which their box centres differ most: the child the ray meets first comes first, so
+// ---- kernel 6b: front-to-back child order per ray-direction OCTANT. Octant o = sign bits of
+// (d.x, d.y, d.z) (bit 0: d.x < 0, bit 1: d.y < 0, bit 2: d.z < 0). Children are ordered along the
+// axis on which their box centres differ most: the child the ray meets first comes first, so
 // hits shrink t_max early and later subtrees are culled by the slab test.
+#define RT_N_ORDERINGS 8
 RT_HD void body_order(const BuildArrays &B, int p) {
   const int l = B.left[p], r = B.right[p];
   const float4 llo = B.nbox_lo[l], lhi = B.nbox_hi[l], rlo = B.nbox_lo[r], rhi = B.nbox_hi[r];
-  const float dx = (rlo.x + rhi.x) - (llo.x + lhi.x), dz = (rlo.z + rhi.z) - (llo.z + lhi.z);
+  const float d[3] = {(rlo.x + rhi.x) - (llo.x + lhi.x), (rlo.y + rhi.y) - (llo.y + lhi.y), (rlo.z + rhi.z) - (llo.z + lhi.z)};
+  int ax = 0;
+  if (fabsf(d[1]) > fabsf(d[ax])) ax = 1;
+  if (fabsf(d[2]) > fabsf(d[ax])) ax = 2;
+  const bool left_low = d[ax] >= 0.f; // left is the low child on that axis
   int mask = 0;
-  if (fabsf(dx) >= fabsf(dz)) { // left is the low-x child iff dx > 0
-    const bool left_low = dx >= 0.f;
-    for (int q = 0; q < 4; q++) { const bool neg = q & 1; if (left_low == neg) mask |= 1 << q; }
-  } else {
-    const bool left_low = dz >= 0.f;
-    for (int q = 0; q < 4; q++) { const bool neg = (q >> 1) & 1; if (left_low == neg) mask |= 1 << q; }
-  }
+  for (int o = 0; o < RT_N_ORDERINGS; o++) { const bool neg = (o >> ax) & 1; if (left_low == neg) mask |= 1 << o; }
   B.swapmask[p] = mask;
 }
 

@@ -191,7 +191,9 @@ template <int PROFILE, bool GENERAL, bool BIG>
 RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &pre, float t_min, HitAcc &h) {
   if (!GENERAL) {
     float4 s = S.sph[id];
-    if (BIG) hit_sphere_big(s, S.sph_k[id], PROFILE == 0, r, pre, t_min, h, id);
+    // K = NaN: the flattening step found the ordinary form more accurate for this sphere (scene_flatten.h)
+    const float K = BIG ? S.sph_k[id] : 0.f;
+    if (BIG && K == K) hit_sphere_big(s, K, PROFILE == 0, r, pre, t_min, h, id);
     else hit_sphere(s, xyz(s), PROFILE == 0, r, pre, t_min, h, id);
     return;
   }
@@ -205,7 +207,8 @@ RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &p
       float4 mv = S.sph_mv[idx];
       if (mv.w != 0.0f) { c = sphere_center_at(s, mv, S.sph_t0[idx], r.tm); closed = true; moving = true; }
     }
-    if (BIG && !moving) hit_sphere_big(s, S.sph_k[idx], closed, r, pre, t_min, h, id);
+    const float K = (BIG && !moving) ? S.sph_k[idx] : 0.f;
+    if (BIG && !moving && K == K) hit_sphere_big(s, K, closed, r, pre, t_min, h, id);
     else hit_sphere(s, c, closed, r, pre, t_min, h, id);
   } else if (type == RT_PRIM_TRIANGLE) {
     const float4 *t = S.tri + 4 * idx;

@@ -35,6 +35,10 @@
 #define RT_BLOCK_OF(GENERAL) ((GENERAL) ? RT_BLOCK_GENERAL : RT_BLOCK)
 #define RT_TILE_W 8
 #define RT_TILE_H 4
+#define RT_Q_MAX 46335 // largest quantised plane: (q << 16) + 0x4B000000 must not carry out of 32 bits (k_render)
+#ifndef RT_N_ORDERINGS
+#define RT_N_ORDERINGS 8 // node orderings = ray-direction octants (bvh_build.cuh body_order)
+#endif
 
 struct RenderParams {
   DevScene S;
@@ -55,7 +59,9 @@ struct RenderParams {
   // sphere-only kernels with single-primitive leaves: the staged leaf payloads name the sphere
   // directly (~(sphere << 3)) and the sphere array sits at this byte offset of the shared copy
   int direct_leaf, off_sph;
-  int hi_off; // bytes from a node's {bmin, escape} slot to its {bmax, payload} slot in the shared copies
+  // 16-byte quantised nodes of the shared-memory copies: plane = qbase + q * qscale per axis (q = 0..65535
+  // over the root box), see the staging loop of k_render
+  float qbase[3], qscale[3], qinv[3];
   // TRACE instantiation (parity hook, rt_trace_closest use_accel = 2): the pool of a work item is a
   // run of caller-supplied rays instead of (pixel, sample) pairs; a finished traversal writes
   // (primitive id, t) instead of being shaded
@@ -94,33 +100,56 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   // 32-bit shared-window address of the staged node copies (they start the dynamic segment)
   const uint32_t nodes_s = SMEM ? (uint32_t)__cvta_generic_to_shared(smem_raw) : 0u;
   if (SMEM) {
-    // Nodes go to shared memory as STRUCTURE OF ARRAYS: all {bmin, escape} first, then all
-    // {bmax, payload}, with links rewritten to ABSOLUTE 32-bit shared addresses of the target's
-    // {bmin, escape} slot in the same copy (0 = traversal finished), so that a BVH step needs no
-    // address arithmetic: LDS [node] and LDS [node + hi_off]. In the 32-byte AoS layout every
-    // LDS.128 of a warp touches only half of the 32 banks (ncu: the shared-memory data pipe was
-    // 90 % busy, 8.9 wavefronts per LDS.128); SoA spreads the 16-byte slots over all banks.
-    // SMEM == 2: four quadrant copies (own visiting order), bmin/bmax pre-swapped on x (bit 0)
-    // and z (bit 1) for the ray direction signs.
+    // Nodes go to shared memory as 16-BYTE QUANTISED records (the global array keeps 32-byte float nodes):
+    //   {x planes, y planes, z planes, link}: each plane word = two 16-bit fixed-point coordinates over the
+    //   root box (entry | exit << 16), rounded outwards with two steps of padding, so the slab test stays
+    //   conservative: a quantised box only ever adds false-positive box hits, never changes a result.
+    // ONE LDS.128 per BVH step instead of two: ncu r1j had the shared-memory data pipe at 89 % of its
+    // wavefront peak (13.5 wavefronts per step for 32 lanes fetching 32 bytes each at unrelated addresses).
+    // One link word is enough in the depth-first threaded layout: the first child of an inner node and the
+    // continuation after a leaf are both the NEXT record, so an inner node stores only its escape (absolute
+    // 32-bit shared address of the target record in the same copy, 0 = traversal finished) and a leaf only
+    // its payload (< 0). A sentinel record (empty box, link 0) follows the last node of every copy.
+    // SMEM == 2: EIGHT copies, one per ray-direction octant (own front-to-back child order from the builder),
+    // with entry / exit planes pre-selected for the octant's direction signs: the step needs no min/max
+    // to order a slab's two planes.
     {
       S.nodes = (const float4 *)(smem_raw + off);
-      const int nn = P.b_nodes >> 5;
-      const int copies = SMEM == 2 ? 4 : 1;
-      for (int i = threadIdx.x; i < copies * nn; i += blockDim.x) {
-        const int q = i / nn, k = i - q * nn;
-        const float4 *src = P.S.nodes + q * (P.S.node_stride >> 4) + 2 * k;
-        float4 lo = __ldg(src), hi = __ldg(src + 1);
-        if (q & 1) { const float t = lo.x; lo.x = hi.x; hi.x = t; }
-        if (q & 2) { const float t = lo.z; lo.z = hi.z; hi.z = t; }
-        const int base_q = (int)nodes_s + q * P.b_nodes;
-        const int esc = RT_F2I(lo.w) >> 1; // 16-byte-slot offset within the copy
-        lo.w = RT_I2F(esc == (nn << 4) ? 0 : base_q + esc);
-        int pay = RT_F2I(hi.w);
-        if (!GENERAL && P.direct_leaf && pay < 0) pay = ~(__ldg(P.S.leaf_prims + ((~pay) >> 3)) << 3);
-        hi.w = RT_I2F(pay >= 0 ? base_q + (pay >> 1) : pay);
-        float4 *dst = (float4 *)(smem_raw + off + q * P.b_nodes);
-        dst[k] = lo;
-        dst[nn + k] = hi;
+      const int nn = S.n_nodes, rec = nn + 1;
+      const int copies = SMEM == 2 ? RT_N_ORDERINGS : 1;
+      for (int i = threadIdx.x; i < copies * rec; i += blockDim.x) {
+        const int q = i / rec, k = i - q * rec;
+        uint4 w;
+        if (k == nn) {
+          // sentinel: entry plane 65535, exit plane 0 on every axis: t(entry) > t(exit) strictly for every ray
+          // with a finite non-zero 1/d, so it is always missed and its link (0) ends the traversal
+          // (entry = the plane the ray reaches LAST: q = 65535 for a positive direction, q = 0 for a negative one)
+          const unsigned fwd = (unsigned)RT_Q_MAX + 0x4B000000u, bwd = ((unsigned)RT_Q_MAX << 16) + 0x4B000000u;
+          w = make_uint4((q & 1) ? bwd : fwd, (q & 2) ? bwd : fwd, (q & 4) ? bwd : fwd, 0u);
+        } else {
+          const float4 *src = P.S.nodes + q * (P.S.node_stride >> 4) + 2 * k;
+          const float4 lo = __ldg(src), hi = __ldg(src + 1);
+          const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
+          unsigned pw[3];
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            const float fl = floorf((l3[a] - P.qbase[a]) * P.qinv[a]) - 2.0f, fh = ceilf((h3[a] - P.qbase[a]) * P.qinv[a]) + 2.0f;
+            const unsigned ql = (unsigned)fminf(fmaxf(fl, 0.0f), (float)RT_Q_MAX), qh = (unsigned)fminf(fmaxf(fh, 0.0f), (float)RT_Q_MAX);
+            const bool neg = SMEM == 2 && ((q >> a) & 1);
+            pw[a] = (neg ? (qh | (ql << 16)) : (ql | (qh << 16))) + 0x4B000000u;
+          }
+          const int base_q = (int)nodes_s + q * P.b_nodes;
+          const int esc = RT_F2I(lo.w) >> RT_NODE_SHIFT; // node index within the copy
+          int pay = RT_F2I(hi.w), link;
+          if (pay < 0) { // leaf
+            if (!GENERAL && P.direct_leaf) pay = ~(__ldg(P.S.leaf_prims + ((~pay) >> 3)) << 3);
+            link = pay;
+          } else { // inner: its first child is record k + 1 by construction
+            link = esc == nn ? 0 : base_q + (esc << 4);
+          }
+          w = make_uint4(pw[0], pw[1], pw[2], (unsigned)link);
+        }
+        ((uint4 *)(smem_raw + off + q * P.b_nodes))[k] = w;
       }
       off += copies * P.b_nodes;
     }
@@ -173,6 +202,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   h.t = INFINITY; h.id = -1;
   RayPre pre;
   pre.inv_d = v3(0, 0, 0); pre.ood = v3(0, 0, 0); pre.inv_a = 0.f;
+  // quantised-node slab test (shared copies): t(plane q) = (2^23 + q) * qS + qC per axis
+  V3f qS = v3(0, 0, 0), qC = v3(0, 0, 0);
   const float t_min = P.sp.t_min;
   // Work items (tile, chunk of samples) are OVERLAPPED: when the current item's pool is
   // drained its in-flight paths become the "old" item and the warp starts regenerating
@@ -216,14 +247,20 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     if (EXT && S.n_media)
       h = apply_media(S.media, S.n_media, r.o, r.d, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, P.seed_lo,
                       P.seed_hi, h);
-    // sign BITS of 1/d (covers d = -0): which quadrant copy (own child order; in shared memory also
-    // pre-swapped planes) this ray walks
-    const unsigned quadrant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 1);
+    // sign BITS of 1/d (covers d = -0): which octant ordering (own child order; in shared memory also
+    // pre-selected entry / exit planes) this ray walks
+    const unsigned octant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.y) >> 31) << 1) |
+                            (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 2);
     if (SMEM == 0) {
       node = 0;
-      nodes_q = nodes_g + quadrant * (unsigned)S.node_stride;
+      nodes_q = nodes_g + octant * (unsigned)S.node_stride;
     } else { // the root's shared address in this ray's copy (no nodes: finished at once)
-      node = S.n_nodes ? (int)(nodes_s + (SMEM == 2 ? quadrant * (unsigned)P.b_nodes : 0u)) : 0;
+      node = S.n_nodes ? (int)(nodes_s + (SMEM == 2 ? octant * (unsigned)P.b_nodes : 0u)) : 0;
+      // plane q (16-bit) enters the slab test as the float 2^23 + q (one PRMT builds it: 0x4B00 | q), so
+      // t = (qbase + q * qscale - o) / d = (2^23 + q) * qS + qC with qS = qscale / d, qC = (qbase - o) / d - 2^23 qS
+      qS = v3(P.qscale[0] * pre.inv_d.x, P.qscale[1] * pre.inv_d.y, P.qscale[2] * pre.inv_d.z);
+      qC = v3(RT_FMA(-8388608.0f, qS.x, (P.qbase[0] - r.o.x) * pre.inv_d.x), RT_FMA(-8388608.0f, qS.y, (P.qbase[1] - r.o.y) * pre.inv_d.y),
+              RT_FMA(-8388608.0f, qS.z, (P.qbase[2] - r.o.z) * pre.inv_d.z));
     }
   };
 
@@ -238,21 +275,53 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
 #pragma unroll
         for (int u = 0; u < RT_STEPS_PER_VOTE(GENERAL); u++) {
           const bool searching = RT_SEARCHING(node);
-          // lanes that are not searching fetch the first node and discard the result
-          const int at = searching ? node : (SMEM ? (int)nodes_s : 0);
-          float4 lo, hi;
           if (SMEM != 0) {
-            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(lo.x), "=f"(lo.y), "=f"(lo.z), "=f"(lo.w) : "r"(at));
-            asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(hi.x), "=f"(hi.y), "=f"(hi.z), "=f"(hi.w) : "r"(at + P.hi_off));
+            // lanes that are not searching (node <= 0) fetch the first record and discard the result
+            const int at = max(node, (int)nodes_s);
+            unsigned w0, w1, w2;
+            int link;
+            asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(link) : "r"(at));
+            if (COUNT) cnt.box_tests += searching ? 1u : 0u;
+            // Decode on the FMA pipe (ncu r2e: with PRMT the half-rate ALU pipe was the limiter at 74 %, the FMA pipe
+            // at 25 %): the stored word is (exit << 16 | entry) + 0x4B000000, so
+            //   exit bits  = mad.hi(w, 2^16, 0x4B000000 - 0x4B00) = 0x4B000000 + exit      (planes <= 46335: no carry)
+            //   entry bits = mad.lo(exit bits, -2^16, w)          = 0x4B000000 + entry     (mod 2^32)
+            // i.e. the floats 2^23 + q, two integer multiply-adds per word.
+            unsigned bx1, by1, bz1, bx0, by0, bz0;
+            asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(bx1) : "r"(w0));
+            asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(by1) : "r"(w1));
+            asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(bz1) : "r"(w2));
+            asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(bx0) : "r"(bx1), "r"(w0));
+            asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(by0) : "r"(by1), "r"(w1));
+            asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(bz0) : "r"(bz1), "r"(w2));
+            const float x0 = RT_FMA(__uint_as_float(bx0), qS.x, qC.x), x1 = RT_FMA(__uint_as_float(bx1), qS.x, qC.x);
+            const float y0 = RT_FMA(__uint_as_float(by0), qS.y, qC.y), y1 = RT_FMA(__uint_as_float(by1), qS.y, qC.y);
+            const float z0 = RT_FMA(__uint_as_float(bz0), qS.z, qC.z), z1 = RT_FMA(__uint_as_float(bz1), qS.z, qC.z);
+            float tn, tf;
+            if (SMEM == 2) { // planes pre-selected for the octant: x0 / y0 / z0 are the entry planes
+              tn = RT_FMAX(RT_FMAX(x0, y0), RT_FMAX(z0, t_min));
+              tf = RT_FMIN(RT_FMIN(x1, y1), RT_FMIN(z1, h.t));
+            } else {
+              tn = RT_FMAX(RT_FMAX(RT_FMIN(x0, x1), RT_FMIN(y0, y1)), RT_FMAX(RT_FMIN(z0, z1), t_min));
+              tf = RT_FMIN(RT_FMIN(RT_FMAX(x0, x1), RT_FMAX(y0, y1)), RT_FMIN(RT_FMAX(z0, z1), h.t));
+            }
+            // hit inner -> next record; hit leaf -> its payload; missed inner -> escape; missed leaf -> next record.
+            // SMEM == 2: the record after the last node is the sentinel (always missed, link 0); the one-copy
+            // plans order planes with min/max, which would re-sort the sentinel's planes, so they end explicitly
+            const int cont = (SMEM == 2 || at + 16 != (int)nodes_s + (S.n_nodes << 4)) ? at + 16 : 0;
+            const bool leaf = link < 0;
+            const int nxt = ((tn <= tf) == leaf) ? link : cont;
+            if (searching) { node = nxt; resume = cont; }
           } else {
-            lo = __ldg((const float4 *)(nodes_q + at));
-            hi = __ldg((const float4 *)(nodes_q + at) + 1);
+            const int at = searching ? node : 0;
+            const float4 lo = __ldg((const float4 *)(nodes_q + at));
+            const float4 hi = __ldg((const float4 *)(nodes_q + at) + 1);
+            if (COUNT) cnt.box_tests += searching ? 1u : 0u;
+            const int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
+            const bool bh = hit_box(lo, hi, pre, t_min, h.t);
+            const int nxt = bh ? pay : esc; // inner: child; leaf: payload < 0
+            if (searching) { node = nxt; resume = esc; }
           }
-          if (COUNT) cnt.box_tests += searching ? 1u : 0u;
-          const int esc = RT_F2I(lo.w), pay = RT_F2I(hi.w);
-          const bool bh = (SMEM == 2) ? hit_box_xz_sorted(lo, hi, pre, t_min, h.t) : hit_box(lo, hi, pre, t_min, h.t);
-          const int nxt = bh ? pay : esc; // inner: child; leaf: payload < 0
-          if (searching) { node = nxt; resume = esc; }
         }
       }
     }

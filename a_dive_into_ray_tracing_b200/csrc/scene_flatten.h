@@ -3,6 +3,7 @@
 // `new sphere(...)/new lambertian(...)` object graph of create_world<<<1,1>>>
 // (accelerated-rt-cuda/final.cu:100-143, rt_next_week/cuda/main.cu:386-467).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -132,6 +133,41 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
     F.sph_k[i] = (float)((double)s.center0[0] * s.center0[0] + (double)s.center0[1] * s.center0[1] +
                          (double)s.center0[2] * s.center0[2] - (double)s.radius * s.radius);
     sph_mat[i] = s.material;
+  }
+  // The origin-expanded quadratic of hit_sphere_big (intersect.cuh) is the accurate one only for a sphere much
+  // larger than the region the rays live in (the r = 1000 ground under a 22-unit scene): its error grows like
+  // (R^2 + 2 R |c|) / 2r with R = how far ray origins lie from the WORLD origin, the ordinary form's like |c| + R.
+  // R = reach of the primitives that are small against the sphere (< r / 4); K = NaN marks "use the ordinary form".
+  {
+    std::vector<std::pair<float, float>> reach; // (size, distance of the farthest point from the world origin)
+    auto len3 = [](const float *p) { return std::sqrt((double)p[0] * p[0] + (double)p[1] * p[1] + (double)p[2] * p[2]); };
+    for (int i = 0; i < ns; i++) reach.push_back({std::fabs(sc->spheres[i].radius), (float)(len3(sc->spheres[i].center0) + std::fabs(sc->spheres[i].radius))});
+    for (int i = 0; i < nt; i++) {
+      const rt_triangle &t = sc->triangles[i];
+      const float e0[3] = {t.v1[0] - t.v0[0], t.v1[1] - t.v0[1], t.v1[2] - t.v0[2]}, e1[3] = {t.v2[0] - t.v0[0], t.v2[1] - t.v0[1], t.v2[2] - t.v0[2]};
+      reach.push_back({(float)std::max(len3(e0), len3(e1)), (float)std::max(len3(t.v0), std::max(len3(t.v1), len3(t.v2)))});
+    }
+    for (int i = 0; i < nq; i++) {
+      const rt_quad &q = sc->quads[i];
+      const float c[3] = {std::max(std::fabs(q.a0), std::fabs(q.a1)), std::max(std::fabs(q.b0), std::fabs(q.b1)), q.k};
+      reach.push_back({std::max(q.a1 - q.a0, q.b1 - q.b0), (float)len3(c)});
+    }
+    std::vector<std::pair<float, float>> by_size = reach;
+    std::sort(by_size.begin(), by_size.end());
+    std::vector<float> prefix_reach(by_size.size()); // max reach among the k smallest primitives
+    for (size_t k = 0; k < by_size.size(); k++) prefix_reach[k] = std::max(by_size[k].second, k ? prefix_reach[k - 1] : 0.f);
+    for (int i = 0; i < ns; i++) {
+      const double r = std::fabs(sc->spheres[i].radius), c = len3(sc->spheres[i].center0);
+      const size_t k = std::lower_bound(by_size.begin(), by_size.end(), std::make_pair((float)(0.25 * r), -1.0f)) - by_size.begin();
+      // camera rays start at the camera: its distance from the world origin counts as reach too (a lone giant
+      // sphere seen from next to its surface keeps the expanded form; a finite camera origin is all that is asked)
+      const double cam = len3(sc->camera.origin);
+      const bool have_cam = std::isfinite(cam) && len3(sc->camera.horizontal) > 0.0; // a zeroed camera says nothing
+      const double R = std::max(k > 0 ? (double)prefix_reach[k - 1] : 0.0, have_cam ? cam : 0.0);
+      // no evidence at all about where rays start (no small primitives, no camera): the ordinary form is the safe one
+      const bool expand = (k > 0 || have_cam) && 2.0 * (R * R + 2.0 * R * c) / (2.0 * r) < c + R;
+      if (!expand) F.sph_k[i] = std::nanf("");
+    }
   }
   for (int i = 0; i < nt; i++) {
     const rt_triangle &t = sc->triangles[i];
