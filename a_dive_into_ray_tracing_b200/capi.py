@@ -26,7 +26,11 @@ STATUS = {0: "RT_OK", 1: "RT_ERR_INVALID", 2: "RT_ERR_CUDA", 3: "RT_ERR_STATE", 
 SYMBOLS = ["rt_version", "rt_device_count", "rt_create", "rt_destroy", "rt_last_error", "rt_scene_upload",
            "rt_accel_build", "rt_accel_download", "rt_trace_closest", "rt_render", "rt_render_device", "rt_render_rows_device",
            "rt_accum_clear", "rt_accum_download", "rt_accum_upload", "rt_accum_device_ptr", "rt_resolve",
-           "rt_resolve_device", "rt_render_aov", "rt_stats", "rt_stats_reset", "rt_sync", "rt_measure_fp32_peak"]
+           "rt_resolve_device", "rt_render_aov", "rt_stats", "rt_stats_reset", "rt_sync", "rt_measure_fp32_peak",
+           "rt_host_alloc", "rt_host_free", "rt_comm_unique_id", "rt_comm_init", "rt_comm_init_all", "rt_reduce"]
+
+RT_REDUCE_UNIFORM_COUNT = 1
+RT_COMM_ID_BYTES = 128
 
 
 class RtError(RuntimeError):
@@ -98,12 +102,33 @@ def load_library():
     L.rt_measure_fp32_peak.argtypes = [_vp, C.POINTER(C.c_float)]
     L.rt_sync.restype = C.c_int
     L.rt_sync.argtypes = [_vp]
+    L.rt_host_alloc.restype = _vp
+    L.rt_host_alloc.argtypes = [_vp, C.c_size_t]
+    L.rt_host_free.restype = None
+    L.rt_host_free.argtypes = [_vp, _vp]
+    L.rt_comm_unique_id.restype = C.c_int
+    L.rt_comm_unique_id.argtypes = [_vp]
+    L.rt_comm_init.restype = C.c_int
+    L.rt_comm_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
+    L.rt_comm_init_all.restype = C.c_int
+    L.rt_comm_init_all.argtypes = [C.POINTER(_vp), C.c_int]
+    L.rt_reduce.restype = C.c_int
+    L.rt_reduce.argtypes = [_vp, C.c_int, C.c_int, _vp, C.c_int, C.c_uint, _vp]
     _lib = L
     return L
 
 
 def device_count():
     return load_library().rt_device_count()
+
+
+def comm_unique_id():
+    """128 bytes naming a new NCCL communicator (rank 0 creates it and ships it to the other ranks)."""
+    buf = C.create_string_buffer(RT_COMM_ID_BYTES)
+    rc = load_library().rt_comm_unique_id(buf)
+    if rc:
+        raise RtError(rc, "rt_comm_unique_id (is libnccl.so.2 loadable?)")
+    return buf.raw
 
 
 class Context:
@@ -121,11 +146,36 @@ class Context:
         self.device = device
         self.W = self.H = 0
         self._scene = None
+        self._pinned = []
 
     def close(self):
         if getattr(self, "h", None):
+            for ptr in self._pinned:
+                self.lib.rt_host_free(self.h, ptr)
+            self._pinned = []
             self.lib.rt_destroy(self.h)
             self.h = None
+
+    def pinned_array(self, shape, dtype):
+        """numpy array over page-locked host memory (rt_host_alloc); lives as long as the context"""
+        dtype = np.dtype(dtype)
+        n = int(np.prod(shape)) * dtype.itemsize
+        ptr = self.lib.rt_host_alloc(self.h, max(n, 1))
+        if not ptr:
+            raise RtError(4, "rt_host_alloc(%d)" % n)
+        self._pinned.append(ptr)
+        buf = (C.c_char * max(n, 1)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def comm_init(self, unique_id, rank, nranks):
+        """join the NCCL communicator `unique_id` (comm_unique_id() of rank 0) as `rank` of `nranks`"""
+        assert len(unique_id) == RT_COMM_ID_BYTES
+        self._ck(self.lib.rt_comm_init(self.h, unique_id, rank, nranks))
+
+    def reduce(self, W, H, d_accum_ptr=None, root=0, uniform_count=True, stream_ptr=None):
+        """sum the ranks' float4 frames onto root's (rt_reduce: pack -> ncclReduce -> unpack), asynchronously"""
+        self._ck(self.lib.rt_reduce(self.h, W, H, d_accum_ptr, root, RT_REDUCE_UNIFORM_COUNT if uniform_count else 0,
+                                    self._stream(stream_ptr)))
 
     def __del__(self):
         try:
@@ -220,9 +270,11 @@ class Context:
                                      rgb.ctypes.data if want_rgb8 else None))
         return lin, rgb
 
-    def resolve_device(self, W, H, d_accum_ptr, want_linear=False, want_rgb8=True, stream_ptr=None):
+    def resolve_device(self, W, H, d_accum_ptr, want_linear=False, want_rgb8=True, stream_ptr=None, out_rgb8=None):
+        """out_rgb8: a caller buffer ([H][W][3] uint8, e.g. pinned_array) to resolve into instead of a new array"""
         lin = np.empty((H, W, 3), np.float32) if want_linear else None
-        rgb = np.empty((H, W, 3), np.uint8) if want_rgb8 else None
+        rgb = (out_rgb8 if out_rgb8 is not None else np.empty((H, W, 3), np.uint8)) if want_rgb8 else None
+        assert rgb is None or (rgb.shape == (H, W, 3) and rgb.dtype == np.uint8 and rgb.flags.c_contiguous)
         self._ck(self.lib.rt_resolve_device(self.h, W, H, d_accum_ptr, lin.ctypes.data if want_linear else None,
                                             rgb.ctypes.data if want_rgb8 else None, self._stream(stream_ptr)))
         return lin, rgb

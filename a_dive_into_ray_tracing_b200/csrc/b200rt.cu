@@ -10,6 +10,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h> // types and prototypes only: the library is loaded with dlopen at the first rt_comm_* call
+
 #include "bvh_build.cuh"
 #include "scene_flatten.h"
 #include "render_kernels.cuh"
@@ -26,6 +29,30 @@ __global__ void k_prim_box(BuildArrays B) {
 __global__ void k_classify(BuildArrays B, int round, float frac) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B.n_prims) body_classify(B, i, round, frac);
+}
+// Oversized primitives as a (count, indices) list: read back through pinned memory (<= RT_MAX_BIG + 1 words,
+// the only device -> host traffic of the classification step).
+__global__ void k_big_collect(BuildArrays B, int *list) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < B.n_prims && B.big_flag[i]) {
+    const int slot = atomicAdd(list, 1);
+    if (slot < RT_MAX_BIG) list[1 + slot] = i;
+  }
+}
+struct BigList {
+  int n;
+  int gid[RT_MAX_BIG]; // ascending
+};
+// The remaining primitives in ascending order: position = index - (big primitives before it), no scan needed
+// because the big list is tiny. Also the per-sphere "is big" bytes of the brute-force parity hook.
+__global__ void k_small_list(BuildArrays B, BigList bl, int *small_gid, uint8_t *sph_is_big) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B.n_prims) return;
+  int before = 0;
+  bool big = false;
+  for (int k = 0; k < bl.n; k++) { before += bl.gid[k] < i ? 1 : 0; big = big || bl.gid[k] == i; }
+  if (i < B.n_spheres) sph_is_big[i] = big ? 1 : 0;
+  if (!big) small_gid[i - before] = i;
 }
 __global__ void k_morton(BuildArrays B, int final_round) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -144,12 +171,14 @@ __global__ void k_order(BuildArrays B) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < B.n_small - 1) body_order(B, i);
 }
-__global__ void k_pack(BuildArrays B, int octant) {
+__global__ void k_pack(BuildArrays B) { // blockIdx.y = ordering (ray-direction octant)
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 2 * B.n_small - 1) body_pack(B, i, octant);
+  if (i < 2 * B.n_small - 1) body_pack(B, i, (int)blockIdx.y);
 }
 
 // ------------------------------------------------------------------ context
+#define RT_N_BUILD_TEMPS 24
+#define RT_EV_RING 64
 struct DevBuf {
   void *p = nullptr;
   size_t bytes = 0;
@@ -160,6 +189,11 @@ struct rt_ctx {
   std::string err;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // render launches since the last rt_stats_reset: a ring of event triples (before k_render, after it, after
+  // k_combine) so that rt_stats can report the MEAN kernel durations of asynchronously queued frames
+  cudaEvent_t ev_k[RT_EV_RING][3];
+  int ev_k_count = 0; // launches recorded since the reset (ring slot = count % RT_EV_RING)
+  cudaStream_t last_render_stream = nullptr; // rt_stats waits for it: renders on caller streams update the device counters
   int sm_count = 0, max_smem_optin = 0;
   // host copy of the scene
   bool have_scene = false, have_accel = false;
@@ -171,9 +205,15 @@ struct rt_ctx {
   bool general = false;
   bool ext = false; // media or noise/image textures: the extended kernel variant
   // device scene
-  DevBuf d_nodes, d_sph, d_sph_k, d_sph_mv, d_sph_t0, d_tri, d_tri_n, d_quad, d_sph_mat, d_tri_mat, d_quad_mat, d_mats, d_big,
-      d_leaf_prims, d_bigq, d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad, d_media, d_perlin_vec, d_perlin_perm, d_image_bytes,
-      d_images;
+  // d_scene: ONE arena holding every flattened array of the scene (16-byte aligned slots, zero padded), filled by
+  // one copy from the pinned staging block h_stage; the d_raw_* pointers (builder input) point into it too
+  DevBuf d_scene, d_nodes, d_big, d_leaf_prims, d_bigq, d_sph_is_big, d_raw_sph, d_raw_tri, d_raw_quad;
+  DevBuf build_tmp[RT_N_BUILD_TEMPS]; // rt_accel_build temporaries: grow-only, never freed between builds
+  ncclComm_t comm = nullptr; // rt_comm_init / rt_comm_init_all
+  int comm_rank = 0, comm_size = 1;
+  DevBuf d_red;              // packed frame travelling through ncclReduce
+  void *h_pin = nullptr, *h_stage = nullptr, *h_out = nullptr; // pinned host blocks: small read-backs, scene staging, frame read-back
+  size_t h_pin_bytes = 0, h_stage_bytes = 0, h_out_bytes = 0;
   DevScene S;
   DevCamera cam;
   ShadeParams sp;
@@ -225,6 +265,73 @@ static void dev_free(DevBuf &b) {
   if (b.p) cudaFree(b.p);
   b.p = nullptr; b.bytes = 0;
 }
+// grow-only pinned host block (contents are NOT preserved when it grows)
+static int host_reserve(rt_ctx *ctx, void *&p, size_t &have, size_t bytes) {
+  if (have >= bytes) return RT_OK;
+  if (p) CK(cudaFreeHost(p));
+  p = nullptr; have = 0;
+  bytes = (bytes + 4095) & ~(size_t)4095;
+  CK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+  have = bytes;
+  return RT_OK;
+}
+static int pin_reserve(rt_ctx *ctx, size_t bytes) { return host_reserve(ctx, ctx->h_pin, ctx->h_pin_bytes, bytes); }
+
+// ------------------------------------------------------------------ NCCL (loaded on demand)
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t *, int, const int *) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  std::string why;
+};
+static NcclApi &nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  // a copy already mapped into the process (torch's) wins, so that one process never holds two NCCLs
+  const char *names[] = {getenv("B200RT_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char *nm : names) {
+    if (!nm || !*nm) continue;
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  for (const char *nm : names) {
+    if (api.handle) break;
+    if (!nm || !*nm) continue;
+    api.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+  }
+  if (!api.handle) { api.why = "NCCL not found (libnccl.so.2; set B200RT_NCCL_LIB)"; return api; }
+#define SYM(field, name) \
+  *(void **)(&api.field) = dlsym(api.handle, name); \
+  if (!api.field) { api.why = std::string("NCCL symbol missing: ") + name; api.handle = nullptr; return api; }
+  SYM(GetUniqueId, "ncclGetUniqueId") SYM(CommInitRank, "ncclCommInitRank") SYM(CommInitAll, "ncclCommInitAll")
+  SYM(CommDestroy, "ncclCommDestroy") SYM(Reduce, "ncclReduce") SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+  return api;
+}
+static void nccl_comm_destroy(ncclComm_t c) {
+  NcclApi &a = nccl_api();
+  if (a.handle && c) a.CommDestroy(c);
+}
+
+// frame <-> travelling buffer of rt_reduce: rgb only (+ one count word at the end) or all four lanes
+__global__ void k_reduce_pack(const float4 *__restrict__ accum, float *__restrict__ red, int n_pix) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  const float4 a = accum[p];
+  red[3 * (size_t)p + 0] = a.x; red[3 * (size_t)p + 1] = a.y; red[3 * (size_t)p + 2] = a.z;
+  if (p == 0) red[3 * (size_t)n_pix] = a.w;
+}
+__global__ void k_reduce_unpack(float4 *__restrict__ accum, const float *__restrict__ red, int n_pix) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pix) return;
+  accum[p] = make_float4(red[3 * (size_t)p + 0], red[3 * (size_t)p + 1], red[3 * (size_t)p + 2], red[3 * (size_t)n_pix]);
+}
 
 extern "C" {
 
@@ -254,6 +361,8 @@ int rt_create(rt_ctx **out, const rt_config *cfg) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+  memset(ctx->ev_k, 0, sizeof ctx->ev_k);
+  for (int i = 0; i < RT_EV_RING * 3 && e == cudaSuccess; i++) e = cudaEventCreate(&ctx->ev_k[i / 3][i % 3]);
   if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
   if (e == cudaSuccess)
     e = cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
@@ -269,14 +378,18 @@ void rt_destroy(rt_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  DevBuf *all[] = {&ctx->d_nodes, &ctx->d_sph, &ctx->d_sph_k, &ctx->d_sph_mv, &ctx->d_sph_t0, &ctx->d_tri, &ctx->d_tri_n, &ctx->d_quad,
-                   &ctx->d_sph_mat, &ctx->d_tri_mat, &ctx->d_quad_mat, &ctx->d_mats, &ctx->d_big, &ctx->d_leaf_prims, &ctx->d_bigq, &ctx->d_sph_is_big,
-                   &ctx->d_raw_sph, &ctx->d_raw_tri, &ctx->d_raw_quad, &ctx->d_media, &ctx->d_perlin_vec,
-                   &ctx->d_perlin_perm, &ctx->d_image_bytes, &ctx->d_images, &ctx->d_accum, &ctx->d_partial, &ctx->d_counter,
-                   &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts};
+  // d_raw_* are views into d_scene
+  if (ctx->comm) nccl_comm_destroy(ctx->comm);
+  DevBuf *all[] = {&ctx->d_red, &ctx->d_scene, &ctx->d_nodes, &ctx->d_big, &ctx->d_leaf_prims, &ctx->d_bigq, &ctx->d_sph_is_big, &ctx->d_accum,
+                   &ctx->d_partial, &ctx->d_counter, &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts};
   for (DevBuf *b : all) dev_free(*b);
+  for (DevBuf &b : ctx->build_tmp) dev_free(b);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_out) cudaFreeHost(ctx->h_out);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int i = 0; i < RT_EV_RING * 3; i++) if (ctx->ev_k[i / 3][i % 3]) cudaEventDestroy(ctx->ev_k[i / 3][i % 3]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -318,46 +431,67 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, nm = sc->n_materials;
   int rc;
-#define UP(buf, vec) \
-  if ((rc = dev_upload(ctx, ctx->buf, (vec).data(), (vec).size() * sizeof((vec)[0])))) return rc
-  UP(d_sph, F.sph); UP(d_sph_k, F.sph_k); UP(d_sph_mv, F.sph_mv); UP(d_sph_t0, F.sph_t0); UP(d_tri, F.tri); UP(d_tri_n, F.tri_n); UP(d_quad, F.quad);
-  UP(d_sph_mat, F.sph_mat); UP(d_tri_mat, F.tri_mat); UP(d_quad_mat, F.quad_mat); UP(d_mats, F.mats);
-  UP(d_raw_sph, ctx->spheres); UP(d_raw_tri, ctx->tris); UP(d_raw_quad, ctx->quads);
-  UP(d_media, F.media); UP(d_perlin_vec, F.perlin_vec); UP(d_perlin_perm, F.perlin_perm); UP(d_image_bytes, F.image_bytes);
+  // ONE packed upload: every array gets a 16-byte aligned, zero-padded slot of the pinned staging block; one
+  // cudaMemcpyAsync moves the block into the device arena (was: a memset + memcpy pair per array, 24 pairs)
+  struct Slot { const void *src; size_t bytes, off; };
+  std::vector<Slot> slots;
+  size_t total = 0;
+  auto add = [&](const void *src, size_t bytes) {
+    slots.push_back({src, bytes, total});
+    total += pad16(std::max<size_t>(bytes, 16));
+    return slots.size() - 1;
+  };
+#define ADD(vec) add((vec).data(), (vec).size() * sizeof((vec)[0]))
+  const size_t i_sph = ADD(F.sph), i_sph_k = ADD(F.sph_k), i_sph_mv = ADD(F.sph_mv), i_sph_t0 = ADD(F.sph_t0), i_tri = ADD(F.tri),
+               i_tri_n = ADD(F.tri_n), i_quad = ADD(F.quad), i_sph_mat = ADD(F.sph_mat), i_tri_mat = ADD(F.tri_mat),
+               i_quad_mat = ADD(F.quad_mat), i_mats = ADD(F.mats), i_raw_sph = ADD(ctx->spheres), i_raw_tri = ADD(ctx->tris),
+               i_raw_quad = ADD(ctx->quads), i_media = ADD(F.media), i_pvec = ADD(F.perlin_vec), i_pperm = ADD(F.perlin_perm),
+               i_img = ADD(F.image_bytes);
   std::vector<DevImage> dimg((size_t)sc->n_images);
+  const size_t i_images = ADD(dimg); // filled below, once the arena's address is known
+#undef ADD
+  if ((rc = dev_reserve(ctx, ctx->d_scene, total))) return rc;
+  if ((rc = host_reserve(ctx, ctx->h_stage, ctx->h_stage_bytes, total))) return rc;
+  unsigned char *hs = (unsigned char *)ctx->h_stage, *ds = (unsigned char *)ctx->d_scene.p;
   for (int i = 0; i < sc->n_images; i++) {
-    dimg[i].rgb = (const uint8_t *)ctx->d_image_bytes.p + F.image_offset[i];
+    dimg[i].rgb = (const uint8_t *)(ds + slots[i_img].off) + F.image_offset[i];
     dimg[i].width = sc->images[i].width;
     dimg[i].height = sc->images[i].height;
   }
-  UP(d_images, dimg);
-#undef UP
-  std::vector<uint8_t> nobig(std::max(ns, 1), 0);
-  if ((rc = dev_upload(ctx, ctx->d_sph_is_big, nobig.data(), nobig.size()))) return rc;
+  slots[i_images].src = dimg.data();
+  memset(hs, 0, total);
+  for (const Slot &sl : slots)
+    if (sl.bytes) memcpy(hs + sl.off, sl.src, sl.bytes);
+  CK(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = dev_reserve(ctx, ctx->d_sph_is_big, (size_t)std::max(ns, 1)))) return rc;
+  CK(cudaMemsetAsync(ctx->d_sph_is_big.p, 0, ctx->d_sph_is_big.bytes, ctx->stream));
   if ((rc = dev_reserve(ctx, ctx->d_big, 16))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_bigq, 32))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_leaf_prims, 16))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_nodes, 32))) return rc;
+  ctx->d_raw_sph.p = ds + slots[i_raw_sph].off;
+  ctx->d_raw_tri.p = ds + slots[i_raw_tri].off;
+  ctx->d_raw_quad.p = ds + slots[i_raw_quad].off;
 
   DevScene &S = ctx->S;
   S.nodes = (const float4 *)ctx->d_nodes.p;
-  S.sph = (const float4 *)ctx->d_sph.p;
-  S.sph_mv = (const float4 *)ctx->d_sph_mv.p;
-  S.sph_t0 = (const float *)ctx->d_sph_t0.p;
-  S.sph_k = (const float *)ctx->d_sph_k.p;
-  S.tri = (const float4 *)ctx->d_tri.p;
-  S.tri_n = (const float4 *)ctx->d_tri_n.p;
-  S.quad = (const float4 *)ctx->d_quad.p;
-  S.sph_mat = (const int32_t *)ctx->d_sph_mat.p;
-  S.tri_mat = (const int32_t *)ctx->d_tri_mat.p;
-  S.quad_mat = (const int32_t *)ctx->d_quad_mat.p;
-  S.mats = (const float4 *)ctx->d_mats.p;
+  S.sph = (const float4 *)(ds + slots[i_sph].off);
+  S.sph_mv = (const float4 *)(ds + slots[i_sph_mv].off);
+  S.sph_t0 = (const float *)(ds + slots[i_sph_t0].off);
+  S.sph_k = (const float *)(ds + slots[i_sph_k].off);
+  S.tri = (const float4 *)(ds + slots[i_tri].off);
+  S.tri_n = (const float4 *)(ds + slots[i_tri_n].off);
+  S.quad = (const float4 *)(ds + slots[i_quad].off);
+  S.sph_mat = (const int32_t *)(ds + slots[i_sph_mat].off);
+  S.tri_mat = (const int32_t *)(ds + slots[i_tri_mat].off);
+  S.quad_mat = (const int32_t *)(ds + slots[i_quad_mat].off);
+  S.mats = (const float4 *)(ds + slots[i_mats].off);
   S.big = (const int32_t *)ctx->d_big.p;
   S.leaf_prims = (const int32_t *)ctx->d_leaf_prims.p;
-  S.media = (const float4 *)ctx->d_media.p;
-  S.perlin_vec = (const float4 *)ctx->d_perlin_vec.p;
-  S.perlin_perm = (const uint8_t *)ctx->d_perlin_perm.p;
-  S.images = (const DevImage *)ctx->d_images.p;
+  S.media = (const float4 *)(ds + slots[i_media].off);
+  S.perlin_vec = (const float4 *)(ds + slots[i_pvec].off);
+  S.perlin_perm = (const uint8_t *)(ds + slots[i_pperm].off);
+  S.images = (const DevImage *)(ds + slots[i_images].off);
   S.n_media = sc->n_media; S.n_perlin = sc->n_perlin; S.n_images = sc->n_images;
   S.bigq = (const float4 *)ctx->d_bigq.p;
   S.n_nodes = 0; S.n_big = 0; S.n_bigq = 0;
@@ -411,60 +545,53 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   B.tris = (const rt_triangle *)ctx->d_raw_tri.p;
   B.quads = (const rt_quad *)ctx->d_raw_quad.p;
   B.thickness = (ctx->sp.flags & RT_FLAG_FLIP_NORMALS) ? 0.01f : 0.1f; // THICKNESS of the two trees
-  DevBuf t_lo, t_hi, t_flag, t_bounds, t_small, t_keys, t_left, t_right, t_parent, t_nflag, t_size, t_lcnt, t_nlo, t_nhi, t_swap;
-  DevBuf *temps[] = {&t_swap, &t_lo, &t_hi, &t_flag, &t_bounds, &t_small, &t_keys, &t_left, &t_right, &t_parent, &t_nflag, &t_size, &t_lcnt, &t_nlo, &t_nhi};
-  auto cleanup = [&]() { for (DevBuf *b : temps) dev_free(*b); };
-#define CKB(call)                                                                                  \
-  do {                                                                                             \
-    cudaError_t e_ = (call);                                                                       \
-    if (e_ != cudaSuccess) {                                                                       \
-      cleanup();                                                                                   \
-      return fail(ctx, RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
-    }                                                                                              \
-  } while (0)
-#define RSV(buf, bytes) do { int rc_ = dev_reserve(ctx, buf, (bytes)); if (rc_) { cleanup(); return rc_; } } while (0)
-  RSV(t_lo, sizeof(float4) * (size_t)n); RSV(t_hi, sizeof(float4) * (size_t)n); RSV(t_flag, sizeof(int) * (size_t)n);
-  RSV(t_bounds, sizeof(BuildBounds) * 4);
-  B.pbox_lo = (float4 *)t_lo.p; B.pbox_hi = (float4 *)t_hi.p; B.big_flag = (int *)t_flag.p;
-  B.bounds = (BuildBounds *)t_bounds.p;
+  // Build temporaries live in the context and only ever grow: a rebuild (every frame of an animated or
+  // re-uploaded scene) calls neither cudaMalloc nor cudaFree, which would synchronise the device.
+  enum { T_LO, T_HI, T_FLAG, T_BOUNDS, T_BIGLIST, T_SMALL, T_KEYS, T_LEFT, T_RIGHT, T_PARENT, T_NFLAG, T_SIZE, T_LCNT, T_NLO,
+         T_NHI, T_SWAP, T_RK0, T_RK1, T_RV0, T_RV1, T_RHIST, T_COUNT };
+  static_assert(T_COUNT <= RT_N_BUILD_TEMPS, "build temporaries");
+  DevBuf *T = ctx->build_tmp;
+  int rc;
+#define RSV(buf, bytes) do { if ((rc = dev_reserve(ctx, buf, (bytes)))) return rc; } while (0)
+  RSV(T[T_LO], sizeof(float4) * (size_t)n); RSV(T[T_HI], sizeof(float4) * (size_t)n); RSV(T[T_FLAG], sizeof(int) * (size_t)n);
+  RSV(T[T_BOUNDS], sizeof(BuildBounds) * 4); RSV(T[T_BIGLIST], sizeof(int) * (RT_MAX_BIG + 1));
+  RSV(ctx->d_sph_is_big, (size_t)std::max(ns, 1));
+  if ((rc = pin_reserve(ctx, 4096))) return rc;
+  B.pbox_lo = (float4 *)T[T_LO].p; B.pbox_hi = (float4 *)T[T_HI].p; B.big_flag = (int *)T[T_FLAG].p;
+  B.bounds = (BuildBounds *)T[T_BOUNDS].p;
+  int *h_words = (int *)ctx->h_pin; // pinned: [0..32] big list, [40] kept nodes, [48..55] root box
   {
-    BuildBounds init[4];
+    BuildBounds *init = (BuildBounds *)(h_words + 64); // 4 x 24 bytes, pinned
     for (int r = 0; r < 4; r++)
       for (int a = 0; a < 3; a++) { init[r].lo[a] = 0x7fffffff; init[r].hi[a] = (int)0x80000000; }
-    CKB(cudaMemcpyAsync(t_bounds.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(T[T_BOUNDS].p, init, sizeof(BuildBounds) * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(T[T_BIGLIST].p, 0, sizeof(int) * (RT_MAX_BIG + 1), st));
   }
   const int TB = 256;
   const int gp = (n + TB - 1) / TB;
   k_prim_box<<<gp, TB, 0, st>>>(B);
-  ctx->launches++;
-  for (int r = 0; r < RT_BIG_ROUNDS; r++) {
-    k_classify<<<gp, TB, 0, st>>>(B, r, RT_BIG_FRAC);
-    ctx->launches++;
-  }
-  CKB(cudaGetLastError());
-  std::vector<int> flags(n);
-  CKB(cudaMemcpyAsync(flags.data(), t_flag.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
-  CKB(cudaStreamSynchronize(st));
-  int n_big = 0;
-  for (int i = 0; i < n; i++) n_big += flags[i] ? 1 : 0;
+  for (int r = 0; r < RT_BIG_ROUNDS; r++) k_classify<<<gp, TB, 0, st>>>(B, r, RT_BIG_FRAC);
+  k_big_collect<<<gp, TB, 0, st>>>(B, (int *)T[T_BIGLIST].p);
+  ctx->launches += 2 + RT_BIG_ROUNDS;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(h_words, T[T_BIGLIST].p, sizeof(int) * (RT_MAX_BIG + 1), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st)); // host round trip 1 of 2: how many primitives stay in the tree sizes every later launch
+  BigList bl;
+  memset(&bl, 0, sizeof bl);
   int final_round = RT_BIG_ROUNDS;
-  if (n_big > RT_MAX_BIG) { // degenerate classification: keep everything in the tree
-    std::fill(flags.begin(), flags.end(), 0);
-    n_big = 0;
+  if (h_words[0] > RT_MAX_BIG) { // degenerate classification: keep everything in the tree
     final_round = 0;
+  } else {
+    bl.n = h_words[0];
+    std::copy(h_words + 1, h_words + 1 + bl.n, bl.gid);
+    std::sort(bl.gid, bl.gid + bl.n);
   }
-  std::vector<int> small;
-  small.reserve(n - n_big);
-  std::vector<uint8_t> sph_is_big(std::max(ns, 1), 0);
-  for (int i = 0; i < n; i++) {
-    if (flags[i]) {
-      int32_t id = i < ns ? RT_PRIM_ID(RT_PRIM_SPHERE, i)
-                          : (i < ns + nt ? RT_PRIM_ID(RT_PRIM_TRIANGLE, i - ns) : RT_PRIM_ID(RT_PRIM_QUAD, i - ns - nt));
-      ctx->big_ids.push_back(id);
-      if (i < ns) sph_is_big[i] = 1;
-    } else small.push_back(i);
+  const int n_big = bl.n, nsm = n - n_big;
+  for (int k = 0; k < n_big; k++) {
+    const int i = bl.gid[k];
+    ctx->big_ids.push_back(i < ns ? RT_PRIM_ID(RT_PRIM_SPHERE, i)
+                                  : (i < ns + nt ? RT_PRIM_ID(RT_PRIM_TRIANGLE, i - ns) : RT_PRIM_ID(RT_PRIM_QUAD, i - ns - nt)));
   }
-  const int nsm = (int)small.size();
   {
     // rects go to their own decoded list (no id fetch / type dispatch in the segment start)
     std::vector<int32_t> others;
@@ -476,41 +603,48 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
       bigq.push_back(make_float4(q.b0, q.b1, RT_I2F(id), 0.f));
     }
     const int n_bigq = (int)bigq.size() / 2;
-    std::vector<int32_t> bigpad(std::max<size_t>(others.size(), 4), 0);
-    std::copy(others.begin(), others.end(), bigpad.begin());
-    bigq.resize(std::max<size_t>(bigq.size(), 2), make_float4(0, 0, 0, 0));
-    int rc = dev_upload(ctx, ctx->d_big, bigpad.data(), bigpad.size() * sizeof(int32_t));
-    if (!rc) rc = dev_upload(ctx, ctx->d_bigq, bigq.data(), bigq.size() * sizeof(float4));
-    if (!rc) rc = dev_upload(ctx, ctx->d_sph_is_big, sph_is_big.data(), sph_is_big.size());
-    if (rc) { cleanup(); return rc; }
+    // both lists through ONE pinned block and one copy each (zero padded to the reserved size)
+    unsigned char *hb = (unsigned char *)ctx->h_pin + 1024;
+    const size_t big_bytes = pad16(std::max<size_t>(others.size(), 4) * sizeof(int32_t));
+    const size_t bigq_bytes = std::max<size_t>(bigq.size(), 2) * sizeof(float4);
+    if ((rc = pin_reserve(ctx, 1024 + big_bytes + bigq_bytes))) return rc;
+    hb = (unsigned char *)ctx->h_pin + 1024;
+    h_words = (int *)ctx->h_pin;
+    memset(hb, 0, big_bytes + bigq_bytes);
+    if (!others.empty()) memcpy(hb, others.data(), others.size() * sizeof(int32_t));
+    if (!bigq.empty()) memcpy(hb + big_bytes, bigq.data(), bigq.size() * sizeof(float4));
+    RSV(ctx->d_big, big_bytes); RSV(ctx->d_bigq, bigq_bytes);
+    CK(cudaMemcpyAsync(ctx->d_big.p, hb, big_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_bigq.p, hb + big_bytes, bigq_bytes, cudaMemcpyHostToDevice, st));
     ctx->S.big = (const int32_t *)ctx->d_big.p;
     ctx->S.n_big = (int)others.size();
     ctx->S.bigq = (const float4 *)ctx->d_bigq.p;
     ctx->S.n_bigq = n_bigq;
   }
   int n_nodes = nsm > 0 ? 2 * nsm - 1 : 0;
+  RSV(T[T_SMALL], sizeof(int) * (size_t)std::max(nsm, 1));
+  k_small_list<<<gp, TB, 0, st>>>(B, bl, (int *)T[T_SMALL].p, (uint8_t *)ctx->d_sph_is_big.p);
+  ctx->launches++;
   if (nsm > 0) {
     int n_pad = 1;
     while (n_pad < nsm) n_pad <<= 1;
     if (n_pad < 2) n_pad = 2;
     B.n_small = nsm; B.n_pad = n_pad;
-    RSV(t_small, sizeof(int) * (size_t)nsm);
-    CKB(cudaMemcpyAsync(t_small.p, small.data(), sizeof(int) * (size_t)nsm, cudaMemcpyHostToDevice, st));
-    RSV(t_keys, sizeof(unsigned long long) * (size_t)n_pad);
-    RSV(t_left, sizeof(int) * (size_t)nsm); RSV(t_right, sizeof(int) * (size_t)nsm);
-    RSV(t_parent, sizeof(int) * (size_t)n_nodes); RSV(t_nflag, sizeof(int) * (size_t)nsm);
-    RSV(t_size, sizeof(int) * (size_t)n_nodes); RSV(t_lcnt, sizeof(int) * (size_t)n_nodes);
-    RSV(t_swap, sizeof(int) * (size_t)nsm);
-    { int rc = dev_reserve(ctx, ctx->d_leaf_prims, sizeof(int32_t) * (size_t)nsm); if (rc) { cleanup(); return rc; } }
-    RSV(t_nlo, sizeof(float4) * (size_t)n_nodes); RSV(t_nhi, sizeof(float4) * (size_t)n_nodes);
+    RSV(T[T_KEYS], sizeof(unsigned long long) * (size_t)n_pad);
+    RSV(T[T_LEFT], sizeof(int) * (size_t)nsm); RSV(T[T_RIGHT], sizeof(int) * (size_t)nsm);
+    RSV(T[T_PARENT], sizeof(int) * (size_t)n_nodes); RSV(T[T_NFLAG], sizeof(int) * (size_t)nsm);
+    RSV(T[T_SIZE], sizeof(int) * (size_t)n_nodes); RSV(T[T_LCNT], sizeof(int) * (size_t)n_nodes);
+    RSV(T[T_SWAP], sizeof(int) * (size_t)nsm);
+    RSV(ctx->d_leaf_prims, sizeof(int32_t) * (size_t)nsm);
+    RSV(T[T_NLO], sizeof(float4) * (size_t)n_nodes); RSV(T[T_NHI], sizeof(float4) * (size_t)n_nodes);
     // eight packed copies, one per ray-direction octant (own front-to-back visiting order)
-    { int rc = dev_reserve(ctx, ctx->d_nodes, RT_N_ORDERINGS * sizeof(float4) * 2 * (size_t)n_nodes); if (rc) { cleanup(); return rc; } }
-    B.small_gid = (const int *)t_small.p;
-    B.keys = (unsigned long long *)t_keys.p;
-    B.left = (int *)t_left.p; B.right = (int *)t_right.p; B.parent = (int *)t_parent.p;
-    B.flag = (int *)t_nflag.p; B.size = (int *)t_size.p; B.lcnt = (int *)t_lcnt.p;
+    RSV(ctx->d_nodes, RT_N_ORDERINGS * sizeof(float4) * 2 * (size_t)n_nodes);
+    B.small_gid = (const int *)T[T_SMALL].p;
+    B.keys = (unsigned long long *)T[T_KEYS].p;
+    B.left = (int *)T[T_LEFT].p; B.right = (int *)T[T_RIGHT].p; B.parent = (int *)T[T_PARENT].p;
+    B.flag = (int *)T[T_NFLAG].p; B.size = (int *)T[T_SIZE].p; B.lcnt = (int *)T[T_LCNT].p;
     B.leaf_prims = (int32_t *)ctx->d_leaf_prims.p;
-    B.swapmask = (int *)t_swap.p;
+    B.swapmask = (int *)T[T_SWAP].p;
     B.packed_stride = 2 * n_nodes;
     {
       const char *e = getenv("B200RT_MAX_LEAF"); // tuning knob (leaf size)
@@ -518,26 +652,23 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
       B.max_leaf = ml < 1 ? 1 : (ml > 8 ? 8 : ml);
       ctx->max_leaf = B.max_leaf;
     }
-    B.nbox_lo = (float4 *)t_nlo.p; B.nbox_hi = (float4 *)t_nhi.p;
+    B.nbox_lo = (float4 *)T[T_NLO].p; B.nbox_hi = (float4 *)T[T_NHI].p;
     B.packed = (float4 *)ctx->d_nodes.p;
     k_morton<<<(n_pad + TB - 1) / TB, TB, 0, st>>>(B, final_round);
     ctx->launches++;
     const char *sort_env = getenv("B200RT_SORT");
-    const bool use_bitonic = sort_env && !strcmp(sort_env, "bitonic"); // verification path (unique 64-bit keys)
+    const int SORT_THREADS = 512, TILE = 2 * SORT_THREADS;
+    // small scenes: the whole sort inside one CTA's shared memory (one launch instead of 26); both sorts order
+    // the same unique 64-bit keys, so the tree does not depend on which one ran (tests: radix == bitonic)
+    const bool use_bitonic = sort_env ? !strcmp(sort_env, "bitonic") : n_pad <= 2 * TILE;
     if (!use_bitonic) {
       // radix sort of (code, primitive) pairs, 8 x 4-bit passes, ping-pong buffers
-      DevBuf r_k0, r_k1, r_v0, r_v1, r_hist;
-      DevBuf *rt[] = {&r_k0, &r_k1, &r_v0, &r_v1, &r_hist};
-      auto rfree = [&]() { for (DevBuf *b : rt) dev_free(*b); };
       const int nb = (nsm + RSORT_TILE - 1) / RSORT_TILE;
-      int rc_ = dev_reserve(ctx, r_k0, sizeof(unsigned) * (size_t)nsm);
-      if (!rc_) rc_ = dev_reserve(ctx, r_k1, sizeof(unsigned) * (size_t)nsm);
-      if (!rc_) rc_ = dev_reserve(ctx, r_v0, sizeof(int) * (size_t)nsm);
-      if (!rc_) rc_ = dev_reserve(ctx, r_v1, sizeof(int) * (size_t)nsm);
-      if (!rc_) rc_ = dev_reserve(ctx, r_hist, sizeof(int) * 16 * (size_t)nb);
-      if (rc_) { rfree(); cleanup(); return rc_; }
-      unsigned *k0 = (unsigned *)r_k0.p, *k1 = (unsigned *)r_k1.p;
-      int *v0 = (int *)r_v0.p, *v1 = (int *)r_v1.p, *hist = (int *)r_hist.p;
+      RSV(T[T_RK0], sizeof(unsigned) * (size_t)nsm); RSV(T[T_RK1], sizeof(unsigned) * (size_t)nsm);
+      RSV(T[T_RV0], sizeof(int) * (size_t)nsm); RSV(T[T_RV1], sizeof(int) * (size_t)nsm);
+      RSV(T[T_RHIST], sizeof(int) * 16 * (size_t)nb);
+      unsigned *k0 = (unsigned *)T[T_RK0].p, *k1 = (unsigned *)T[T_RK1].p;
+      int *v0 = (int *)T[T_RV0].p, *v1 = (int *)T[T_RV1].p, *hist = (int *)T[T_RHIST].p;
       k_radix_split<<<(nsm + TB - 1) / TB, TB, 0, st>>>(B.keys, k0, v0, nsm);
       for (int pass = 0; pass < 8; pass++) {
         k_radix_hist<<<nb, RSORT_THREADS, 0, st>>>(k0, nsm, 4 * pass, hist, nb);
@@ -548,14 +679,10 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
       }
       k_radix_join<<<(nsm + TB - 1) / TB, TB, 0, st>>>(k0, v0, B.keys, nsm);
       ctx->launches += 26;
-      cudaError_t e_ = cudaGetLastError();
-      if (e_ == cudaSuccess) e_ = cudaStreamSynchronize(st);
-      rfree();
-      if (e_ != cudaSuccess) { cleanup(); return fail(ctx, RT_ERR_CUDA, "radix sort failed: %s", cudaGetErrorString(e_)); }
+      CK(cudaGetLastError());
     } else {
-    // bitonic sort of the unique 64-bit keys: steps with j < TILE run in shared memory
-      const int SORT_THREADS = 512, TILE = 2 * SORT_THREADS;
-      if (n_pad <= TILE) {
+      // bitonic sort of the unique 64-bit keys: steps with j < TILE run in shared memory
+      if (n_pad <= 2 * TILE && !(sort_env && n_pad > TILE)) {
         k_bitonic_smem<<<1, n_pad / 2, sizeof(unsigned long long) * (size_t)n_pad, st>>>(B.keys, n_pad, 2, n_pad, 1);
         ctx->launches++;
       } else {
@@ -578,26 +705,26 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     }
     const int rounds = quality > 0 ? 1 + 2 * std::min(quality, 4) : 1;
     for (int r = 0; r < rounds; r++) {
-      if (r > 0) CKB(cudaMemsetAsync(B.flag, 0, sizeof(int) * (size_t)nsm, st));
+      if (r > 0) CK(cudaMemsetAsync(B.flag, 0, sizeof(int) * (size_t)nsm, st));
       k_fit<<<(nsm + TB - 1) / TB, TB, 0, st>>>(B, (quality > 0 && r < rounds - 1) ? 1 : 0);
       ctx->launches++;
     }
     if (nsm > 1) k_order<<<(nsm - 1 + TB - 1) / TB, TB, 0, st>>>(B);
-    for (int q = 0; q < RT_N_ORDERINGS; q++) k_pack<<<(n_nodes + TB - 1) / TB, TB, 0, st>>>(B, q);
-    ctx->launches += 1 + RT_N_ORDERINGS;
-    CKB(cudaGetLastError());
-    int kept = 0; // nodes that survive leaf collapsing = kept size of the root (build node 0)
-    CKB(cudaMemcpyAsync(&kept, B.size, sizeof(int), cudaMemcpyDeviceToHost, st));
-    // the root's box (record 0 of every ordering) = the frame of the render kernel's 16-bit quantised nodes
-    CKB(cudaMemcpyAsync(ctx->root_box, ctx->d_nodes.p, sizeof ctx->root_box, cudaMemcpyDeviceToHost, st));
-    CKB(cudaStreamSynchronize(st));
-    n_nodes = kept;
+    k_pack<<<dim3((n_nodes + TB - 1) / TB, RT_N_ORDERINGS), TB, 0, st>>>(B);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    // nodes that survive leaf collapsing = kept size of the root (build node 0); the root's box (record 0 of every
+    // ordering) = the frame of the render kernel's 16-bit quantised nodes
+    CK(cudaMemcpyAsync(h_words + 40, B.size, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_words + 48, ctx->d_nodes.p, sizeof ctx->root_box, cudaMemcpyDeviceToHost, st));
   }
-  CKB(cudaEventRecord(ctx->ev1, st));
-  CKB(cudaStreamSynchronize(st));
-  CKB(cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev0, ctx->ev1));
-  cleanup();
-#undef CKB
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaStreamSynchronize(st)); // host round trip 2 of 2
+  CK(cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev0, ctx->ev1));
+  if (nsm > 0) {
+    n_nodes = h_words[40];
+    memcpy(ctx->root_box, h_words + 48, sizeof ctx->root_box);
+  }
 #undef RSV
   ctx->S.nodes = (const float4 *)ctx->d_nodes.p;
   ctx->S.leaf_prims = (const int32_t *)ctx->d_leaf_prims.p;
@@ -867,13 +994,19 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   CK(cudaFuncGetAttributes(&fa, (const void *)kern));
   CK(cudaMemsetAsync(P.work_counter, 0, 4, st));
   if (timed) CK(cudaEventRecord(ctx->ev0, st));
+  cudaEvent_t *evk = ctx->ev_k[ctx->ev_k_count % RT_EV_RING];
+  CK(cudaEventRecord(evk[0], st));
+  ctx->last_render_stream = st;
   kern<<<grid, block, smem_bytes, st>>>(P);
   CK(cudaGetLastError());
+  CK(cudaEventRecord(evk[1], st));
   const int first_px = y0 * W, n_band = (y1 - y0) * W;
   k_combine<<<(unsigned)((n_band + 255) / 256), 256, 0, st>>>((float4 *)d_accum, P.partial, (int)n_pix, P.n_chunks, first_px,
                                                               n_band);
   CK(cudaGetLastError());
   ctx->launches += 2;
+  CK(cudaEventRecord(evk[2], st));
+  ctx->ev_k_count++;
   if (timed) CK(cudaEventRecord(ctx->ev1, st));
   ctx->stats.smem_bytes = (int)smem_bytes;
   ctx->stats.smem_plan = smem;
@@ -991,11 +1124,27 @@ int rt_resolve_device(rt_ctx *ctx, int width, int height, const float *d_accum, 
                                                              rgb8 ? (uint8_t *)ctx->d_rgb8.p : nullptr);
   ctx->launches++;
   CK(cudaGetLastError());
-  if (linear_rgb)
-    CK(cudaMemcpyAsync(linear_rgb, ctx->d_linear.p, sizeof(float) * 3 * n_pix, cudaMemcpyDeviceToHost, st));
-  if (rgb8) CK(cudaMemcpyAsync(rgb8, ctx->d_rgb8.p, 3 * n_pix, cudaMemcpyDeviceToHost, st));
+  // device -> host: straight into the caller's buffer when it is page-locked (rt_host_alloc, cudaHostRegister,
+  // torch pinned tensors); otherwise through the context's pinned block + one host memcpy, which beats the
+  // driver's pageable path (it stages through small internal buffers and blocks the stream meanwhile)
+  auto is_pinned = [](const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const size_t lin_bytes = linear_rgb ? sizeof(float) * 3 * n_pix : 0, rgb_bytes = rgb8 ? 3 * n_pix : 0;
+  const bool lin_direct = linear_rgb && is_pinned(linear_rgb), rgb_direct = rgb8 && is_pinned(rgb8);
+  const size_t stage_lin = lin_direct ? 0 : pad16(lin_bytes), stage_rgb = rgb_direct ? 0 : rgb_bytes;
+  if (stage_lin + stage_rgb) {
+    if ((rc = host_reserve(ctx, ctx->h_out, ctx->h_out_bytes, stage_lin + stage_rgb))) return rc;
+  }
+  unsigned char *ho = (unsigned char *)ctx->h_out;
+  if (linear_rgb) CK(cudaMemcpyAsync(lin_direct ? (void *)linear_rgb : (void *)ho, ctx->d_linear.p, lin_bytes, cudaMemcpyDeviceToHost, st));
+  if (rgb8) CK(cudaMemcpyAsync(rgb_direct ? (void *)rgb8 : (void *)(ho + stage_lin), ctx->d_rgb8.p, rgb_bytes, cudaMemcpyDeviceToHost, st));
   CK(cudaEventRecord(ctx->ev1, st));
   CK(cudaStreamSynchronize(st));
+  if (linear_rgb && !lin_direct) memcpy(linear_rgb, ho, lin_bytes);
+  if (rgb8 && !rgb_direct) memcpy(rgb8, ho + stage_lin, rgb_bytes);
   CK(cudaEventElapsedTime(&ctx->stats.ms_resolve, ctx->ev0, ctx->ev1));
   return RT_OK;
 }
@@ -1051,11 +1200,115 @@ int rt_stats(rt_ctx *ctx, rt_stats_t *out) {
   unsigned long long h[4] = {0, 0, 0, 0};
   if (ctx->d_stats.p) {
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->last_render_stream && ctx->last_render_stream != ctx->stream) CK(cudaStreamSynchronize(ctx->last_render_stream));
     CK(cudaMemcpy(h, ctx->d_stats.p, sizeof h, cudaMemcpyDeviceToHost));
   }
   ctx->stats.paths = h[0]; ctx->stats.segments = h[1]; ctx->stats.box_tests = h[2]; ctx->stats.prim_tests = h[3];
   ctx->stats.kernel_launches = ctx->launches;
+  { // mean kernel durations of the (last <= RT_EV_RING) render launches since the reset, whichever stream they ran on
+    const int n = std::min(ctx->ev_k_count, RT_EV_RING);
+    double sr = 0, sc = 0;
+    int got = 0;
+    for (int i = 0; i < n; i++) {
+      float a = 0, b = 0;
+      if (cudaEventSynchronize(ctx->ev_k[i][2]) == cudaSuccess && cudaEventElapsedTime(&a, ctx->ev_k[i][0], ctx->ev_k[i][1]) == cudaSuccess &&
+          cudaEventElapsedTime(&b, ctx->ev_k[i][1], ctx->ev_k[i][2]) == cudaSuccess) { sr += a; sc += b; got++; }
+    }
+    ctx->stats.ms_k_render = got ? (float)(sr / got) : 0.f;
+    ctx->stats.ms_k_combine = got ? (float)(sc / got) : 0.f;
+    cudaGetLastError();
+  }
   *out = ctx->stats;
+  return RT_OK;
+}
+
+void *rt_host_alloc(rt_ctx *ctx, size_t bytes) {
+  if (!ctx || bytes == 0) return nullptr;
+  if (cudaSetDevice(ctx->cfg.device) != cudaSuccess) return nullptr;
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void rt_host_free(rt_ctx *ctx, void *p) {
+  (void)ctx;
+  if (p) cudaFreeHost(p);
+}
+
+// ------------------------------------------------------------------ multi-GPU reduce
+int rt_comm_unique_id(void *id128) {
+  if (!id128) return RT_ERR_INVALID;
+  NcclApi &a = nccl_api();
+  if (!a.handle) return RT_ERR_STATE;
+  static_assert(sizeof(ncclUniqueId) == RT_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  if (a.GetUniqueId(&id) != ncclSuccess) return RT_ERR_CUDA;
+  memcpy(id128, &id, sizeof id);
+  return RT_OK;
+}
+
+int rt_comm_init(rt_ctx *ctx, const void *id128, int rank, int nranks) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return RT_ERR_INVALID;
+  NcclApi &a = nccl_api();
+  if (!a.handle) return fail(ctx, RT_ERR_STATE, "%s", a.why.c_str());
+  CK(cudaSetDevice(ctx->cfg.device));
+  if (ctx->comm) { a.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclResult_t r = a.CommInitRank(&ctx->comm, nranks, id, rank);
+  if (r != ncclSuccess) { ctx->comm = nullptr; return fail(ctx, RT_ERR_CUDA, "ncclCommInitRank: %s", a.GetErrorString(r)); }
+  ctx->comm_rank = rank; ctx->comm_size = nranks;
+  return RT_OK;
+}
+
+int rt_comm_init_all(rt_ctx **ctxs, int n) {
+  if (!ctxs || n < 1 || n > 64) return RT_ERR_INVALID;
+  for (int i = 0; i < n; i++) if (!ctxs[i]) return RT_ERR_INVALID;
+  rt_ctx *ctx = ctxs[0];
+  NcclApi &a = nccl_api();
+  if (!a.handle) return fail(ctx, RT_ERR_STATE, "%s", a.why.c_str());
+  int devs[64];
+  ncclComm_t comms[64];
+  for (int i = 0; i < n; i++) {
+    devs[i] = ctxs[i]->cfg.device;
+    if (ctxs[i]->comm) { a.CommDestroy(ctxs[i]->comm); ctxs[i]->comm = nullptr; }
+  }
+  ncclResult_t r = a.CommInitAll(comms, n, devs);
+  if (r != ncclSuccess) return fail(ctx, RT_ERR_CUDA, "ncclCommInitAll: %s", a.GetErrorString(r));
+  for (int i = 0; i < n; i++) { ctxs[i]->comm = comms[i]; ctxs[i]->comm_rank = i; ctxs[i]->comm_size = n; }
+  return RT_OK;
+}
+
+int rt_reduce(rt_ctx *ctx, int width, int height, float *d_accum, int root, unsigned flags, void *stream) {
+  if (!ctx || width < 1 || height < 1) return RT_ERR_INVALID;
+  if (!d_accum) d_accum = (float *)ctx->d_accum.p;
+  if (!d_accum) return fail(ctx, RT_ERR_STATE, "rt_reduce: no frame");
+  if (ctx->comm_size == 1 && !ctx->comm) return RT_OK; // a single rank: nothing to exchange
+  if (!ctx->comm) return fail(ctx, RT_ERR_STATE, "rt_reduce before rt_comm_init");
+  if (root < 0 || root >= ctx->comm_size) return RT_ERR_INVALID;
+  NcclApi &a = nccl_api();
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const size_t n_pix = (size_t)width * height;
+  ncclResult_t r;
+  if (flags & RT_REDUCE_UNIFORM_COUNT) {
+    int rc = dev_reserve(ctx, ctx->d_red, sizeof(float) * (3 * n_pix + 4));
+    if (rc) return rc;
+    float *red = (float *)ctx->d_red.p;
+    const unsigned g = (unsigned)((n_pix + 255) / 256);
+    k_reduce_pack<<<g, 256, 0, st>>>((const float4 *)d_accum, red, (int)n_pix);
+    CK(cudaGetLastError());
+    r = a.Reduce(red, red, 3 * n_pix + 1, ncclFloat32, ncclSum, root, ctx->comm, st);
+    if (r == ncclSuccess && ctx->comm_rank == root) {
+      k_reduce_unpack<<<g, 256, 0, st>>>((float4 *)d_accum, red, (int)n_pix);
+      CK(cudaGetLastError());
+      ctx->launches++;
+    }
+    ctx->launches++;
+  } else {
+    r = a.Reduce(d_accum, d_accum, 4 * n_pix, ncclFloat32, ncclSum, root, ctx->comm, st);
+  }
+  if (r != ncclSuccess) return fail(ctx, RT_ERR_CUDA, "ncclReduce: %s", a.GetErrorString(r));
   return RT_OK;
 }
 
@@ -1064,6 +1317,7 @@ int rt_stats_reset(rt_ctx *ctx) {
   CK(cudaSetDevice(ctx->cfg.device));
   if (ctx->d_stats.p) CK(cudaMemsetAsync(ctx->d_stats.p, 0, 64, ctx->stream));
   ctx->launches = 0;
+  ctx->ev_k_count = 0;
   return RT_OK;
 }
 

@@ -94,7 +94,8 @@ class RtStats(C.Structure):
                 ("ms_resolve", C.c_float),
                 ("n_nodes", C.c_int32), ("n_big_prims", C.c_int32), ("smem_bytes", C.c_int32),
                 ("block_threads", C.c_int32), ("grid_blocks", C.c_int32), ("regs_per_thread", C.c_int32),
-                ("smem_plan", C.c_int32), ("reserved", C.c_int32)]
+                ("smem_plan", C.c_int32), ("reserved", C.c_int32),
+                ("ms_k_render", C.c_float), ("ms_k_combine", C.c_float)]
 
 
 def camera_from_lookat(lookfrom, lookat, vup, vfov_deg, aspect, aperture, focus_dist, time0=0.0, time1=0.0,

@@ -25,10 +25,24 @@ def row_range(H, rank, world, align=4):
 
 
 def reduce_frames(accum, dst=0):
-    """Sum the per-rank accumulation frames onto `dst` (in place on dst)."""
+    """Sum the per-rank accumulation frames onto `dst` (in place on dst) with torch.distributed: the
+    host-logic path of the gloo CPU tests. On GPUs the frames go through the library's own rt_reduce
+    (init_comm + render_frame below)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.reduce(accum, dst=dst, op=dist.ReduceOp.SUM)
     return accum
+
+
+def init_comm(ctx, rank=None, world=None):
+    """Give the context its NCCL communicator (C ABI rt_comm_init): rank 0 creates the unique id,
+    torch.distributed ships the 128 bytes - plumbing only, the reduce itself is rt_reduce."""
+    from . import capi
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    box = [capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], rank, world)
+    ctx._has_comm = True
 
 
 def render_frame(ctx, W, H, spp, accum, rank=0, world=1, stream=None, split="samples"):
@@ -46,5 +60,11 @@ def render_frame(ctx, W, H, spp, accum, rank=0, world=1, stream=None, split="sam
     else:
         begin, count = sample_range(spp, rank, world)
         ctx.render_device(W, H, count, begin, accum.data_ptr(), s.cuda_stream)
-    reduce_frames(accum)
+    if world > 1:
+        if getattr(ctx, "_has_comm", False):  # the library's own reduce: R,G,B (+ one count word) for the sample split
+            ctx.reduce(W, H, accum.data_ptr(), root=0, uniform_count=(split != "rows"), stream_ptr=s.cuda_stream)
+        else:
+            if stream is not None:  # torch's collective is ordered against the CURRENT stream only
+                torch.cuda.current_stream().wait_stream(s)
+            reduce_frames(accum)
     return accum

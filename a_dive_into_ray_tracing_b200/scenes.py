@@ -3,7 +3,7 @@
 The reference hard-codes its scenes inside `main()`s; here they are data:
   weekend()    rt_in_one_weekend/main.cpp:86-131 random_scene() under glibc's default
                seed, extracted once from the compiled reference (tools/make_golden.py)
-               and stored float-rounded in tests/golden/weekend_scene.npy;
+               and stored float-rounded in scenes/weekend_scene.npy;
   final_cu()   accelerated-rt-cuda/final.cu:100-143 distribution (cuRAND stream not
                reproducible -> Philox-free numpy generator with the same law);
   next_week()  rt_next_week/cuda/main.cu:153-198 (moving spheres, checker ground);
@@ -18,7 +18,8 @@ from .ctypes_defs import (MATERIAL_DT, MEDIUM_DT, PERLIN_DT, QUAD_DT, RT_FLAG_DE
                           RT_PROFILE_FINAL_CU, RT_PROFILE_NEXT_WEEK, RT_PROFILE_WEEKEND_CPU, RT_TEX_CHECKER,
                           RT_TEX_IMAGE, RT_TEX_NOISE, RT_TEX_SOLID, SPHERE_DT, TRIANGLE_DT, Scene, camera_from_lookat)
 
-GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+# scene data shipped with the product (not the test tree): the headline scene and the stand-in meshes
+DATA_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scenes")
 
 
 def _mat(mtype, albedo=(0, 0, 0), param=0.0, texture=RT_TEX_SOLID, albedo2=(0, 0, 0)):
@@ -81,7 +82,7 @@ def weekend_camera(aspect, dtype=np.float64):
 
 def weekend(width=1200, height=800):
     """Configs 1, 2, 5: the reference's deterministic 487-sphere scene."""
-    rows = np.load(os.path.join(GOLDEN_DIR, "weekend_scene.npy"))
+    rows = np.load(os.path.join(DATA_DIR, "weekend_scene.npy"))
     sc = scene_from_rows(rows, "weekend")
     sc.camera = weekend_camera(width / height)
     sc.sky_gradient = 1
@@ -230,11 +231,16 @@ def make_blob_mesh(path, subdivisions=2, seed=1984):
             nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
         faces = nf
     V = np.array(verts)
+    return _write_displaced_mesh(path, V, faces, seed)
+
+
+def _write_displaced_mesh(path, V, faces, seed):
+    """unit-sphere vertices V displaced radially by a smooth seeded field, area-weighted vertex normals, written
+    in the `v` / `vn` / `f a//n b//n c//n` form the reference parser accepts"""
     rng = np.random.Generator(np.random.Philox(seed))
     k = rng.normal(size=(4, 3))
     disp = 1.0 + 0.12 * np.sin(3.0 * V @ k[0]) + 0.08 * np.sin(5.0 * V @ k[1] + 1.0) + 0.05 * np.cos(7.0 * V @ k[2])
     P = V * disp[:, None]
-    # vertex normals: area-weighted face normals
     N = np.zeros_like(P)
     for a, b, c in faces:
         fn = np.cross(P[b] - P[a], P[c] - P[a])
@@ -251,6 +257,33 @@ def make_blob_mesh(path, subdivisions=2, seed=1984):
         for a, b, c in faces:
             fh.write("f %d//%d %d//%d %d//%d\n" % (a + 1, a + 1, b + 1, b + 1, c + 1, c + 1))
     return len(faces)
+
+
+def make_blob_mesh_968(path, seed=1984):
+    """The config-3 mesh at the triangle count of the reference's asset (objs/blender_monkey.obj, Suzanne: 968
+    triangles): a displaced UV sphere, 22 slices x 23 stacks = 2 * 22 * 22 = 968 faces, unit
+    bounding radius before displacement."""
+    slices, stacks = 22, 23
+    verts = [np.array([0.0, 1.0, 0.0])]
+    for i in range(1, stacks):
+        th = np.pi * i / stacks
+        for j in range(slices):
+            ph = 2.0 * np.pi * j / slices
+            verts.append(np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)]))
+    verts.append(np.array([0.0, -1.0, 0.0]))
+    ring = lambda i, j: 1 + (i - 1) * slices + (j % slices)  # ring i = 1 .. stacks-1
+    faces = []
+    for j in range(slices):
+        faces.append((0, ring(1, j + 1), ring(1, j)))
+    for i in range(1, stacks - 1):
+        for j in range(slices):
+            a, b, c, d = ring(i, j), ring(i, j + 1), ring(i + 1, j), ring(i + 1, j + 1)
+            faces += [(a, b, d), (a, d, c)]
+    last = len(verts) - 1
+    for j in range(slices):
+        faces.append((last, ring(stacks - 1, j), ring(stacks - 1, j + 1)))
+    assert len(faces) == 968
+    return _write_displaced_mesh(path, np.array(verts), faces, seed)
 
 
 def bake_instance(tv, scale=2.5, angle_deg=30.0, offset=(0.0, 1.5, 0.0)):
@@ -278,12 +311,16 @@ def rotate_normals(tn, angle_deg=30.0):
     return np.stack([x, n[..., 1], z], -1).astype(f)
 
 
-def obj_room(obj_path=None, width=800, height=800, subdivisions=2):
+def obj_room(obj_path=None, width=800, height=800, subdivisions=2, mesh=None):
     """Config 3 — triangles/cuda/obj_render.cu:384-524 (obj_model) with camera
     :716-724,736-738: (1,3,7)->(0,2,0), vfov 60, aperture 0, black background,
     t_min 1e-5 (:33), flipping normals (include/hittable.h:29)."""
+    if obj_path is None and mesh == "blob968":  # the bench's config 3: Suzanne's triangle count
+        obj_path = os.path.join(DATA_DIR, "blob_968.obj")
+        if not os.path.exists(obj_path):
+            make_blob_mesh_968(obj_path)
     if obj_path is None:
-        obj_path = os.path.join(GOLDEN_DIR, "blob_%d.obj" % subdivisions)
+        obj_path = os.path.join(DATA_DIR, "blob_%d.obj" % subdivisions)
         if not os.path.exists(obj_path):
             make_blob_mesh(obj_path, subdivisions)
     tv, tn = read_obj_triangles(obj_path)

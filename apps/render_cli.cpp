@@ -6,7 +6,8 @@
 //              [--image map.ppm] [--width W] [--height H] [--spp N] [--seed S] [--device D]
 //              [--binary | --png]   (image on stdout; scene numbers 1-8 of rt_next_week/cuda/main.cu:402-459)
 //              [--gpus N]  sample split over N devices, one host thread and one context per device,
-//                          frames summed on the host (the NCCL variant is dist.py)
+//                          frames combined by rt_reduce (ncclReduce over NVLink);
+//                          --host-combine sums the downloaded frames on the CPU instead (no NCCL needed)
 //   render_cli --scene-file FILE.scene [--width W --height H --spp N ...]   (include/rtx/scene_file.h)
 #include <chrono>
 #include <cstring>
@@ -21,7 +22,7 @@ int main(int argc, char **argv) {
   int W = 0, H = 0, spp = 0, device = 0, gpus = 1;
   unsigned long long seed = 1984;
   bool have_seed = false;
-  bool binary = false, png = false;
+  bool binary = false, png = false, host_combine = false;
   for (int i = 1; i < argc; i++) {
     auto is = [&](const char *f) { return !strcmp(argv[i], f) && i + 1 < argc; };
     if (is("--scene")) scene = argv[++i];
@@ -36,6 +37,7 @@ int main(int argc, char **argv) {
     else if (is("--gpus")) gpus = atoi(argv[++i]);
     else if (!strcmp(argv[i], "--binary")) binary = true;
     else if (!strcmp(argv[i], "--png")) png = true;
+    else if (!strcmp(argv[i], "--host-combine")) host_combine = true;
     else { std::cerr << "unknown argument " << argv[i] << "\n"; return 2; }
   }
   try {
@@ -136,20 +138,29 @@ int main(int argc, char **argv) {
       more.back()->set_scene(*root, cam);
     }
     auto share = [&](int g) { return std::make_pair((int)((long long)spp * g / gpus), (int)((long long)spp * (g + 1) / gpus)); };
+    if (gpus > 1 && !host_combine) {
+      std::vector<renderer *> all{&r};
+      for (auto &m : more) all.push_back(m.get());
+      renderer::group(all);
+    }
     auto t0 = std::chrono::steady_clock::now();
     {
+      // one host thread per device: render its share, then join the reduce (a single-process NCCL group needs the
+      // ranks' calls issued concurrently)
       std::vector<std::thread> workers;
       std::vector<std::string> errors(gpus);
-      for (int g = 1; g < gpus; g++)
-        workers.emplace_back([&, g]() {
-          try { more[g - 1]->render(W, H, share(g).second - share(g).first, share(g).first); }
-          catch (const std::exception &e) { errors[g] = e.what(); }
-        });
-      r.render(W, H, share(0).second - share(0).first, share(0).first);
+      auto job = [&](renderer &rr, int g) {
+        try {
+          rr.render(W, H, share(g).second - share(g).first, share(g).first);
+          if (gpus > 1 && !host_combine) rr.reduce(0);
+        } catch (const std::exception &e) { errors[g] = e.what(); }
+      };
+      for (int g = 1; g < gpus; g++) workers.emplace_back([&, g]() { job(*more[g - 1], g); });
+      job(r, 0); // never throws: the workers are always joined
       for (auto &w : workers) w.join();
       for (auto &e : errors) if (!e.empty()) throw std::runtime_error(e);
     }
-    if (gpus > 1) { // combine: sum of the float4 frames (fixed device order -> deterministic)
+    if (gpus > 1 && host_combine) { // sum of the downloaded float4 frames (fixed device order)
       std::vector<float> sum = r.accum_download();
       for (auto &m : more) {
         std::vector<float> f = m->accum_download();

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RT_CAPI_VERSION 3
+#define RT_CAPI_VERSION 4
 
 typedef struct rt_ctx rt_ctx;
 
@@ -218,9 +218,11 @@ typedef struct rt_stats_t {
   uint64_t kernel_launches;/* kernels of this library launched */
   float ms_upload, ms_build, ms_render, ms_resolve; /* last call of each phase (CUDA events) */
   int32_t n_nodes, n_big_prims, smem_bytes, block_threads, grid_blocks, regs_per_thread;
-  int32_t smem_plan;       /* residency plan of the last render / trace launch: 2 = scene + four node orderings in
+  int32_t smem_plan;       /* residency plan of the last render / trace launch: 2 = scene + eight node orderings in
                             * shared memory, 1 = scene + one ordering, 3 = nodes only, 0 = everything through L1/L2 */
   int32_t reserved;
+  float ms_k_render, ms_k_combine; /* version 4: mean CUDA-event duration of k_render / k_combine over the (last <= 64)
+                                    * render launches since rt_stats_reset, on whichever stream they ran */
 } rt_stats_t;
 
 int rt_version(void);
@@ -254,7 +256,10 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
  * which call / which GPU rendered it. */
 int rt_render(rt_ctx *ctx, int width, int height, int spp_begin, int spp_count);
 /* Same, into a caller-provided DEVICE buffer (float[H*W*4]) on a caller stream
- * (cudaStream_t as void*; NULL = the context's stream). No host sync. */
+ * (cudaStream_t as void*; NULL = the context's stream). No host sync.
+ * ONE render in flight per context: the work counter, the per-chunk partial frames and the statistics words
+ * are per-context scratch, so two un-synchronised renders of the same context on different streams race.
+ * Use one context per concurrent render (contexts are cheap: the scene of config 2 is 60 KB). */
 int rt_render_device(rt_ctx *ctx, int width, int height, int spp_begin, int spp_count, float *d_accum,
                      void *stream);
 /* Image-space split (SURVEY.md 8e alternative / 8f: tile split for interactive latency): as rt_render_device,
@@ -286,6 +291,35 @@ int rt_render_aov(rt_ctx *ctx, int width, int height, int spp, float *aov);
 int rt_stats(rt_ctx *ctx, rt_stats_t *out);
 int rt_stats_reset(rt_ctx *ctx);
 int rt_sync(rt_ctx *ctx);
+
+/* Page-locked host memory for the buffers the caller hands to rt_resolve / rt_accum_download /
+ * rt_scene_upload: a device <-> host copy of pinned memory runs at link speed without the driver's staging
+ * copy (2.9 MB rgb8 frame: 0.12 ms instead of ~0.4 ms). Any host pointer works everywhere; pinned ones are
+ * faster. rt_host_free(NULL) is a no-op. */
+void *rt_host_alloc(rt_ctx *ctx, size_t bytes);
+void rt_host_free(rt_ctx *ctx, void *p);
+
+/* ---- multi-GPU: the one exchange step of the path (north_star (4): "per-GPU sample
+ * buffers combined by an NCCL reduce"). One context per GPU, each renders its share of the samples
+ * (rt_render / rt_render_device with its own [spp_begin, spp_begin+spp_count)); rt_reduce sums the frames
+ * onto `root`. Replaces the std::thread join + shared image array of main.cpp:292-355.
+ *
+ * One PROCESS per GPU (torchrun, MPI): rank 0 calls rt_comm_unique_id, ships the 128 bytes to the other
+ * ranks by its own means, every rank calls rt_comm_init.
+ * One process, several GPUs (apps/render_cli --gpus N): rt_comm_init_all on the array of contexts (one host
+ * thread per context must then call rt_reduce concurrently, as NCCL requires of a single-process group).
+ * NCCL is loaded at the first comm call (dlopen libnccl.so.2); without it these return RT_ERR_STATE. */
+#define RT_COMM_ID_BYTES 128
+int rt_comm_unique_id(void *id128);
+int rt_comm_init(rt_ctx *ctx, const void *id128, int rank, int nranks);
+int rt_comm_init_all(rt_ctx **ctxs, int n);
+/* flags of rt_reduce */
+#define RT_REDUCE_UNIFORM_COUNT 1u /* every pixel of a rank's frame holds the same sample count (the sample
+                                    * split): only R,G,B travel (+ one count word), 25 % fewer bytes */
+/* Sum-reduce the float4 frames of all ranks onto `root`'s d_accum (NULL = the context's own accumulation
+ * buffer), asynchronously on `stream` (NULL = the context's stream): pack -> ncclReduce(sum, fp32) -> unpack
+ * on root. Non-root frames are left unchanged. width*height must match on all ranks. */
+int rt_reduce(rt_ctx *ctx, int width, int height, float *d_accum, int root, unsigned flags, void *stream);
 
 /* Diagnostic: measured FP32 FMA throughput of the device (TFLOP/s, FMA = 2 flops), the
  * roofline denominator for this compute-bound path. */

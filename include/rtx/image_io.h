@@ -4,6 +4,7 @@
 // (8-bit RGB, zlib "stored" blocks: no compression library needed).
 #ifndef RTX_IMAGE_IO_H
 #define RTX_IMAGE_IO_H
+#include <algorithm>
 #include <cstdint>
 #include <fstream>
 #include <ostream>

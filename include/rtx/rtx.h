@@ -184,7 +184,8 @@ public:
     if (!(in >> magic) || (magic != "P6" && magic != "P3")) return;
     auto skip = [&]() { while (in >> std::ws && in.peek() == '#') { std::string l; std::getline(in, l); } };
     skip(); in >> width; skip(); in >> height; skip(); in >> maxv;
-    if (!in || width < 1 || height < 1 || maxv < 1 || maxv > 255) { width = height = 0; return; }
+    // dimensions from an untrusted header: cap at 32768 x 32768 before sizing the buffer
+    if (!in || width < 1 || height < 1 || width > 32768 || height > 32768 || maxv < 1 || maxv > 255) { width = height = 0; return; }
     data.resize((size_t)width * height * 3);
     if (magic == "P6") {
       in.get();
@@ -823,6 +824,18 @@ public:
   void accum_upload(int width, int height, const std::vector<float> &f) {
     W = width; H = height;
     check(rt_accum_upload(ctx, width, height, f.data(), f.size()));
+  }
+  // multi-GPU sample split inside ONE process: group() gives every renderer (one per device) its NCCL
+  // communicator, reduce() - called concurrently from one host thread per renderer - sums the frames onto
+  // renderer `root` of the group (rt_reduce: R,G,B through ncclReduce)
+  static void group(const std::vector<renderer *> &rs) {
+    std::vector<rt_ctx *> h;
+    for (renderer *r : rs) h.push_back(r->ctx);
+    if (!h.empty()) rs[0]->check(rt_comm_init_all(h.data(), (int)h.size()));
+  }
+  void reduce(int root = 0) {
+    check(rt_reduce(ctx, W, H, nullptr, root, RT_REDUCE_UNIFORM_COUNT, nullptr));
+    check(rt_sync(ctx));
   }
   rt_stats_t stats() { rt_stats_t s; check(rt_stats(ctx, &s)); return s; }
   rt_ctx *handle() { return ctx; }

@@ -25,14 +25,14 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.SYMBOLS) == syms
     for s in syms:
         assert hasattr(lib, s), s
-    assert capi.load_library().rt_version() == 3
+    assert capi.load_library().rt_version() == 4
 
 
 def test_struct_sizes_match_header():
     # include/rt_capi.h: plain structs, natural alignment
     assert C.sizeof(D.RtConfig) == 24
     assert C.sizeof(D.RtCamera) == 96
-    assert C.sizeof(D.RtStats) == 88
+    assert C.sizeof(D.RtStats) == 96
     assert D.SPHERE_DT.itemsize == 48 and D.TRIANGLE_DT.itemsize == 52 and D.QUAD_DT.itemsize == 28
     assert D.MATERIAL_DT.itemsize == 40 and D.BVH_NODE_DT.itemsize == 32
     assert C.sizeof(D.RtSceneDesc) == 4 * 16 + 96 + 32 + 3 * 16

@@ -42,7 +42,7 @@ def test_weekend_scene_built_with_cpp_classes_equals_reference(host, golden_dir)
     """random_scene() written against include/rtx reproduces the reference's scene exactly
     (487 spheres, same values after float rounding) and the camera of camera.h:8-45."""
     s, t, q, m, cam, accel = host(0, seed=1, aspect=1200 / 800)
-    rows = np.load(golden_dir + "/weekend_scene.npy")
+    rows = np.load(os.path.join(scenes.DATA_DIR, "weekend_scene.npy"))
     assert len(s) == 487 and len(m) == 487 and len(t) == 0 and len(q) == 0
     np.testing.assert_array_equal(s["center0"], rows[:, 0:3].astype(np.float32))
     np.testing.assert_array_equal(s["radius"], rows[:, 3].astype(np.float32))

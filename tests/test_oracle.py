@@ -2,6 +2,8 @@
 were produced by the UNMODIFIED reference (tools/make_golden.py), and — where the
 compiled reference oracle/_ref/libref_l0.so is available — bit-exact pinning of the
 restatement against it."""
+import os
+
 import numpy as np
 
 from a_dive_into_ray_tracing_b200 import ctypes_defs as D
@@ -10,7 +12,7 @@ from tests import stats_util as SU
 
 
 def test_scene_fixture(golden_dir):
-    rows = np.load(golden_dir + "/weekend_scene.npy")
+    rows = np.load(os.path.join(scenes.DATA_DIR, "weekend_scene.npy"))
     assert rows.shape == (487, 12)
     kinds = np.bincount(rows[:, 4].astype(int))
     assert kinds.tolist() == [394, 64, 29]  # lambertian / metal / dielectric
@@ -104,7 +106,7 @@ def _cam22(c):
 
 
 def test_pin_closest_hit_against_compiled_reference(l0, l1_64, golden_dir):
-    rows = np.load(golden_dir + "/weekend_scene.npy")
+    rows = np.load(os.path.join(scenes.DATA_DIR, "weekend_scene.npy"))
     l0.scene_set(rows)
     sc = scenes.weekend(400, 225)
     rng = np.random.Generator(np.random.Philox(11))
@@ -121,7 +123,7 @@ def test_pin_render_loop_against_compiled_reference(l0, l1_64, golden_dir):
     """Same rand() stream, same float-rounded scene and camera -> the restatement's whole
     pixel/sample/bounce loop reproduces the reference's sums BIT-EXACTLY."""
     from oracle import pyoracle
-    rows = np.load(golden_dir + "/weekend_scene.npy")
+    rows = np.load(os.path.join(scenes.DATA_DIR, "weekend_scene.npy"))
     l0.scene_set(rows)
     W, H, spp = 40, 22, 4
     sc = scenes.weekend(W, H)

@@ -215,7 +215,7 @@ def case_nw_media():
 
 
 def _room_triangles(baked):
-    path = os.path.join(GOLDEN, "blob_2.obj")
+    path = os.path.join(scenes.DATA_DIR, "blob_2.obj")
     tv, tn = scenes.read_obj_triangles(path)
     f = np.float32
     if baked:

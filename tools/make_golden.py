@@ -50,7 +50,7 @@ def main():
     assert rows64.shape == (487, 12)
     np.save(os.path.join(G, "weekend_scene_f64.npy"), rows64)
     rows = rows64.astype(np.float32).astype(np.float64)
-    np.save(os.path.join(G, "weekend_scene.npy"), rows)
+    np.save(os.path.join(ROOT, "scenes", "weekend_scene.npy"), rows)
     meta = {"n": 487, "kinds": np.bincount(rows[:, 4].astype(int)).tolist(),
             "fnv1a64_f64_rows": "%016x" % fnv1a64(rows64[:, :9].tobytes()),
             "fnv1a64_f32_rows": "%016x" % fnv1a64(rows[:, :9].astype(np.float32).tobytes())}
