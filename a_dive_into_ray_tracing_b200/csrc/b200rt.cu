@@ -3,6 +3,7 @@
 // There is NO CPU fallback in this library: without a CUDA device rt_create fails
 // with RT_ERR_NODEVICE.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -861,7 +862,7 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
     P.b_quad_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_quads);
     scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat + P.b_bigq;
   }
-  const size_t acc_bytes = (size_t)(block / 32) * 256 * sizeof(float); // two 32-pixel tiles per warp
+  const size_t acc_bytes = (size_t)(block / 32) * RT_ACC_WORDS * sizeof(unsigned); // two 32-pixel tiles per warp, 64-bit fixed-point sums
   // shared-memory plan: 2 = scene + eight octant orderings of the (quantised) nodes, 1 = scene, 0 = global
   smem = 0;
   if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;
@@ -965,11 +966,35 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   // end-of-frame imbalance (few items per warp) costs far more than the per-item drain
   // tail, so aim for >= 64 items per resident warp while keeping >= 8 samples per item.
   int n_chunks = (int)((64LL * n_warps + P.n_tiles - 1) / P.n_tiles);
-  n_chunks = std::min(n_chunks, std::max(1, spp_count / 8));
+  n_chunks = std::min(n_chunks, std::max(spp_count >= 4 ? 2 : 1, spp_count / 12));
   if (const char *e = getenv("B200RT_CHUNKS")) n_chunks = atoi(e); // tuning knob
-  n_chunks = std::max(1, std::min(n_chunks, std::min(spp_count, 64)));
-  P.chunk_spp = (spp_count + n_chunks - 1) / n_chunks;
-  P.n_chunks = (spp_count + P.chunk_spp - 1) / P.chunk_spp;
+  n_chunks = std::max(1, std::min(n_chunks, std::min(spp_count, RT_MAX_CHUNKS)));
+  {
+    // Chunk sizes fall geometrically (ratio q per level, at least 1 sample): the work list is chunk-major, so the
+    // last items every warp fetches are the small ones and the end-of-frame imbalance shrinks with them, while
+    // most samples still travel in large items (an item boundary costs a partial drain of the warp).
+    // Measured (B200, config 2): uniform chunks leave ~0.6 ms of tail per launch, which is what an 8-GPU sample
+    // split (62 spp per GPU) loses against 1/8 of the single-GPU frame.
+    double q = 0.65;
+    if (const char *e = getenv("B200RT_CHUNK_RATIO")) q = std::min(1.0, std::max(0.05, atof(e))); // tuning knob; 1 = uniform
+    std::vector<double> w((size_t)n_chunks);
+    double sum = 0;
+    for (int c = 0; c < n_chunks; c++) { w[c] = std::pow(q, c); sum += w[c]; }
+    int given = 0;
+    double acc = 0;
+    P.chunk_begin[0] = 0;
+    for (int c = 0; c < n_chunks; c++) {
+      acc += w[c];
+      int end = (int)std::llround(acc / sum * spp_count);
+      end = std::max(end, given + 1);                          // every chunk holds at least one sample
+      end = std::min(end, spp_count - (n_chunks - 1 - c));     // and leaves one for each later chunk
+      if (c == n_chunks - 1) end = spp_count;
+      P.chunk_begin[c + 1] = end;
+      given = end;
+    }
+  }
+  P.chunk_spp = P.chunk_begin[1];
+  P.n_chunks = n_chunks;
   P.spp_begin = spp_begin; P.spp_count = spp_count;
   P.n_work = P.n_tiles * P.n_chunks;
   int rc;

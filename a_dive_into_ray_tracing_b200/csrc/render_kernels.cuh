@@ -35,6 +35,8 @@
 #define RT_BLOCK_OF(GENERAL) ((GENERAL) ? RT_BLOCK_GENERAL : RT_BLOCK)
 #define RT_TILE_W 8
 #define RT_TILE_H 4
+#define RT_MAX_CHUNKS 64
+#define RT_ACC_WORDS 384 // per-warp accumulator words: 2 tiles x 3 channels x {lo, hi} x 32 pixels
 #define RT_Q_MAX 46335 // largest quantised plane: (q << 16) + 0x4B000000 must not carry out of 32 bits (k_render)
 #ifndef RT_N_ORDERINGS
 #define RT_N_ORDERINGS 8 // node orderings = ray-direction octants (bvh_build.cuh body_order)
@@ -47,6 +49,9 @@ struct RenderParams {
   int W, H, tiles_x, n_tiles;
   int y0, y1; // rows rendered by this launch: [y0, y1) (the whole frame: 0, H)
   int n_chunks, chunk_spp, spp_begin, spp_count, n_work;
+  // samples [chunk_begin[c], chunk_begin[c + 1]) (relative to spp_begin) form chunk c: sizes DECREASE towards the end of
+  // the work list, so that the frame's tail - warps waiting for the last items - is as short as the smallest chunk
+  int chunk_begin[RT_MAX_CHUNKS + 1];
   float4 *partial;               // [n_chunks][H*W]
   int *work_counter;
   unsigned long long *stats;     // paths, segments, box tests, prim tests
@@ -173,7 +178,30 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float *acc = (float *)(smem_raw + off) + warp * 256; // [2 tiles in flight][32 pixels][4]
+  // Per-warp pixel accumulators, ORDER-INDEPENDENT: each channel of each pixel is a 64-bit fixed-point sum (32.32,
+  // two 32-bit words: [2 tiles in flight][3 channels][lo, hi][32 pixels]) fed by native integer ATOMS.ADD with an explicit
+  // carry. Integer addition commutes, so a pixel's sum does not depend on which lane traced which sample or in
+  // which order the paths ended - run-to-run bit-identical frames although work items are handed out by a racing
+  // atomic counter and overlap inside a warp. (The float atomicAdd this replaces is a CAS spin loop on shared
+  // memory and made the fp32 summation order schedule-dependent.) Lanes address different pixels -> different banks.
+  unsigned *acc = (unsigned *)(smem_raw + off) + warp * RT_ACC_WORDS;
+  auto acc_add = [&](int pix_, V3f L_) {
+    const float c3[3] = {L_.x, L_.y, L_.z};
+    unsigned *a = acc + (pix_ >> 5) * 192 + (pix_ & 31);
+#ifdef RT_ACC_FLOAT // measurement build: the schedule-dependent float sums this scheme replaced
+    for (int c = 0; c < 3; c++) atomicAdd((float *)(a + c * 64), c3[c]);
+    return;
+#endif
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      // clamp to [0, 2^30]: fmaxf drops a NaN (-> 0), the upper bound keeps 2^32 * x inside 63 bits
+      const long long q = __float2ll_rn(fminf(fmaxf(c3[c], 0.0f), 1073741824.0f) * 4294967296.0f);
+      const unsigned lo = (unsigned)q, hi = (unsigned)((unsigned long long)q >> 32);
+      const unsigned old = atomicAdd(a + c * 64, lo);
+      const unsigned carry = (old + lo) < lo ? 1u : 0u;
+      atomicAdd(a + c * 64 + 32, hi + carry);
+    }
+  };
   __syncthreads();
 
   const unsigned FULL = 0xffffffffu;
@@ -369,8 +397,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           chunk = w / P.n_tiles;
           tile_x0 = (tile % P.tiles_x) * RT_TILE_W;
           tile_y0 = P.y0 + (tile / P.tiles_x) * RT_TILE_H;
-          s0 = P.spp_begin + chunk * P.chunk_spp;
-          chunk_n = min(P.chunk_spp, P.spp_count - chunk * P.chunk_spp);
+          s0 = P.spp_begin + P.chunk_begin[chunk];
+          chunk_n = P.chunk_begin[chunk + 1] - P.chunk_begin[chunk];
           pool_next = 0;
           pool_end = chunk_n * 32;
           if (TRACE) { // item w = the rays [w * trace_item, (w + 1) * trace_item)
@@ -379,8 +407,9 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           }
           cur_buf = old_buf ^ 1;
           have_cur = true;
-          float *a = acc + cur_buf * 128 + lane * 4;
-          a[0] = 0.f; a[1] = 0.f; a[2] = 0.f; a[3] = 0.f;
+          unsigned *a = acc + cur_buf * 192 + lane;
+#pragma unroll
+          for (int k = 0; k < 6; k++) a[k * 32] = 0u;
           __syncwarp();
         }
       }
@@ -400,9 +429,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           ended = true;
         } else if (!hit) {
           L = L + beta * miss_radiance(P.sp, r.d);
-          atomicAdd(&acc[pix * 4 + 0], L.x);
-          atomicAdd(&acc[pix * 4 + 1], L.y);
-          atomicAdd(&acc[pix * 4 + 2], L.z);
+          acc_add(pix, L); // (one accumulation site per way of ending: a merged site after the shading measured 2 % slower)
           alive = false;
           ended = true;
         }
@@ -455,14 +482,15 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
               L = v3(0, 0, 0); // main.cpp:58-60, final.cu:53
             }
           } // else: absorbed (L is 0 for profiles 0/1) or hit a light
-          atomicAdd(&acc[pix * 4 + 0], L.x);
-          atomicAdd(&acc[pix * 4 + 1], L.y);
-          atomicAdd(&acc[pix * 4 + 2], L.z);
+          acc_add(pix, L);
           alive = false; // regenerated in the next round
           ended = true;
           node = node_end;
         }
-      } else if (TRACE && fresh_path) {
+      }
+      // ONE accumulation site for every path that ended in this round - rays that left the scene in (a), possibly
+      // already re-assigned to a new (pixel, sample) whose L is reset only below, and paths the shading terminated
+      if (TRACE && fresh_path) { // (a hit lane keeps its path: it never takes a new item in the same round)
         const float4 ra = __ldg(P.trace_rays + 2 * (size_t)pixel_index), rb = __ldg(P.trace_rays + 2 * (size_t)pixel_index + 1);
         r.o = v3(ra.x, ra.y, ra.z); r.tm = ra.w; r.d = v3(rb.x, rb.y, rb.z);
         alive = true;
@@ -492,9 +520,17 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       __syncwarp();
       const int i = old_x0 + (lane & 7), j = old_y0 + (lane >> 3);
       if (!TRACE && i < P.W && j < P.y1) {
-        const float *a = acc + old_buf * 128 + lane * 4;
+        const unsigned *a = acc + old_buf * 192 + lane;
+        float c3[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) // one rounding: the exact 64-bit sum -> float
+#ifdef RT_ACC_FLOAT
+          c3[c] = __uint_as_float(a[c * 64]);
+#else
+          c3[c] = __ull2float_rn(((unsigned long long)a[c * 64 + 32] << 32) | a[c * 64]) * 2.3283064365386963e-10f;
+#endif
         P.partial[(size_t)old_chunk * ((size_t)P.W * P.H) + (size_t)j * P.W + i] =
-            make_float4(a[0], a[1], a[2], (float)old_chunk_n);
+            make_float4(c3[0], c3[1], c3[2], (float)old_chunk_n);
       }
       old_valid = false;
     }

@@ -294,7 +294,9 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
 
   const float4 m0 = S.mats[2 * mat], m1 = S.mats[2 * mat + 1];
   const int mtype = RT_F2I(m0.w) & 0xff;
-  const float u1 = u01(rnd.x), u2 = u01(rnd.y), u3 = u01(rnd.z);
+  // u3 scales a unit vector into the ball (radius cbrt(u3)): kept off 0 so that an isotropic scatter never
+  // yields the zero direction (u01 returns [0, 1): 0 with probability 2^-24 per event)
+  const float u1 = u01(rnd.x), u2 = u01(rnd.y), u3 = fmaxf(u01(rnd.z), 5.9604645e-8f);
 
   if (PROFILE == 2 && mtype == RT_MAT_DIFFUSE_LIGHT) {
     L = L + beta * material_color<EXT>(S, m0, m1, p, outward, h.id); // emitted; never scatters

@@ -14,6 +14,8 @@
 #include <iostream>
 #include <thread>
 
+#include <unistd.h>
+
 #include "scenes.h"
 #include "scene_file.h"
 
@@ -40,6 +42,11 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--host-combine")) host_combine = true;
     else { std::cerr << "unknown argument " << argv[i] << "\n"; return 2; }
   }
+  // The image goes to stdout; libraries write there too (NCCL prints its version banner on fd 1): point fd 1 at
+  // stderr while working and give stdout back just before the image is written.
+  fflush(stdout);
+  const int image_fd = dup(1);
+  dup2(2, 1);
   try {
     render_options opt;
     scene_file sf;
@@ -174,6 +181,10 @@ int main(int argc, char **argv) {
     for (auto &m : more) { rt_stats_t sg = m->stats(); st.segments += sg.segments; st.ms_render = std::max(st.ms_render, sg.ms_render); }
     std::cerr << "took " << secs << " seconds. (" << st.segments / 1e6 / (st.ms_render * 1e-3) << " Mpath-bounces/s, BVH "
               << st.n_nodes << " nodes built in " << st.ms_build << " ms)\n";
+    fflush(stdout);
+    std::cout.flush();
+    dup2(image_fd, 1);
+    close(image_fd);
     if (png) im.write_png(std::cout);
     else if (binary) im.write_ppm_binary(std::cout);
     else im.write_ppm(std::cout);

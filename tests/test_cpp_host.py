@@ -277,18 +277,20 @@ def test_render_cli_final_scene(tmp_path):
 
 @pytest.mark.gpu
 def test_render_cli_multi_gpu_sample_split(tmp_path):
-    """render_cli --gpus 2: one context and host thread per device, frames summed on the host; the
-    image equals the single-device one up to fp32 summation order (counter-based RNG)."""
+    """render_cli --gpus 2: one context and host thread per device, frames combined by rt_reduce (ncclReduce) or,
+    with --host-combine, summed on the host; both equal the single-device image up to fp32 summation order
+    (counter-based RNG)."""
     from a_dive_into_ray_tracing_b200 import capi
     if capi.device_count() < 2:
         pytest.skip("needs two CUDA devices")
     subprocess.check_call(["make", "-C", os.path.join(ROOT, "apps"), "-s"])
     imgs = []
-    for g in (1, 2):
+    for extra in ([], ["--gpus", "2"], ["--gpus", "2", "--host-combine"]):
         p = subprocess.run([os.path.join(ROOT, "build", "render_cli"), "--scene", "weekend", "--width", "120", "--height",
-                            "80", "--spp", "32", "--gpus", str(g), "--binary"], capture_output=True, timeout=300)
+                            "80", "--spp", "32", "--binary"] + extra, capture_output=True, timeout=300)
         assert p.returncode == 0, p.stderr.decode()
         head = b"P6\n120 80\n255\n"
         imgs.append(np.frombuffer(p.stdout[len(head):], np.uint8).reshape(80, 120, 3).astype(np.int32))
-    d = np.abs(imgs[0] - imgs[1])
-    assert d.max() <= 1 and (d > 0).mean() < 0.01, (d.max(), (d > 0).mean())
+    for other in imgs[1:]:
+        d = np.abs(imgs[0] - other)
+        assert d.max() <= 1 and (d > 0).mean() < 0.01, (d.max(), (d > 0).mean())
