@@ -32,6 +32,9 @@ static inline int flat_fail(std::string &err, const char *fmt, ...) {
   return RT_ERR_INVALID;
 }
 
+// 2 * RT_MAX_PRIMS nodes * 32 bytes * 8 orderings = 2^31 - one node
+#define RT_MAX_PRIMS ((1 << 22) - 1)
+
 static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &F, std::string &err) {
 #define FAIL(...) return flat_fail(err, __VA_ARGS__)
   if (sc->n_spheres < 0 || sc->n_triangles < 0 || sc->n_quads < 0 || sc->n_materials < 0)
@@ -39,8 +42,12 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
   if ((sc->n_spheres && !sc->spheres) || (sc->n_triangles && !sc->triangles) || (sc->n_quads && !sc->quads) ||
       (sc->n_materials && !sc->materials))
     FAIL("null array with non-zero count");
-  if (sc->n_spheres >= (1 << 28) || sc->n_triangles >= (1 << 28) || sc->n_quads >= (1 << 28))
-    FAIL("too many primitives");
+  // Node links and array offsets on the device are signed 32-bit BYTE offsets: 2 n - 1 nodes of 32 bytes, times
+  // the eight octant orderings addressed from one base (node_stride * 7 + n_nodes * 32 < 2^31), and 64 bytes per
+  // flattened triangle. RT_MAX_PRIMS keeps every one of them inside 31 bits.
+  if ((long long)sc->n_spheres + sc->n_triangles + sc->n_quads > RT_MAX_PRIMS)
+    FAIL("too many primitives: %lld > %d (32-bit byte offsets of the node array)",
+         (long long)sc->n_spheres + sc->n_triangles + sc->n_quads, RT_MAX_PRIMS);
   if (sc->max_depth < 1) FAIL("max_depth must be >= 1");
   // non-finite geometry would poison the bounds / Morton codes of the builder: reject it here
   auto finite3 = [](const float *p) { return std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]); };

@@ -181,6 +181,36 @@ RT_HD V3f material_color(const DevScene &S, float4 m0, float4 m1, V3f p, V3f out
 // must lie before the closest surface (the reference ignores t_max) and scattering continues
 // from the scatter point (the reference restarts at the boundary entry point, :66).
 // Random numbers: Philox stream 2 + m/4 of (pixel, sample, segment).
+// [t1, t2] = the whole line's intersection with medium m's convex boundary (constant_medium.h:42-52), unclamped
+RT_COLD bool medium_interval(const float4 *__restrict__ media, int m, V3f ro, V3f rd, float &t1, float &t2) {
+  const float4 a0 = media[4 * m], a1 = media[4 * m + 1];
+  if (RT_F2I(a0.w) == 0) {
+    const V3f oc = ro - xyz(a0);
+    const float a = dot(rd, rd), hb = dot(oc, rd), c = RT_FMA(-a1.x, a1.x, dot(oc, oc));
+    const float disc = RT_FMA(hb, hb, -a * c);
+    if (!(disc > 0.0f)) return false;
+    const float sq = RT_SQRT(disc);
+    t1 = (-hb - sq) / a;
+    t2 = (-hb + sq) / a;
+    return true;
+  }
+  const float4 a2 = media[4 * m + 2], a3 = media[4 * m + 3];
+  const V3f o = ro - xyz(a2);
+  const float sn = a3.x, cs = a3.y;
+  const float ol[3] = {cs * o.x - sn * o.z, o.y, sn * o.x + cs * o.z};
+  const float dl[3] = {cs * rd.x - sn * rd.z, rd.y, sn * rd.x + cs * rd.z};
+  const float lo[3] = {a0.x, a0.y, a0.z}, hi[3] = {a1.x, a1.y, a1.z};
+  t1 = -INFINITY; t2 = INFINITY;
+  bool miss = false;
+  for (int k = 0; k < 3; k++) {
+    if (dl[k] == 0.0f) { miss = miss || ol[k] < lo[k] || ol[k] > hi[k]; continue; }
+    const float ta = (lo[k] - ol[k]) / dl[k], tb = (hi[k] - ol[k]) / dl[k];
+    t1 = RT_FMAX(t1, RT_FMIN(ta, tb));
+    t2 = RT_FMIN(t2, RT_FMAX(ta, tb));
+  }
+  return !miss && t1 < t2;
+}
+
 RT_COLD HitAcc apply_media(const float4 *__restrict__ media, int n_media, V3f ro, V3f rd, uint32_t pixel, uint32_t smp,
                            uint32_t segment, uint32_t seed_lo, uint32_t seed_hi, HitAcc h) {
   const float len = RT_SQRT(dot(rd, rd));
@@ -188,37 +218,12 @@ RT_COLD HitAcc apply_media(const float4 *__restrict__ media, int n_media, V3f ro
   for (int m = 0; m < n_media; m++) {
     if ((m & 3) == 0) q = philox4x32_10(pixel, smp, segment, 2u + (uint32_t)(m >> 2), seed_lo, seed_hi);
     const uint32_t word = (m & 3) == 0 ? q.x : ((m & 3) == 1 ? q.y : ((m & 3) == 2 ? q.z : q.w));
-    const float4 a0 = media[4 * m], a1 = media[4 * m + 1];
     float t1, t2;
-    if (RT_F2I(a0.w) == 0) {
-      const V3f oc = ro - xyz(a0);
-      const float a = dot(rd, rd), hb = dot(oc, rd), c = RT_FMA(-a1.x, a1.x, dot(oc, oc));
-      const float disc = RT_FMA(hb, hb, -a * c);
-      if (!(disc > 0.0f)) continue;
-      const float sq = RT_SQRT(disc);
-      t1 = (-hb - sq) / a;
-      t2 = (-hb + sq) / a;
-    } else {
-      const float4 a2 = media[4 * m + 2], a3 = media[4 * m + 3];
-      const V3f o = ro - xyz(a2);
-      const float sn = a3.x, cs = a3.y;
-      const float ol[3] = {cs * o.x - sn * o.z, o.y, sn * o.x + cs * o.z};
-      const float dl[3] = {cs * rd.x - sn * rd.z, rd.y, sn * rd.x + cs * rd.z};
-      const float lo[3] = {a0.x, a0.y, a0.z}, hi[3] = {a1.x, a1.y, a1.z};
-      t1 = -INFINITY; t2 = INFINITY;
-      bool miss = false;
-      for (int k = 0; k < 3; k++) {
-        if (dl[k] == 0.0f) { miss = miss || ol[k] < lo[k] || ol[k] > hi[k]; continue; }
-        const float ta = (lo[k] - ol[k]) / dl[k], tb = (hi[k] - ol[k]) / dl[k];
-        t1 = RT_FMAX(t1, RT_FMIN(ta, tb));
-        t2 = RT_FMIN(t2, RT_FMAX(ta, tb));
-      }
-      if (miss || !(t1 < t2)) continue;
-    }
+    if (!medium_interval(media, m, ro, rd, t1, t2)) continue;
     t1 = RT_FMAX(t1, 0.0f);
     // u in (0, 1]: log(0) cannot occur
     const float u = (float)((word >> 8) + 1u) * (1.0f / 16777216.0f);
-    const float hit_distance = a1.w * logf(u);
+    const float hit_distance = media[4 * m + 1].w * logf(u);
     if (hit_distance > (t2 - t1) * len) continue;
     const float t = t1 + hit_distance / len;
     if (t < h.t) { h.t = t; h.id = RT_PRIM_ID(RT_PRIM_MEDIUM, m); }
@@ -373,7 +378,15 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
     }
   }
   beta = beta * att;
-  r.o = p;
+  V3f o_next = p;
+  if (EXT && (sp.flags & RT_FLAG_REFERENCE_MEDIUM) && RT_PRIM_TYPE_OF(h.id) == RT_PRIM_MEDIUM) {
+    // the reference restarts the scattered ray at the boundary ENTRY point: rec.p = r.at(rec1.t), entry clamped
+    // to the ray's origin (constant_medium.h:56-58,74)
+    float t1 = 0.f, t2 = 0.f;
+    medium_interval(S.media, RT_PRIM_INDEX_OF(h.id), r.o, r.d, t1, t2);
+    o_next = madd(r.o, RT_FMAX(t1, 0.0f), r.d);
+  }
+  r.o = o_next;
   r.d = dir;
   return true;
 }

@@ -14,6 +14,7 @@ RT_PROFILE_NEXT_WEEK = 2
 RT_FLAG_FLIP_NORMALS = 1
 RT_FLAG_DEPTH_BACKGROUND = 2
 RT_FLAG_COUNTERS = 4
+RT_FLAG_REFERENCE_MEDIUM = 8
 
 RT_PRIM_SPHERE, RT_PRIM_TRIANGLE, RT_PRIM_QUAD, RT_PRIM_MEDIUM = 0, 1, 2, 3
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 0, 1, 2, 3, 4

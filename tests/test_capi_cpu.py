@@ -81,3 +81,23 @@ def test_graft_entry_build_runs():
     """the driver's "does it build" entry point (kept in step with the ABI version)"""
     import __graft_entry__ as g
     g.build()
+
+
+def test_scene_size_limit_is_rejected_not_wrapped():
+    """Node links and strides are signed 32-bit byte offsets (8 orderings x 2n nodes x 32 B): a scene past
+    RT_MAX_PRIMS must be refused with RT_ERR_INVALID at flatten time, not wrap around. The count is
+    checked before any array is read, so a lying count with a tiny array is enough to exercise it - through the
+    host build of the very same flatten_scene() (tests/emu)."""
+    from a_dive_into_ray_tracing_b200 import scenes
+    from tests.emu import pyemu
+    pyemu.build()
+    L = C.CDLL(pyemu.PATH)
+    L.emu_create.restype = C.c_void_p
+    L.emu_create.argtypes = [C.POINTER(D.RtSceneDesc), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, C.c_char_p,
+                             C.c_int]
+    sc = scenes.weekend(64, 36)
+    d = sc.desc()
+    err = C.create_string_buffer(256)
+    d.n_spheres = (1 << 22)  # > RT_MAX_PRIMS = 2^22 - 1
+    assert not L.emu_create(C.byref(d), 0, 1, 0.3, 3, 0, 4, err, 256)
+    assert b"too many primitives" in err.value, err.value

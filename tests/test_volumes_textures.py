@@ -272,3 +272,59 @@ def test_reference_medium_semantics_depend_on_object_order(l1_64):
     assert abs(s.mean() / spp - want) < 4 * se + 2e-3, s.mean() / spp
     r, _, _ = l1_64.render_parallel(sc2, 2, W, H, spp, seed=9)
     assert abs(r.mean() / spp - want) < 4 * se + 2e-3, r.mean() / spp
+
+
+def _reference_medium_scene(W, H, flags):
+    """a dense, bright scattering ball lit by a white sky over a dark floor: where the scattered ray restarts
+    (scatter point vs boundary entry point) changes how much light leaves the ball on which side"""
+    mats = np.array([_mat(D.RT_MAT_ISOTROPIC, (0.95, 0.9, 0.8)), _mat(D.RT_MAT_LAMBERTIAN, (0.1, 0.1, 0.1))], D.MATERIAL_DT)
+    sc = D.Scene(quads=np.array([_quad(1, -20, 20, -20, 20, -1.2, 1)], D.QUAD_DT), materials=mats,
+                 media=np.array([_medium_sphere((0, 0, 0), 1.0, 2.5, 0)], D.MEDIUM_DT), profile=D.RT_PROFILE_NEXT_WEEK,
+                 background=(1, 1, 1), sky_gradient=0, max_depth=50, flags=flags)
+    sc.camera = D.camera_from_lookat((0, 0.5, 5), (0, 0, 0), (0, 1, 0), 30.0, W / H, 0.0, 5.0, dtype=np.float32)
+    return sc
+
+
+def test_reference_medium_flag_emulated_device_code_vs_oracle(l1_32):
+    """RT_FLAG_REFERENCE_MEDIUM (constant_medium.h:74, rec.p = r.at(rec1.t)): the device code's flag path against the
+    oracle's (which is pinned to the reference's own constant_medium::hit, tests/test_cuda_ref_pinning.py)."""
+    W, H, spp = 24, 16, 256
+    imgs = {}
+    for flags in (0, D.RT_FLAG_REFERENCE_MEDIUM):
+        sc = _reference_medium_scene(W, H, flags)
+        r, r2, _ = l1_32.render_parallel(sc, 2, W, H, spp, seed=3)
+        s, s2, _ = Emu(sc).render(W, H, spp, seed=11)
+        mu_o, var_o = SU.mean_var(r, r2, spp)
+        mu_e, var_e = SU.mean_var(s, s2, spp)
+        ok, d, b = SU.three_sigma_check(mu_e, var_e, spp, mu_o, var_o, spp)
+        assert ok, (flags, d, b)
+        imgs[flags] = (mu_e, var_e)
+    # the two semantics are different pictures (many sigma apart on the ball), so the flag is observable
+    ball = np.s_[4:12, 8:16]
+    diff = np.abs(imgs[0][0][ball].mean() - imgs[D.RT_FLAG_REFERENCE_MEDIUM][0][ball].mean())
+    se = np.sqrt((imgs[0][1][ball].mean() + imgs[D.RT_FLAG_REFERENCE_MEDIUM][1][ball].mean()) / (spp * 64 * 3))
+    assert diff > 6 * se, (diff, se)
+
+
+@pytest.mark.gpu
+def test_gpu_reference_medium_flag_vs_oracle(l1_32):
+    from a_dive_into_ray_tracing_b200 import capi
+    W, H, spp, K = 48, 32, 256, 8
+    for flags in (0, D.RT_FLAG_REFERENCE_MEDIUM):
+        sc = _reference_medium_scene(W, H, flags)
+        with capi.Context(profile=2, seed=9) as ctx:
+            ctx.upload(sc).build_accel(1)
+            batches = []
+            for k in range(K):
+                ctx.clear()
+                ctx.render(W, H, spp // K, spp_begin=k * (spp // K))
+                a = ctx.accum().astype(np.float64)
+                batches.append(a[..., :3] / a[..., 3:4])
+        mu_a, var_mean_a = SU.batch_variance(batches)
+        r, r2, _ = l1_32.render_parallel(sc, 2, W, H, spp, seed=3)
+        mu_b, var_b = SU.mean_var(r, r2, spp)
+        ok, d, b = SU.three_sigma_check(mu_a, var_mean_a, 1, mu_b, var_b, spp)
+        assert ok, (flags, d, b)
+        dm = np.abs(mu_a.mean() - mu_b.mean())
+        se = np.sqrt(var_mean_a.mean() / (W * H * 3) + var_b.mean() / (spp * W * H * 3))
+        assert dm < 4 * se + 1e-4, (flags, dm, se)
