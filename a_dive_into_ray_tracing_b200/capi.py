@@ -27,7 +27,8 @@ SYMBOLS = ["rt_version", "rt_device_count", "rt_create", "rt_destroy", "rt_last_
            "rt_accel_build", "rt_accel_download", "rt_trace_closest", "rt_render", "rt_render_device", "rt_render_rows_device",
            "rt_accum_clear", "rt_accum_download", "rt_accum_upload", "rt_accum_device_ptr", "rt_resolve",
            "rt_resolve_device", "rt_render_aov", "rt_stats", "rt_stats_reset", "rt_sync", "rt_measure_fp32_peak",
-           "rt_host_alloc", "rt_host_free", "rt_comm_unique_id", "rt_comm_init", "rt_comm_init_all", "rt_reduce"]
+           "rt_host_alloc", "rt_host_free", "rt_comm_unique_id", "rt_comm_init", "rt_comm_init_all", "rt_reduce",
+           "rt_trace_closest_inst", "rt_instances_update"]
 
 RT_REDUCE_UNIFORM_COUNT = 1
 RT_COMM_ID_BYTES = 128
@@ -74,6 +75,10 @@ def load_library():
     L.rt_accel_download.argtypes = [_vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp]
     L.rt_trace_closest.restype = C.c_int
     L.rt_trace_closest.argtypes = [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_int, _vp, _vp]
+    L.rt_trace_closest_inst.restype = C.c_int
+    L.rt_trace_closest_inst.argtypes = [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]
+    L.rt_instances_update.restype = C.c_int
+    L.rt_instances_update.argtypes = [_vp, _vp, C.c_int]
     L.rt_render.restype = C.c_int
     L.rt_render.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int]
     L.rt_render_device.restype = C.c_int
@@ -215,16 +220,31 @@ class Context:
                                             None, big.ctypes.data, len(big), None))
         return nodes[:nn.value], leaf[:nl.value], big[:nb.value]
 
-    def trace_closest(self, rays, t_min=1e-3, t_max=np.inf, use_accel=True):
+    def trace_closest(self, rays, t_min=1e-3, t_max=np.inf, use_accel=True, with_instances=False):
+        """(prim ids, t) of the closest hits; with_instances: (prim ids, instance ids, t) - the instance whose
+        object holds the hit primitive, -1 for world-level primitives and misses."""
         rays = np.ascontiguousarray(rays, np.float32)
         assert rays.ndim == 2 and rays.shape[1] == 8
         n = len(rays)
         ids = np.empty(n, np.int32)
         ts = np.empty(n, np.float32)
         tmax = float("inf") if not np.isfinite(t_max) else float(t_max)
+        if with_instances:
+            inst = np.empty(n, np.int32)
+            self._ck(self.lib.rt_trace_closest_inst(self.h, rays.ctypes.data, n, t_min, tmax, int(use_accel),
+                                                    ids.ctypes.data, inst.ctypes.data, ts.ctypes.data))
+            return ids, inst, ts
         self._ck(self.lib.rt_trace_closest(self.h, rays.ctypes.data, n, t_min, tmax, int(use_accel),
                                            ids.ctypes.data, ts.ctypes.data))
         return ids, ts
+
+    def update_instances(self, instances):
+        """Transform-only update of a two-level scene: rebuilds the top level, keeps the objects' trees."""
+        instances = np.ascontiguousarray(instances)
+        from .ctypes_defs import INSTANCE_DT
+        assert instances.dtype == INSTANCE_DT
+        self._ck(self.lib.rt_instances_update(self.h, instances.ctypes.data if len(instances) else None, len(instances)))
+        return self
 
     def render(self, W, H, spp_count, spp_begin=0):
         self._ck(self.lib.rt_render(self.h, W, H, spp_begin, spp_count))

@@ -35,7 +35,7 @@ __global__ void k_classify(BuildArrays B, int round, float frac) {
 // the only device -> host traffic of the classification step).
 __global__ void k_big_collect(BuildArrays B, int *list) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B.n_prims && B.big_flag[i]) {
+  if (i < B.n_prims && B.big_flag[i] == 1) {
     const int slot = atomicAdd(list, 1);
     if (slot < RT_MAX_BIG) list[1 + slot] = i;
   }
@@ -53,7 +53,7 @@ __global__ void k_small_list(BuildArrays B, BigList bl, int *small_gid, uint8_t 
   bool big = false;
   for (int k = 0; k < bl.n; k++) { before += bl.gid[k] < i ? 1 : 0; big = big || bl.gid[k] == i; }
   if (i < B.n_spheres) sph_is_big[i] = big ? 1 : 0;
-  if (!big) small_gid[i - before] = i;
+  if (!big && small_gid) small_gid[i - before] = i;
 }
 __global__ void k_morton(BuildArrays B, int final_round) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,6 +185,22 @@ struct DevBuf {
   size_t bytes = 0;
 };
 
+// One build unit = one tree: the whole scene, the top level of an instanced scene (world primitives + instances)
+// or one group (an object in its own space). All units share the builder kernels, the grow-only temporaries of the
+// context and the packed node / leaf_prims arrays, where each unit owns a slot.
+struct BuildUnit {
+  int first[3] = {0, 0, 0}, count[3] = {0, 0, 0}; // sub-ranges of the scene's sphere / triangle / quad arrays
+  int n_inst = 0;                     // instances (top level only): builder gids after the geometry
+  const uint8_t *d_exclude = nullptr; // top level of an instanced scene: geometry owned by a group (device / host copy)
+  const uint8_t *h_exclude = nullptr;
+  bool classify = true;               // split oversized primitives off into the always-tested lists
+  int link_base = 0, leaf_base = 0, end_link = -1;
+  int stride_nodes = -1;              // nodes per ordering of the packed array; -1: this unit alone (2 n_small - 1)
+  // results
+  int n_small = 0, n_big = 0, kept_nodes = 0;
+  float root_box[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
 struct rt_ctx {
   rt_config cfg;
   std::string err;
@@ -219,6 +235,17 @@ struct rt_ctx {
   DevCamera cam;
   ShadeParams sp;
   std::vector<int32_t> big_ids;
+  // two-level scenes (rt_group / rt_instance)
+  bool two_level = false;
+  std::vector<rt_group> groups;
+  std::vector<rt_instance> instances;
+  std::vector<uint8_t> grouped;      // per primitive (spheres, triangles, quads): owned by a group
+  std::vector<BuildUnit> group_units; // layout + root box of every group's tree
+  BuildUnit top_unit;
+  std::vector<int> group_root_off, h_small;
+  std::vector<float4> h_inst_rec, h_inst_box;
+  DevBuf d_exclude, d_inst_lo, d_inst_hi, d_inst_ids; // d_exclude: a view into d_scene
+  int total_nodes = 0, build_quality = 1;
   int n_leaf_prims = 0, max_leaf = 1;
   float root_box[8] = {0, 0, 0, 0, 0, 0, 0, 0}; // {bmin.xyz, -, bmax.xyz, -} of the BVH root
   // frame
@@ -382,7 +409,8 @@ void rt_destroy(rt_ctx *ctx) {
   // d_raw_* are views into d_scene
   if (ctx->comm) nccl_comm_destroy(ctx->comm);
   DevBuf *all[] = {&ctx->d_red, &ctx->d_scene, &ctx->d_nodes, &ctx->d_big, &ctx->d_leaf_prims, &ctx->d_bigq, &ctx->d_sph_is_big, &ctx->d_accum,
-                   &ctx->d_partial, &ctx->d_counter, &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts};
+                   &ctx->d_partial, &ctx->d_counter, &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts,
+                   &ctx->d_inst_lo, &ctx->d_inst_hi, &ctx->d_inst_ids};
   for (DevBuf *b : all) dev_free(*b);
   for (DevBuf &b : ctx->build_tmp) dev_free(b);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -450,6 +478,8 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
                i_img = ADD(F.image_bytes);
   std::vector<DevImage> dimg((size_t)sc->n_images);
   const size_t i_images = ADD(dimg); // filled below, once the arena's address is known
+  std::vector<rt_group> groups_copy(sc->groups, sc->groups + sc->n_groups);
+  const size_t i_inst = ADD(F.inst), i_excl = ADD(F.grouped), i_groups = ADD(groups_copy);
 #undef ADD
   if ((rc = dev_reserve(ctx, ctx->d_scene, total))) return rc;
   if ((rc = host_reserve(ctx, ctx->h_stage, ctx->h_stage_bytes, total))) return rc;
@@ -494,6 +524,16 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   S.perlin_perm = (const uint8_t *)(ds + slots[i_pperm].off);
   S.images = (const DevImage *)(ds + slots[i_images].off);
   S.n_media = sc->n_media; S.n_perlin = sc->n_perlin; S.n_images = sc->n_images;
+  S.inst = (const float4 *)(ds + slots[i_inst].off);
+  S.n_inst = sc->n_instances;
+  S.groups = (const int32_t *)(ds + slots[i_groups].off);
+  ctx->d_exclude.p = ds + slots[i_excl].off; // (a view into the arena, like d_raw_*: never freed on its own)
+  ctx->two_level = sc->n_groups > 0 || sc->n_instances > 0;
+  ctx->groups.assign(sc->groups, sc->groups + sc->n_groups);
+  ctx->instances.assign(sc->instances, sc->instances + sc->n_instances);
+  ctx->grouped = F.grouped;
+  ctx->group_units.clear();
+
   S.bigq = (const float4 *)ctx->d_bigq.p;
   S.n_nodes = 0; S.n_big = 0; S.n_bigq = 0;
   S.n_spheres = ns; S.n_tris = nt; S.n_quads = nq; S.n_mats = nm;
@@ -525,26 +565,24 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   return RT_OK;
 }
 
-int rt_accel_build(rt_ctx *ctx, int quality) {
-  if (!ctx) return RT_ERR_INVALID;
-  if (!ctx->have_scene) return fail(ctx, RT_ERR_STATE, "rt_accel_build before rt_scene_upload");
-  CK(cudaSetDevice(ctx->cfg.device));
+static int build_unit(rt_ctx *ctx, BuildUnit &U, int quality) {
   cudaStream_t st = ctx->stream;
-  const int ns = ctx->S.n_spheres, nt = ctx->S.n_tris, nq = ctx->S.n_quads;
-  const int n = ns + nt + nq;
-  ctx->big_ids.clear();
-  ctx->S.n_nodes = 0; ctx->S.n_big = 0; ctx->S.n_bigq = 0; ctx->n_leaf_prims = 0;
-  ctx->stats.n_nodes = 0; ctx->stats.n_big_prims = 0;
-  memset(ctx->root_box, 0, sizeof ctx->root_box);
-  if (n == 0) { ctx->have_accel = true; ctx->stats.ms_build = 0; return RT_OK; }
-  CK(cudaEventRecord(ctx->ev0, st));
+  const int ns = U.count[0], nt = U.count[1], nq = U.count[2];
+  const int n_geom = ns + nt + nq, n = n_geom + U.n_inst;
+  U.n_small = 0; U.n_big = 0; U.kept_nodes = 0;
+  memset(U.root_box, 0, sizeof U.root_box);
+  if (n == 0) return RT_OK;
 
   BuildArrays B;
   memset(&B, 0, sizeof B);
-  B.n_prims = n; B.n_spheres = ns; B.n_tris = nt; B.n_quads = nq;
-  B.spheres = (const rt_sphere *)ctx->d_raw_sph.p;
-  B.tris = (const rt_triangle *)ctx->d_raw_tri.p;
-  B.quads = (const rt_quad *)ctx->d_raw_quad.p;
+  B.n_prims = n; B.n_spheres = ns; B.n_tris = nt; B.n_quads = nq; B.n_inst = U.n_inst;
+  B.spheres = (const rt_sphere *)ctx->d_raw_sph.p + U.first[0];
+  B.tris = (const rt_triangle *)ctx->d_raw_tri.p + U.first[1];
+  B.quads = (const rt_quad *)ctx->d_raw_quad.p + U.first[2];
+  for (int k = 0; k < 3; k++) B.id_base[k] = U.first[k];
+  B.inst_lo = (const float4 *)ctx->d_inst_lo.p; B.inst_hi = (const float4 *)ctx->d_inst_hi.p;
+  B.exclude = U.d_exclude;
+  B.link_base = U.link_base; B.leaf_base = U.leaf_base; B.end_link = U.end_link;
   B.thickness = (ctx->sp.flags & RT_FLAG_FLIP_NORMALS) ? 0.01f : 0.1f; // THICKNESS of the two trees
   // Build temporaries live in the context and only ever grow: a rebuild (every frame of an animated or
   // re-uploaded scene) calls neither cudaMalloc nor cudaFree, which would synchronise the device.
@@ -556,7 +594,6 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
 #define RSV(buf, bytes) do { if ((rc = dev_reserve(ctx, buf, (bytes)))) return rc; } while (0)
   RSV(T[T_LO], sizeof(float4) * (size_t)n); RSV(T[T_HI], sizeof(float4) * (size_t)n); RSV(T[T_FLAG], sizeof(int) * (size_t)n);
   RSV(T[T_BOUNDS], sizeof(BuildBounds) * 4); RSV(T[T_BIGLIST], sizeof(int) * (RT_MAX_BIG + 1));
-  RSV(ctx->d_sph_is_big, (size_t)std::max(ns, 1));
   if ((rc = pin_reserve(ctx, 4096))) return rc;
   B.pbox_lo = (float4 *)T[T_LO].p; B.pbox_hi = (float4 *)T[T_HI].p; B.big_flag = (int *)T[T_FLAG].p;
   B.bounds = (BuildBounds *)T[T_BOUNDS].p;
@@ -571,29 +608,32 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
   const int TB = 256;
   const int gp = (n + TB - 1) / TB;
   k_prim_box<<<gp, TB, 0, st>>>(B);
-  for (int r = 0; r < RT_BIG_ROUNDS; r++) k_classify<<<gp, TB, 0, st>>>(B, r, RT_BIG_FRAC);
-  k_big_collect<<<gp, TB, 0, st>>>(B, (int *)T[T_BIGLIST].p);
-  ctx->launches += 2 + RT_BIG_ROUNDS;
-  CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(h_words, T[T_BIGLIST].p, sizeof(int) * (RT_MAX_BIG + 1), cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st)); // host round trip 1 of 2: how many primitives stay in the tree sizes every later launch
+  ctx->launches++;
   BigList bl;
   memset(&bl, 0, sizeof bl);
-  int final_round = RT_BIG_ROUNDS;
-  if (h_words[0] > RT_MAX_BIG) { // degenerate classification: keep everything in the tree
-    final_round = 0;
-  } else {
-    bl.n = h_words[0];
-    std::copy(h_words + 1, h_words + 1 + bl.n, bl.gid);
-    std::sort(bl.gid, bl.gid + bl.n);
-  }
-  const int n_big = bl.n, nsm = n - n_big;
-  for (int k = 0; k < n_big; k++) {
-    const int i = bl.gid[k];
-    ctx->big_ids.push_back(i < ns ? RT_PRIM_ID(RT_PRIM_SPHERE, i)
-                                  : (i < ns + nt ? RT_PRIM_ID(RT_PRIM_TRIANGLE, i - ns) : RT_PRIM_ID(RT_PRIM_QUAD, i - ns - nt)));
-  }
-  {
+  int final_round = 0;
+  if (U.classify) {
+    for (int r = 0; r < RT_BIG_ROUNDS; r++) k_classify<<<gp, TB, 0, st>>>(B, r, RT_BIG_FRAC);
+    k_big_collect<<<gp, TB, 0, st>>>(B, (int *)T[T_BIGLIST].p);
+    ctx->launches += 1 + RT_BIG_ROUNDS;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_words, T[T_BIGLIST].p, sizeof(int) * (RT_MAX_BIG + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); // host round trip 1 of 2: how many primitives stay in the tree sizes every later launch
+    final_round = RT_BIG_ROUNDS;
+    if (h_words[0] > RT_MAX_BIG) { // degenerate classification: keep everything in the tree
+      final_round = 0;
+    } else {
+      bl.n = h_words[0];
+      std::copy(h_words + 1, h_words + 1 + bl.n, bl.gid);
+      std::sort(bl.gid, bl.gid + bl.n);
+    }
+    ctx->big_ids.clear();
+    for (int k = 0; k < bl.n; k++) {
+      const int i = bl.gid[k];
+      ctx->big_ids.push_back(i < ns ? RT_PRIM_ID(RT_PRIM_SPHERE, U.first[0] + i)
+                                    : (i < ns + nt ? RT_PRIM_ID(RT_PRIM_TRIANGLE, U.first[1] + i - ns)
+                                                   : RT_PRIM_ID(RT_PRIM_QUAD, U.first[2] + i - ns - nt)));
+    }
     // rects go to their own decoded list (no id fetch / type dispatch in the segment start)
     std::vector<int32_t> others;
     std::vector<float4> bigq;
@@ -605,11 +645,10 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     }
     const int n_bigq = (int)bigq.size() / 2;
     // both lists through ONE pinned block and one copy each (zero padded to the reserved size)
-    unsigned char *hb = (unsigned char *)ctx->h_pin + 1024;
     const size_t big_bytes = pad16(std::max<size_t>(others.size(), 4) * sizeof(int32_t));
     const size_t bigq_bytes = std::max<size_t>(bigq.size(), 2) * sizeof(float4);
     if ((rc = pin_reserve(ctx, 1024 + big_bytes + bigq_bytes))) return rc;
-    hb = (unsigned char *)ctx->h_pin + 1024;
+    unsigned char *hb = (unsigned char *)ctx->h_pin + 1024;
     h_words = (int *)ctx->h_pin;
     memset(hb, 0, big_bytes + bigq_bytes);
     if (!others.empty()) memcpy(hb, others.data(), others.size() * sizeof(int32_t));
@@ -622,10 +661,31 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     ctx->S.bigq = (const float4 *)ctx->d_bigq.p;
     ctx->S.n_bigq = n_bigq;
   }
-  int n_nodes = nsm > 0 ? 2 * nsm - 1 : 0;
-  RSV(T[T_SMALL], sizeof(int) * (size_t)std::max(nsm, 1));
-  k_small_list<<<gp, TB, 0, st>>>(B, bl, (int *)T[T_SMALL].p, (uint8_t *)ctx->d_sph_is_big.p);
+  const int n_big = bl.n;
+  U.n_big = n_big;
+  // the primitives that stay in the tree, ascending
+  int nsm;
+  if (U.h_exclude) { // the top level of an instanced scene: the host knows which primitives the groups own
+    std::vector<int> &small = ctx->h_small;
+    small.clear();
+    int kb = 0;
+    for (int i = 0; i < n; i++) {
+      while (kb < bl.n && bl.gid[kb] < i) kb++;
+      if ((kb < bl.n && bl.gid[kb] == i) || (i < n_geom && U.h_exclude[i])) continue;
+      small.push_back(i);
+    }
+    nsm = (int)small.size();
+    RSV(T[T_SMALL], sizeof(int) * (size_t)std::max(nsm, 1));
+    if (nsm) CK(cudaMemcpyAsync(T[T_SMALL].p, small.data(), sizeof(int) * (size_t)nsm, cudaMemcpyHostToDevice, st));
+    k_small_list<<<gp, TB, 0, st>>>(B, bl, nullptr, (uint8_t *)ctx->d_sph_is_big.p + U.first[0]);
+  } else {
+    nsm = n - n_big;
+    RSV(T[T_SMALL], sizeof(int) * (size_t)std::max(nsm, 1));
+    k_small_list<<<gp, TB, 0, st>>>(B, bl, (int *)T[T_SMALL].p, (uint8_t *)ctx->d_sph_is_big.p + U.first[0]);
+  }
   ctx->launches++;
+  U.n_small = nsm;
+  int n_nodes = nsm > 0 ? 2 * nsm - 1 : 0;
   if (nsm > 0) {
     int n_pad = 1;
     while (n_pad < nsm) n_pad <<= 1;
@@ -636,22 +696,26 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     RSV(T[T_PARENT], sizeof(int) * (size_t)n_nodes); RSV(T[T_NFLAG], sizeof(int) * (size_t)nsm);
     RSV(T[T_SIZE], sizeof(int) * (size_t)n_nodes); RSV(T[T_LCNT], sizeof(int) * (size_t)n_nodes);
     RSV(T[T_SWAP], sizeof(int) * (size_t)nsm);
-    RSV(ctx->d_leaf_prims, sizeof(int32_t) * (size_t)nsm);
     RSV(T[T_NLO], sizeof(float4) * (size_t)n_nodes); RSV(T[T_NHI], sizeof(float4) * (size_t)n_nodes);
-    // eight packed copies, one per ray-direction octant (own front-to-back visiting order)
-    RSV(ctx->d_nodes, RT_N_ORDERINGS * sizeof(float4) * 2 * (size_t)n_nodes);
+    const int stride_nodes = U.stride_nodes >= 0 ? U.stride_nodes : n_nodes;
+    if (U.stride_nodes < 0) { // a single-level scene: the arrays are exactly this unit's (multi-unit scenes reserve them up front)
+      RSV(ctx->d_leaf_prims, sizeof(int32_t) * (size_t)nsm);
+      // eight packed copies, one per ray-direction octant (own front-to-back visiting order)
+      RSV(ctx->d_nodes, RT_N_ORDERINGS * sizeof(float4) * 2 * (size_t)n_nodes);
+    }
     B.small_gid = (const int *)T[T_SMALL].p;
     B.keys = (unsigned long long *)T[T_KEYS].p;
     B.left = (int *)T[T_LEFT].p; B.right = (int *)T[T_RIGHT].p; B.parent = (int *)T[T_PARENT].p;
     B.flag = (int *)T[T_NFLAG].p; B.size = (int *)T[T_SIZE].p; B.lcnt = (int *)T[T_LCNT].p;
     B.leaf_prims = (int32_t *)ctx->d_leaf_prims.p;
     B.swapmask = (int *)T[T_SWAP].p;
-    B.packed_stride = 2 * n_nodes;
+    B.packed_stride = 2 * stride_nodes;
     {
       const char *e = getenv("B200RT_MAX_LEAF"); // tuning knob (leaf size)
       int ml = e ? atoi(e) : 1; // while-while traversal: single-primitive leaves measured fastest
       B.max_leaf = ml < 1 ? 1 : (ml > 8 ? 8 : ml);
-      ctx->max_leaf = B.max_leaf;
+      if (U.n_inst) B.max_leaf = 1; // an instance leaf holds exactly one instance (the traversal enters it)
+      ctx->max_leaf = std::max(ctx->max_leaf, B.max_leaf);
     }
     B.nbox_lo = (float4 *)T[T_NLO].p; B.nbox_hi = (float4 *)T[T_NHI].p;
     B.packed = (float4 *)ctx->d_nodes.p;
@@ -715,26 +779,179 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     ctx->launches += 2;
     CK(cudaGetLastError());
     // nodes that survive leaf collapsing = kept size of the root (build node 0); the root's box (record 0 of every
-    // ordering) = the frame of the render kernel's 16-bit quantised nodes
+    // ordering) = the frame of the render kernel's 16-bit quantised nodes / the object box of a group
     CK(cudaMemcpyAsync(h_words + 40, B.size, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_words + 48, ctx->d_nodes.p, sizeof ctx->root_box, cudaMemcpyDeviceToHost, st));
-  }
-  CK(cudaEventRecord(ctx->ev1, st));
-  CK(cudaStreamSynchronize(st)); // host round trip 2 of 2
-  CK(cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev0, ctx->ev1));
-  if (nsm > 0) {
-    n_nodes = h_words[40];
-    memcpy(ctx->root_box, h_words + 48, sizeof ctx->root_box);
+    CK(cudaMemcpyAsync(h_words + 48, (const char *)ctx->d_nodes.p + 32 * (size_t)U.link_base, sizeof U.root_box,
+                       cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st)); // host round trip 2 of 2
+    U.kept_nodes = h_words[40];
+    memcpy(U.root_box, h_words + 48, sizeof U.root_box);
   }
 #undef RSV
+  return RT_OK;
+}
+
+// World box of every instance from its group's root box (object space): the eight corners through M in double,
+// rounded outwards.
+static int upload_instance_boxes(rt_ctx *ctx) {
+  const int ni = (int)ctx->instances.size();
+  int rc;
+  if ((rc = dev_reserve(ctx, ctx->d_inst_lo, sizeof(float4) * (size_t)std::max(ni, 1)))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_inst_hi, sizeof(float4) * (size_t)std::max(ni, 1)))) return rc;
+  ctx->h_inst_box.assign(2 * (size_t)ni, make_float4(0, 0, 0, 0));
+  for (int i = 0; i < ni; i++) {
+    const rt_instance &I = ctx->instances[i];
+    const float *rb = ctx->group_units[I.group].root_box;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int c = 0; c < 8; c++) {
+      const double p[3] = {(c & 1) ? rb[4] : rb[0], (c & 2) ? rb[5] : rb[1], (c & 4) ? rb[6] : rb[2]};
+      for (int a = 0; a < 3; a++) {
+        const double w = (double)I.m[4 * a] * p[0] + (double)I.m[4 * a + 1] * p[1] + (double)I.m[4 * a + 2] * p[2] + (double)I.m[4 * a + 3];
+        lo[a] = std::min(lo[a], w); hi[a] = std::max(hi[a], w);
+      }
+    }
+    float l[3], h[3];
+    for (int a = 0; a < 3; a++) {
+      // the object-space ray is rounded when it is transformed: pad by a few ulps of the box's reach
+      const double e = 4e-7 * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-9;
+      l[a] = nextafterf((float)(lo[a] - e), -INFINITY);
+      h[a] = nextafterf((float)(hi[a] + e), INFINITY);
+    }
+    ctx->h_inst_box[i] = make_float4(l[0], l[1], l[2], 0.f);
+    ctx->h_inst_box[ni + i] = make_float4(h[0], h[1], h[2], 0.f);
+  }
+  if (ni) {
+    CK(cudaMemcpyAsync(ctx->d_inst_lo.p, ctx->h_inst_box.data(), sizeof(float4) * (size_t)ni, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_inst_hi.p, ctx->h_inst_box.data() + ni, sizeof(float4) * (size_t)ni, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return RT_OK;
+}
+
+// The top level of an instanced scene: one tree over (world primitives, instances); its slot is the head of the
+// packed array, sized for the worst case, so the groups' trees behind it never move.
+static int build_top_level(rt_ctx *ctx, int quality) {
+  int rc;
+  if ((rc = upload_instance_boxes(ctx))) return rc;
+  BuildUnit &U = ctx->top_unit;
+  U = BuildUnit();
+  U.count[0] = ctx->S.n_spheres; U.count[1] = ctx->S.n_tris; U.count[2] = ctx->S.n_quads;
+  U.n_inst = (int)ctx->instances.size();
+  U.d_exclude = (const uint8_t *)ctx->d_exclude.p;
+  U.h_exclude = ctx->grouped.data();
+  U.classify = true;
+  U.link_base = 0; U.leaf_base = 0;
+  U.stride_nodes = ctx->total_nodes;
+  U.end_link = ctx->total_nodes << RT_NODE_SHIFT;
+  if ((rc = build_unit(ctx, U, quality))) return rc;
+  memcpy(ctx->root_box, U.root_box, sizeof ctx->root_box);
+  // no top-level tree at all (nothing but always-tested primitives): nothing to traverse
+  ctx->S.n_nodes = U.n_small > 0 ? ctx->total_nodes : 0;
+  ctx->stats.n_nodes = U.kept_nodes;
+  for (const BuildUnit &G : ctx->group_units) ctx->stats.n_nodes += G.kept_nodes;
+  ctx->stats.n_big_prims = U.n_big;
+  return RT_OK;
+}
+
+int rt_accel_build(rt_ctx *ctx, int quality) {
+  if (!ctx) return RT_ERR_INVALID;
+  if (!ctx->have_scene) return fail(ctx, RT_ERR_STATE, "rt_accel_build before rt_scene_upload");
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = ctx->stream;
+  const int ns = ctx->S.n_spheres, nt = ctx->S.n_tris, nq = ctx->S.n_quads;
+  const int n = ns + nt + nq;
+  ctx->big_ids.clear();
+  ctx->S.n_nodes = 0; ctx->S.n_big = 0; ctx->S.n_bigq = 0; ctx->n_leaf_prims = 0;
+  ctx->stats.n_nodes = 0; ctx->stats.n_big_prims = 0;
+  ctx->max_leaf = 1;
+  ctx->build_quality = quality;
+  memset(ctx->root_box, 0, sizeof ctx->root_box);
+  if (n == 0) { ctx->have_accel = true; ctx->stats.ms_build = 0; return RT_OK; }
+  CK(cudaEventRecord(ctx->ev0, st));
+  int rc;
+  if ((rc = dev_reserve(ctx, ctx->d_sph_is_big, (size_t)std::max(ns, 1)))) return rc;
+  CK(cudaMemsetAsync(ctx->d_sph_is_big.p, 0, (size_t)std::max(ns, 1), st));
+  if (!ctx->two_level) {
+    BuildUnit U;
+    U.count[0] = ns; U.count[1] = nt; U.count[2] = nq;
+    if ((rc = build_unit(ctx, U, quality))) return rc;
+    memcpy(ctx->root_box, U.root_box, sizeof ctx->root_box);
+    ctx->n_leaf_prims = U.n_small;
+    ctx->S.n_nodes = U.kept_nodes;
+    ctx->S.node_stride = U.n_small > 0 ? (2 * U.n_small - 1) * 32 : 0;
+    ctx->stats.n_nodes = U.kept_nodes;
+    ctx->stats.n_big_prims = U.n_big;
+  } else {
+    // layout of the packed arrays: [top level: worst case 2 (world + instances) - 1 nodes][group 0][group 1]...
+    const int ng = (int)ctx->groups.size(), ni = (int)ctx->instances.size();
+    int n_world = 0;
+    for (int i = 0; i < n; i++) n_world += ctx->grouped[i] ? 0 : 1;
+    const int top_leaves = n_world + ni;
+    int node_at = std::max(2 * top_leaves - 1, 1), leaf_at = std::max(top_leaves, 1);
+    ctx->group_units.assign(ng, BuildUnit());
+    for (int g = 0; g < ng; g++) {
+      const rt_group &G = ctx->groups[g];
+      BuildUnit &U = ctx->group_units[g];
+      U.first[0] = G.first_sphere; U.count[0] = G.n_spheres;
+      U.first[1] = G.first_triangle; U.count[1] = G.n_triangles;
+      U.first[2] = G.first_quad; U.count[2] = G.n_quads;
+      U.classify = false;
+      U.link_base = node_at; U.leaf_base = leaf_at;
+      const int m = G.n_spheres + G.n_triangles + G.n_quads;
+      node_at += std::max(2 * m - 1, 0);
+      leaf_at += m;
+    }
+    ctx->total_nodes = node_at;
+    if ((long long)node_at * 32 * RT_N_ORDERINGS >= (1ll << 31))
+      return fail(ctx, RT_ERR_INVALID, "two-level scene too large for 32-bit node offsets");
+    if ((rc = dev_reserve(ctx, ctx->d_nodes, RT_N_ORDERINGS * sizeof(float4) * 2 * (size_t)node_at))) return rc;
+    if ((rc = dev_reserve(ctx, ctx->d_leaf_prims, sizeof(int32_t) * (size_t)leaf_at))) return rc;
+    ctx->n_leaf_prims = leaf_at;
+    std::vector<int> root_off(ng, 0);
+    for (int g = 0; g < ng; g++) {
+      BuildUnit &U = ctx->group_units[g];
+      U.stride_nodes = node_at;
+      U.end_link = RT_POP_LINK(node_at);
+      if ((rc = build_unit(ctx, U, quality))) return rc;
+      root_off[g] = U.link_base << RT_NODE_SHIFT;
+    }
+    ctx->group_root_off = root_off;
+    // instance records with the groups' root offsets
+    std::vector<float4> rec;
+    if ((rc = make_instance_records(ctx->instances.data(), ni, ng, root_off.data(), rec, ctx->err))) return rc;
+    ctx->h_inst_rec = rec;
+    if (ni) CK(cudaMemcpyAsync((void *)ctx->S.inst, ctx->h_inst_rec.data(), sizeof(float4) * 4 * (size_t)ni, cudaMemcpyHostToDevice, st));
+    ctx->S.node_stride = node_at * 32;
+    if ((rc = build_top_level(ctx, quality))) return rc;
+  }
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev0, ctx->ev1));
   ctx->S.nodes = (const float4 *)ctx->d_nodes.p;
   ctx->S.leaf_prims = (const int32_t *)ctx->d_leaf_prims.p;
-  ctx->n_leaf_prims = nsm;
-  ctx->S.n_nodes = n_nodes;
-  ctx->S.node_stride = nsm > 0 ? (2 * nsm - 1) * 32 : 0;
-  ctx->stats.n_nodes = n_nodes;
-  ctx->stats.n_big_prims = n_big;
   ctx->have_accel = true;
+  return RT_OK;
+}
+
+int rt_instances_update(rt_ctx *ctx, const rt_instance *instances, int n) {
+  if (!ctx || (n && !instances)) return RT_ERR_INVALID;
+  if (!ctx->have_accel || !ctx->two_level) return fail(ctx, RT_ERR_STATE, "rt_instances_update needs a built two-level scene");
+  if (n != (int)ctx->instances.size()) return fail(ctx, RT_ERR_INVALID, "rt_instances_update: %d instances, the scene has %d", n, (int)ctx->instances.size());
+  for (int i = 0; i < n; i++)
+    if (instances[i].group != ctx->instances[i].group) return fail(ctx, RT_ERR_INVALID, "rt_instances_update: instance %d changes its group", i);
+  CK(cudaSetDevice(ctx->cfg.device));
+  cudaStream_t st = ctx->stream;
+  std::vector<float4> rec;
+  int rc;
+  if ((rc = make_instance_records(instances, n, (int)ctx->groups.size(), ctx->group_root_off.data(), rec, ctx->err))) return rc;
+  CK(cudaEventRecord(ctx->ev0, st));
+  ctx->instances.assign(instances, instances + n);
+  ctx->h_inst_rec = rec;
+  if (n) CK(cudaMemcpyAsync((void *)ctx->S.inst, ctx->h_inst_rec.data(), sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  ctx->S.n_big = 0; ctx->S.n_bigq = 0;
+  if ((rc = build_top_level(ctx, ctx->build_quality))) return rc;
+  CK(cudaEventRecord(ctx->ev1, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaEventElapsedTime(&ctx->stats.ms_build, ctx->ev0, ctx->ev1));
   return RT_OK;
 }
 
@@ -770,8 +987,8 @@ int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nod
 
 static int trace_through_render_kernel(rt_ctx *ctx, int n, float t_min, float t_max, cudaStream_t st);
 
-int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *prim_id,
-                     float *t) {
+static int trace_closest_impl(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *prim_id,
+                              int32_t *inst_id, float *t) {
   if (!ctx || n < 0 || (n && (!rays || !prim_id || !t))) return RT_ERR_INVALID;
   if (!ctx->have_scene) return fail(ctx, RT_ERR_STATE, "rt_trace_closest before rt_scene_upload");
   if (use_accel && !ctx->have_accel) return fail(ctx, RT_ERR_STATE, "use_accel=1 before rt_accel_build");
@@ -781,6 +998,7 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
   if ((rc = dev_reserve(ctx, ctx->d_rays, sizeof(float) * 8 * (size_t)n))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_ids, sizeof(int32_t) * (size_t)n))) return rc;
   if ((rc = dev_reserve(ctx, ctx->d_ts, sizeof(float) * (size_t)n))) return rc;
+  if ((rc = dev_reserve(ctx, ctx->d_inst_ids, sizeof(int32_t) * (size_t)n))) return rc;
   cudaStream_t st = ctx->stream;
   CK(cudaMemcpyAsync(ctx->d_rays.p, rays, sizeof(float) * 8 * (size_t)n, cudaMemcpyHostToDevice, st));
   DevScene S = ctx->S;
@@ -788,10 +1006,13 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
   const int TB = 128, g = (n + TB - 1) / TB;
   const uint8_t *isbig = (const uint8_t *)ctx->d_sph_is_big.p;
   const float4 *dr = (const float4 *)ctx->d_rays.p;
-  int32_t *di = (int32_t *)ctx->d_ids.p;
+  int32_t *di = (int32_t *)ctx->d_ids.p, *dn = (int32_t *)ctx->d_inst_ids.p;
   float *dt = (float *)ctx->d_ts.p;
+  if (!ctx->two_level) CK(cudaMemsetAsync(dn, 0xff, sizeof(int32_t) * (size_t)n, st)); // every hit is a world-level primitive
   if (use_accel == 2) { // through k_render's own scheduler and traversal (TRACE instantiation)
     if ((rc = trace_through_render_kernel(ctx, n, t_min, t_max, st))) return rc;
+  } else if (ctx->two_level) {
+    k_trace_closest<2, true, true><<<g, TB, 0, st>>>(S, isbig, dr, n, t_min, t_max, use_accel, di, dt, (const uint8_t *)ctx->d_exclude.p, dn);
   } else
   switch (ctx->cfg.profile) {
   case 0: k_trace_closest<0, false><<<g, TB, 0, st>>>(S, isbig, dr, n, t_min, t_max, use_accel, di, dt); break;
@@ -802,13 +1023,28 @@ int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(prim_id, di, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(t, dt, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+  if (inst_id) CK(cudaMemcpyAsync(inst_id, dn, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
   return RT_OK;
 }
 
+int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *prim_id,
+                     float *t) {
+  return trace_closest_impl(ctx, rays, n, t_min, t_max, use_accel, prim_id, nullptr, t);
+}
+
+int rt_trace_closest_inst(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *prim_id,
+                          int32_t *inst_id, float *t) {
+  return trace_closest_impl(ctx, rays, n, t_min, t_max, use_accel, prim_id, inst_id, t);
+}
+
 // ------------------------------------------------------------------ render
 typedef void (*render_kernel_t)(const RenderParams);
-static render_kernel_t pick_render_kernel(int profile, int smem, bool count, bool ext) {
+static render_kernel_t pick_render_kernel(int profile, int smem, bool count, bool ext, bool inst) {
+  if (inst) { // two-level scenes: general kernel, global-memory plan (plan_scene_residency)
+    if (ext) return count ? k_render<2, true, 0, true, true, false, true> : k_render<2, true, 0, false, true, false, true>;
+    return count ? k_render<2, true, 0, true, false, false, true> : k_render<2, true, 0, false, false, false, true>;
+  }
 #define PICK3(P, G, C, E) \
   (smem == 2 ? k_render<P, G, 2, C, E>                                                                  \
              : (smem == 1 ? k_render<P, G, 1, C, E> : (smem == 3 ? k_render<P, G, 3, C, E> : k_render<P, G, 0, C, E>)))
@@ -869,6 +1105,9 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
   if (scene_bytes + (RT_N_ORDERINGS - 1) * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
   // nodes only: one node copy resident, primitives through L1/L2
   if (smem == 0 && (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin && S.n_nodes > 0) smem = 3;
+  // two-level scenes: the objects' trees live in their own spaces (one quantisation frame per object would be
+  // needed for the 16-bit shared-memory records): everything through L1/L2
+  if (ctx->two_level) smem = 0;
   if (const char *e = getenv("B200RT_SMEM")) { // tuning knob: cap the plan (3 ranks between 0 and 1)
     const int cap = atoi(e);
     const int rank_of[4] = {0, 2, 3, 1}; // plan -> rank
@@ -888,7 +1127,8 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
   P.direct_leaf = (!ctx->general && (smem == 1 || smem == 2) && ctx->max_leaf == 1) ? 1 : 0;
 }
 
-static render_kernel_t pick_trace_kernel(int profile, int smem) {
+static render_kernel_t pick_trace_kernel(int profile, int smem, bool inst) {
+  if (inst) return k_render<2, true, 0, false, false, true, true>;
 #define PICKT(P, G) \
   return smem == 2 ? k_render<P, G, 2, false, false, true>                                              \
                    : (smem == 1 ? k_render<P, G, 1, false, false, true>                                 \
@@ -910,6 +1150,7 @@ static int trace_through_render_kernel(rt_ctx *ctx, int n, float t_min, float t_
   P.trace_rays = (const float4 *)ctx->d_rays.p;
   P.trace_id = (int32_t *)ctx->d_ids.p;
   P.trace_t = (float *)ctx->d_ts.p;
+  P.trace_inst = ctx->two_level ? (int32_t *)ctx->d_inst_ids.p : nullptr;
   P.trace_tmax = t_max;
   P.n_rays = n;
   P.trace_item = 256; // 8 "samples" of a 32-lane pool, like a render work item
@@ -929,7 +1170,7 @@ static int trace_through_render_kernel(rt_ctx *ctx, int n, float t_min, float t_
   int smem = 0;
   size_t smem_bytes = 0;
   plan_scene_residency(ctx, P, block, smem, smem_bytes);
-  render_kernel_t kern = pick_trace_kernel(ctx->cfg.profile, smem);
+  render_kernel_t kern = pick_trace_kernel(ctx->cfg.profile, smem, ctx->two_level);
   CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   CK(cudaMemsetAsync(P.work_counter, 0, 4, st));
   kern<<<grid, block, smem_bytes, st>>>(P);
@@ -1013,7 +1254,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   size_t smem_bytes = 0;
   plan_scene_residency(ctx, P, block, smem, smem_bytes);
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
-  render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext);
+  render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext, ctx->two_level);
   CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, (const void *)kern));
@@ -1123,7 +1364,10 @@ int rt_render_aov(rt_ctx *ctx, int width, int height, int spp, float *aov) {
   switch (ctx->cfg.profile) {
   case 0: k_aov<0, false><<<grid, 128, 0, st>>>(ctx->S, ctx->cam, ctx->sp, width, height, spp, k0, k1, out); break;
   case 1: k_aov<1, false><<<grid, 128, 0, st>>>(ctx->S, ctx->cam, ctx->sp, width, height, spp, k0, k1, out); break;
-  default: k_aov<2, true><<<grid, 128, 0, st>>>(ctx->S, ctx->cam, ctx->sp, width, height, spp, k0, k1, out); break;
+  default:
+    if (ctx->two_level) k_aov<2, true, true><<<grid, 128, 0, st>>>(ctx->S, ctx->cam, ctx->sp, width, height, spp, k0, k1, out);
+    else k_aov<2, true><<<grid, 128, 0, st>>>(ctx->S, ctx->cam, ctx->sp, width, height, spp, k0, k1, out);
+    break;
   }
   ctx->launches++;
   CK(cudaGetLastError());

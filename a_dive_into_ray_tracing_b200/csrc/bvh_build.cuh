@@ -38,11 +38,19 @@ struct BuildBounds { // ordered-int encoded
 };
 
 struct BuildArrays {
-  // primitives, unified index gid: spheres, then triangles, then quads
-  int n_prims, n_spheres, n_tris, n_quads;
-  const rt_sphere *spheres;
+  // primitives of this build unit, unified index gid: spheres, then triangles, then quads, then instances.
+  // A unit is the whole scene (single level), the top level of an instanced scene (world primitives + instances,
+  // primitives owned by groups are skipped through `exclude`) or one group (its sub-ranges of the three arrays).
+  int n_prims, n_spheres, n_tris, n_quads, n_inst;
+  const rt_sphere *spheres;   // already offset to the unit's first sphere / triangle / quad ...
   const rt_triangle *tris;
   const rt_quad *quads;
+  int id_base[3];             // ... whose indices in the scene arrays these are (RT_PRIM_IDs are scene-wide)
+  const float4 *inst_lo, *inst_hi; // [n_inst] world boxes of the instances (host-computed from the groups' root boxes)
+  const uint8_t *exclude;     // [n_prims - n_inst] or null: 1 = owned by a group, not part of this unit
+  int link_base;              // node index of this unit's root inside an ordering of the packed array
+  int leaf_base;              // index of this unit's first entry in leaf_prims
+  int end_link;               // link stored where the traversal leaves this unit's tree (finished / back to the top level)
   float thickness;      // flat-box padding (THICKNESS, rtweekend.h:60 of each tree)
   float4 *pbox_lo, *pbox_hi; // [n_prims]
   int *big_flag;             // [n_prims] 0/1
@@ -66,16 +74,27 @@ struct BuildArrays {
 };
 
 RT_HD int32_t gid_to_prim_id(const BuildArrays &B, int gid) {
-  if (gid < B.n_spheres) return RT_PRIM_ID(RT_PRIM_SPHERE, gid);
-  if (gid < B.n_spheres + B.n_tris) return RT_PRIM_ID(RT_PRIM_TRIANGLE, gid - B.n_spheres);
-  return RT_PRIM_ID(RT_PRIM_QUAD, gid - B.n_spheres - B.n_tris);
+  if (gid < B.n_spheres) return RT_PRIM_ID(RT_PRIM_SPHERE, B.id_base[0] + gid);
+  if (gid < B.n_spheres + B.n_tris) return RT_PRIM_ID(RT_PRIM_TRIANGLE, B.id_base[1] + gid - B.n_spheres);
+  if (gid < B.n_spheres + B.n_tris + B.n_quads) return RT_PRIM_ID(RT_PRIM_QUAD, B.id_base[2] + gid - B.n_spheres - B.n_tris);
+  return RT_PRIM_ID(RT_PRIM_INSTANCE, gid - B.n_spheres - B.n_tris - B.n_quads);
 }
 
 // ---- kernel 1: primitive boxes (sphere.h:79-84, moving_sphere.h:74-82,
 // triangle.h:74-100, aarect.h:26-31) + round-0 scene bounds
 RT_HD void body_prim_box(const BuildArrays &B, int gid) {
   float lo[3], hi[3];
-  if (gid < B.n_spheres) {
+  const int n_geom = B.n_spheres + B.n_tris + B.n_quads;
+  if (gid < n_geom && B.exclude && B.exclude[gid]) { // owned by a group: neither in this tree nor in its bounds
+    B.pbox_lo[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.pbox_hi[gid] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.big_flag[gid] = 2;
+    return;
+  }
+  if (gid >= n_geom) {
+    const float4 l = B.inst_lo[gid - n_geom], h = B.inst_hi[gid - n_geom];
+    lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
+  } else if (gid < B.n_spheres) {
     const rt_sphere &s = B.spheres[gid];
     float r = fabsf(s.radius);
     for (int a = 0; a < 3; a++) {
@@ -119,7 +138,8 @@ RT_HD void body_classify(const BuildArrays &B, int gid, int round, float frac) {
         sz = ord2f(bb.hi[2]) - ord2f(bb.lo[2]);
   float4 lo = B.pbox_lo[gid], hi = B.pbox_hi[gid];
   float area = box_half_area(hi.x - lo.x, hi.y - lo.y, hi.z - lo.z);
-  if (area > frac * box_half_area(sx, sy, sz)) { B.big_flag[gid] = 1; return; }
+  // (an instance is never split off: the always-tested list holds primitives only)
+  if (gid < B.n_spheres + B.n_tris + B.n_quads && area > frac * box_half_area(sx, sy, sz)) { B.big_flag[gid] = 1; return; }
   BuildBounds &nb = B.bounds[round + 1];
   RT_ATOMIC_MIN(&nb.lo[0], f2ord(lo.x)); RT_ATOMIC_MIN(&nb.lo[1], f2ord(lo.y)); RT_ATOMIC_MIN(&nb.lo[2], f2ord(lo.z));
   RT_ATOMIC_MAX(&nb.hi[0], f2ord(hi.x)); RT_ATOMIC_MAX(&nb.hi[1], f2ord(hi.y)); RT_ATOMIC_MAX(&nb.hi[2], f2ord(hi.z));
@@ -310,7 +330,7 @@ RT_HD void body_pack(const BuildArrays &B, int v, int quadrant) {
     cur = p;
   }
   const bool build_leaf = v >= n - 1;
-  if (build_leaf && quadrant == 0) B.leaf_prims[lpos] = gid_to_prim_id(B, (int)(B.keys[v - (n - 1)] & 0xffffffffull));
+  if (build_leaf && quadrant == 0) B.leaf_prims[B.leaf_base + lpos] = gid_to_prim_id(B, (int)(B.keys[v - (n - 1)] & 0xffffffffull));
   const int par = B.parent[v];
   if (par >= 0 && B.lcnt[par] <= B.max_leaf) return; // inside a collapsed subtree
   float4 lo = B.nbox_lo[v], hi = B.nbox_hi[v];
@@ -319,13 +339,15 @@ RT_HD void body_pack(const BuildArrays &B, int v, int quadrant) {
   hi.x += RT_FMA(e[0], 4e-7f, 1e-9f); hi.y += RT_FMA(e[1], 4e-7f, 1e-9f); hi.z += RT_FMA(e[2], 4e-7f, 1e-9f);
   const int escape = pos + B.size[v];
   int payload;
-  if (build_leaf || B.lcnt[v] <= B.max_leaf) payload = ~((lpos << 3) | (B.lcnt[v] - 1));
-  else payload = pos + 1;
+  if (build_leaf || B.lcnt[v] <= B.max_leaf) payload = ~(((B.leaf_base + lpos) << 3) | (B.lcnt[v] - 1));
+  else payload = B.link_base + pos + 1;
   // links are stored as BYTE offsets (index * 32) so that traversal needs no address
-  // arithmetic; rt_accel_download converts them back to indices
-  lo.w = RT_I2F(escape << RT_NODE_SHIFT);
+  // arithmetic; rt_accel_download converts them back to indices. The link that leaves this unit's tree
+  // (escape == its kept node count) is the unit's end link.
+  // (end_link < 0: a single-level scene, where "finished" is simply the node count)
+  lo.w = RT_I2F((escape == B.size[0] && B.end_link >= 0) ? B.end_link : ((B.link_base + escape) << RT_NODE_SHIFT));
   hi.w = RT_I2F(payload >= 0 ? (payload << RT_NODE_SHIFT) : payload);
-  float4 *dst = B.packed + (size_t)quadrant * B.packed_stride;
+  float4 *dst = B.packed + (size_t)quadrant * B.packed_stride + 2 * (size_t)B.link_base;
   dst[2 * pos] = lo;
   dst[2 * pos + 1] = hi;
 }

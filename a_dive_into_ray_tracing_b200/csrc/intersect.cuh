@@ -227,11 +227,16 @@ struct TraceCounters {
 // the threaded BVH — no stack: every node carries the index to continue with when
 // its box is missed (or its subtree is done).  while-while form: lanes first walk
 // to their next leaf, then the warp tests primitives together.
-template <int PROFILE, bool GENERAL, bool COUNT>
-RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r, float t_min, float t_max, TraceCounters *cnt) {
+// INST (two-level scenes): a top-level leaf may name an rt_instance; the ray is moved into the object's space
+// (rigid: t is preserved, rt_next_week/cuda/hittable.h:66-79,156-190), the object's tree is walked until its end
+// link RT_POP_LINK, and the top-level walk resumes with the world ray. *hit_inst = instance of the closest hit (-1: world).
+template <int PROFILE, bool GENERAL, bool COUNT, bool INST = false>
+RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r_world, float t_min, float t_max, TraceCounters *cnt,
+                           int *hit_inst = nullptr) {
   HitAcc h;
   h.t = t_max;
   h.id = -1;
+  Ray r = r_world;
   RayPre pre = ray_precompute(r);
   for (int i = 0; i < S.n_big; i++) {
     int32_t id = S.big[i];
@@ -249,10 +254,20 @@ RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r, float t_min, float t
   }
   int node = 0; // byte offset of the current node
   const int n_nodes = S.n_nodes << RT_NODE_SHIFT;
+  const int pop = RT_POP_LINK(S.n_nodes);
   int first = 0, left = 0; // pending primitives of the last hit leaf: leaf_prims[first .. first+left)
-  while (node < n_nodes || left > 0) {
+  int cur_inst = -1, best_inst = -1, node_top = 0, first_top = 0, left_top = 0;
+  for (;;) {
     if (left == 0) {
-      while (node < n_nodes) {
+      if (INST && node == pop) { // the object's tree is done: back to the top level with the world ray
+        r = r_world;
+        pre = ray_precompute(r);
+        node = node_top; first = first_top; left = left_top;
+        cur_inst = -1;
+        continue;
+      }
+      if (!((unsigned)node < (unsigned)n_nodes)) break;
+      while ((unsigned)node < (unsigned)n_nodes) {
         const float4 *np = (const float4 *)((const char *)S.nodes + node);
         float4 lo = np[0], hi = np[1];
         if (COUNT) cnt->box_tests++;
@@ -268,32 +283,69 @@ RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r, float t_min, float t
       }
     }
     if (left > 0) { // one primitive per outer iteration keeps the warp converged here
-      if (COUNT) cnt->prim_tests++;
-      hit_prim<PROFILE, GENERAL, false>(S, S.leaf_prims[first], r, pre, t_min, h);
+      const int32_t id = S.leaf_prims[first];
       first++;
       left--;
+      if (INST && RT_PRIM_TYPE_OF(id) == RT_PRIM_INSTANCE) {
+        const float4 *rec = S.inst + 4 * RT_PRIM_INDEX_OF(id);
+        node_top = node; first_top = first; left_top = left;
+        r.o = inst_point_to_object(rec, r_world.o);
+        r.d = inst_vector_to_object(rec, r_world.d);
+        pre = ray_precompute(r);
+        node = RT_F2I(rec[3].x);
+        first = 0; left = 0;
+        cur_inst = RT_PRIM_INDEX_OF(id);
+      } else {
+        if (COUNT) cnt->prim_tests++;
+        const HitAcc old = h;
+        hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
+        if (INST && (h.id != old.id || h.t != old.t)) best_inst = cur_inst;
+      }
     }
   }
+  if (INST && hit_inst) *hit_inst = best_inst;
   return h;
 }
 
 // Brute force over the flattened arrays in list order (parity hook; the reference's
 // hittable_list::hit). Spheres in the big list still use the big-sphere formula so that the
-// result is identical to the BVH path's.
-template <int PROFILE, bool GENERAL>
-RT_HD HitAcc trace_brute(const DevScene &S, const uint8_t *is_big, const Ray &r, float t_min, float t_max) {
+// result is identical to the BVH path's. Two-level scenes: the world primitives (those no group owns), then
+// every instance's object with the ray moved into its space.
+template <int PROFILE, bool GENERAL, bool INST = false>
+RT_HD HitAcc trace_brute(const DevScene &S, const uint8_t *is_big, const Ray &r, float t_min, float t_max,
+                         const uint8_t *grouped = nullptr, int *hit_inst = nullptr) {
   HitAcc h;
   h.t = t_max;
   h.id = -1;
   RayPre pre = ray_precompute(r);
   for (int i = 0; i < S.n_spheres; i++) {
+    if (INST && grouped[i]) continue;
     int32_t id = RT_PRIM_ID(RT_PRIM_SPHERE, i);
     if (is_big[i]) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
     else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
   }
   if (GENERAL) {
-    for (int i = 0; i < S.n_tris; i++) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_TRIANGLE, i), r, pre, t_min, h);
-    for (int i = 0; i < S.n_quads; i++) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_QUAD, i), r, pre, t_min, h);
+    for (int i = 0; i < S.n_tris; i++)
+      if (!(INST && grouped[S.n_spheres + i])) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_TRIANGLE, i), r, pre, t_min, h);
+    for (int i = 0; i < S.n_quads; i++)
+      if (!(INST && grouped[S.n_spheres + S.n_tris + i])) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_QUAD, i), r, pre, t_min, h);
+  }
+  if (INST) {
+    int best_inst = -1;
+    for (int k = 0; k < S.n_inst; k++) {
+      const float4 *rec = S.inst + 4 * k;
+      const int32_t *G = S.groups + 8 * RT_F2I(rec[3].y); // rt_group: first/count of spheres, triangles, quads
+      Ray ro = r;
+      ro.o = inst_point_to_object(rec, r.o);
+      ro.d = inst_vector_to_object(rec, r.d);
+      const RayPre po = ray_precompute(ro);
+      const HitAcc old = h;
+      for (int i = 0; i < G[1]; i++) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_SPHERE, G[0] + i), ro, po, t_min, h);
+      for (int i = 0; i < G[3]; i++) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_TRIANGLE, G[2] + i), ro, po, t_min, h);
+      for (int i = 0; i < G[5]; i++) hit_prim<PROFILE, true, false>(S, RT_PRIM_ID(RT_PRIM_QUAD, G[4] + i), ro, po, t_min, h);
+      if (h.id != old.id || h.t != old.t) best_inst = k;
+    }
+    if (hit_inst) *hit_inst = best_inst;
   }
   return h;
 }

@@ -72,6 +72,7 @@ struct RenderParams {
   // (primitive id, t) instead of being shaded
   const float4 *trace_rays; // [n_rays][2]: {origin, time} {direction, -}
   int32_t *trace_id;
+  int32_t *trace_inst; // two-level scenes: instance of the hit primitive (may be null)
   float *trace_t;
   float trace_tmax;
   int n_rays, trace_item; // rays per work item
@@ -97,7 +98,12 @@ __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &o
 // state machine, same warp-voted search bursts / primitive-test rounds / regeneration by ballot
 // rank, same ray_precompute_fast and quadrant copies - only the two ends differ: a new "path" is a
 // caller ray (no camera, no Philox) and a finished traversal is written out instead of shaded.
-template <int PROFILE, bool GENERAL, int SMEM, bool COUNT, bool EXT, bool TRACE = false>
+// INST: two-level scenes (rt_group / rt_instance; general kernel, global-memory plan only). A top-level leaf may
+// name an instance: the lane moves its ray into the object's space (rigid map: t is preserved, as
+// translate::hit / rotate_y::hit do, rt_next_week/cuda/hittable.h:66-79,156-190), remembers where the top-level walk
+// goes on, and continues the SAME search bursts in the object's tree; that tree's end link (RT_POP_LINK) is a
+// fourth lane state handled in the primitive-test phase: restore the world ray, resume the top level.
+template <int PROFILE, bool GENERAL, int SMEM, bool COUNT, bool EXT, bool TRACE = false, bool INST = false>
 __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid_constant__ RenderParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevScene S = P.S;
@@ -223,6 +229,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   //   node < 0           LEAF: a hit leaf is pending, node = its payload
   //                      ~(first << 3 | count-1) into leaf_prims; `resume` = where to go on
   const int node_end = SMEM ? 0 : (S.n_nodes << RT_NODE_SHIFT);
+  const int node_pop = RT_POP_LINK(S.n_nodes); // INST: the end link of an object's tree
 #define RT_SEARCHING(n) (SMEM ? ((n) > 0) : ((unsigned)(n) < (unsigned)node_end))
   bool alive = false;
   int node = node_end, resume = 0;
@@ -243,6 +250,10 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   bool have_cur = false, old_valid = false, more_work = true;
   Ray r;
   r.o = v3(0, 0, 0); r.d = v3(0, 0, 1); r.tm = 0;
+  // INST: while a lane walks an object's tree, `r` is the object-space ray and these hold the world ray, where the
+  // top-level walk resumes, the instance being walked and the instance of the closest hit so far
+  V3f w_o = v3(0, 0, 0), w_d = v3(0, 0, 1);
+  int resume_top = 0, cur_inst = -1, hit_inst = -1;
   V3f beta = v3(1, 1, 1), L = v3(0, 0, 0);
   int bounce = 0, pix = 0, smp = 0, pixel_index = 0;
   unsigned n_seg = 0, n_paths = 0;
@@ -257,6 +268,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   auto begin_segment = [&]() {
     pre = ray_precompute_fast(r);
     h.t = TRACE ? P.trace_tmax : INFINITY; h.id = -1;
+    if (INST) { cur_inst = -1; hit_inst = -1; }
     for (int i = 0; i < S.n_big; i++) {
       const int32_t id = S.big[i];
       if (COUNT) cnt.prim_tests++;
@@ -354,11 +366,34 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       }
     }
     // ---- phase 2: pending primitive tests (one per lane per round)
-    const unsigned m_leaf = __ballot_sync(FULL, node < 0);
+    const unsigned m_leaf = __ballot_sync(FULL, node < 0 || (INST && node == node_pop));
     if (m_leaf && (__popc(m_leaf) >= P.leaf_min || !__ballot_sync(FULL, RT_SEARCHING(node)))) {
-      if (node < 0) {
+      if (INST && node == node_pop) { // the object's tree is done: back to the top level with the world ray
+        r.o = w_o; r.d = w_d;
+        pre = ray_precompute_fast(r);
+        const unsigned octant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.y) >> 31) << 1) |
+                                (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 2);
+        nodes_q = nodes_g + octant * (unsigned)S.node_stride;
+        node = resume_top;
+        cur_inst = -1;
+      } else if (INST && node < 0 && RT_PRIM_TYPE_OF(S.leaf_prims[(~node) >> 3]) == RT_PRIM_INSTANCE) {
+        // enter the instance named by this top-level leaf (instance leaves hold exactly one instance)
+        const int k = RT_PRIM_INDEX_OF(S.leaf_prims[(~node) >> 3]);
+        const float4 *rec = S.inst + 4 * k;
+        w_o = r.o; w_d = r.d;
+        resume_top = resume;
+        r.o = inst_point_to_object(rec, w_o);
+        r.d = inst_vector_to_object(rec, w_d);
+        pre = ray_precompute_fast(r);
+        const unsigned octant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.y) >> 31) << 1) |
+                                (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 2);
+        nodes_q = nodes_g + octant * (unsigned)S.node_stride;
+        node = RT_F2I(rec[3].x);
+        cur_inst = k;
+      } else if (node < 0) {
         const int enc = ~node;
         if (COUNT) cnt.prim_tests++;
+        const HitAcc h_before = h;
         if (!GENERAL && SMEM != 0 && P.direct_leaf) {
           // single-sphere leaf named by the payload itself: one LDS.128 from a 32-bit shared address
           const int id = enc >> 3;
@@ -371,6 +406,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           hit_prim<PROFILE, GENERAL, false>(S, S.leaf_prims[enc >> 3], r, pre, t_min, h);
           node = (enc & 7) ? node - 7 : resume; // next primitive of the leaf (first+1, count-1) or go on
         }
+        if (INST && (h.id != h_before.id || h.t != h_before.t)) hit_inst = cur_inst;
       }
     }
     // ---- phase 3: shade + regenerate once enough lanes are out of the traversal
@@ -425,6 +461,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         if (TRACE) { // the traversal's result IS the output
           P.trace_id[pixel_index] = h.id;
           P.trace_t[pixel_index] = h.id >= 0 ? h.t : 0.f;
+          if (INST && P.trace_inst) P.trace_inst[pixel_index] = h.id >= 0 ? hit_inst : -1;
           alive = false;
           ended = true;
         } else if (!hit) {
@@ -469,7 +506,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
       bool fresh_ray = false;
       if (hit) {
-        const bool cont = shade_hit<PROFILE, GENERAL, EXT>(S, P.sp, r, h, beta, L, q);
+        const bool cont = shade_hit<PROFILE, GENERAL, EXT, INST>(S, P.sp, r, h, beta, L, q, hit_inst);
         bounce++;
         if (cont && bounce < P.sp.max_depth) {
           fresh_ray = true;
@@ -590,7 +627,7 @@ __global__ void k_resolve(const float4 *__restrict__ accum, int W, int H, int pr
 // Denoiser feature buffers: one thread per pixel, `spp` camera samples with the same Philox camera
 // streams as k_render (event 0, streams 0 and 1), first SURFACE hit only (media are ignored).
 // out: float[H*W][8] = albedo.rgb, normal.xyz, t, hit fraction.
-template <int PROFILE, bool GENERAL>
+template <int PROFILE, bool GENERAL, bool INST = false>
 RT_HD void aov_pixel(const DevScene &S, const DevCamera &cam, const ShadeParams &sp, int W, int H, int spp, uint32_t seed_lo,
                      uint32_t seed_hi, int p, float *out) {
   const int i = p % W, j = p / W;
@@ -600,10 +637,11 @@ RT_HD void aov_pixel(const DevScene &S, const DevCamera &cam, const ShadeParams 
     float x5 = 0.f;
     if (PROFILE == 2 && cam.time1 != cam.time0) x5 = u01(philox4x32_10((uint32_t)p, (uint32_t)smp, 0u, 1u, seed_lo, seed_hi).x);
     const Ray r = gen_camera_ray<PROFILE>(cam, W, H, i, j, u01(q.x), u01(q.y), u01(q.z), u01(q.w), x5);
-    const HitAcc h = trace_closest<PROFILE, GENERAL, false>(S, r, sp.t_min, INFINITY, nullptr);
+    int inst = -1;
+    const HitAcc h = trace_closest<PROFILE, GENERAL, false, INST>(S, r, sp.t_min, INFINITY, nullptr, &inst);
     V3f albedo, normal = v3(0, 0, 0);
     if (h.id >= 0) {
-      first_hit_features<PROFILE, GENERAL>(S, sp, r, h, albedo, normal);
+      first_hit_features<PROFILE, GENERAL, INST>(S, sp, r, h, albedo, normal, inst);
       acc[6] += h.t; acc[7] += 1.0f;
     } else {
       albedo = miss_radiance(sp, r.d);
@@ -615,25 +653,28 @@ RT_HD void aov_pixel(const DevScene &S, const DevCamera &cam, const ShadeParams 
   for (int k = 0; k < 8; k++) out[8 * (size_t)p + k] = acc[k] * inv;
 }
 
-template <int PROFILE, bool GENERAL>
+template <int PROFILE, bool GENERAL, bool INST = false>
 __global__ void k_aov(const DevScene S, const DevCamera cam, const ShadeParams sp, int W, int H, int spp, uint32_t seed_lo,
                       uint32_t seed_hi, float *__restrict__ out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < W * H) aov_pixel<PROFILE, GENERAL>(S, cam, sp, W, H, spp, seed_lo, seed_hi, p, out);
+  if (p < W * H) aov_pixel<PROFILE, GENERAL, INST>(S, cam, sp, W, H, spp, seed_lo, seed_hi, p, out);
 }
 
-template <int PROFILE, bool GENERAL>
+template <int PROFILE, bool GENERAL, bool INST = false>
 __global__ void k_trace_closest(const DevScene S, const uint8_t *__restrict__ sphere_is_big,
                                 const float4 *__restrict__ rays, int n, float t_min, float t_max, int use_accel,
-                                int32_t *__restrict__ out_id, float *__restrict__ out_t) {
+                                int32_t *__restrict__ out_id, float *__restrict__ out_t,
+                                const uint8_t *__restrict__ grouped = nullptr, int32_t *__restrict__ out_inst = nullptr) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   float4 a = rays[2 * k], b = rays[2 * k + 1];
   Ray r;
   r.o = v3(a.x, a.y, a.z); r.tm = a.w; r.d = v3(b.x, b.y, b.z);
   HitAcc h;
-  if (use_accel) h = trace_closest<PROFILE, GENERAL, false>(S, r, t_min, t_max, nullptr);
-  else h = trace_brute<PROFILE, GENERAL>(S, sphere_is_big, r, t_min, t_max);
+  int inst = -1;
+  if (use_accel) h = trace_closest<PROFILE, GENERAL, false, INST>(S, r, t_min, t_max, nullptr, &inst);
+  else h = trace_brute<PROFILE, GENERAL, INST>(S, sphere_is_big, r, t_min, t_max, grouped, &inst);
   out_id[k] = h.id;
   out_t[k] = h.id >= 0 ? h.t : 0.f;
+  if (INST && out_inst) out_inst[k] = h.id >= 0 ? inst : -1;
 }

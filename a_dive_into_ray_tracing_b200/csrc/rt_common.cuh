@@ -105,6 +105,13 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 //                              {sin_y, cos_y, 0, 0}            (global memory; not in the BVH)
 //  perlin_vec float4[256*n_perlin], perlin_perm uint8[768*n_perlin] (x, y, z tables)
 //  images  DevImage[n_images]  8-bit RGB rows, top row first
+//  inst    float4[4*n_inst]    per rt_instance: three rows {Rinv_k.xyz, tinv_k} of the WORLD -> OBJECT map
+//                              (p_obj = Rinv p_world + tinv; rigid, so t is preserved and normals go back with
+//                              the transpose), then {as_float(byte offset of the object's root node),
+//                              as_float(group), 0, 0}
+// Two-level scenes (n_inst > 0): `nodes` holds the top-level tree first (root = node 0; its leaves name world
+// primitives or RT_PRIM_INSTANCE ids) and then one tree per group in OBJECT space; a link that leaves a group's
+// tree is RT_POP_LINK(n_nodes) = "back to the top level" (intersect.cuh, render_kernels.cuh).
 struct DevImage {
   const uint8_t *rgb;
   int width, height;
@@ -135,7 +142,31 @@ struct DevScene {
   const uint8_t *perlin_perm;
   const DevImage *images;
   int n_media, n_perlin, n_images;
+  const float4 *inst;
+  const int32_t *groups; // rt_group[n_groups] as 8 ints each (brute-force parity hook)
+  int n_inst;
 };
+
+// link value that ends an object's (bottom-level) tree: one node past "traversal finished"
+#define RT_POP_LINK(n_nodes) (((n_nodes) << RT_NODE_SHIFT) + (1 << RT_NODE_SHIFT))
+
+// world -> object for an instance record (rigid: directions only rotate, t is preserved)
+RT_HD V3f inst_point_to_object(const float4 *rec, V3f p) {
+  const float4 a = rec[0], b = rec[1], c = rec[2];
+  return v3(RT_FMA(a.z, p.z, RT_FMA(a.y, p.y, RT_FMA(a.x, p.x, a.w))), RT_FMA(b.z, p.z, RT_FMA(b.y, p.y, RT_FMA(b.x, p.x, b.w))),
+            RT_FMA(c.z, p.z, RT_FMA(c.y, p.y, RT_FMA(c.x, p.x, c.w))));
+}
+RT_HD V3f inst_vector_to_object(const float4 *rec, V3f d) {
+  const float4 a = rec[0], b = rec[1], c = rec[2];
+  return v3(RT_FMA(a.z, d.z, RT_FMA(a.y, d.y, a.x * d.x)), RT_FMA(b.z, d.z, RT_FMA(b.y, d.y, b.x * d.x)),
+            RT_FMA(c.z, d.z, RT_FMA(c.y, d.y, c.x * d.x)));
+}
+// object -> world for a direction / normal: the transpose of the rotation rows
+RT_HD V3f inst_vector_to_world(const float4 *rec, V3f n) {
+  const float4 a = rec[0], b = rec[1], c = rec[2];
+  return v3(RT_FMA(c.x, n.z, RT_FMA(b.x, n.y, a.x * n.x)), RT_FMA(c.y, n.z, RT_FMA(b.y, n.y, a.y * n.x)),
+            RT_FMA(c.z, n.z, RT_FMA(b.z, n.y, a.z * n.x)));
+}
 
 struct DevCamera {
   V3f origin, llc, horizontal, vertical, u, v;

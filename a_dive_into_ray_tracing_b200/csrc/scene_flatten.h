@@ -20,6 +20,10 @@ struct HostFlat {
   std::vector<uint8_t> perlin_perm, image_bytes;
   std::vector<size_t> image_offset; // into image_bytes, per image
   bool any_moving = false;
+  // two-level scenes: device instance records (rt_common.cuh DevScene::inst), and per primitive in unified order
+  // (spheres, triangles, quads) whether some group owns it (= not part of the world level)
+  std::vector<float4> inst;
+  std::vector<uint8_t> grouped;
 };
 
 static inline int flat_fail(std::string &err, const char *fmt, ...) {
@@ -30,6 +34,35 @@ static inline int flat_fail(std::string &err, const char *fmt, ...) {
   va_end(ap);
   err = buf;
   return RT_ERR_INVALID;
+}
+
+// Device records of rt_instance[n]: the inverse of the rigid map M = [R | T] in double (R^T, -R^T T), rounded
+// once. `root_offset_of_group` (byte offsets of the groups' root nodes) may be null before the build.
+static inline int make_instance_records(const rt_instance *inst, int n, int n_groups, const int *root_offset_of_group,
+                                        std::vector<float4> &out, std::string &err) {
+  out.assign(4 * (size_t)n, make_float4(0, 0, 0, 0));
+  for (int i = 0; i < n; i++) {
+    const float *m = inst[i].m;
+    for (int k = 0; k < 12; k++)
+      if (!std::isfinite(m[k])) return flat_fail(err, "instance %d: non-finite matrix", i);
+    if (inst[i].group < 0 || inst[i].group >= n_groups) return flat_fail(err, "instance %d: group index", i);
+    const double R[3][3] = {{m[0], m[1], m[2]}, {m[4], m[5], m[6]}, {m[8], m[9], m[10]}}, T[3] = {m[3], m[7], m[11]};
+    // rigid: R R^T = I (1e-4) and det R = +1 - the ray parameter t must mean the same in both spaces
+    for (int a = 0; a < 3; a++)
+      for (int b = 0; b < 3; b++) {
+        const double d = R[a][0] * R[b][0] + R[a][1] * R[b][1] + R[a][2] * R[b][2];
+        if (std::fabs(d - (a == b ? 1.0 : 0.0)) > 1e-4) return flat_fail(err, "instance %d: matrix is not rigid (rotation + translation only)", i);
+      }
+    const double det = R[0][0] * (R[1][1] * R[2][2] - R[1][2] * R[2][1]) - R[0][1] * (R[1][0] * R[2][2] - R[1][2] * R[2][0]) +
+                       R[0][2] * (R[1][0] * R[2][1] - R[1][1] * R[2][0]);
+    if (det < 0.0) return flat_fail(err, "instance %d: mirrored matrix (det < 0)", i);
+    for (int k = 0; k < 3; k++) { // row k of R^T = column k of R
+      const double ti = -(R[0][k] * T[0] + R[1][k] * T[1] + R[2][k] * T[2]);
+      out[4 * (size_t)i + k] = make_float4((float)R[0][k], (float)R[1][k], (float)R[2][k], (float)ti);
+    }
+    out[4 * (size_t)i + 3] = make_float4(RT_I2F(root_offset_of_group ? root_offset_of_group[inst[i].group] : 0), RT_I2F(inst[i].group), 0.f, 0.f);
+  }
+  return RT_OK;
 }
 
 // 2 * RT_MAX_PRIMS nodes * 32 bytes * 8 orderings = 2^31 - one node
@@ -119,6 +152,33 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
     if (sc->images[i].width < 1 || sc->images[i].height < 1 || !sc->images[i].rgb) FAIL("image %d: empty", i);
   if (profile != RT_PROFILE_NEXT_WEEK && (sc->n_triangles || sc->n_quads || any_moving))
     FAIL("triangles, rects and moving spheres need profile 2 (next-week / triangles trees)");
+
+  // instancing
+  if (sc->n_groups < 0 || sc->n_instances < 0) FAIL("negative count");
+  if ((sc->n_groups && !sc->groups) || (sc->n_instances && !sc->instances)) FAIL("null array with non-zero count");
+  if ((sc->n_groups || sc->n_instances) && profile != RT_PROFILE_NEXT_WEEK) FAIL("instances need profile 2");
+  // every instance adds a top-level leaf, every group its own tree: the same 32-bit offset budget
+  if ((long long)sc->n_spheres + sc->n_triangles + sc->n_quads + sc->n_instances + sc->n_groups > RT_MAX_PRIMS)
+    FAIL("too many primitives + instances");
+  F.grouped.assign((size_t)sc->n_spheres + sc->n_triangles + sc->n_quads, 0);
+  for (int g = 0; g < sc->n_groups; g++) {
+    const rt_group &G = sc->groups[g];
+    if (G.first_sphere < 0 || G.n_spheres < 0 || (long long)G.first_sphere + G.n_spheres > sc->n_spheres ||
+        G.first_triangle < 0 || G.n_triangles < 0 || (long long)G.first_triangle + G.n_triangles > sc->n_triangles ||
+        G.first_quad < 0 || G.n_quads < 0 || (long long)G.first_quad + G.n_quads > sc->n_quads)
+      FAIL("group %d: primitive range", g);
+    for (int i = 0; i < G.n_spheres; i++) F.grouped[(size_t)G.first_sphere + i] = 1;
+    for (int i = 0; i < G.n_triangles; i++) F.grouped[(size_t)sc->n_spheres + G.first_triangle + i] = 1;
+    for (int i = 0; i < G.n_quads; i++) F.grouped[(size_t)sc->n_spheres + sc->n_triangles + G.first_quad + i] = 1;
+  }
+  {
+    int rc = make_instance_records(sc->instances, sc->n_instances, sc->n_groups, nullptr, F.inst, err);
+    if (rc) return rc;
+    for (int i = 0; i < sc->n_instances; i++) { // (the traversal enters an instance at its object's root node)
+      const rt_group &G = sc->groups[sc->instances[i].group];
+      if (G.n_spheres + G.n_triangles + G.n_quads == 0) FAIL("instance %d places an empty group", i);
+    }
+  }
 
   const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, nm = sc->n_materials;
   std::vector<float4> &sph = F.sph, &sph_mv = F.sph_mv, &tri = F.tri, &tri_n = F.tri_n, &quad = F.quad, &mats = F.mats;

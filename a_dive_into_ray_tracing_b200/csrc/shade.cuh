@@ -111,9 +111,12 @@ RT_COLD float perlin_noise(const float4 *__restrict__ vec, const uint8_t *__rest
 // perlin.h:58-70) and image lookups with the primitive's (u, v).
 // (Everything is passed and returned BY VALUE: handing the kernel's DevScene / hit record to an
 // out-of-line function by reference would pin them in local memory for the whole kernel.)
+// p = the hit point the reference hands to texture::value (world space: translate / rotate_y move rec.p back,
+// hittable.h:73,181); p_uv / outward = hit point and outward normal in the PRIMITIVE's space, where sphere::hit /
+// xy_rect::hit compute (u, v) (the same as p / the world normal for primitives that are not instanced).
 RT_COLD V3f texture_ext(const float4 *__restrict__ perlin_vec, const uint8_t *__restrict__ perlin_perm,
                         const DevImage *__restrict__ images, const float4 *__restrict__ quads, float4 m0, float4 m1,
-                        V3f p, V3f outward, int32_t prim) {
+                        V3f p, V3f p_uv, V3f outward, int32_t prim) {
   const int tex = (RT_F2I(m0.w) >> 8) & 0xff;
   if (tex == RT_TEX_NOISE) {
     const int table = (int)m1.y;
@@ -142,7 +145,7 @@ RT_COLD V3f texture_ext(const float4 *__restrict__ perlin_vec, const uint8_t *__
   } else if (type == RT_PRIM_QUAD) { // aarect.h:52-53
     const float4 q0 = quads[2 * idx], q1 = quads[2 * idx + 1];
     const int ax = RT_F2I(q0.w);
-    const float a = ax == 0 ? p.y : p.x, b = ax == 2 ? p.y : p.z;
+    const float a = ax == 0 ? p_uv.y : p_uv.x, b = ax == 2 ? p_uv.y : p_uv.z;
     u = (a - q0.y) / (q0.z - q0.y);
     v = (b - q1.x) / (q1.y - q1.x);
   }
@@ -161,13 +164,13 @@ RT_COLD V3f texture_ext(const float4 *__restrict__ perlin_vec, const uint8_t *__
 // EXT: the scene uses noise / image textures or media (a separate kernel instantiation, so that
 // scenes without them keep the leaner code).
 template <bool EXT>
-RT_HD V3f material_color(const DevScene &S, float4 m0, float4 m1, V3f p, V3f outward, int32_t prim) {
+RT_HD V3f material_color(const DevScene &S, float4 m0, float4 m1, V3f p, V3f p_uv, V3f outward, int32_t prim) {
   int tex = (RT_F2I(m0.w) >> 8) & 0xff;
   if (tex == RT_TEX_CHECKER) {
     float sines = rt_fast_sin(10.0f * p.x) * rt_fast_sin(10.0f * p.y) * rt_fast_sin(10.0f * p.z);
     if (sines < 0.0f) return xyz(m1); // odd
   } else if (EXT && tex >= RT_TEX_NOISE) {
-    return texture_ext(S.perlin_vec, S.perlin_perm, S.images, S.quad, m0, m1, p, outward, prim);
+    return texture_ext(S.perlin_vec, S.perlin_perm, S.images, S.quad, m0, m1, p, p_uv, outward, prim);
   }
   return xyz(m0);
 }
@@ -260,23 +263,44 @@ RT_HD void surface_at(const DevScene &S, const Ray &r, const HitAcc &h, V3f p, V
   }
 }
 
+// The same for a hit inside instance `inst` of a two-level scene (inst < 0: a world-level primitive): the
+// primitive lives in object space, so the hit point and the ray go there, and the normal comes back with the
+// rotation (rotate_y::hit, hittable.h:181-187). p_uv / n_uv = object-space hit point and normal (texture (u, v)).
+template <bool GENERAL, bool EXT, bool INST>
+RT_HD void surface_at_inst(const DevScene &S, const Ray &r, const HitAcc &h, V3f p, int inst, V3f &outward, int &mat,
+                           V3f &p_uv, V3f &n_uv) {
+  if (INST && inst >= 0) {
+    const float4 *rec = S.inst + 4 * inst;
+    Ray ro = r;
+    ro.o = inst_point_to_object(rec, r.o);
+    ro.d = inst_vector_to_object(rec, r.d);
+    p_uv = madd(ro.o, h.t, ro.d);
+    surface_at<GENERAL, EXT>(S, ro, h, p_uv, n_uv, mat);
+    outward = inst_vector_to_world(rec, n_uv);
+  } else {
+    surface_at<GENERAL, EXT>(S, r, h, p, outward, mat);
+    p_uv = p;
+    n_uv = outward;
+  }
+}
+
 // First-hit features of a camera ray for denoisers (rt_render_aov): albedo = the texture colour the
 // integrator would multiply by (1 for glass, emission clamped to 1 for lights), normal = the
 // shading normal (facing the ray where the profile flips it), t = the ray parameter.
-template <int PROFILE, bool GENERAL>
+template <int PROFILE, bool GENERAL, bool INST = false>
 RT_HD void first_hit_features(const DevScene &S, const ShadeParams &sp, const Ray &r, const HitAcc &h, V3f &albedo,
-                              V3f &normal) {
+                              V3f &normal, int inst = -1) {
   const V3f p = madd(r.o, h.t, r.d);
-  V3f outward;
+  V3f outward, p_uv, n_uv;
   int mat;
-  surface_at<GENERAL, GENERAL>(S, r, h, p, outward, mat);
+  surface_at_inst<GENERAL, GENERAL, INST>(S, r, h, p, inst, outward, mat, p_uv, n_uv);
   normal = outward;
   if (PROFILE == 0 || (PROFILE == 2 && (sp.flags & RT_FLAG_FLIP_NORMALS)))
     if (!(dot(r.d, outward) < 0.0f)) normal = -outward;
   const float4 m0 = S.mats[2 * mat], m1 = S.mats[2 * mat + 1];
   const int mtype = RT_F2I(m0.w) & 0xff;
   if (mtype == RT_MAT_DIELECTRIC) albedo = v3(1.f, 1.f, 1.f);
-  else albedo = (PROFILE == 2) ? material_color<GENERAL>(S, m0, m1, p, outward, h.id) : xyz(m0);
+  else albedo = (PROFILE == 2) ? material_color<GENERAL>(S, m0, m1, p, p_uv, n_uv, h.id) : xyz(m0);
   if (mtype == RT_MAT_DIFFUSE_LIGHT) albedo = v3(RT_FMIN(albedo.x, 1.f), RT_FMIN(albedo.y, 1.f), RT_FMIN(albedo.z, 1.f));
 }
 
@@ -284,13 +308,13 @@ RT_HD void first_hit_features(const DevScene &S, const ShadeParams &sp, const Ra
 // new direction), the throughput `beta` and (profile 2) the radiance `L`.
 // Returns true when the path continues.
 //   rnd: the four random words of this bounce.
-template <int PROFILE, bool GENERAL, bool EXT = false>
+template <int PROFILE, bool GENERAL, bool EXT = false, bool INST = false>
 RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const HitAcc &h, V3f &beta, V3f &L,
-                     Philox4 rnd) {
+                     Philox4 rnd, int inst = -1) {
   const V3f p = madd(r.o, h.t, r.d);
-  V3f outward;
+  V3f outward, p_uv, n_uv;
   int mat;
-  surface_at<GENERAL, EXT>(S, r, h, p, outward, mat);
+  surface_at_inst<GENERAL, EXT, INST>(S, r, h, p, inst, outward, mat, p_uv, n_uv);
   const float dn_out = dot(r.d, outward);
   const bool front_face = dn_out < 0.0f;
   V3f n = outward;
@@ -304,7 +328,7 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
   const float u1 = u01(rnd.x), u2 = u01(rnd.y), u3 = fmaxf(u01(rnd.z), 5.9604645e-8f);
 
   if (PROFILE == 2 && mtype == RT_MAT_DIFFUSE_LIGHT) {
-    L = L + beta * material_color<EXT>(S, m0, m1, p, outward, h.id); // emitted; never scatters
+    L = L + beta * material_color<EXT>(S, m0, m1, p, p_uv, n_uv, h.id); // emitted; never scatters
     return false;
   }
   V3f dir, att;
@@ -324,7 +348,7 @@ RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const Hit
       v = cbrtf(u3) * v;
 #endif
     }
-    att = (PROFILE == 2) ? material_color<EXT>(S, m0, m1, p, outward, h.id) : xyz(m0);
+    att = (PROFILE == 2) ? material_color<EXT>(S, m0, m1, p, p_uv, n_uv, h.id) : xyz(m0);
     if (mtype == RT_MAT_LAMBERTIAN) {
       dir = n + v;
       if (PROFILE == 0 && dot(dir, dir) < 1e-16f) dir = n; // degenerate direction guard (material.h:24-26)

@@ -16,7 +16,7 @@ RT_FLAG_DEPTH_BACKGROUND = 2
 RT_FLAG_COUNTERS = 4
 RT_FLAG_REFERENCE_MEDIUM = 8
 
-RT_PRIM_SPHERE, RT_PRIM_TRIANGLE, RT_PRIM_QUAD, RT_PRIM_MEDIUM = 0, 1, 2, 3
+RT_PRIM_SPHERE, RT_PRIM_TRIANGLE, RT_PRIM_QUAD, RT_PRIM_MEDIUM, RT_PRIM_INSTANCE = 0, 1, 2, 3, 4
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 0, 1, 2, 3, 4
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_NOISE, RT_TEX_IMAGE = 0, 1, 2, 3
 
@@ -53,11 +53,29 @@ MEDIUM_DT = np.dtype(
     [("shape", "<i4"), ("p0", "<f4", 3), ("p1", "<f4", 3), ("sin_y", "<f4"), ("cos_y", "<f4"), ("offset", "<f4", 3),
      ("density", "<f4"), ("material", "<i4")]
 )
+# two-level scenes (rt_group / rt_instance): an object = ranges of the primitive arrays in OBJECT space; an
+# instance places it with a rigid 3x4 matrix (rows: rotation | translation), p_world = M p_object
+GROUP_DT = np.dtype([("first_sphere", "<i4"), ("n_spheres", "<i4"), ("first_triangle", "<i4"), ("n_triangles", "<i4"),
+                     ("first_quad", "<i4"), ("n_quads", "<i4"), ("reserved", "<i4", 2)])
+INSTANCE_DT = np.dtype([("m", "<f4", 12), ("group", "<i4"), ("reserved", "<i4", 3)])
 BVH_NODE_DT = np.dtype([("bmin", "<f4", 3), ("escape", "<i4"), ("bmax", "<f4", 3), ("payload", "<i4")])
 
 assert SPHERE_DT.itemsize == 48 and TRIANGLE_DT.itemsize == 52 and QUAD_DT.itemsize == 28
 assert MATERIAL_DT.itemsize == 40 and BVH_NODE_DT.itemsize == 32
 assert PERLIN_DT.itemsize == 6144 and MEDIUM_DT.itemsize == 56
+assert GROUP_DT.itemsize == 32 and INSTANCE_DT.itemsize == 64
+
+
+def rigid_y(angle_deg, offset=(0.0, 0.0, 0.0), sin_cos=None):
+    """The 3x4 matrix of translate(rotate_y(object, angle), offset) - rt_next_week/cuda/hittable.h:49-190:
+    rotate_y maps object p to (cos x + sin z, y, -sin x + cos z) (:176-177), translate adds the offset (:73).
+    sin_cos: use these (sin, cos) instead of computing them (e.g. the float values the reference computed)."""
+    if sin_cos is None:
+        rad = np.float32(np.float32(np.pi / 180.0) * np.float32(angle_deg))
+        sn, cs = np.float32(np.sin(rad)), np.float32(np.cos(rad))
+    else:
+        sn, cs = np.float32(sin_cos[0]), np.float32(sin_cos[1])
+    return np.array([cs, 0, sn, offset[0], 0, 1, 0, offset[1], -sn, 0, cs, offset[2]], np.float32)
 
 
 class RtConfig(C.Structure):
@@ -81,7 +99,9 @@ class RtSceneDesc(C.Structure):
                 ("max_depth", C.c_int32), ("flags", C.c_uint32), ("reserved", C.c_uint32),
                 ("n_media", C.c_int32), ("media", C.c_void_p),
                 ("n_perlin", C.c_int32), ("perlin", C.c_void_p),
-                ("n_images", C.c_int32), ("images", C.c_void_p)]
+                ("n_images", C.c_int32), ("images", C.c_void_p),
+                ("n_groups", C.c_int32), ("groups", C.c_void_p),
+                ("n_instances", C.c_int32), ("instances", C.c_void_p)]
 
 
 class RtImage(C.Structure):
@@ -153,7 +173,10 @@ class Scene:
 
     def __init__(self, spheres=None, triangles=None, quads=None, materials=None, camera=None,
                  background=(0.0, 0.0, 0.0), sky_gradient=1, t_min=1e-3, max_depth=50, flags=0, name="",
-                 profile=RT_PROFILE_WEEKEND_CPU, media=None, perlin=None, images=None):
+                 profile=RT_PROFILE_WEEKEND_CPU, media=None, perlin=None, images=None, groups=None, instances=None):
+        self.groups = np.ascontiguousarray(groups if groups is not None else np.zeros(0, GROUP_DT))
+        self.instances = np.ascontiguousarray(instances if instances is not None else np.zeros(0, INSTANCE_DT))
+        assert self.groups.dtype == GROUP_DT and self.instances.dtype == INSTANCE_DT
         self.media = np.ascontiguousarray(media if media is not None else np.zeros(0, MEDIUM_DT))
         self.perlin = np.ascontiguousarray(perlin if perlin is not None else np.zeros(0, PERLIN_DT))
         # image textures: list of uint8 arrays [h][w][3], row 0 = top
@@ -206,13 +229,17 @@ class Scene:
                 arr[k].width, arr[k].height, arr[k].rgb = im.shape[1], im.shape[0], im.ctypes.data
             d._images = arr
             d.images = C.addressof(arr)
+        d.n_groups = len(self.groups)
+        d.groups = self.groups.ctypes.data if len(self.groups) else None
+        d.n_instances = len(self.instances)
+        d.instances = self.instances.ctypes.data if len(self.instances) else None
         d._keepalive = self
         return d
 
     def with_camera(self, camera):
         s = Scene(self.spheres, self.triangles, self.quads, self.materials, camera, self.background,
                   self.sky_gradient, self.t_min, self.max_depth, self.flags, self.name, self.profile,
-                  self.media, self.perlin, self.images)
+                  self.media, self.perlin, self.images, self.groups, self.instances)
         return s
 
 

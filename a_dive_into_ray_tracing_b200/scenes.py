@@ -13,7 +13,7 @@ import os
 
 import numpy as np
 
-from .ctypes_defs import (MATERIAL_DT, MEDIUM_DT, PERLIN_DT, QUAD_DT, RT_FLAG_DEPTH_BACKGROUND, RT_FLAG_FLIP_NORMALS,
+from .ctypes_defs import (GROUP_DT, INSTANCE_DT, rigid_y, MATERIAL_DT, MEDIUM_DT, PERLIN_DT, QUAD_DT, RT_FLAG_DEPTH_BACKGROUND, RT_FLAG_FLIP_NORMALS,
                           RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC, RT_MAT_LAMBERTIAN, RT_MAT_METAL,
                           RT_PROFILE_FINAL_CU, RT_PROFILE_NEXT_WEEK, RT_PROFILE_WEEKEND_CPU, RT_TEX_CHECKER,
                           RT_TEX_IMAGE, RT_TEX_NOISE, RT_TEX_SOLID, SPHERE_DT, TRIANGLE_DT, Scene, camera_from_lookat)
@@ -311,10 +311,58 @@ def rotate_normals(tn, angle_deg=30.0):
     return np.stack([x, n[..., 1], z], -1).astype(f)
 
 
-def obj_room(obj_path=None, width=800, height=800, subdivisions=2, mesh=None):
+def _group(spheres=(0, 0), triangles=(0, 0), quads=(0, 0)):
+    """rt_group: (first, count) ranges of the scene's primitive arrays, in object space"""
+    g = np.zeros((), GROUP_DT)
+    g["first_sphere"], g["n_spheres"] = spheres
+    g["first_triangle"], g["n_triangles"] = triangles
+    g["first_quad"], g["n_quads"] = quads
+    return g
+
+
+def _instance(group, angle_deg=0.0, offset=(0.0, 0.0, 0.0), sin_cos=None):
+    """rt_instance: translate(rotate_y(object, angle), offset) as a rigid 3x4 matrix"""
+    i = np.zeros((), INSTANCE_DT)
+    i["m"] = rigid_y(angle_deg, offset, sin_cos)
+    i["group"] = group
+    return i
+
+
+def wrap_per_primitive(scene, inst):
+    """The reference's way of instancing, as in triangles/cuda/obj_render.cu:498-511: EVERY object is wrapped in
+    its own translate(rotate_y(...)). inst: per object in flat list order (spheres, triangles, quads) a record
+    with fields flag, sin_y, cos_y, offset. Consecutive primitives of one type that
+    share a transform become one group + one instance (the two-level form of the same scene); primitives with
+    flag 0 stay at the world level. Returns a copy of `scene` with groups / instances set."""
+    ns, nt, nq = len(scene.spheres), len(scene.triangles), len(scene.quads)
+    groups, instances = [], []
+    for lo, n, field in ((0, ns, "spheres"), (ns, nt, "triangles"), (ns + nt, nq, "quads")):
+        k = 0
+        while k < n:
+            if not inst["flag"][lo + k]:
+                k += 1
+                continue
+            key = (float(inst["sin_y"][lo + k]), float(inst["cos_y"][lo + k]), tuple(float(x) for x in inst["offset"][lo + k]))
+            e = k + 1
+            while e < n and inst["flag"][lo + e] and (float(inst["sin_y"][lo + e]), float(inst["cos_y"][lo + e]),
+                                                       tuple(float(x) for x in inst["offset"][lo + e])) == key:
+                e += 1
+            groups.append(_group(**{field: (k, e - k)}))
+            instances.append(_instance(len(groups) - 1, 0.0, key[2], sin_cos=key[:2]))
+            k = e
+    out = scene.with_camera(scene.camera)
+    out.groups = np.array(groups, GROUP_DT) if groups else np.zeros(0, GROUP_DT)
+    out.instances = np.array(instances, INSTANCE_DT) if instances else np.zeros(0, INSTANCE_DT)
+    return out
+
+
+def obj_room(obj_path=None, width=800, height=800, subdivisions=2, mesh=None, instanced=False):
     """Config 3 — triangles/cuda/obj_render.cu:384-524 (obj_model) with camera
     :716-724,736-738: (1,3,7)->(0,2,0), vfov 60, aperture 0, black background,
-    t_min 1e-5 (:33), flipping normals (include/hittable.h:29)."""
+    t_min 1e-5 (:33), flipping normals (include/hittable.h:29).
+    instanced: the mesh stays in OBJECT space (scaled vertices, as triangle(v*scale) stores them) as one rt_group
+    placed by one rt_instance = the translate(rotate_y(., 30), (0, 1.5, 0)) the reference wraps around every
+    triangle (obj_render.cu:498-511) - the two-level BVH instead of baked vertices."""
     if obj_path is None and mesh == "blob968":  # the bench's config 3: Suzanne's triangle count
         obj_path = os.path.join(DATA_DIR, "blob_968.obj")
         if not os.path.exists(obj_path):
@@ -360,13 +408,20 @@ def obj_room(obj_path=None, width=800, height=800, subdivisions=2, mesh=None):
     quad(YZ, -4, 4 + 1, -4, 4, 4, blue_1)
     quad(YZ, -1, 3 + 1, -4, 4, -3.999, mirror())
     quad(YZ, -1, 3 + 1 - 0.001, -4, 4, 3.999, mirror())
-    wv = bake_instance(tv)
-    wn = rotate_normals(tn)
+    if instanced:
+        wv = (np.asarray(tv, np.float32) * np.float32(2.5)).astype(np.float32)
+        wn = np.asarray(tn, np.float32)
+    else:
+        wv = bake_instance(tv)
+        wn = rotate_normals(tn)
     tris = np.zeros(len(wv), TRIANGLE_DT)
     for i in range(len(wv)):
         tris[i] = triangle_record(wv[i, 0], wv[i, 1], wv[i, 2], wn[i, 0], wn[i, 1], wn[i, 2], gold)
     sc = Scene(spheres=np.array(spheres, SPHERE_DT), triangles=tris, quads=np.array(quads, QUAD_DT),
                materials=np.array(mats, MATERIAL_DT), name="obj_room")
+    if instanced:
+        sc.groups = np.array([_group(triangles=(0, len(tris)))], GROUP_DT)
+        sc.instances = np.array([_instance(0, 30.0, (0.0, 1.5, 0.0))], INSTANCE_DT)
     lookfrom = np.array([1, 3, 7], np.float32)
     lookat = np.array([0, 2, 0], np.float32)
     dv = lookfrom - lookat
@@ -433,7 +488,10 @@ def box_as_triangles(p0, p1, angle_deg, offset, material):
     for axis, a0, a1, b0, b1, k in sides:
         ia, ib = (1 if axis == 0 else 0), (1 if axis == 2 else 2)
         corners = np.zeros((4, 3), f)
-        for q, (a, b) in enumerate(((a0, b0), (a1, b0), (a1, b1), (a0, b1))):
+        # counter-clockwise seen from the +axis side (the triangle's edge tests follow the vertex order,
+        # triangle.h:172-202): (a, b) = (x, z) is left-handed about +y, so the xz rect runs the other way round
+        order = ((a0, b0), (a0, b1), (a1, b1), (a1, b0)) if axis == 1 else ((a0, b0), (a1, b0), (a1, b1), (a0, b1))
+        for q, (a, b) in enumerate(order):
             corners[q, axis], corners[q, ia], corners[q, ib] = k, a, b
         w = (_rot_y_f32(corners, angle_deg) + np.asarray(offset, f)).astype(f)
         n = np.zeros(3, f)
@@ -444,9 +502,11 @@ def box_as_triangles(p0, p1, angle_deg, offset, material):
     return out
 
 
-def cornell_box(width=600, height=600):
+def cornell_box(width=600, height=600, instanced=False):
     """rt_next_week/cuda/main.cu:252-281,436-443: Cornell box with two rotated boxes, one
-    area light, black background; profile 2 (rt_next_week tree: normals never flip)."""
+    area light, black background; profile 2 (rt_next_week tree: normals never flip).
+    instanced: the two boxes stay axis-aligned rects in object space (box.h:41-58), each an rt_group placed by
+    an rt_instance = translate(rotate_y(box, angle), offset) (main.cu:269-275)."""
     mats = [_mat(RT_MAT_LAMBERTIAN, (.65, .05, .05)), _mat(RT_MAT_LAMBERTIAN, (.73, .73, .73)),
             _mat(RT_MAT_LAMBERTIAN, (.12, .45, .15)), _mat(RT_MAT_DIFFUSE_LIGHT, (15, 15, 15))]
     red, white, green, light = 0, 1, 2, 3
@@ -463,8 +523,16 @@ def cornell_box(width=600, height=600):
     quad(1, 0, 555, 0, 555, 0, white)
     quad(1, 0, 555, 0, 555, 555, white)
     quad(2, 0, 555, 0, 555, 555, white)
-    tris = box_as_triangles((0, 0, 0), (165, 330, 165), 15, (265, 0, 295), white)
-    tris += box_as_triangles((0, 0, 0), (165, 165, 165), -18, (130, 0, 65), white)
+    groups, instances = [], []
+    if instanced:
+        tris = []
+        for p1, angle, off in (((165, 330, 165), 15, (265, 0, 295)), ((165, 165, 165), -18, (130, 0, 65))):
+            groups.append(_group(quads=(len(quads), 6)))
+            instances.append(_instance(len(groups) - 1, angle, off))
+            quads += box_as_quads((0, 0, 0), p1, white)
+    else:
+        tris = box_as_triangles((0, 0, 0), (165, 330, 165), 15, (265, 0, 295), white)
+        tris += box_as_triangles((0, 0, 0), (165, 165, 165), -18, (130, 0, 65), white)
     # materials in first-use order as the C++ flattening registers them: green, red, light, white
     order = [green, red, light, white]
     remap = {m: i for i, m in enumerate(order)}
@@ -472,8 +540,10 @@ def cornell_box(width=600, height=600):
         q["material"] = remap[int(q["material"])]
     for t in tris:
         t["material"] = remap[int(t["material"])]
-    sc = Scene(quads=np.array(quads, QUAD_DT), triangles=np.array(tris, TRIANGLE_DT),
-               materials=np.array([mats[m] for m in order], MATERIAL_DT), name="cornell_box")
+    sc = Scene(quads=np.array(quads, QUAD_DT), triangles=np.array(tris, TRIANGLE_DT) if tris else None,
+               materials=np.array([mats[m] for m in order], MATERIAL_DT), name="cornell_box",
+               groups=np.array(groups, GROUP_DT) if groups else None,
+               instances=np.array(instances, INSTANCE_DT) if instances else None)
     sc.camera = camera_from_lookat((278, 278, -800), (278, 278, 0), (0, 1, 0), 40.0,
                                    np.float32(width) / np.float32(height), 0.0, 800.0, 0.0, 1.0, dtype=np.float32)
     sc.background = (0.0, 0.0, 0.0)
@@ -613,11 +683,13 @@ def box_as_quads(p0, p1, material):
             _quad(0, p0[1], p1[1], p0[2], p1[2], p1[0], material), _quad(0, p0[1], p1[1], p0[2], p1[2], p0[0], material)]
 
 
-def next_week_final(width=800, height=800, seed=1984, image=None):
+def next_week_final(width=800, height=800, seed=1984, image=None, instanced=False):
     """rt_next_week/cuda/main.cu:312-383,453-459 — the tree's default scene: 400 ground boxes, an
     area light, a moving sphere, glass and metal balls, a blue subsurface ball (dielectric
     boundary + dense medium), thin global fog, an image-textured and a perlin ball, and a
-    rotated, translated cluster of 1000 small spheres."""
+    rotated, translated cluster of 1000 small spheres.
+    instanced: the cluster stays in object space ([0,165)^3) as one rt_group under one rt_instance
+    (main.cu:373-381: translate(rotate_y(bvh_node(boxes2), 15), vec3(-100, 270, 395)))."""
     rng = np.random.Generator(np.random.Philox(seed))
     f = np.float32
     mats = [_mat(RT_MAT_LAMBERTIAN, (0.48, 0.83, 0.53)),  # 0 ground
@@ -645,11 +717,17 @@ def next_week_final(width=800, height=800, seed=1984, image=None):
     media = [_medium_sphere((360, 150, 145), 70, 0.2, 5), _medium_sphere((0, 0, 0), 5000, 0.0001, 6)]
     # cluster: translate(rotate_y(bvh(1000 spheres in [0,165)^3, r = 10), 15), (-100, 270, 395))
     centres = rng.uniform(0.0, 165.0, (1000, 3)).astype(f)
-    centres = (_rot_y_f32(centres, 15) + np.array((-100, 270, 395), f)).astype(f)
+    groups = instances = None
+    if instanced:
+        groups = np.array([_group(spheres=(len(spheres), 1000))], GROUP_DT)
+        instances = np.array([_instance(0, 15.0, (-100.0, 270.0, 395.0))], INSTANCE_DT)
+    else:
+        centres = (_rot_y_f32(centres, 15) + np.array((-100, 270, 395), f)).astype(f)
     spheres += [_sphere(tuple(c), 10, 9) for c in centres]
     sc = Scene(spheres=np.array(spheres, SPHERE_DT), quads=np.array(quads, QUAD_DT), materials=np.array(mats, MATERIAL_DT),
                media=np.array(media, MEDIUM_DT), perlin=np.array([make_perlin(seed)], PERLIN_DT),
-               images=[procedural_earth() if image is None else image], name="next_week_final")
+               images=[procedural_earth() if image is None else image], name="next_week_final",
+               groups=groups, instances=instances)
     sc.background = (0.0, 0.0, 0.0)
     return _nw_camera(sc, (478, 278, -600), (278, 278, 0), 40.0, width, height)
 

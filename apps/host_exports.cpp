@@ -6,12 +6,14 @@
 
 static flat_scene g_flat;
 static rt_camera g_cam;
+static bool g_instancing = false; // rtx_host_set_instancing: translate / rotate_y as rt_instance instead of baked
+static flat_scene fresh_flat() { flat_scene f; f.instancing = g_instancing; return f; }
 
 extern "C" {
 // which: 0 = weekend random_scene() under srand(seed) (seed 1 = glibc default), 1 = next_week
 int rtx_host_build(int which, unsigned seed, double aspect, const char *obj_path) {
   srand(seed);
-  g_flat = flat_scene();
+  g_flat = fresh_flat();
   if (which == 0) {
     hittable_list w = random_scene();
     w.flatten(g_flat, transform());
@@ -49,6 +51,13 @@ int rtx_host_build(int which, unsigned seed, double aspect, const char *obj_path
   }
   return 0;
 }
+void rtx_host_set_instancing(int on) { g_instancing = on != 0; }
+// n[0..1] = groups, instances
+void rtx_host_counts3(int *n) { n[0] = (int)g_flat.groups.size(); n[1] = (int)g_flat.instances.size(); }
+void rtx_host_get3(rt_group *g, rt_instance *i) {
+  if (g) memcpy(g, g_flat.groups.data(), sizeof(rt_group) * g_flat.groups.size());
+  if (i) memcpy(i, g_flat.instances.data(), sizeof(rt_instance) * g_flat.instances.size());
+}
 void rtx_host_counts(int *n) {
   n[0] = (int)g_flat.spheres.size(); n[1] = (int)g_flat.triangles.size();
   n[2] = (int)g_flat.quads.size(); n[3] = (int)g_flat.materials.size(); n[4] = g_flat.wants_accel;
@@ -83,7 +92,7 @@ extern "C" int rtx_host_load_scene_file(const char *path, int width, int height,
                                         int errcap) {
   try {
     scene_file sf = load_scene_file(path);
-    g_flat = flat_scene();
+    g_flat = fresh_flat();
     static scene_file keep; // the flattened image pointers refer to textures owned by the scene
     keep = sf;
     keep.world.flatten(g_flat, transform());

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define RT_CAPI_VERSION 4
+#define RT_CAPI_VERSION 5
 
 typedef struct rt_ctx rt_ctx;
 
@@ -75,7 +75,8 @@ typedef enum rt_prim_type {
   RT_PRIM_SPHERE = 0,
   RT_PRIM_TRIANGLE = 1,
   RT_PRIM_QUAD = 2,
-  RT_PRIM_MEDIUM = 3 /* constant_medium: never returned by rt_trace_closest (stochastic) */
+  RT_PRIM_MEDIUM = 3, /* constant_medium: never returned by rt_trace_closest (stochastic) */
+  RT_PRIM_INSTANCE = 4 /* leaf of the top-level tree naming an rt_instance: internal, never returned */
 } rt_prim_type;
 /* primitive id returned by rt_trace_closest: (type << 28) | index-within-type; -1 = miss */
 #define RT_PRIM_ID(type, index) ((int32_t)(((uint32_t)(type) << 28) | (uint32_t)(index)))
@@ -179,6 +180,30 @@ typedef struct rt_camera {
   float time0, time1;
 } rt_camera;
 
+/* ---- version 5: first-class instancing (two-level BVH). Replaces the reference's `translate` / `rotate_y`
+ * wrappers (rt_next_week/cuda/hittable.h:49-190; per triangle in triangles/cuda/obj_render.cu:498-511, around the
+ * 1000-sphere cluster in rt_next_week/cuda/main.cu:373-381): the wrapped object keeps its OBJECT-space primitives and
+ * its own bottom-level tree, the ray is moved into object space on entry and t is preserved, exactly as
+ * translate::hit / rotate_y::hit do (hittable.h:66-79,156-190).
+ *
+ * rt_group = one object: ranges of the scene's primitive arrays, given in object space. Primitives covered by any
+ * group are NOT part of the world level; groups may share primitives. An empty group is allowed.
+ * rt_instance = one placement of a group: p_world = M p_object with M = {m[0..3]; m[4..7]; m[8..11]} (rows of a
+ * 3x4 matrix: rotation | translation). M must be RIGID (orthonormal rotation, det +1, no scale): only then is the
+ * ray parameter t the same in both spaces, which is what the reference's wrappers rely on. */
+typedef struct rt_group {
+  int32_t first_sphere, n_spheres;
+  int32_t first_triangle, n_triangles;
+  int32_t first_quad, n_quads;
+  int32_t reserved[2];
+} rt_group;
+
+typedef struct rt_instance {
+  float m[12];
+  int32_t group;
+  int32_t reserved[3];
+} rt_instance;
+
 typedef struct rt_scene_desc {
   int32_t n_spheres;   const rt_sphere *spheres;
   int32_t n_triangles; const rt_triangle *triangles;
@@ -195,6 +220,9 @@ typedef struct rt_scene_desc {
   int32_t n_media;     const rt_medium *media;
   int32_t n_perlin;    const rt_perlin *perlin;
   int32_t n_images;    const rt_image *images;
+  /* version 5: instancing (profile 2 only) */
+  int32_t n_groups;    const rt_group *groups;
+  int32_t n_instances; const rt_instance *instances;
 } rt_scene_desc;
 
 /* 32-byte packed BVH node as downloaded by rt_accel_download (device layout).
@@ -249,6 +277,17 @@ int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nod
  * so that the closest-hit parity tests cover the code that is timed. */
 int rt_trace_closest(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel,
                      int32_t *prim_id, float *t);
+/* Same for instanced scenes: inst_id[k] = the rt_instance whose object holds the hit primitive, -1 for a
+ * world-level primitive or a miss (may be NULL). */
+int rt_trace_closest_inst(rt_ctx *ctx, const float *rays, int n, float t_min, float t_max, int use_accel,
+                          int32_t *prim_id, int32_t *inst_id, float *t);
+
+/* Transform-only update of an instanced scene (animation): new matrices for ALL n == n_instances instances
+ * (group indices must not change). Only the top level is rebuilt - instance boxes + one tree over
+ * (world primitives, instances); the objects' own trees and every primitive array stay as they are on the device.
+ * The reference has no counterpart: its transforms are baked into a device-side object graph that
+ * create_world<<<1,1>>> must rebuild from scratch (rt_next_week/cuda/main.cu:386-467). */
+int rt_instances_update(rt_ctx *ctx, const rt_instance *instances, int n);
 
 /* Accumulate samples [spp_begin, spp_begin+spp_count) of every pixel into the
  * context's accumulation buffer (float4 per pixel: sum R,G,B and sample count).

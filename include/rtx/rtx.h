@@ -306,8 +306,17 @@ struct transform {
   }
 };
 
+class hittable;
 class flat_scene {
 public:
+  // First-class instancing (rt_group / rt_instance, the two-level BVH of the GPU core): an object under
+  // translate / rotate_y keeps its OBJECT-space primitives as a group and is placed by a rigid matrix, instead of
+  // having the transform baked into its vertices. Off: everything is baked (one single-level tree).
+  bool instancing = false;
+  std::vector<rt_group> groups;
+  std::vector<rt_instance> instances;
+  // `obj` under the accumulated transform `t` (called by the translate / rotate_y wrappers)
+  inline void place(const hittable &obj, const transform &t);
   std::vector<rt_sphere> spheres;
   std::vector<rt_triangle> triangles;
   std::vector<rt_quad> quads;
@@ -342,6 +351,7 @@ public:
   }
 
 private:
+  bool in_group = false;
   std::vector<const material *> seen;
   std::vector<const perlin *> seen_perlin;
   std::vector<const image_texture *> seen_images;
@@ -375,7 +385,48 @@ public:
   // shape of this object as the boundary of a constant_medium (sphere or box, possibly under
   // rotate_y / translate); false = unsupported
   virtual bool as_medium_boundary(rt_medium &, const transform &) const { return false; }
+  virtual bool is_wrapper() const { return false; }   // translate / rotate_y: keep accumulating the transform
+  virtual bool instanceable() const { return true; }  // false: holds something that is not a BVH primitive (a medium)
 };
+
+inline void flat_scene::place(const hittable &obj, const transform &t) {
+  if (obj.is_wrapper() || !instancing || in_group || t.identity() || t.scale != 1 || !obj.instanceable()) {
+    obj.flatten(*this, t); // bake (also: a transform nested inside a group is baked relative to that group)
+    return;
+  }
+  const int s0 = (int)spheres.size(), t0 = (int)triangles.size(), q0 = (int)quads.size();
+  in_group = true;
+  obj.flatten(*this, transform());
+  in_group = false;
+  rt_group g = {};
+  g.first_sphere = s0; g.n_spheres = (int)spheres.size() - s0;
+  g.first_triangle = t0; g.n_triangles = (int)triangles.size() - t0;
+  g.first_quad = q0; g.n_quads = (int)quads.size() - q0;
+  if (g.n_spheres + g.n_triangles + g.n_quads == 0) return;
+  rt_instance I = {};
+  const float m[12] = {(float)t.c, 0.f, (float)t.s, (float)t.offset[0], 0.f, 1.f, 0.f, (float)t.offset[1],
+                       -(float)t.s, 0.f, (float)t.c, (float)t.offset[2]};
+  for (int k = 0; k < 12; k++) I.m[k] = m[k];
+  // The reference wraps EVERY triangle of a mesh in its own translate(rotate_y()) (obj_render.cu:498-511):
+  // adjacent objects under the same transform form one group under one instance.
+  if (!instances.empty()) {
+    rt_group &b = groups[instances.back().group];
+    bool same = instances.back().group == (int)groups.size() - 1;
+    for (int k = 0; k < 12; k++) same = same && instances.back().m[k] == I.m[k];
+    same = same && (g.n_spheres == 0 || b.n_spheres == 0 || b.first_sphere + b.n_spheres == g.first_sphere) &&
+           (g.n_triangles == 0 || b.n_triangles == 0 || b.first_triangle + b.n_triangles == g.first_triangle) &&
+           (g.n_quads == 0 || b.n_quads == 0 || b.first_quad + b.n_quads == g.first_quad);
+    if (same) {
+      if (g.n_spheres) { if (!b.n_spheres) b.first_sphere = g.first_sphere; b.n_spheres += g.n_spheres; }
+      if (g.n_triangles) { if (!b.n_triangles) b.first_triangle = g.first_triangle; b.n_triangles += g.n_triangles; }
+      if (g.n_quads) { if (!b.n_quads) b.first_quad = g.first_quad; b.n_quads += g.n_quads; }
+      return;
+    }
+  }
+  I.group = (int)groups.size();
+  groups.push_back(g);
+  instances.push_back(I);
+}
 
 // triangle ctor — triangles/cuda/include/triangle.h:17-53 in float arithmetic
 inline void triangle_face_normal(const float v0[3], const float v1[3], const float v2[3], const float vn0[3],
@@ -481,7 +532,12 @@ public:
       // axis aligned: emit it as two triangles whose face normal is the rect's nominal
       // (+axis, never flipped: rt_next_week/cuda/hittable.h:29) normal, rotated
       float c[4][3], w[4][3], n[3] = {0, 0, 0}, nw[3];
-      const double aa[4] = {a0, a1, a1, a0}, bb[4] = {b0, b0, b1, b1};
+      // corner order = counter-clockwise seen from the +axis side, so that the triangle's edge tests (which follow
+      // the vertex order, triangle.h:172-202) agree with the +axis face normal: (a, b) = (x, z) is left-handed
+      // about +y, so the xz rect runs the other way round
+      const double aa1[4] = {a0, a0, a1, a1}, bb1[4] = {b0, b1, b1, b0};
+      const double aa0[4] = {a0, a1, a1, a0}, bb0[4] = {b0, b0, b1, b1};
+      const double *aa = axis == 1 ? aa1 : aa0, *bb = axis == 1 ? bb1 : bb0;
       for (int q = 0; q < 4; q++) { c[q][axis] = (float)k; c[q][ia] = (float)aa[q]; c[q][ib] = (float)bb[q]; xf.apply(c[q], w[q]); }
       n[axis] = 1.0f;
       xf.rotate(n, nw);
@@ -568,6 +624,10 @@ public:
   void flatten(flat_scene &out, const transform &xf) const override {
     for (const auto &o : objects) o->flatten(out, xf);
   }
+  bool instanceable() const override {
+    for (const auto &o : objects) if (!o->instanceable()) return false;
+    return true;
+  }
   std::vector<shared_ptr<hittable>> objects;
 };
 
@@ -575,7 +635,9 @@ class translate : public hittable {
 public:
   translate(shared_ptr<hittable> p, const vec3 &d) : ptr(p), offset(d) {}
   translate(hittable *p, const vec3 &d) : ptr(borrow(p)), offset(d) {}
-  void flatten(flat_scene &out, const transform &xf) const override { ptr->flatten(out, xf.then_translate(offset)); }
+  void flatten(flat_scene &out, const transform &xf) const override { out.place(*ptr, xf.then_translate(offset)); }
+  bool is_wrapper() const override { return true; }
+  bool instanceable() const override { return ptr->instanceable(); }
   bool as_medium_boundary(rt_medium &m, const transform &xf) const override {
     return ptr->as_medium_boundary(m, xf.then_translate(offset));
   }
@@ -586,7 +648,9 @@ class rotate_y : public hittable {
 public:
   rotate_y(shared_ptr<hittable> p, double angle_deg) : ptr(p), angle(angle_deg) {}
   rotate_y(hittable *p, double angle_deg) : ptr(borrow(p)), angle(angle_deg) {}
-  void flatten(flat_scene &out, const transform &xf) const override { ptr->flatten(out, xf.then_rotate_y(angle)); }
+  void flatten(flat_scene &out, const transform &xf) const override { out.place(*ptr, xf.then_rotate_y(angle)); }
+  bool is_wrapper() const override { return true; }
+  bool instanceable() const override { return ptr->instanceable(); }
   bool as_medium_boundary(rt_medium &m, const transform &xf) const override {
     return ptr->as_medium_boundary(m, xf.then_rotate_y(angle));
   }
@@ -613,6 +677,7 @@ public:
     m.material = out.add_material(phase_function.get());
     out.media.push_back(m);
   }
+  bool instanceable() const override { return false; } // media are not BVH primitives: their transform is baked
   shared_ptr<hittable> boundary;
   double density;
   shared_ptr<material> phase_function;
@@ -628,6 +693,10 @@ public:
   void flatten(flat_scene &out, const transform &xf) const override {
     out.wants_accel = true;
     for (const auto &o : objects) o->flatten(out, xf);
+  }
+  bool instanceable() const override {
+    for (const auto &o : objects) if (!o->instanceable()) return false;
+    return true;
   }
   std::vector<shared_ptr<hittable>> objects;
 };
@@ -744,6 +813,7 @@ struct render_options {
   double t_min = 0.001;
   int max_depth = 50;
   uint32_t flags = 0;
+  bool instancing = true; // translate / rotate_y as rt_instance (two-level BVH); false = baked into the vertices
 };
 
 struct image8 {
@@ -784,6 +854,8 @@ public:
     d.n_media = (int)fs.media.size(); d.media = fs.media.data();
     d.n_perlin = (int)fs.perlin_tables.size(); d.perlin = fs.perlin_tables.data();
     d.n_images = (int)fs.images.size(); d.images = fs.images.data();
+    d.n_groups = (int)fs.groups.size(); d.groups = fs.groups.data();
+    d.n_instances = (int)fs.instances.size(); d.instances = fs.instances.data();
     d.camera = cam.describe();
     for (int a = 0; a < 3; a++) d.background[a] = (float)o.background[a];
     d.sky_gradient = o.sky_gradient ? 1 : 0;
@@ -792,6 +864,7 @@ public:
   }
   void set_scene(const hittable &world, const camera &cam) {
     flat = flat_scene();
+    flat.instancing = opt.instancing;
     world.flatten(flat, transform());
     rt_scene_desc d = describe(flat, cam, opt);
     check(rt_scene_upload(ctx, &d));

@@ -25,6 +25,10 @@ struct EmuScene {
   DevCamera cam;
   ShadeParams sp;
   int profile;
+  // two-level scenes
+  bool two_level = false;
+  int n_nodes_total = 0;
+  std::vector<float4> inst_lo, inst_hi;
 };
 
 static void bind(EmuScene &E, const rt_scene_desc *sc) {
@@ -34,7 +38,8 @@ static void bind(EmuScene &E, const rt_scene_desc *sc) {
   S.tri = E.F.tri.data(); S.tri_n = E.F.tri_n.data(); S.quad = E.F.quad.data();
   S.sph_mat = E.F.sph_mat.data(); S.tri_mat = E.F.tri_mat.data(); S.quad_mat = E.F.quad_mat.data();
   S.mats = E.F.mats.data(); S.big = E.big.data(); S.leaf_prims = E.leaf_prims.data();
-  S.n_nodes = (int)E.nodes.size() / 2; S.n_big = (int)E.big.size();
+  S.n_nodes = E.n_nodes_total; S.n_big = (int)E.big.size();
+  S.inst = E.F.inst.data(); S.n_inst = sc->n_instances; S.groups = (const int32_t *)sc->groups;
   S.n_spheres = sc->n_spheres; S.n_tris = sc->n_triangles; S.n_quads = sc->n_quads; S.n_mats = sc->n_materials;
   S.any_moving = E.F.any_moving;
   E.images.resize((size_t)sc->n_images);
@@ -54,15 +59,30 @@ static void bind(EmuScene &E, const rt_scene_desc *sc) {
   E.sp.t_min = sc->t_min; E.sp.max_depth = sc->max_depth;
 }
 
-// serial replay of rt_accel_build (csrc/b200rt.cu) with the same kernel bodies
-static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_frac, int big_rounds, int shuffle, int max_leaf, int quadrant = 0) {
-  const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, n = ns + nt + nq;
-  E.nodes.clear(); E.big.clear(); E.leaf_prims.clear(); E.sph_is_big.assign(std::max(ns, 1), 0);
+// serial replay of rt_accel_build (csrc/b200rt.cu) with the same kernel bodies: one unit = one tree (the whole
+// scene, the top level of a two-level scene, or one group in object space)
+struct EmuUnit {
+  int first[3] = {0, 0, 0}, count[3] = {0, 0, 0};
+  int n_inst = 0;
+  const uint8_t *exclude = nullptr;
+  bool classify = true;
+  int link_base = 0, leaf_base = 0, end_link = -1;
+  bool own_arrays = true; // single-level: the unit sizes E.nodes / E.leaf_prims itself
+  int n_small = 0, kept = 0;
+  float root_box[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+static void build_unit(EmuScene &E, const rt_scene_desc *sc, EmuUnit &U, int quality, float big_frac, int big_rounds, int shuffle, int max_leaf) {
+  const int ns = U.count[0], nt = U.count[1], nq = U.count[2], n_geom = ns + nt + nq, n = n_geom + U.n_inst;
   if (n == 0) return;
   BuildArrays B;
   memset(&B, 0, sizeof B);
-  B.n_prims = n; B.n_spheres = ns; B.n_tris = nt; B.n_quads = nq;
-  B.spheres = sc->spheres; B.tris = sc->triangles; B.quads = sc->quads;
+  B.n_prims = n; B.n_spheres = ns; B.n_tris = nt; B.n_quads = nq; B.n_inst = U.n_inst;
+  B.spheres = sc->spheres + U.first[0]; B.tris = sc->triangles + U.first[1]; B.quads = sc->quads + U.first[2];
+  for (int k = 0; k < 3; k++) B.id_base[k] = U.first[k];
+  B.inst_lo = E.inst_lo.data(); B.inst_hi = E.inst_hi.data();
+  B.exclude = U.exclude;
+  B.link_base = U.link_base; B.leaf_base = U.leaf_base; B.end_link = U.end_link;
   B.thickness = (sc->flags & RT_FLAG_FLIP_NORMALS) ? 0.01f : 0.1f;
   std::vector<float4> lo(n), hi(n);
   std::vector<int> flag(n);
@@ -70,19 +90,23 @@ static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_f
   for (int r = 0; r < 4; r++) for (int a = 0; a < 3; a++) { bounds[r].lo[a] = 0x7fffffff; bounds[r].hi[a] = (int)0x80000000; }
   B.pbox_lo = lo.data(); B.pbox_hi = hi.data(); B.big_flag = flag.data(); B.bounds = bounds;
   for (int i = 0; i < n; i++) body_prim_box(B, i);
-  for (int r = 0; r < big_rounds; r++) for (int i = 0; i < n; i++) body_classify(B, i, r, big_frac);
-  int n_big = 0;
-  for (int i = 0; i < n; i++) n_big += flag[i];
-  int final_round = big_rounds;
-  if (n_big > 32) { std::fill(flag.begin(), flag.end(), 0); n_big = 0; final_round = 0; }
+  int final_round = 0, n_big = 0;
+  if (U.classify) {
+    for (int r = 0; r < big_rounds; r++) for (int i = 0; i < n; i++) body_classify(B, i, r, big_frac);
+    for (int i = 0; i < n; i++) n_big += flag[i] == 1;
+    final_round = big_rounds;
+    if (n_big > 32) { for (int &f : flag) if (f == 1) f = 0; n_big = 0; final_round = 0; }
+  }
   std::vector<int> small;
   for (int i = 0; i < n; i++) {
-    if (flag[i]) {
-      E.big.push_back(i < ns ? RT_PRIM_ID(RT_PRIM_SPHERE, i) : (i < ns + nt ? RT_PRIM_ID(RT_PRIM_TRIANGLE, i - ns) : RT_PRIM_ID(RT_PRIM_QUAD, i - ns - nt)));
-      if (i < ns) E.sph_is_big[i] = 1;
-    } else small.push_back(i);
+    if (flag[i] == 1) {
+      E.big.push_back(i < ns ? RT_PRIM_ID(RT_PRIM_SPHERE, U.first[0] + i)
+                             : (i < ns + nt ? RT_PRIM_ID(RT_PRIM_TRIANGLE, U.first[1] + i - ns) : RT_PRIM_ID(RT_PRIM_QUAD, U.first[2] + i - ns - nt)));
+      if (i < ns) E.sph_is_big[U.first[0] + i] = 1;
+    } else if (flag[i] == 0) small.push_back(i);
   }
   const int nsm = (int)small.size();
+  U.n_small = nsm;
   if (nsm == 0) return;
   const int n_nodes = 2 * nsm - 1;
   int n_pad = 2;
@@ -90,12 +114,15 @@ static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_f
   B.n_small = nsm; B.n_pad = n_pad; B.small_gid = small.data();
   std::vector<unsigned long long> keys(n_pad);
   std::vector<int> left(nsm), right(nsm), parent(n_nodes), nflag(nsm), size(n_nodes), lcnt(n_nodes);
-  E.leaf_prims.assign(nsm, 0);
   std::vector<float4> nlo(n_nodes), nhi(n_nodes);
-  E.nodes.assign(2 * (size_t)n_nodes, make_float4(0, 0, 0, 0));
+  if (U.own_arrays) {
+    E.leaf_prims.assign(nsm, 0);
+    E.nodes.assign(2 * (size_t)n_nodes, make_float4(0, 0, 0, 0));
+  }
   B.keys = keys.data(); B.left = left.data(); B.right = right.data(); B.parent = parent.data(); B.flag = nflag.data();
   B.size = size.data(); B.lcnt = lcnt.data(); B.leaf_prims = E.leaf_prims.data();
   B.max_leaf = max_leaf < 1 ? 1 : (max_leaf > 8 ? 8 : max_leaf);
+  if (U.n_inst) B.max_leaf = 1;
   B.nbox_lo = nlo.data(); B.nbox_hi = nhi.data(); B.packed = E.nodes.data();
   for (int i = 0; i < n_pad; i++) body_morton(B, i, final_round);
   for (int k = 2; k <= n_pad; k <<= 1) for (int j = k >> 1; j > 0; j >>= 1) for (int i = 0; i < n_pad; i++) body_bitonic(B.keys, i, j, k);
@@ -118,8 +145,80 @@ static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_f
   B.swapmask = swapmask.data();
   B.packed_stride = 2 * n_nodes;
   for (int i = 0; i < nsm - 1; i++) body_order(B, i);
-  for (int v = 0; v < n_nodes; v++) body_pack(B, v, quadrant);
-  E.nodes.resize(2 * (size_t)size[0]); // kept nodes after leaf collapsing
+  for (int v = 0; v < n_nodes; v++) body_pack(B, v, 0);
+  U.kept = size[0];
+  memcpy(U.root_box, &E.nodes[2 * (size_t)U.link_base], sizeof U.root_box);
+  if (U.own_arrays) E.nodes.resize(2 * (size_t)size[0]); // kept nodes after leaf collapsing
+}
+
+static void build(EmuScene &E, const rt_scene_desc *sc, int quality, float big_frac, int big_rounds, int shuffle, int max_leaf) {
+  const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, n = ns + nt + nq;
+  E.nodes.clear(); E.big.clear(); E.leaf_prims.clear(); E.sph_is_big.assign(std::max(ns, 1), 0);
+  E.two_level = sc->n_groups > 0 || sc->n_instances > 0;
+  E.n_nodes_total = 0;
+  if (n == 0) return;
+  if (!E.two_level) {
+    EmuUnit U;
+    U.count[0] = ns; U.count[1] = nt; U.count[2] = nq;
+    build_unit(E, sc, U, quality, big_frac, big_rounds, shuffle, max_leaf);
+    E.n_nodes_total = (int)E.nodes.size() / 2;
+    return;
+  }
+  // the layout of rt_accel_build: [top level, worst case][group 0][group 1]...
+  const int ng = sc->n_groups, ni = sc->n_instances;
+  int n_world = 0;
+  for (int i = 0; i < n; i++) n_world += E.F.grouped[i] ? 0 : 1;
+  int node_at = std::max(2 * (n_world + ni) - 1, 1), leaf_at = std::max(n_world + ni, 1);
+  std::vector<EmuUnit> G(ng);
+  for (int g = 0; g < ng; g++) {
+    const rt_group &R = sc->groups[g];
+    G[g].first[0] = R.first_sphere; G[g].count[0] = R.n_spheres;
+    G[g].first[1] = R.first_triangle; G[g].count[1] = R.n_triangles;
+    G[g].first[2] = R.first_quad; G[g].count[2] = R.n_quads;
+    G[g].classify = false; G[g].own_arrays = false;
+    G[g].link_base = node_at; G[g].leaf_base = leaf_at;
+    const int m = R.n_spheres + R.n_triangles + R.n_quads;
+    node_at += std::max(2 * m - 1, 0);
+    leaf_at += m;
+  }
+  E.nodes.assign(2 * (size_t)node_at, make_float4(0, 0, 0, 0));
+  E.leaf_prims.assign(leaf_at, 0);
+  std::vector<int> root_off(ng, 0);
+  for (int g = 0; g < ng; g++) {
+    G[g].end_link = RT_POP_LINK(node_at);
+    build_unit(E, sc, G[g], quality, big_frac, big_rounds, shuffle, max_leaf);
+    root_off[g] = G[g].link_base << RT_NODE_SHIFT;
+  }
+  std::string err;
+  make_instance_records(sc->instances, ni, ng, root_off.data(), E.F.inst, err);
+  E.inst_lo.assign(std::max(ni, 1), make_float4(0, 0, 0, 0)); E.inst_hi = E.inst_lo;
+  for (int i = 0; i < ni; i++) { // upload_instance_boxes of csrc/b200rt.cu
+    const rt_instance &I = sc->instances[i];
+    const float *rb = G[I.group].root_box;
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int c = 0; c < 8; c++) {
+      const double p[3] = {(c & 1) ? rb[4] : rb[0], (c & 2) ? rb[5] : rb[1], (c & 4) ? rb[6] : rb[2]};
+      for (int a = 0; a < 3; a++) {
+        const double w = (double)I.m[4 * a] * p[0] + (double)I.m[4 * a + 1] * p[1] + (double)I.m[4 * a + 2] * p[2] + (double)I.m[4 * a + 3];
+        lo[a] = std::min(lo[a], w); hi[a] = std::max(hi[a], w);
+      }
+    }
+    float l[3], h[3];
+    for (int a = 0; a < 3; a++) {
+      const double e = 4e-7 * std::max(std::fabs(lo[a]), std::fabs(hi[a])) + 1e-9;
+      l[a] = nextafterf((float)(lo[a] - e), -INFINITY);
+      h[a] = nextafterf((float)(hi[a] + e), INFINITY);
+    }
+    E.inst_lo[i] = make_float4(l[0], l[1], l[2], 0.f);
+    E.inst_hi[i] = make_float4(h[0], h[1], h[2], 0.f);
+  }
+  EmuUnit T;
+  T.count[0] = ns; T.count[1] = nt; T.count[2] = nq;
+  T.n_inst = ni; T.exclude = E.F.grouped.data();
+  T.own_arrays = false;
+  T.end_link = node_at << RT_NODE_SHIFT;
+  build_unit(E, sc, T, quality, big_frac, big_rounds, shuffle, max_leaf);
+  E.n_nodes_total = T.n_small > 0 ? node_at : 0;
 }
 
 template <int PROFILE, bool GENERAL>
@@ -145,12 +244,13 @@ static void render_t(EmuScene *E, int W, int H, int spp_begin, int spp_count, ui
           hm.t = INFINITY; hm.id = -1;
           if (GENERAL && E->S.n_media)
             hm = apply_media(E->S.media, E->S.n_media, r.o, r.d, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, k0, k1, hm);
-          HitAcc h = trace_closest<PROFILE, GENERAL, true>(E->S, r, E->sp.t_min, hm.t, &cnt);
-          if (h.id < 0) h = hm;
+          int inst = -1;
+          HitAcc h = trace_closest<PROFILE, GENERAL, true, GENERAL>(E->S, r, E->sp.t_min, hm.t, &cnt, &inst);
+          if (h.id < 0) { h = hm; inst = -1; }
           nseg++;
           if (h.id < 0) { L = L + beta * miss_radiance(E->sp, r.d); break; }
           Philox4 qq = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, k0, k1);
-          bool cont = shade_hit<PROFILE, GENERAL, GENERAL>(E->S, E->sp, r, h, beta, L, qq);
+          bool cont = shade_hit<PROFILE, GENERAL, GENERAL, GENERAL>(E->S, E->sp, r, h, beta, L, qq, inst);
           bounce++;
           if (!cont) break;
           if (bounce >= E->sp.max_depth) {
@@ -193,7 +293,9 @@ int emu_download(void *p, rt_bvh_node *nodes, int32_t *leaf, int32_t *big) {
   return 0;
 }
 
+int emu_trace_inst(void *p, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *ids, int32_t *insts, float *ts);
 int emu_trace(void *p, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *ids, float *ts, unsigned long long *counters) {
+  if (((EmuScene *)p)->two_level) { if (counters) counters[0] = counters[1] = 0; return emu_trace_inst(p, rays, n, t_min, t_max, use_accel, ids, nullptr, ts); }
   EmuScene *E = (EmuScene *)p;
   TraceCounters cnt; cnt.box_tests = cnt.prim_tests = 0;
   unsigned long long cb = 0, cp = 0;
@@ -219,6 +321,23 @@ int emu_trace(void *p, const float *rays, int n, float t_min, float t_max, int u
   return 0;
 }
 
+// two-level scenes: also the instance of the hit primitive
+int emu_trace_inst(void *p, const float *rays, int n, float t_min, float t_max, int use_accel, int32_t *ids, int32_t *insts, float *ts) {
+  EmuScene *E = (EmuScene *)p;
+  for (int k = 0; k < n; k++) {
+    Ray r;
+    r.o = v3(rays[8 * k], rays[8 * k + 1], rays[8 * k + 2]); r.tm = rays[8 * k + 3];
+    r.d = v3(rays[8 * k + 4], rays[8 * k + 5], rays[8 * k + 6]);
+    int inst = -1;
+    HitAcc h;
+    if (use_accel) h = trace_closest<2, true, false, true>(E->S, r, t_min, t_max, nullptr, &inst);
+    else h = trace_brute<2, true, true>(E->S, E->sph_is_big.data(), r, t_min, t_max, E->F.grouped.data(), &inst);
+    ids[k] = h.id; ts[k] = h.id >= 0 ? h.t : 0.f;
+    if (insts) insts[k] = h.id >= 0 ? inst : -1;
+  }
+  return 0;
+}
+
 int emu_render(void *p, int W, int H, int spp_begin, int spp_count, uint64_t seed, int j0, int j1, double *sum, double *sumsq,
                unsigned long long *stats) {
   EmuScene *E = (EmuScene *)p;
@@ -235,7 +354,7 @@ extern "C" void emu_texture(void *p_, int material, int n, const int32_t *prim, 
   EmuScene *E = (EmuScene *)p_;
   const float4 m0 = E->S.mats[2 * material], m1 = E->S.mats[2 * material + 1];
   for (int k = 0; k < n; k++) {
-    V3f c = material_color<true>(E->S, m0, m1, v3_from(p + 3 * k), v3_from(outward + 3 * k), prim[k]);
+    V3f c = material_color<true>(E->S, m0, m1, v3_from(p + 3 * k), v3_from(p + 3 * k), v3_from(outward + 3 * k), prim[k]);
     rgb[3 * k] = c.x; rgb[3 * k + 1] = c.y; rgb[3 * k + 2] = c.z;
   }
 }
@@ -247,7 +366,7 @@ extern "C" int emu_aov(void *p_, int W, int H, int spp, uint64_t seed, float *ou
   for (int p = 0; p < W * H; p++) {
     if (E->profile == 0) aov_pixel<0, false>(E->S, E->cam, E->sp, W, H, spp, k0, k1, p, out);
     else if (E->profile == 1) aov_pixel<1, false>(E->S, E->cam, E->sp, W, H, spp, k0, k1, p, out);
-    else aov_pixel<2, true>(E->S, E->cam, E->sp, W, H, spp, k0, k1, p, out);
+    else aov_pixel<2, true, true>(E->S, E->cam, E->sp, W, H, spp, k0, k1, p, out);
   }
   return 0;
 }

@@ -34,6 +34,7 @@ class Emu:
         L.emu_counts.argtypes = [_vp, _vp, _vp, _vp]
         L.emu_download.argtypes = [_vp, _vp, _vp, _vp]
         L.emu_trace.argtypes = [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]
+        L.emu_trace_inst.argtypes = [_vp, _vp, C.c_int, C.c_float, C.c_float, C.c_int, _vp, _vp, _vp]
         L.emu_render.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int, C.c_int, _vp, _vp, _vp]
         self.scene = scene
         self.profile = scene.profile if profile is None else profile
@@ -66,6 +67,15 @@ class Emu:
         self.lib.emu_trace(self.h, rays.ctypes.data, n, t_min, t_max, use_accel, ids.ctypes.data, ts.ctypes.data,
                            cnt.ctypes.data)
         return ids, ts, cnt
+
+    def trace_inst(self, rays, t_min=1e-3, t_max=np.inf, use_accel=1):
+        """two-level scenes: (prim ids, instance ids, t)"""
+        rays = np.ascontiguousarray(rays, np.float32)
+        n = len(rays)
+        ids, inst, ts = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float32)
+        self.lib.emu_trace_inst(self.h, rays.ctypes.data, n, t_min, t_max, use_accel, ids.ctypes.data, inst.ctypes.data,
+                                ts.ctypes.data)
+        return ids, inst, ts
 
     def texture(self, material, prim, p, outward):
         """material colour at hit points p of primitives `prim` with outward normals (device code)"""

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(capi.SYMBOLS) == syms
     for s in syms:
         assert hasattr(lib, s), s
-    assert capi.load_library().rt_version() == 4
+    assert capi.load_library().rt_version() == 5
 
 
 def test_struct_sizes_match_header():
@@ -35,7 +35,8 @@ def test_struct_sizes_match_header():
     assert C.sizeof(D.RtStats) == 96
     assert D.SPHERE_DT.itemsize == 48 and D.TRIANGLE_DT.itemsize == 52 and D.QUAD_DT.itemsize == 28
     assert D.MATERIAL_DT.itemsize == 40 and D.BVH_NODE_DT.itemsize == 32
-    assert C.sizeof(D.RtSceneDesc) == 4 * 16 + 96 + 32 + 3 * 16
+    assert C.sizeof(D.RtSceneDesc) == 4 * 16 + 96 + 32 + 3 * 16 + 2 * 16
+    assert D.GROUP_DT.itemsize == 32 and D.INSTANCE_DT.itemsize == 64
     assert D.MEDIUM_DT.itemsize == 56 and D.PERLIN_DT.itemsize == 6144 and C.sizeof(D.RtImage) == 16
 
 
@@ -43,7 +44,7 @@ def test_struct_sizes_against_the_c_compiler(tmp_path):
     """sizeof() of every struct of the header as gcc sees it == the ctypes / numpy mirrors"""
     import subprocess
     names = ["rt_config", "rt_sphere", "rt_triangle", "rt_quad", "rt_material", "rt_perlin", "rt_image", "rt_medium",
-             "rt_camera", "rt_scene_desc", "rt_bvh_node", "rt_stats_t"]
+             "rt_camera", "rt_scene_desc", "rt_bvh_node", "rt_stats_t", "rt_group", "rt_instance"]
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "rt_capi.h"\nint main(void) {\n' +
                    "".join('  printf("%%zu\\n", sizeof(%s));\n' % n for n in names) + "  return 0;\n}\n")
@@ -52,7 +53,8 @@ def test_struct_sizes_against_the_c_compiler(tmp_path):
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [C.sizeof(D.RtConfig), D.SPHERE_DT.itemsize, D.TRIANGLE_DT.itemsize, D.QUAD_DT.itemsize,
             D.MATERIAL_DT.itemsize, D.PERLIN_DT.itemsize, C.sizeof(D.RtImage), D.MEDIUM_DT.itemsize,
-            C.sizeof(D.RtCamera), C.sizeof(D.RtSceneDesc), D.BVH_NODE_DT.itemsize, C.sizeof(D.RtStats)]
+            C.sizeof(D.RtCamera), C.sizeof(D.RtSceneDesc), D.BVH_NODE_DT.itemsize, C.sizeof(D.RtStats),
+            D.GROUP_DT.itemsize, D.INSTANCE_DT.itemsize]
     assert got == want, list(zip(names, got, want))
 
 

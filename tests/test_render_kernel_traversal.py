@@ -103,7 +103,10 @@ def test_render_kernel_traversal_vs_brute_force(name, plan, monkeypatch):
         ia, ta = ctx.trace_closest(rays, t_min=t_min, use_accel=2)
         ib, tb = ctx.trace_closest(rays, t_min=t_min, use_accel=0)
         ic, tc = ctx.trace_closest(rays, t_min=t_min, use_accel=1)
-    _compare(ia, ta, ib, tb, rays)
+    # cornell_box: the baked boxes stand ON the floor rect - their bottom faces are coplanar with it, so rays that
+    # start inside a box and go down meet an exact tie between a triangle and the rect, and the rect's t comes from
+    # the ray's hardware reciprocal in the render kernel (2 ulp): more (true) ties than silhouettes alone give
+    _compare(ia, ta, ib, tb, rays, max_tie_frac=5e-3 if name == "cornell_box" else 2e-4)
     np.testing.assert_array_equal(ic, ib)
     assert (ia >= 0).mean() > 0.3
 
