@@ -243,6 +243,9 @@ struct rt_ctx {
   std::vector<BuildUnit> group_units; // layout + root box of every group's tree
   BuildUnit top_unit;
   std::vector<int> group_root_off, h_small;
+  std::vector<float> group_frames; // per group {qbase[3], qscale[3]}
+  std::vector<float4> h_units;     // unit table of the shared-memory staging loop (render_kernels.cuh)
+  DevBuf d_units;
   std::vector<float4> h_inst_rec, h_inst_box;
   DevBuf d_exclude, d_inst_lo, d_inst_hi, d_inst_ids; // d_exclude: a view into d_scene
   int total_nodes = 0, build_quality = 1;
@@ -410,7 +413,7 @@ void rt_destroy(rt_ctx *ctx) {
   if (ctx->comm) nccl_comm_destroy(ctx->comm);
   DevBuf *all[] = {&ctx->d_red, &ctx->d_scene, &ctx->d_nodes, &ctx->d_big, &ctx->d_leaf_prims, &ctx->d_bigq, &ctx->d_sph_is_big, &ctx->d_accum,
                    &ctx->d_partial, &ctx->d_counter, &ctx->d_stats, &ctx->d_linear, &ctx->d_rgb8, &ctx->d_rays, &ctx->d_ids, &ctx->d_ts,
-                   &ctx->d_inst_lo, &ctx->d_inst_hi, &ctx->d_inst_ids};
+                   &ctx->d_inst_lo, &ctx->d_inst_hi, &ctx->d_inst_ids, &ctx->d_units};
   for (DevBuf *b : all) dev_free(*b);
   for (DevBuf &b : ctx->build_tmp) dev_free(b);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
@@ -849,6 +852,20 @@ static int build_top_level(rt_ctx *ctx, int quality) {
   ctx->stats.n_nodes = U.kept_nodes;
   for (const BuildUnit &G : ctx->group_units) ctx->stats.n_nodes += G.kept_nodes;
   ctx->stats.n_big_prims = U.n_big;
+  // unit table for the shared-memory staging loop: per tree {first record, kept nodes, end code, -} {qbase} {qinv},
+  // ascending by first record (the top level, then the groups in layout order)
+  const int nu = 1 + (int)ctx->group_units.size();
+  ctx->h_units.assign(3 * (size_t)nu, make_float4(0, 0, 0, 0));
+  for (int u = 0; u < nu; u++) {
+    const BuildUnit &B = u == 0 ? U : ctx->group_units[u - 1];
+    float qb[3], qs[3], qi[3];
+    quant_frame(B.root_box, RT_Q_MAX, qb, qs, qi);
+    ctx->h_units[3 * (size_t)u] = make_float4(RT_I2F(B.link_base), RT_I2F(B.kept_nodes), RT_I2F(u == 0 ? 0 : RT_POP_SHARED), 0.f);
+    ctx->h_units[3 * (size_t)u + 1] = make_float4(qb[0], qb[1], qb[2], 0.f);
+    ctx->h_units[3 * (size_t)u + 2] = make_float4(qi[0], qi[1], qi[2], 0.f);
+  }
+  if ((rc = dev_reserve(ctx, ctx->d_units, sizeof(float4) * 3 * (size_t)nu))) return rc;
+  CK(cudaMemcpyAsync(ctx->d_units.p, ctx->h_units.data(), sizeof(float4) * 3 * (size_t)nu, cudaMemcpyHostToDevice, ctx->stream));
   return RT_OK;
 }
 
@@ -886,7 +903,8 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
     int n_world = 0;
     for (int i = 0; i < n; i++) n_world += ctx->grouped[i] ? 0 : 1;
     const int top_leaves = n_world + ni;
-    int node_at = std::max(2 * top_leaves - 1, 1), leaf_at = std::max(top_leaves, 1);
+    // (every slot ends with one spare record: the sentinel of the shared-memory copies, k_render staging loop)
+    int node_at = std::max(2 * top_leaves, 2), leaf_at = std::max(top_leaves, 1);
     ctx->group_units.assign(ng, BuildUnit());
     for (int g = 0; g < ng; g++) {
       const rt_group &G = ctx->groups[g];
@@ -897,7 +915,7 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
       U.classify = false;
       U.link_base = node_at; U.leaf_base = leaf_at;
       const int m = G.n_spheres + G.n_triangles + G.n_quads;
-      node_at += std::max(2 * m - 1, 0);
+      node_at += 2 * m;
       leaf_at += m;
     }
     ctx->total_nodes = node_at;
@@ -915,11 +933,16 @@ int rt_accel_build(rt_ctx *ctx, int quality) {
       root_off[g] = U.link_base << RT_NODE_SHIFT;
     }
     ctx->group_root_off = root_off;
-    // instance records with the groups' root offsets
+    // instance records with the groups' root offsets and quantisation frames
+    ctx->group_frames.assign(6 * (size_t)ng, 0.f);
+    for (int g = 0; g < ng; g++) {
+      float qinv[3];
+      quant_frame(ctx->group_units[g].root_box, RT_Q_MAX, &ctx->group_frames[6 * (size_t)g], &ctx->group_frames[6 * (size_t)g + 3], qinv);
+    }
     std::vector<float4> rec;
-    if ((rc = make_instance_records(ctx->instances.data(), ni, ng, root_off.data(), rec, ctx->err))) return rc;
+    if ((rc = make_instance_records(ctx->instances.data(), ni, ng, root_off.data(), rec, ctx->err, ctx->group_frames.data()))) return rc;
     ctx->h_inst_rec = rec;
-    if (ni) CK(cudaMemcpyAsync((void *)ctx->S.inst, ctx->h_inst_rec.data(), sizeof(float4) * 4 * (size_t)ni, cudaMemcpyHostToDevice, st));
+    if (ni) CK(cudaMemcpyAsync((void *)ctx->S.inst, ctx->h_inst_rec.data(), sizeof(float4) * RT_INST_STRIDE * (size_t)ni, cudaMemcpyHostToDevice, st));
     ctx->S.node_stride = node_at * 32;
     if ((rc = build_top_level(ctx, quality))) return rc;
   }
@@ -942,11 +965,13 @@ int rt_instances_update(rt_ctx *ctx, const rt_instance *instances, int n) {
   cudaStream_t st = ctx->stream;
   std::vector<float4> rec;
   int rc;
-  if ((rc = make_instance_records(instances, n, (int)ctx->groups.size(), ctx->group_root_off.data(), rec, ctx->err))) return rc;
+  if ((rc = make_instance_records(instances, n, (int)ctx->groups.size(), ctx->group_root_off.data(), rec, ctx->err,
+                                  ctx->group_frames.data())))
+    return rc;
   CK(cudaEventRecord(ctx->ev0, st));
   ctx->instances.assign(instances, instances + n);
   ctx->h_inst_rec = rec;
-  if (n) CK(cudaMemcpyAsync((void *)ctx->S.inst, ctx->h_inst_rec.data(), sizeof(float4) * 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (n) CK(cudaMemcpyAsync((void *)ctx->S.inst, ctx->h_inst_rec.data(), sizeof(float4) * RT_INST_STRIDE * (size_t)n, cudaMemcpyHostToDevice, st));
   ctx->S.n_big = 0; ctx->S.n_bigq = 0;
   if ((rc = build_top_level(ctx, ctx->build_quality))) return rc;
   CK(cudaEventRecord(ctx->ev1, st));
@@ -1041,9 +1066,15 @@ int rt_trace_closest_inst(rt_ctx *ctx, const float *rays, int n, float t_min, fl
 // ------------------------------------------------------------------ render
 typedef void (*render_kernel_t)(const RenderParams);
 static render_kernel_t pick_render_kernel(int profile, int smem, bool count, bool ext, bool inst) {
-  if (inst) { // two-level scenes: general kernel, global-memory plan (plan_scene_residency)
-    if (ext) return count ? k_render<2, true, 0, true, true, false, true> : k_render<2, true, 0, false, true, false, true>;
-    return count ? k_render<2, true, 0, true, false, false, true> : k_render<2, true, 0, false, false, false, true>;
+  if (inst) { // two-level scenes: the general kernel's INST instantiations (the counting variant: global plan only)
+    if (count) return ext ? k_render<2, true, 0, true, true, false, true> : k_render<2, true, 0, true, false, false, true>;
+#define PICKI(E) \
+  return smem == 2 ? k_render<2, true, 2, false, E, false, true>                                        \
+                   : (smem == 1 ? k_render<2, true, 1, false, E, false, true>                           \
+                                : (smem == 3 ? k_render<2, true, 3, false, E, false, true> : k_render<2, true, 0, false, E, false, true>))
+    if (ext) { PICKI(true); }
+    PICKI(false);
+#undef PICKI
   }
 #define PICK3(P, G, C, E) \
   (smem == 2 ? k_render<P, G, 2, C, E>                                                                  \
@@ -1072,14 +1103,11 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
   }
   const DevScene &S = ctx->S;
   // shared-memory node copies: 16-byte quantised records + one sentinel per copy (k_render staging loop)
-  P.b_nodes = S.n_nodes ? 16 * (S.n_nodes + 1) : 0;
-  for (int a = 0; a < 3; a++) {
-    const float lo = ctx->root_box[a], hi = ctx->root_box[4 + a];
-    const float ext = std::max(hi - lo, 1e-6f * std::max(std::max(fabsf(lo), fabsf(hi)), 1e-30f));
-    P.qbase[a] = lo;
-    P.qscale[a] = ext * (1.0f / (float)(RT_Q_MAX - 8)); // the root spans 0..RT_Q_MAX-8: room for the outward padding steps
-    P.qinv[a] = 1.0f / P.qscale[a];
-  }
+  // (two-level scenes: S.n_nodes counts the slots of every tree, each of which ends with its own sentinel record)
+  P.b_nodes = S.n_nodes ? 16 * (S.n_nodes + (ctx->two_level ? 0 : 1)) : 0;
+  quant_frame(ctx->root_box, RT_Q_MAX, P.qbase, P.qscale, P.qinv);
+  P.units = (const float4 *)ctx->d_units.p;
+  P.n_units = ctx->two_level ? 1 + (int)ctx->group_units.size() : 0;
   P.b_sph = (int)pad16(sizeof(float4) * (size_t)S.n_spheres);
   P.b_sph_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_spheres);
   P.b_sph_k = (int)pad16(sizeof(float) * (size_t)S.n_spheres);
@@ -1105,9 +1133,9 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
   if (scene_bytes + (RT_N_ORDERINGS - 1) * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
   // nodes only: one node copy resident, primitives through L1/L2
   if (smem == 0 && (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin && S.n_nodes > 0) smem = 3;
-  // two-level scenes: the objects' trees live in their own spaces (one quantisation frame per object would be
-  // needed for the 16-bit shared-memory records): everything through L1/L2
-  if (ctx->two_level) smem = 0;
+  // two-level scenes: every tree is quantised in its own frame (unit table); the staging loop looks the tree of a
+  // record up by binary search, which is only worth it for a moderate number of trees
+  if (ctx->two_level && (P.n_units > 4096 || (ctx->sp.flags & RT_FLAG_COUNTERS))) smem = 0;
   if (const char *e = getenv("B200RT_SMEM")) { // tuning knob: cap the plan (3 ranks between 0 and 1)
     const int cap = atoi(e);
     const int rank_of[4] = {0, 2, 3, 1}; // plan -> rank
@@ -1128,7 +1156,10 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
 }
 
 static render_kernel_t pick_trace_kernel(int profile, int smem, bool inst) {
-  if (inst) return k_render<2, true, 0, false, false, true, true>;
+  if (inst)
+    return smem == 2 ? k_render<2, true, 2, false, false, true, true>
+                     : (smem == 1 ? k_render<2, true, 1, false, false, true, true>
+                                  : (smem == 3 ? k_render<2, true, 3, false, false, true, true> : k_render<2, true, 0, false, false, true, true>));
 #define PICKT(P, G) \
   return smem == 2 ? k_render<P, G, 2, false, false, true>                                              \
                    : (smem == 1 ? k_render<P, G, 1, false, false, true>                                 \

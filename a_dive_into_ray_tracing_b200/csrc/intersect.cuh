@@ -287,7 +287,7 @@ RT_HD HitAcc trace_closest(const DevScene &S, const Ray &r_world, float t_min, f
       first++;
       left--;
       if (INST && RT_PRIM_TYPE_OF(id) == RT_PRIM_INSTANCE) {
-        const float4 *rec = S.inst + 4 * RT_PRIM_INDEX_OF(id);
+        const float4 *rec = S.inst + RT_INST_STRIDE * RT_PRIM_INDEX_OF(id);
         node_top = node; first_top = first; left_top = left;
         r.o = inst_point_to_object(rec, r_world.o);
         r.d = inst_vector_to_object(rec, r_world.d);
@@ -333,7 +333,7 @@ RT_HD HitAcc trace_brute(const DevScene &S, const uint8_t *is_big, const Ray &r,
   if (INST) {
     int best_inst = -1;
     for (int k = 0; k < S.n_inst; k++) {
-      const float4 *rec = S.inst + 4 * k;
+      const float4 *rec = S.inst + RT_INST_STRIDE * k;
       const int32_t *G = S.groups + 8 * RT_F2I(rec[3].y); // rt_group: first/count of spheres, triangles, quads
       Ray ro = r;
       ro.o = inst_point_to_object(rec, r.o);

@@ -38,6 +38,9 @@
 #define RT_MAX_CHUNKS 64
 #define RT_ACC_WORDS 384 // per-warp accumulator words: 2 tiles x 3 channels x {lo, hi} x 32 pixels
 #define RT_Q_MAX 46335 // largest quantised plane: (q << 16) + 0x4B000000 must not carry out of 32 bits (k_render)
+// two-level scenes, shared-memory plans: the link that ends an object's tree (shared addresses are multiples of 16
+// above it, 0 = finished, negative = leaf payload)
+#define RT_POP_SHARED 8
 #ifndef RT_N_ORDERINGS
 #define RT_N_ORDERINGS 8 // node orderings = ray-direction octants (bvh_build.cuh body_order)
 #endif
@@ -67,6 +70,10 @@ struct RenderParams {
   // 16-byte quantised nodes of the shared-memory copies: plane = qbase + q * qscale per axis (q = 0..65535
   // over the root box), see the staging loop of k_render
   float qbase[3], qscale[3], qinv[3];
+  // two-level scenes: one entry per tree, ascending by first record - {as_int first record, kept nodes, end code}
+  // {qbase.xyz} {qinv.xyz}: the staging loop quantises every tree in its own frame (the top level's is qbase / qinv)
+  const float4 *units;
+  int n_units;
   // TRACE instantiation (parity hook, rt_trace_closest use_accel = 2): the pool of a work item is a
   // run of caller-supplied rays instead of (pixel, sample) pairs; a finished traversal writes
   // (primitive id, t) instead of being shaded
@@ -126,17 +133,35 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     // to order a slab's two planes.
     {
       S.nodes = (const float4 *)(smem_raw + off);
-      const int nn = S.n_nodes, rec = nn + 1;
+      const int nn = S.n_nodes, rec = INST ? nn : nn + 1; // (two-level scenes: every tree's slot ends with its own sentinel)
       const int copies = SMEM == 2 ? RT_N_ORDERINGS : 1;
       for (int i = threadIdx.x; i < copies * rec; i += blockDim.x) {
         const int q = i / rec, k = i - q * rec;
         uint4 w;
-        if (k == nn) {
+        // two-level scenes: the tree this record belongs to (binary search in the unit table), its frame, where its
+        // kept nodes end (= its sentinel) and the code that ends it (0 = finished, RT_POP_SHARED = back to the top level)
+        float fb[3] = {P.qbase[0], P.qbase[1], P.qbase[2]}, fi[3] = {P.qinv[0], P.qinv[1], P.qinv[2]};
+        int u_end = nn, u_code = 0;
+        if (INST) {
+          int lo_u = 0, hi_u = P.n_units - 1;
+          while (lo_u < hi_u) {
+            const int mid = (lo_u + hi_u + 1) >> 1;
+            if (RT_F2I(__ldg(P.units + 3 * mid).x) <= k) lo_u = mid; else hi_u = mid - 1;
+          }
+          const float4 u0 = __ldg(P.units + 3 * lo_u), u1 = __ldg(P.units + 3 * lo_u + 1), u2 = __ldg(P.units + 3 * lo_u + 2);
+          u_end = RT_F2I(u0.x) + RT_F2I(u0.y);
+          u_code = RT_F2I(u0.z);
+          fb[0] = u1.x; fb[1] = u1.y; fb[2] = u1.z; fi[0] = u2.x; fi[1] = u2.y; fi[2] = u2.z;
+        }
+        if (INST ? k >= u_end : k == nn) {
           // sentinel: entry plane 65535, exit plane 0 on every axis: t(entry) > t(exit) strictly for every ray
           // with a finite non-zero 1/d, so it is always missed and its link (0) ends the traversal
           // (entry = the plane the ray reaches LAST: q = 65535 for a positive direction, q = 0 for a negative one)
           const unsigned fwd = (unsigned)RT_Q_MAX + 0x4B000000u, bwd = ((unsigned)RT_Q_MAX << 16) + 0x4B000000u;
           w = make_uint4((q & 1) ? bwd : fwd, (q & 2) ? bwd : fwd, (q & 4) ? bwd : fwd, 0u);
+          // one-copy plans keep (low plane | high plane << 16): low = RT_Q_MAX, high = 0 is missed by either direction
+          if (SMEM != 2) w = make_uint4((unsigned)RT_Q_MAX, (unsigned)RT_Q_MAX, (unsigned)RT_Q_MAX, 0u);
+          if (INST) w.w = (unsigned)u_code; // (records between a tree's sentinel and the next tree are never reached)
         } else {
           const float4 *src = P.S.nodes + q * (P.S.node_stride >> 4) + 2 * k;
           const float4 lo = __ldg(src), hi = __ldg(src + 1);
@@ -144,10 +169,10 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           unsigned pw[3];
 #pragma unroll
           for (int a = 0; a < 3; a++) {
-            const float fl = floorf((l3[a] - P.qbase[a]) * P.qinv[a]) - 2.0f, fh = ceilf((h3[a] - P.qbase[a]) * P.qinv[a]) + 2.0f;
+            const float fl = floorf((l3[a] - fb[a]) * fi[a]) - 2.0f, fh = ceilf((h3[a] - fb[a]) * fi[a]) + 2.0f;
             const unsigned ql = (unsigned)fminf(fmaxf(fl, 0.0f), (float)RT_Q_MAX), qh = (unsigned)fminf(fmaxf(fh, 0.0f), (float)RT_Q_MAX);
             const bool neg = SMEM == 2 && ((q >> a) & 1);
-            pw[a] = (neg ? (qh | (ql << 16)) : (ql | (qh << 16))) + 0x4B000000u;
+            pw[a] = (neg ? (qh | (ql << 16)) : (ql | (qh << 16))) + (SMEM == 2 ? 0x4B000000u : 0u);
           }
           const int base_q = (int)nodes_s + q * P.b_nodes;
           const int esc = RT_F2I(lo.w) >> RT_NODE_SHIFT; // node index within the copy
@@ -155,6 +180,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           if (pay < 0) { // leaf
             if (!GENERAL && P.direct_leaf) pay = ~(__ldg(P.S.leaf_prims + ((~pay) >> 3)) << 3);
             link = pay;
+          } else if (INST) { // a link that leaves the tree is its end code (global form: finished / RT_POP_LINK)
+            link = esc >= nn ? u_code : base_q + (esc << 4);
           } else { // inner: its first child is record k + 1 by construction
             link = esc == nn ? 0 : base_q + (esc << 4);
           }
@@ -229,8 +256,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   //   node < 0           LEAF: a hit leaf is pending, node = its payload
   //                      ~(first << 3 | count-1) into leaf_prims; `resume` = where to go on
   const int node_end = SMEM ? 0 : (S.n_nodes << RT_NODE_SHIFT);
-  const int node_pop = RT_POP_LINK(S.n_nodes); // INST: the end link of an object's tree
-#define RT_SEARCHING(n) (SMEM ? ((n) > 0) : ((unsigned)(n) < (unsigned)node_end))
+  const int node_pop = SMEM ? RT_POP_SHARED : RT_POP_LINK(S.n_nodes); // INST: the end link of an object's tree
+#define RT_SEARCHING(n) (SMEM ? ((n) > (INST ? RT_POP_SHARED : 0)) : ((unsigned)(n) < (unsigned)node_end))
   bool alive = false;
   int node = node_end, resume = 0;
   HitAcc h;
@@ -239,6 +266,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   pre.inv_d = v3(0, 0, 0); pre.ood = v3(0, 0, 0); pre.inv_a = 0.f;
   // quantised-node slab test (shared copies): t(plane q) = (2^23 + q) * qS + qC per axis
   V3f qS = v3(0, 0, 0), qC = v3(0, 0, 0);
+  // one-copy plans: per-lane byte-permute selectors of the entry / exit plane of each axis (see the step)
+  struct U3 { unsigned x, y, z; } selE = {0x7610u, 0x7610u, 0x7610u}, selX = {0x7632u, 0x7632u, 0x7632u};
   const float t_min = P.sp.t_min;
   // Work items (tile, chunk of samples) are OVERLAPPED: when the current item's pool is
   // drained its in-flight paths become the "old" item and the warp starts regenerating
@@ -264,6 +293,30 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   const char *nodes_g = (const char *)S.nodes;
   const char *nodes_q = nodes_g; // SMEM == 0: the current ray's quadrant copy in global memory
 
+  // Point the lane at the root of a tree for the ray in `r` / `pre`: root_index = the root's record index (0 = the
+  // scene's / top level's; an object's tree of a two-level scene otherwise), fb / fs = that tree's quantisation frame.
+  auto enter_tree = [&](int root_index, V3f fb, V3f fs) {
+    // sign BITS of 1/d (covers d = -0): which octant ordering (own child order; in shared memory also
+    // pre-selected entry / exit planes) this ray walks
+    const unsigned octant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.y) >> 31) << 1) |
+                            (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 2);
+    if (SMEM == 0) {
+      node = root_index << RT_NODE_SHIFT;
+      nodes_q = nodes_g + octant * (unsigned)S.node_stride;
+    } else { // the root's shared address in this ray's copy
+      node = (int)(nodes_s + (SMEM == 2 ? octant * (unsigned)P.b_nodes : 0u)) + (root_index << 4);
+      // plane q (16-bit) enters the slab test as the float 2^23 + q (one PRMT builds it: 0x4B00 | q), so
+      // t = (qbase + q * qscale - o) / d = (2^23 + q) * qS + qC with qS = qscale / d, qC = (qbase - o) / d - 2^23 qS
+      qS = v3(fs.x * pre.inv_d.x, fs.y * pre.inv_d.y, fs.z * pre.inv_d.z);
+      qC = v3(RT_FMA(-8388608.0f, qS.x, (fb.x - r.o.x) * pre.inv_d.x), RT_FMA(-8388608.0f, qS.y, (fb.y - r.o.y) * pre.inv_d.y),
+              RT_FMA(-8388608.0f, qS.z, (fb.z - r.o.z) * pre.inv_d.z));
+      if (SMEM != 2) { // a negative direction enters through the HIGH plane
+        selE.x = (octant & 1u) ? 0x7632u : 0x7610u; selX.x = selE.x ^ 0x0022u;
+        selE.y = (octant & 2u) ? 0x7632u : 0x7610u; selX.y = selE.y ^ 0x0022u;
+        selE.z = (octant & 4u) ? 0x7632u : 0x7610u; selX.z = selE.z ^ 0x0022u;
+      }
+    }
+  };
   // start a segment: per-ray constants, the always-tested big primitives, enter at the root
   auto begin_segment = [&]() {
     pre = ray_precompute_fast(r);
@@ -287,21 +340,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     if (EXT && S.n_media)
       h = apply_media(S.media, S.n_media, r.o, r.d, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, P.seed_lo,
                       P.seed_hi, h);
-    // sign BITS of 1/d (covers d = -0): which octant ordering (own child order; in shared memory also
-    // pre-selected entry / exit planes) this ray walks
-    const unsigned octant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.y) >> 31) << 1) |
-                            (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 2);
-    if (SMEM == 0) {
-      node = 0;
-      nodes_q = nodes_g + octant * (unsigned)S.node_stride;
-    } else { // the root's shared address in this ray's copy (no nodes: finished at once)
-      node = S.n_nodes ? (int)(nodes_s + (SMEM == 2 ? octant * (unsigned)P.b_nodes : 0u)) : 0;
-      // plane q (16-bit) enters the slab test as the float 2^23 + q (one PRMT builds it: 0x4B00 | q), so
-      // t = (qbase + q * qscale - o) / d = (2^23 + q) * qS + qC with qS = qscale / d, qC = (qbase - o) / d - 2^23 qS
-      qS = v3(P.qscale[0] * pre.inv_d.x, P.qscale[1] * pre.inv_d.y, P.qscale[2] * pre.inv_d.z);
-      qC = v3(RT_FMA(-8388608.0f, qS.x, (P.qbase[0] - r.o.x) * pre.inv_d.x), RT_FMA(-8388608.0f, qS.y, (P.qbase[1] - r.o.y) * pre.inv_d.y),
-              RT_FMA(-8388608.0f, qS.z, (P.qbase[2] - r.o.z) * pre.inv_d.z));
-    }
+    enter_tree(0, v3(P.qbase[0], P.qbase[1], P.qbase[2]), v3(P.qscale[0], P.qscale[1], P.qscale[2]));
+    if (S.n_nodes == 0) node = node_end; // no tree at all: finished at once
   };
 
   for (;;) {
@@ -328,27 +368,34 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
             //   entry bits = mad.lo(exit bits, -2^16, w)          = 0x4B000000 + entry     (mod 2^32)
             // i.e. the floats 2^23 + q, two integer multiply-adds per word.
             unsigned bx1, by1, bz1, bx0, by0, bz0;
-            asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(bx1) : "r"(w0));
-            asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(by1) : "r"(w1));
-            asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(bz1) : "r"(w2));
-            asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(bx0) : "r"(bx1), "r"(w0));
-            asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(by0) : "r"(by1), "r"(w1));
-            asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(bz0) : "r"(bz1), "r"(w2));
+            if (SMEM == 2) {
+              asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(bx1) : "r"(w0));
+              asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(by1) : "r"(w1));
+              asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(bz1) : "r"(w2));
+              asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(bx0) : "r"(bx1), "r"(w0));
+              asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(by0) : "r"(by1), "r"(w1));
+              asm("mad.lo.u32 %0, %1, 0xFFFF0000, %2;" : "=r"(bz0) : "r"(bz1), "r"(w2));
+            } else {
+              // One copy for every direction: the word is (low plane | high plane << 16) and each LANE picks its entry
+              // and exit half with a byte permute whose selector depends on the sign of its direction (0x7610: low
+              // half under 0x4B00, 0x7632: high half) - extraction and selection in one instruction, so the slab
+              // needs no min/max to order its two planes here either.
+              asm("prmt.b32 %0, %1, 0x4B000000, %2;" : "=r"(bx0) : "r"(w0), "r"(selE.x));
+              asm("prmt.b32 %0, %1, 0x4B000000, %2;" : "=r"(by0) : "r"(w1), "r"(selE.y));
+              asm("prmt.b32 %0, %1, 0x4B000000, %2;" : "=r"(bz0) : "r"(w2), "r"(selE.z));
+              asm("prmt.b32 %0, %1, 0x4B000000, %2;" : "=r"(bx1) : "r"(w0), "r"(selX.x));
+              asm("prmt.b32 %0, %1, 0x4B000000, %2;" : "=r"(by1) : "r"(w1), "r"(selX.y));
+              asm("prmt.b32 %0, %1, 0x4B000000, %2;" : "=r"(bz1) : "r"(w2), "r"(selX.z));
+            }
             const float x0 = RT_FMA(__uint_as_float(bx0), qS.x, qC.x), x1 = RT_FMA(__uint_as_float(bx1), qS.x, qC.x);
             const float y0 = RT_FMA(__uint_as_float(by0), qS.y, qC.y), y1 = RT_FMA(__uint_as_float(by1), qS.y, qC.y);
             const float z0 = RT_FMA(__uint_as_float(bz0), qS.z, qC.z), z1 = RT_FMA(__uint_as_float(bz1), qS.z, qC.z);
-            float tn, tf;
-            if (SMEM == 2) { // planes pre-selected for the octant: x0 / y0 / z0 are the entry planes
-              tn = RT_FMAX(RT_FMAX(x0, y0), RT_FMAX(z0, t_min));
-              tf = RT_FMIN(RT_FMIN(x1, y1), RT_FMIN(z1, h.t));
-            } else {
-              tn = RT_FMAX(RT_FMAX(RT_FMIN(x0, x1), RT_FMIN(y0, y1)), RT_FMAX(RT_FMIN(z0, z1), t_min));
-              tf = RT_FMIN(RT_FMIN(RT_FMAX(x0, x1), RT_FMAX(y0, y1)), RT_FMIN(RT_FMAX(z0, z1), h.t));
-            }
+            // x0 / y0 / z0 are the entry planes: pre-selected per octant copy (SMEM == 2) or per lane (one copy)
+            const float tn = RT_FMAX(RT_FMAX(x0, y0), RT_FMAX(z0, t_min));
+            const float tf = RT_FMIN(RT_FMIN(x1, y1), RT_FMIN(z1, h.t));
             // hit inner -> next record; hit leaf -> its payload; missed inner -> escape; missed leaf -> next record.
-            // SMEM == 2: the record after the last node is the sentinel (always missed, link 0); the one-copy
-            // plans order planes with min/max, which would re-sort the sentinel's planes, so they end explicitly
-            const int cont = (SMEM == 2 || at + 16 != (int)nodes_s + (S.n_nodes << 4)) ? at + 16 : 0;
+            // The record after the last node is the sentinel (always missed, link 0 = finished).
+            const int cont = at + 16;
             const bool leaf = link < 0;
             const int nxt = ((tn <= tf) == leaf) ? link : cont;
             if (searching) { node = nxt; resume = cont; }
@@ -371,24 +418,19 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       if (INST && node == node_pop) { // the object's tree is done: back to the top level with the world ray
         r.o = w_o; r.d = w_d;
         pre = ray_precompute_fast(r);
-        const unsigned octant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.y) >> 31) << 1) |
-                                (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 2);
-        nodes_q = nodes_g + octant * (unsigned)S.node_stride;
-        node = resume_top;
+        enter_tree(0, v3(P.qbase[0], P.qbase[1], P.qbase[2]), v3(P.qscale[0], P.qscale[1], P.qscale[2]));
+        node = resume_top; // (the same octant copy as before the instance: the world ray has not changed)
         cur_inst = -1;
       } else if (INST && node < 0 && RT_PRIM_TYPE_OF(S.leaf_prims[(~node) >> 3]) == RT_PRIM_INSTANCE) {
         // enter the instance named by this top-level leaf (instance leaves hold exactly one instance)
         const int k = RT_PRIM_INDEX_OF(S.leaf_prims[(~node) >> 3]);
-        const float4 *rec = S.inst + 4 * k;
+        const float4 *rec = S.inst + RT_INST_STRIDE * k;
         w_o = r.o; w_d = r.d;
         resume_top = resume;
         r.o = inst_point_to_object(rec, w_o);
         r.d = inst_vector_to_object(rec, w_d);
         pre = ray_precompute_fast(r);
-        const unsigned octant = ((unsigned)RT_F2I(pre.inv_d.x) >> 31) | (((unsigned)RT_F2I(pre.inv_d.y) >> 31) << 1) |
-                                (((unsigned)RT_F2I(pre.inv_d.z) >> 31) << 2);
-        nodes_q = nodes_g + octant * (unsigned)S.node_stride;
-        node = RT_F2I(rec[3].x);
+        enter_tree(RT_F2I(rec[3].x) >> RT_NODE_SHIFT, xyz(rec[4]), xyz(rec[5]));
         cur_inst = k;
       } else if (node < 0) {
         const int enc = ~node;

@@ -108,7 +108,8 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 //  inst    float4[4*n_inst]    per rt_instance: three rows {Rinv_k.xyz, tinv_k} of the WORLD -> OBJECT map
 //                              (p_obj = Rinv p_world + tinv; rigid, so t is preserved and normals go back with
 //                              the transpose), then {as_float(byte offset of the object's root node),
-//                              as_float(group), 0, 0}
+//                              as_float(group), 0, 0}, then the quantisation frame of the object's tree for the
+//                              16-bit shared-memory node records: {qbase.xyz, 0} {qscale.xyz, 0} (RT_INST_STRIDE = 6)
 // Two-level scenes (n_inst > 0): `nodes` holds the top-level tree first (root = node 0; its leaves name world
 // primitives or RT_PRIM_INSTANCE ids) and then one tree per group in OBJECT space; a link that leaves a group's
 // tree is RT_POP_LINK(n_nodes) = "back to the top level" (intersect.cuh, render_kernels.cuh).
@@ -147,6 +148,7 @@ struct DevScene {
   int n_inst;
 };
 
+#define RT_INST_STRIDE 6 // float4 per instance record
 // link value that ends an object's (bottom-level) tree: one node past "traversal finished"
 #define RT_POP_LINK(n_nodes) (((n_nodes) << RT_NODE_SHIFT) + (1 << RT_NODE_SHIFT))
 

@@ -36,11 +36,24 @@ static inline int flat_fail(std::string &err, const char *fmt, ...) {
   return RT_ERR_INVALID;
 }
 
+// Frame of the 16-bit quantised node records of a tree with this root box {bmin.xyz, -, bmax.xyz, -}: plane =
+// qbase + q * qscale, q = 0 .. q_max - 8 over the box (room for the outward padding steps of the staging loop)
+static inline void quant_frame(const float *root_box, int q_max, float qbase[3], float qscale[3], float qinv[3]) {
+  for (int a = 0; a < 3; a++) {
+    const float lo = root_box[a], hi = root_box[4 + a];
+    const float ext = std::max(hi - lo, 1e-6f * std::max(std::max(std::fabs(lo), std::fabs(hi)), 1e-30f));
+    qbase[a] = lo;
+    qscale[a] = ext * (1.0f / (float)(q_max - 8));
+    qinv[a] = 1.0f / qscale[a];
+  }
+}
+
 // Device records of rt_instance[n]: the inverse of the rigid map M = [R | T] in double (R^T, -R^T T), rounded
 // once. `root_offset_of_group` (byte offsets of the groups' root nodes) may be null before the build.
+// group_frames: per group {qbase[3], qscale[3]} of its tree (null before the build).
 static inline int make_instance_records(const rt_instance *inst, int n, int n_groups, const int *root_offset_of_group,
-                                        std::vector<float4> &out, std::string &err) {
-  out.assign(4 * (size_t)n, make_float4(0, 0, 0, 0));
+                                        std::vector<float4> &out, std::string &err, const float *group_frames = nullptr) {
+  out.assign(RT_INST_STRIDE * (size_t)n, make_float4(0, 0, 0, 0));
   for (int i = 0; i < n; i++) {
     const float *m = inst[i].m;
     for (int k = 0; k < 12; k++)
@@ -58,9 +71,14 @@ static inline int make_instance_records(const rt_instance *inst, int n, int n_gr
     if (det < 0.0) return flat_fail(err, "instance %d: mirrored matrix (det < 0)", i);
     for (int k = 0; k < 3; k++) { // row k of R^T = column k of R
       const double ti = -(R[0][k] * T[0] + R[1][k] * T[1] + R[2][k] * T[2]);
-      out[4 * (size_t)i + k] = make_float4((float)R[0][k], (float)R[1][k], (float)R[2][k], (float)ti);
+      out[RT_INST_STRIDE * (size_t)i + k] = make_float4((float)R[0][k], (float)R[1][k], (float)R[2][k], (float)ti);
     }
-    out[4 * (size_t)i + 3] = make_float4(RT_I2F(root_offset_of_group ? root_offset_of_group[inst[i].group] : 0), RT_I2F(inst[i].group), 0.f, 0.f);
+    out[RT_INST_STRIDE * (size_t)i + 3] = make_float4(RT_I2F(root_offset_of_group ? root_offset_of_group[inst[i].group] : 0), RT_I2F(inst[i].group), 0.f, 0.f);
+    if (group_frames) {
+      const float *f = group_frames + 6 * (size_t)inst[i].group;
+      out[RT_INST_STRIDE * (size_t)i + 4] = make_float4(f[0], f[1], f[2], 0.f);
+      out[RT_INST_STRIDE * (size_t)i + 5] = make_float4(f[3], f[4], f[5], 0.f);
+    }
   }
   return RT_OK;
 }

@@ -270,7 +270,7 @@ template <bool GENERAL, bool EXT, bool INST>
 RT_HD void surface_at_inst(const DevScene &S, const Ray &r, const HitAcc &h, V3f p, int inst, V3f &outward, int &mat,
                            V3f &p_uv, V3f &n_uv) {
   if (INST && inst >= 0) {
-    const float4 *rec = S.inst + 4 * inst;
+    const float4 *rec = S.inst + RT_INST_STRIDE * inst;
     Ray ro = r;
     ro.o = inst_point_to_object(rec, r.o);
     ro.d = inst_vector_to_object(rec, r.d);

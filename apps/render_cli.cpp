@@ -8,6 +8,7 @@
 //              [--gpus N]  sample split over N devices, one host thread and one context per device,
 //                          frames combined by rt_reduce (ncclReduce over NVLink);
 //                          --host-combine sums the downloaded frames on the CPU instead (no NCCL needed)
+//              [--instancing]  translate / rotate_y as instances of a two-level BVH instead of baked vertices
 //   render_cli --scene-file FILE.scene [--width W --height H --spp N ...]   (include/rtx/scene_file.h)
 #include <chrono>
 #include <cstring>
@@ -24,7 +25,7 @@ int main(int argc, char **argv) {
   int W = 0, H = 0, spp = 0, device = 0, gpus = 1;
   unsigned long long seed = 1984;
   bool have_seed = false;
-  bool binary = false, png = false, host_combine = false;
+  bool binary = false, png = false, host_combine = false, instancing = false;
   for (int i = 1; i < argc; i++) {
     auto is = [&](const char *f) { return !strcmp(argv[i], f) && i + 1 < argc; };
     if (is("--scene")) scene = argv[++i];
@@ -40,6 +41,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[i], "--binary")) binary = true;
     else if (!strcmp(argv[i], "--png")) png = true;
     else if (!strcmp(argv[i], "--host-combine")) host_combine = true;
+    else if (!strcmp(argv[i], "--instancing")) instancing = true;
     else { std::cerr << "unknown argument " << argv[i] << "\n"; return 2; }
   }
   // The image goes to stdout; libraries write there too (NCCL prints its version banner on fd 1): point fd 1 at
@@ -64,6 +66,7 @@ int main(int argc, char **argv) {
     if (!spp) spp = 500;
     opt.device = device;
     opt.seed = seed;
+    opt.instancing = instancing;
     const double aspect = double(W) / H;
     hittable_list world;
     hittable *root = nullptr;
@@ -133,7 +136,8 @@ int main(int argc, char **argv) {
     r.set_scene(*root, cam);
     std::cerr << "Rendering a " << W << "x" << H << " image with " << spp << " samples per pixel ("
               << r.flat.spheres.size() << " spheres, " << r.flat.triangles.size() << " triangles, " << r.flat.quads.size()
-              << " rects, " << r.flat.media.size() << " media)\n";
+              << " rects, " << r.flat.media.size() << " media, " << r.flat.instances.size() << " instances of "
+              << r.flat.groups.size() << " objects)\n";
     // further devices: the same scene, each its own context; device g renders the global sample
     // indices [g*spp/G, (g+1)*spp/G) (counter-based RNG: the image does not depend on G)
     if (gpus < 1 || device + gpus > rt_device_count()) throw std::runtime_error("--gpus: not that many CUDA devices");

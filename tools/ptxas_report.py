@@ -21,8 +21,10 @@ for line in out.splitlines():
     if cur is None:
         continue
     m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
-    if m:
-        cur["stack"], cur["st"], cur["ld"] = (int(x) for x in m.groups())
+    if m:  # (out-of-line callees report their own frames too: keep the largest)
+        v = tuple(int(x) for x in m.groups())
+        if v[0] >= cur.get("stack", 0):
+            cur["stack"], cur["st"], cur["ld"] = v
     m = re.search(r"Used (\d+) registers", line)
     if m:
         cur["regs"] = int(m.group(1))
