@@ -191,8 +191,7 @@ struct DevBuf {
 struct BuildUnit {
   int first[3] = {0, 0, 0}, count[3] = {0, 0, 0}; // sub-ranges of the scene's sphere / triangle / quad arrays
   int n_inst = 0;                     // instances (top level only): builder gids after the geometry
-  const uint8_t *d_exclude = nullptr; // top level of an instanced scene: geometry owned by a group (device / host copy)
-  const uint8_t *h_exclude = nullptr;
+  bool top_level = false;             // the top level of a two-level scene: geometry owned by groups is not its business
   bool classify = true;               // split oversized primitives off into the always-tested lists
   int link_base = 0, leaf_base = 0, end_link = -1;
   int stride_nodes = -1;              // nodes per ordering of the packed array; -1: this unit alone (2 n_small - 1)
@@ -244,6 +243,9 @@ struct rt_ctx {
   BuildUnit top_unit;
   std::vector<int> group_root_off, h_small;
   std::vector<float> group_frames; // per group {qbase[3], qscale[3]}
+  std::vector<int> box_first_quad; // boxes recognised by scene_flatten.h: first of the six rects
+  std::vector<uint8_t> h_mask;     // build_unit scratch
+  std::vector<int> h_unit_boxes;
   std::vector<float4> h_units;     // unit table of the shared-memory staging loop (render_kernels.cuh)
   DevBuf d_units;
   std::vector<float4> h_inst_rec, h_inst_box;
@@ -482,7 +484,7 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   std::vector<DevImage> dimg((size_t)sc->n_images);
   const size_t i_images = ADD(dimg); // filled below, once the arena's address is known
   std::vector<rt_group> groups_copy(sc->groups, sc->groups + sc->n_groups);
-  const size_t i_inst = ADD(F.inst), i_excl = ADD(F.grouped), i_groups = ADD(groups_copy);
+  const size_t i_inst = ADD(F.inst), i_excl = ADD(F.grouped), i_groups = ADD(groups_copy), i_box = ADD(F.box);
 #undef ADD
   if ((rc = dev_reserve(ctx, ctx->d_scene, total))) return rc;
   if ((rc = host_reserve(ctx, ctx->h_stage, ctx->h_stage_bytes, total))) return rc;
@@ -530,6 +532,10 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   S.inst = (const float4 *)(ds + slots[i_inst].off);
   S.n_inst = sc->n_instances;
   S.groups = (const int32_t *)(ds + slots[i_groups].off);
+  S.box = (const float4 *)(ds + slots[i_box].off);
+  S.n_boxes = (int)F.box.size() / 2;
+  ctx->box_first_quad.clear();
+  for (int b = 0; b < S.n_boxes; b++) ctx->box_first_quad.push_back(RT_F2I(F.box[2 * (size_t)b].w));
   ctx->d_exclude.p = ds + slots[i_excl].off; // (a view into the arena, like d_raw_*: never freed on its own)
   ctx->two_level = sc->n_groups > 0 || sc->n_instances > 0;
   ctx->groups.assign(sc->groups, sc->groups + sc->n_groups);
@@ -571,7 +577,8 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
 static int build_unit(rt_ctx *ctx, BuildUnit &U, int quality) {
   cudaStream_t st = ctx->stream;
   const int ns = U.count[0], nt = U.count[1], nq = U.count[2];
-  const int n_geom = ns + nt + nq, n = n_geom + U.n_inst;
+  const int n_geom = ns + nt + nq;
+  int n = n_geom + U.n_inst;
   U.n_small = 0; U.n_big = 0; U.kept_nodes = 0;
   memset(U.root_box, 0, sizeof U.root_box);
   if (n == 0) return RT_OK;
@@ -584,13 +591,33 @@ static int build_unit(rt_ctx *ctx, BuildUnit &U, int quality) {
   B.quads = (const rt_quad *)ctx->d_raw_quad.p + U.first[2];
   for (int k = 0; k < 3; k++) B.id_base[k] = U.first[k];
   B.inst_lo = (const float4 *)ctx->d_inst_lo.p; B.inst_hi = (const float4 *)ctx->d_inst_hi.p;
-  B.exclude = U.d_exclude;
+  // Geometry that is NOT a leaf of this unit: primitives owned by groups (top level of a two-level scene) and the
+  // sides of the unit's boxes, which get one leaf per box instead (RT_PRIM_BOX, gids after the instances)
+  std::vector<uint8_t> &mask = ctx->h_mask;
+  std::vector<int> &unit_boxes = ctx->h_unit_boxes;
+  mask.assign((size_t)std::max(n_geom, 1), 0);
+  unit_boxes.clear();
+  bool any_mask = false;
+  if (U.top_level)
+    for (int i = 0; i < n_geom; i++) { mask[i] = ctx->grouped[i]; any_mask = any_mask || mask[i]; }
+  for (int b = 0; b < (int)ctx->box_first_quad.size(); b++) {
+    const int fq = ctx->box_first_quad[b];
+    if (fq < U.first[2] || fq + 6 > U.first[2] + nq) continue;
+    if (U.top_level && ctx->grouped[(size_t)ctx->S.n_spheres + ctx->S.n_tris + fq]) continue;
+    unit_boxes.push_back(b);
+    for (int k = 0; k < 6; k++) mask[(size_t)ns + nt + (fq - U.first[2]) + k] = 1;
+    any_mask = true;
+  }
+  const int n_boxes = (int)unit_boxes.size();
+  n += n_boxes;
+  B.n_prims = n; B.n_boxes = n_boxes;
+  B.box_rec = ctx->S.box;
   B.link_base = U.link_base; B.leaf_base = U.leaf_base; B.end_link = U.end_link;
   B.thickness = (ctx->sp.flags & RT_FLAG_FLIP_NORMALS) ? 0.01f : 0.1f; // THICKNESS of the two trees
   // Build temporaries live in the context and only ever grow: a rebuild (every frame of an animated or
   // re-uploaded scene) calls neither cudaMalloc nor cudaFree, which would synchronise the device.
   enum { T_LO, T_HI, T_FLAG, T_BOUNDS, T_BIGLIST, T_SMALL, T_KEYS, T_LEFT, T_RIGHT, T_PARENT, T_NFLAG, T_SIZE, T_LCNT, T_NLO,
-         T_NHI, T_SWAP, T_RK0, T_RK1, T_RV0, T_RV1, T_RHIST, T_COUNT };
+         T_NHI, T_SWAP, T_RK0, T_RK1, T_RV0, T_RV1, T_RHIST, T_MASK, T_BOXIDS, T_COUNT };
   static_assert(T_COUNT <= RT_N_BUILD_TEMPS, "build temporaries");
   DevBuf *T = ctx->build_tmp;
   int rc;
@@ -600,6 +627,13 @@ static int build_unit(rt_ctx *ctx, BuildUnit &U, int quality) {
   if ((rc = pin_reserve(ctx, 4096))) return rc;
   B.pbox_lo = (float4 *)T[T_LO].p; B.pbox_hi = (float4 *)T[T_HI].p; B.big_flag = (int *)T[T_FLAG].p;
   B.bounds = (BuildBounds *)T[T_BOUNDS].p;
+  if (any_mask) {
+    RSV(T[T_MASK], mask.size()); RSV(T[T_BOXIDS], sizeof(int) * (size_t)std::max(n_boxes, 1));
+    CK(cudaMemcpyAsync(T[T_MASK].p, mask.data(), mask.size(), cudaMemcpyHostToDevice, st));
+    if (n_boxes) CK(cudaMemcpyAsync(T[T_BOXIDS].p, unit_boxes.data(), sizeof(int) * (size_t)n_boxes, cudaMemcpyHostToDevice, st));
+    B.exclude = (const uint8_t *)T[T_MASK].p;
+    B.box_ids = (const int *)T[T_BOXIDS].p;
+  }
   int *h_words = (int *)ctx->h_pin; // pinned: [0..32] big list, [40] kept nodes, [48..55] root box
   {
     BuildBounds *init = (BuildBounds *)(h_words + 64); // 4 x 24 bytes, pinned
@@ -668,13 +702,13 @@ static int build_unit(rt_ctx *ctx, BuildUnit &U, int quality) {
   U.n_big = n_big;
   // the primitives that stay in the tree, ascending
   int nsm;
-  if (U.h_exclude) { // the top level of an instanced scene: the host knows which primitives the groups own
+  if (any_mask) { // the host knows which primitives are not leaves of this unit
     std::vector<int> &small = ctx->h_small;
     small.clear();
     int kb = 0;
     for (int i = 0; i < n; i++) {
       while (kb < bl.n && bl.gid[kb] < i) kb++;
-      if ((kb < bl.n && bl.gid[kb] == i) || (i < n_geom && U.h_exclude[i])) continue;
+      if ((kb < bl.n && bl.gid[kb] == i) || (i < n_geom && mask[i])) continue;
       small.push_back(i);
     }
     nsm = (int)small.size();
@@ -839,8 +873,7 @@ static int build_top_level(rt_ctx *ctx, int quality) {
   U = BuildUnit();
   U.count[0] = ctx->S.n_spheres; U.count[1] = ctx->S.n_tris; U.count[2] = ctx->S.n_quads;
   U.n_inst = (int)ctx->instances.size();
-  U.d_exclude = (const uint8_t *)ctx->d_exclude.p;
-  U.h_exclude = ctx->grouped.data();
+  U.top_level = true;
   U.classify = true;
   U.link_base = 0; U.leaf_base = 0;
   U.stride_nodes = ctx->total_nodes;
@@ -1124,11 +1157,19 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
     P.b_quad = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_quads);
     P.b_tri_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_tris);
     P.b_quad_mat = (int)pad16(sizeof(int32_t) * (size_t)S.n_quads);
-    scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat + P.b_bigq;
+    P.b_box = (int)pad16(sizeof(float4) * 2 * (size_t)S.n_boxes);
+    scene_bytes += (size_t)P.b_sph_mv + P.b_sph_t0 + P.b_tri + P.b_tri_n + P.b_quad + P.b_tri_mat + P.b_quad_mat + P.b_bigq + P.b_box;
   }
   const size_t acc_bytes = (size_t)(block / 32) * RT_ACC_WORDS * sizeof(unsigned); // two 32-pixel tiles per warp, 64-bit fixed-point sums
   // shared-memory plan: 2 = scene + eight octant orderings of the (quantised) nodes, 1 = scene, 0 = global
   smem = 0;
+  if (scene_bytes + acc_bytes + 1024 > (size_t)ctx->max_smem_optin && ctx->general && S.n_boxes > 0 &&
+      scene_bytes - P.b_quad - P.b_quad_mat + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) {
+    // everything but the rect arrays fits, and the rects are mostly sides of boxes, whose records are resident:
+    // leave the rects in global memory (shading reads axis / material / uv extents from there)
+    scene_bytes -= (size_t)P.b_quad + P.b_quad_mat;
+    P.b_quad = 0; P.b_quad_mat = 0;
+  }
   if (scene_bytes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 1;
   if (scene_bytes + (RT_N_ORDERINGS - 1) * (size_t)P.b_nodes + acc_bytes + 1024 <= (size_t)ctx->max_smem_optin) smem = 2;
   // nodes only: one node copy resident, primitives through L1/L2
@@ -1141,6 +1182,32 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
     const int rank_of[4] = {0, 2, 3, 1}; // plan -> rank
     if (rank_of[smem] > rank_of[cap < 0 || cap > 3 ? 0 : cap]) smem = cap < 0 || cap > 3 ? 0 : cap;
   }
+  // one-ordering plans with room to spare: 2 or 4 of the eight octant orderings (the per-lane plane selection of
+  // those plans works for any ordering), chosen along the widest axes of the root box
+  P.n_copies = 1; P.copy_oct[0] = P.copy_oct[1] = P.copy_oct[2] = P.copy_oct[3] = 0; P.oct_lut = 0u;
+  // (only where the whole scene is resident: with primitives or textures still coming through L1 the extra shared
+  // memory costs more cache than the better visiting order saves - measured on the rt_next_week final scene,
+  // rects and textures in global memory: 113.8 ms with one copy, 117.6 ms with two)
+  const bool all_resident = smem == 1 && !ctx->ext && !(ctx->general && S.n_quads > 0 && P.b_quad == 0);
+  if ((all_resident || getenv("B200RT_COPIES")) && (smem == 1 || smem == 3) && S.n_nodes > 0 && S.node_stride != 0) {
+    const size_t base = acc_bytes + 1024 + (smem == 3 ? (size_t)P.b_nodes : scene_bytes);
+    int k = 1;
+    if (base + 3 * (size_t)P.b_nodes <= (size_t)ctx->max_smem_optin) k = 4;
+    else if (base + (size_t)P.b_nodes <= (size_t)ctx->max_smem_optin) k = 2;
+    if (const char *e = getenv("B200RT_COPIES")) k = std::min(k, std::max(1, atoi(e))) >= 4 ? 4 : (std::min(k, std::max(1, atoi(e))) >= 2 ? 2 : 1); // measurement knob
+    if (k > 1) {
+      const float ext[3] = {ctx->root_box[4] - ctx->root_box[0], ctx->root_box[5] - ctx->root_box[1], ctx->root_box[6] - ctx->root_box[2]};
+      int ax[3] = {0, 1, 2};
+      std::sort(ax, ax + 3, [&](int a, int b) { return ext[a] > ext[b]; });
+      const unsigned mask = k == 4 ? ((1u << ax[0]) | (1u << ax[1])) : (1u << ax[0]);
+      int n = 0;
+      int index_of[8];
+      for (unsigned o = 0; o < 8; o++)
+        if ((o & ~mask) == 0) { index_of[o] = n; P.copy_oct[n++] = (int)o; }
+      for (unsigned o = 0; o < 8; o++) P.oct_lut |= (unsigned)index_of[o & mask] << (4 * o);
+      P.n_copies = k;
+    }
+  }
   if (smem == 0) {
     // Global-memory node path: the octant-ordered copies pay while they stay cache
     // resident (measured: neutral up to 164 k nodes, one copy +14 % at 655 k nodes = 84 MB of copies).
@@ -1149,9 +1216,9 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
     if (one_copy) P.S.node_stride = 0;
   }
   smem_bytes = acc_bytes + (smem == 3 ? (size_t)P.b_nodes : (smem ? scene_bytes : 0)) +
-                            (smem == 2 ? (RT_N_ORDERINGS - 1) * (size_t)P.b_nodes : 0);
+                            (smem == 2 ? (RT_N_ORDERINGS - 1) * (size_t)P.b_nodes : (size_t)(P.n_copies - 1) * P.b_nodes);
   // staging order in k_render: node copies first, then the sphere array
-  P.off_sph = (smem == 2 ? RT_N_ORDERINGS : 1) * P.b_nodes;
+  P.off_sph = (smem == 2 ? RT_N_ORDERINGS : P.n_copies) * P.b_nodes;
   P.direct_leaf = (!ctx->general && (smem == 1 || smem == 2) && ctx->max_leaf == 1) ? 1 : 0;
 }
 

@@ -41,13 +41,15 @@ struct BuildArrays {
   // primitives of this build unit, unified index gid: spheres, then triangles, then quads, then instances.
   // A unit is the whole scene (single level), the top level of an instanced scene (world primitives + instances,
   // primitives owned by groups are skipped through `exclude`) or one group (its sub-ranges of the three arrays).
-  int n_prims, n_spheres, n_tris, n_quads, n_inst;
+  int n_prims, n_spheres, n_tris, n_quads, n_inst, n_boxes;
   const rt_sphere *spheres;   // already offset to the unit's first sphere / triangle / quad ...
   const rt_triangle *tris;
   const rt_quad *quads;
   int id_base[3];             // ... whose indices in the scene arrays these are (RT_PRIM_IDs are scene-wide)
   const float4 *inst_lo, *inst_hi; // [n_inst] world boxes of the instances (host-computed from the groups' root boxes)
-  const uint8_t *exclude;     // [n_prims - n_inst] or null: 1 = owned by a group, not part of this unit
+  const float4 *box_rec;      // the scene's box records {p0, first rect} {p1, -}
+  const int *box_ids;         // [n_boxes] the boxes of this unit (gids after the instances), indices into box_rec
+  const uint8_t *exclude;     // [geometry gids] or null: 1 = not a leaf of this unit (owned by a group / a side of a box)
   int link_base;              // node index of this unit's root inside an ordering of the packed array
   int leaf_base;              // index of this unit's first entry in leaf_prims
   int end_link;               // link stored where the traversal leaves this unit's tree (finished / back to the top level)
@@ -77,7 +79,9 @@ RT_HD int32_t gid_to_prim_id(const BuildArrays &B, int gid) {
   if (gid < B.n_spheres) return RT_PRIM_ID(RT_PRIM_SPHERE, B.id_base[0] + gid);
   if (gid < B.n_spheres + B.n_tris) return RT_PRIM_ID(RT_PRIM_TRIANGLE, B.id_base[1] + gid - B.n_spheres);
   if (gid < B.n_spheres + B.n_tris + B.n_quads) return RT_PRIM_ID(RT_PRIM_QUAD, B.id_base[2] + gid - B.n_spheres - B.n_tris);
-  return RT_PRIM_ID(RT_PRIM_INSTANCE, gid - B.n_spheres - B.n_tris - B.n_quads);
+  gid -= B.n_spheres + B.n_tris + B.n_quads;
+  if (gid < B.n_inst) return RT_PRIM_ID(RT_PRIM_INSTANCE, gid);
+  return RT_PRIM_ID(RT_PRIM_BOX, B.box_ids[gid - B.n_inst]);
 }
 
 // ---- kernel 1: primitive boxes (sphere.h:79-84, moving_sphere.h:74-82,
@@ -91,7 +95,10 @@ RT_HD void body_prim_box(const BuildArrays &B, int gid) {
     B.big_flag[gid] = 2;
     return;
   }
-  if (gid >= n_geom) {
+  if (gid >= n_geom + B.n_inst) { // a box: its corners
+    const float4 *b = B.box_rec + 2 * B.box_ids[gid - n_geom - B.n_inst];
+    lo[0] = b[0].x; lo[1] = b[0].y; lo[2] = b[0].z; hi[0] = b[1].x; hi[1] = b[1].y; hi[2] = b[1].z;
+  } else if (gid >= n_geom) {
     const float4 l = B.inst_lo[gid - n_geom], h = B.inst_hi[gid - n_geom];
     lo[0] = l.x; lo[1] = l.y; lo[2] = l.z; hi[0] = h.x; hi[1] = h.y; hi[2] = h.z;
   } else if (gid < B.n_spheres) {

@@ -164,6 +164,22 @@ RT_HD void hit_quad(float4 q0, float4 q1, const Ray &r, const RayPre &pre, float
   h.id = take ? id : h.id;
 }
 
+// box(p0, p1) = six rects in box.h's order (rt_next_week/cuda/box.h:41-58: xy@z1, xy@z0, xz@y1, xz@y0, yz@x1,
+// yz@x0), rects first .. first + 5 of the scene. The six rect tests run on the same numbers the six rects hold
+// (scene_flatten.h recognises a box by exact equality), in rect order, with the rects' ids: the result is
+// bit-identical to six separate leaves, at one leaf visit instead of up to six.
+RT_HD void hit_box_sides(float4 b0, float4 b1, const Ray &r, const RayPre &pre, float t_min, HitAcc &h) {
+  const int first = RT_F2I(b0.w);
+  const float lo[3] = {b0.x, b0.y, b0.z}, hi[3] = {b1.x, b1.y, b1.z};
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const int ax = 2 - (j >> 1), ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
+    const float4 q0 = make_float4((j & 1) ? lo[ax] : hi[ax], lo[ia], hi[ia], RT_I2F(ax));
+    const float4 q1 = make_float4(lo[ib], hi[ib], 0.f, 0.f);
+    hit_quad(q0, q1, r, pre, t_min, h, RT_PRIM_ID(RT_PRIM_QUAD, first + j));
+  }
+}
+
 // Slab test against a packed node box (closed interval). 1/d is finite (rt_safe_dir), so the
 // only NaN left is 0 * huge - 0 * huge = 0 handled exactly; fminf/fmaxf would drop any other.
 RT_HD bool hit_box(float4 lo, float4 hi, const RayPre &pre, float t_min, float t_max) {
@@ -213,9 +229,12 @@ RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &p
   } else if (type == RT_PRIM_TRIANGLE) {
     const float4 *t = S.tri + 4 * idx;
     hit_triangle(t[0], t[1], t[2], t[3], r, t_min, h, id);
-  } else {
+  } else if (type == RT_PRIM_QUAD) {
     const float4 *q = S.quad + 2 * idx;
     hit_quad(q[0], q[1], r, pre, t_min, h, id);
+  } else { // RT_PRIM_BOX: six rects of a box in one leaf
+    const float4 *b = S.box + 2 * idx;
+    hit_box_sides(b[0], b[1], r, pre, t_min, h);
   }
 }
 

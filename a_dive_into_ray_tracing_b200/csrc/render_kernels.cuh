@@ -63,7 +63,7 @@ struct RenderParams {
   int leaf_min; // run the pending primitive tests when this many lanes wait (or nobody searches)
   int frac8;  // a BVH burst ends when fewer than frac8/8 of its entry lanes are still searching
   // bytes of each array staged to shared memory (all multiples of 16)
-  int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big, b_leaf_prims, b_bigq;
+  int b_nodes, b_sph, b_sph_k, b_sph_mv, b_sph_t0, b_tri, b_tri_n, b_quad, b_sph_mat, b_tri_mat, b_quad_mat, b_mats, b_big, b_leaf_prims, b_bigq, b_box;
   // sphere-only kernels with single-primitive leaves: the staged leaf payloads name the sphere
   // directly (~(sphere << 3)) and the sphere array sits at this byte offset of the shared copy
   int direct_leaf, off_sph;
@@ -74,6 +74,11 @@ struct RenderParams {
   // {qbase.xyz} {qinv.xyz}: the staging loop quantises every tree in its own frame (the top level's is qbase / qinv)
   const float4 *units;
   int n_units;
+  // one-ordering plans (SMEM 1 / 3) with room to spare hold 2 or 4 of the builder's eight octant orderings: copy c
+  // is ordering copy_oct[c]; a ray of octant o walks copy (oct_lut >> 4 o) & 7 (the ordering that agrees with its
+  // direction signs on the one or two axes along which the scene is widest)
+  int n_copies, copy_oct[4];
+  unsigned oct_lut;
   // TRACE instantiation (parity hook, rt_trace_closest use_accel = 2): the pool of a work item is a
   // run of caller-supplied rays instead of (pixel, sample) pairs; a finished traversal writes
   // (primitive id, t) instead of being shaded
@@ -134,7 +139,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     {
       S.nodes = (const float4 *)(smem_raw + off);
       const int nn = S.n_nodes, rec = INST ? nn : nn + 1; // (two-level scenes: every tree's slot ends with its own sentinel)
-      const int copies = SMEM == 2 ? RT_N_ORDERINGS : 1;
+      const int copies = SMEM == 2 ? RT_N_ORDERINGS : P.n_copies;
       for (int i = threadIdx.x; i < copies * rec; i += blockDim.x) {
         const int q = i / rec, k = i - q * rec;
         uint4 w;
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           if (SMEM != 2) w = make_uint4((unsigned)RT_Q_MAX, (unsigned)RT_Q_MAX, (unsigned)RT_Q_MAX, 0u);
           if (INST) w.w = (unsigned)u_code; // (records between a tree's sentinel and the next tree are never reached)
         } else {
-          const float4 *src = P.S.nodes + q * (P.S.node_stride >> 4) + 2 * k;
+          const float4 *src = P.S.nodes + (SMEM == 2 ? q : P.copy_oct[q]) * (P.S.node_stride >> 4) + 2 * k;
           const float4 lo = __ldg(src), hi = __ldg(src + 1);
           const float l3[3] = {lo.x, lo.y, lo.z}, h3[3] = {hi.x, hi.y, hi.z};
           unsigned pw[3];
@@ -203,10 +208,13 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       S.sph_t0 = (const float *)stage_to_smem(smem_raw, off, P.S.sph_t0, P.b_sph_t0);
       S.tri = (const float4 *)stage_to_smem(smem_raw, off, P.S.tri, P.b_tri);
       S.tri_n = (const float4 *)stage_to_smem(smem_raw, off, P.S.tri_n, P.b_tri_n);
-      S.quad = (const float4 *)stage_to_smem(smem_raw, off, P.S.quad, P.b_quad);
+      // (b_quad == 0 with rects present: they all but fit - the rects stay in global memory, read at shading time
+      // and for the few that are not sides of a box; the box records below carry what the traversal needs)
+      if (P.b_quad) S.quad = (const float4 *)stage_to_smem(smem_raw, off, P.S.quad, P.b_quad);
       S.tri_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.tri_mat, P.b_tri_mat);
-      S.quad_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.quad_mat, P.b_quad_mat);
+      if (P.b_quad_mat) S.quad_mat = (const int32_t *)stage_to_smem(smem_raw, off, P.S.quad_mat, P.b_quad_mat);
       S.bigq = (const float4 *)stage_to_smem(smem_raw, off, P.S.bigq, P.b_bigq);
+      if (P.b_box) S.box = (const float4 *)stage_to_smem(smem_raw, off, P.S.box, P.b_box);
     }
     }
   }
@@ -304,7 +312,8 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       node = root_index << RT_NODE_SHIFT;
       nodes_q = nodes_g + octant * (unsigned)S.node_stride;
     } else { // the root's shared address in this ray's copy
-      node = (int)(nodes_s + (SMEM == 2 ? octant * (unsigned)P.b_nodes : 0u)) + (root_index << 4);
+      const unsigned copy = SMEM == 2 ? octant : ((P.oct_lut >> (4u * octant)) & 7u);
+      node = (int)(nodes_s + copy * (unsigned)P.b_nodes) + (root_index << 4);
       // plane q (16-bit) enters the slab test as the float 2^23 + q (one PRMT builds it: 0x4B00 | q), so
       // t = (qbase + q * qscale - o) / d = (2^23 + q) * qS + qC with qS = qscale / d, qC = (qbase - o) / d - 2^23 qS
       qS = v3(fs.x * pre.inv_d.x, fs.y * pre.inv_d.y, fs.z * pre.inv_d.z);
@@ -318,6 +327,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     }
   };
   // start a segment: per-ray constants, the always-tested big primitives, enter at the root
+  unsigned media_seed = 0u; // EXT: the fourth word of the Philox block that produced the current ray (apply_media)
   auto begin_segment = [&]() {
     pre = ray_precompute_fast(r);
     h.t = TRACE ? P.trace_tmax : INFINITY; h.id = -1;
@@ -337,9 +347,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       }
     }
     // participating media: a sampled scatter event becomes the initial closest hit
-    if (EXT && S.n_media)
-      h = apply_media(S.media, S.n_media, r.o, r.d, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, P.seed_lo,
-                      P.seed_hi, h);
+    if (EXT && S.n_media) h = apply_media(S.media, S.n_media, r.o, r.d, media_seed, h);
     enter_tree(0, v3(P.qbase[0], P.qbase[1], P.qbase[2]), v3(P.qscale[0], P.qscale[1], P.qscale[2]));
     if (S.n_nodes == 0) node = node_end; // no tree at all: finished at once
   };
@@ -590,6 +598,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         fresh_ray = true;
       }
       // (d) every lane with a new ray starts its segment together
+      if (EXT) media_seed = q.w;
       if (fresh_ray) begin_segment();
       // paths of the old item that ended in this round (their pix was captured before (b))
       if (old_valid) old_inflight -= __popc(__ballot_sync(FULL, ended && ((old_pix >> 5) == old_buf)));

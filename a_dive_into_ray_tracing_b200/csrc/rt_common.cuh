@@ -110,6 +110,10 @@ RT_HD V3f xyz(float4 q) { return v3(q.x, q.y, q.z); }
 //                              the transpose), then {as_float(byte offset of the object's root node),
 //                              as_float(group), 0, 0}, then the quantisation frame of the object's tree for the
 //                              16-bit shared-memory node records: {qbase.xyz, 0} {qscale.xyz, 0} (RT_INST_STRIDE = 6)
+//  box     float4[2*n_boxes]   {p0.xyz, as_float(first rect)} {p1.xyz, 0}: six consecutive rects that are the sides of
+//                              an axis-aligned box in box.h's order (xy@z1, xy@z0, xz@y1, xz@y0, yz@x1, yz@x0). The
+//                              builder gives the box ONE leaf (RT_PRIM_BOX) instead of six; the test evaluates the six
+//                              rect formulas on the same numbers, so hits (rect id, t) are bit-identical.
 // Two-level scenes (n_inst > 0): `nodes` holds the top-level tree first (root = node 0; its leaves name world
 // primitives or RT_PRIM_INSTANCE ids) and then one tree per group in OBJECT space; a link that leaves a group's
 // tree is RT_POP_LINK(n_nodes) = "back to the top level" (intersect.cuh, render_kernels.cuh).
@@ -143,6 +147,8 @@ struct DevScene {
   const uint8_t *perlin_perm;
   const DevImage *images;
   int n_media, n_perlin, n_images;
+  const float4 *box;
+  int n_boxes;
   const float4 *inst;
   const int32_t *groups; // rt_group[n_groups] as 8 ints each (brute-force parity hook)
   int n_inst;

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -24,6 +25,9 @@ struct HostFlat {
   // (spheres, triangles, quads) whether some group owns it (= not part of the world level)
   std::vector<float4> inst;
   std::vector<uint8_t> grouped;
+  // rects that form boxes (six consecutive rects in box.h's order): device records + per rect "inside a box"
+  std::vector<float4> box;
+  std::vector<uint8_t> quad_in_box;
 };
 
 static inline int flat_fail(std::string &err, const char *fmt, ...) {
@@ -275,6 +279,39 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
     quad[2 * (size_t)i] = make_float4(q.k, q.a0, q.a1, RT_I2F(q.axis));
     quad[2 * (size_t)i + 1] = make_float4(q.b0, q.b1, 0.f, 0.f);
     quad_mat[i] = q.material;
+  }
+  // `box` objects (rt_next_week/cuda/box.h:41-58): six rects xy@z1, xy@z0, xz@y1, xz@y0, yz@x1, yz@x0 over the same
+  // corner pair. Recognised by exact equality of the numbers, so that testing the six sides from the two corners
+  // is the same arithmetic as testing the six rects. (B200RT_BOXES=0 keeps six leaves: measurement / verification.)
+  F.box.clear();
+  F.quad_in_box.assign((size_t)nq, 0);
+  {
+    const char *e = getenv("B200RT_BOXES");
+    const bool on = profile == RT_PROFILE_NEXT_WEEK && !(e && atoi(e) == 0);
+    for (int i = 0; on && i + 6 <= nq;) {
+      const rt_quad *q = sc->quads + i;
+      const float x0 = q[0].a0, x1 = q[0].a1, y0 = q[0].b0, y1 = q[0].b1, z1 = q[0].k, z0 = q[1].k;
+      bool is_box = q[0].axis == 2 && q[1].axis == 2 && q[2].axis == 1 && q[3].axis == 1 && q[4].axis == 0 && q[5].axis == 0 &&
+                    x0 < x1 && y0 < y1 && z0 < z1 &&
+                    q[1].a0 == x0 && q[1].a1 == x1 && q[1].b0 == y0 && q[1].b1 == y1 &&
+                    q[2].a0 == x0 && q[2].a1 == x1 && q[2].b0 == z0 && q[2].b1 == z1 && q[2].k == y1 &&
+                    q[3].a0 == x0 && q[3].a1 == x1 && q[3].b0 == z0 && q[3].b1 == z1 && q[3].k == y0 &&
+                    q[4].a0 == y0 && q[4].a1 == y1 && q[4].b0 == z0 && q[4].b1 == z1 && q[4].k == x1 &&
+                    q[5].a0 == y0 && q[5].a1 == y1 && q[5].b0 == z0 && q[5].b1 == z1 && q[5].k == x0;
+      // all six rects must belong to the same trees: none or all owned by groups, and no group boundary inside
+      if (is_box && sc->n_groups) {
+        for (int g = 0; g < sc->n_groups && is_box; g++) {
+          const int lo = sc->groups[g].first_quad, hi = lo + sc->groups[g].n_quads;
+          const bool first_in = i >= lo && i < hi, last_in = i + 5 >= lo && i + 5 < hi;
+          if (first_in != last_in) is_box = false;
+        }
+      }
+      if (!is_box) { i++; continue; }
+      F.box.push_back(make_float4(x0, y0, z0, RT_I2F(i)));
+      F.box.push_back(make_float4(x1, y1, z1, 0.f));
+      for (int k = 0; k < 6; k++) F.quad_in_box[(size_t)i + k] = 1;
+      i += 6;
+    }
   }
   for (int i = 0; i < nm; i++) {
     const rt_material &m = sc->materials[i];

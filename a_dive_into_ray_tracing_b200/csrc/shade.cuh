@@ -183,8 +183,10 @@ RT_HD V3f material_color(const DevScene &S, float4 m0, float4 m1, V3f p, V3f p_u
 // distance = -1/density * log(u) (:60-61). Deviations from the reference: the event
 // must lie before the closest surface (the reference ignores t_max) and scattering continues
 // from the scatter point (the reference restarts at the boundary entry point, :66).
-// Random numbers: Philox stream 2 + m/4 of (pixel, sample, segment).
-// [t1, t2] = the whole line's intersection with medium m's convex boundary (constant_medium.h:42-52), unclamped
+// Random numbers: one word per medium derived from the Philox block of the event that produced the ray (medium_word).
+// [t1, t2] = the whole line's intersection with medium m's convex boundary (constant_medium.h:42-52), unclamped.
+// (Hardware division / square root: free-path sampling is checked statistically; the IEEE sequences made this the
+// largest piece of straight-line code of every segment start of a foggy scene.)
 RT_COLD bool medium_interval(const float4 *__restrict__ media, int m, V3f ro, V3f rd, float &t1, float &t2) {
   const float4 a0 = media[4 * m], a1 = media[4 * m + 1];
   if (RT_F2I(a0.w) == 0) {
@@ -192,9 +194,9 @@ RT_COLD bool medium_interval(const float4 *__restrict__ media, int m, V3f ro, V3
     const float a = dot(rd, rd), hb = dot(oc, rd), c = RT_FMA(-a1.x, a1.x, dot(oc, oc));
     const float disc = RT_FMA(hb, hb, -a * c);
     if (!(disc > 0.0f)) return false;
-    const float sq = RT_SQRT(disc);
-    t1 = (-hb - sq) / a;
-    t2 = (-hb + sq) / a;
+    const float sq = RT_SQRT(disc), ia = RT_FDIV(1.0f, a);
+    t1 = (-hb - sq) * ia;
+    t2 = (-hb + sq) * ia;
     return true;
   }
   const float4 a2 = media[4 * m + 2], a3 = media[4 * m + 3];
@@ -207,28 +209,40 @@ RT_COLD bool medium_interval(const float4 *__restrict__ media, int m, V3f ro, V3
   bool miss = false;
   for (int k = 0; k < 3; k++) {
     if (dl[k] == 0.0f) { miss = miss || ol[k] < lo[k] || ol[k] > hi[k]; continue; }
-    const float ta = (lo[k] - ol[k]) / dl[k], tb = (hi[k] - ol[k]) / dl[k];
+    const float id = RT_FDIV(1.0f, dl[k]);
+    const float ta = (lo[k] - ol[k]) * id, tb = (hi[k] - ol[k]) * id;
     t1 = RT_FMAX(t1, RT_FMIN(ta, tb));
     t2 = RT_FMIN(t2, RT_FMAX(ta, tb));
   }
   return !miss && t1 < t2;
 }
 
-RT_COLD HitAcc apply_media(const float4 *__restrict__ media, int n_media, V3f ro, V3f rd, uint32_t pixel, uint32_t smp,
-                           uint32_t segment, uint32_t seed_lo, uint32_t seed_hi, HitAcc h) {
+// One 32-bit word per medium from ONE word of the Philox block that produced this ray (the camera event's or the
+// bounce's fourth word): two rounds of a multiply-xorshift finaliser over word + m * golden ratio. (A Philox call of
+// its own per segment start was 100 straight-line instructions for one or two words.)
+RT_HD uint32_t medium_word(uint32_t seed, int m) {
+  uint32_t x = seed + 0x9E3779B9u * (uint32_t)(m + 1);
+  x ^= x >> 16; x *= 0x85EBCA6Bu;
+  x ^= x >> 13; x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  return x;
+}
+
+RT_COLD HitAcc apply_media(const float4 *__restrict__ media, int n_media, V3f ro, V3f rd, uint32_t seed, HitAcc h) {
   const float len = RT_SQRT(dot(rd, rd));
-  Philox4 q = {0u, 0u, 0u, 0u};
   for (int m = 0; m < n_media; m++) {
-    if ((m & 3) == 0) q = philox4x32_10(pixel, smp, segment, 2u + (uint32_t)(m >> 2), seed_lo, seed_hi);
-    const uint32_t word = (m & 3) == 0 ? q.x : ((m & 3) == 1 ? q.y : ((m & 3) == 2 ? q.z : q.w));
     float t1, t2;
     if (!medium_interval(media, m, ro, rd, t1, t2)) continue;
     t1 = RT_FMAX(t1, 0.0f);
     // u in (0, 1]: log(0) cannot occur
-    const float u = (float)((word >> 8) + 1u) * (1.0f / 16777216.0f);
+    const float u = (float)((medium_word(seed, m) >> 8) + 1u) * (1.0f / 16777216.0f);
+#ifdef __CUDA_ARCH__
+    const float hit_distance = media[4 * m + 1].w * __logf(u);
+#else
     const float hit_distance = media[4 * m + 1].w * logf(u);
+#endif
     if (hit_distance > (t2 - t1) * len) continue;
-    const float t = t1 + hit_distance / len;
+    const float t = t1 + RT_FDIV(hit_distance, len);
     if (t < h.t) { h.t = t; h.id = RT_PRIM_ID(RT_PRIM_MEDIUM, m); }
   }
   return h;

@@ -16,7 +16,7 @@ RT_FLAG_DEPTH_BACKGROUND = 2
 RT_FLAG_COUNTERS = 4
 RT_FLAG_REFERENCE_MEDIUM = 8
 
-RT_PRIM_SPHERE, RT_PRIM_TRIANGLE, RT_PRIM_QUAD, RT_PRIM_MEDIUM, RT_PRIM_INSTANCE = 0, 1, 2, 3, 4
+RT_PRIM_SPHERE, RT_PRIM_TRIANGLE, RT_PRIM_QUAD, RT_PRIM_MEDIUM, RT_PRIM_INSTANCE, RT_PRIM_BOX = 0, 1, 2, 3, 4, 5
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 0, 1, 2, 3, 4
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_NOISE, RT_TEX_IMAGE = 0, 1, 2, 3
 

@@ -76,7 +76,9 @@ typedef enum rt_prim_type {
   RT_PRIM_TRIANGLE = 1,
   RT_PRIM_QUAD = 2,
   RT_PRIM_MEDIUM = 3, /* constant_medium: never returned by rt_trace_closest (stochastic) */
-  RT_PRIM_INSTANCE = 4 /* leaf of the top-level tree naming an rt_instance: internal, never returned */
+  RT_PRIM_INSTANCE = 4, /* leaf of the top-level tree naming an rt_instance: internal, never returned */
+  RT_PRIM_BOX = 5       /* leaf naming six rects that form a `box` (box.h:41-58), tested together: internal, the
+                         * hit reports the rect (RT_PRIM_QUAD) that was hit */
 } rt_prim_type;
 /* primitive id returned by rt_trace_closest: (type << 28) | index-within-type; -1 = miss */
 #define RT_PRIM_ID(type, index) ((int32_t)(((uint32_t)(type) << 28) | (uint32_t)(index)))

@@ -40,6 +40,7 @@ static void bind(EmuScene &E, const rt_scene_desc *sc) {
   S.mats = E.F.mats.data(); S.big = E.big.data(); S.leaf_prims = E.leaf_prims.data();
   S.n_nodes = E.n_nodes_total; S.n_big = (int)E.big.size();
   S.inst = E.F.inst.data(); S.n_inst = sc->n_instances; S.groups = (const int32_t *)sc->groups;
+  S.box = E.F.box.data(); S.n_boxes = (int)E.F.box.size() / 2;
   S.n_spheres = sc->n_spheres; S.n_tris = sc->n_triangles; S.n_quads = sc->n_quads; S.n_mats = sc->n_materials;
   S.any_moving = E.F.any_moving;
   E.images.resize((size_t)sc->n_images);
@@ -73,7 +74,8 @@ struct EmuUnit {
 };
 
 static void build_unit(EmuScene &E, const rt_scene_desc *sc, EmuUnit &U, int quality, float big_frac, int big_rounds, int shuffle, int max_leaf) {
-  const int ns = U.count[0], nt = U.count[1], nq = U.count[2], n_geom = ns + nt + nq, n = n_geom + U.n_inst;
+  const int ns = U.count[0], nt = U.count[1], nq = U.count[2], n_geom = ns + nt + nq;
+  int n = n_geom + U.n_inst;
   if (n == 0) return;
   BuildArrays B;
   memset(&B, 0, sizeof B);
@@ -81,7 +83,21 @@ static void build_unit(EmuScene &E, const rt_scene_desc *sc, EmuUnit &U, int qua
   B.spheres = sc->spheres + U.first[0]; B.tris = sc->triangles + U.first[1]; B.quads = sc->quads + U.first[2];
   for (int k = 0; k < 3; k++) B.id_base[k] = U.first[k];
   B.inst_lo = E.inst_lo.data(); B.inst_hi = E.inst_hi.data();
-  B.exclude = U.exclude;
+  // geometry that is not a leaf of this unit (owned by groups / sides of the unit's boxes): build_unit of csrc/b200rt.cu
+  std::vector<uint8_t> mask((size_t)std::max(n_geom, 1), 0);
+  std::vector<int> unit_boxes;
+  if (U.exclude) for (int i = 0; i < n_geom; i++) mask[i] = U.exclude[i];
+  for (int b = 0; b < (int)E.F.box.size() / 2; b++) {
+    const int fq = RT_F2I(E.F.box[2 * (size_t)b].w);
+    if (fq < U.first[2] || fq + 6 > U.first[2] + nq) continue;
+    if (U.exclude && U.exclude[(size_t)sc->n_spheres + sc->n_triangles + fq]) continue;
+    unit_boxes.push_back(b);
+    for (int k = 0; k < 6; k++) mask[(size_t)ns + nt + (fq - U.first[2]) + k] = 1;
+  }
+  n += (int)unit_boxes.size();
+  B.n_prims = n; B.n_boxes = (int)unit_boxes.size();
+  B.box_rec = E.F.box.data(); B.box_ids = unit_boxes.data();
+  B.exclude = mask.data();
   B.link_base = U.link_base; B.leaf_base = U.leaf_base; B.end_link = U.end_link;
   B.thickness = (sc->flags & RT_FLAG_FLIP_NORMALS) ? 0.01f : 0.1f;
   std::vector<float4> lo(n), hi(n);
@@ -238,18 +254,20 @@ static void render_t(EmuScene *E, int W, int H, int spp_begin, int spp_count, ui
         Ray r = gen_camera_ray<PROFILE>(E->cam, W, H, i, j, u01(q.x), u01(q.y), u01(q.z), u01(q.w), x5);
         V3f beta = v3(1, 1, 1), L = v3(0, 0, 0);
         int bounce = 0;
+        uint32_t media_seed = q.w; // the fourth word of the Philox block that produced the current ray (k_render)
         npath++;
         for (;;) {
           HitAcc hm;
           hm.t = INFINITY; hm.id = -1;
           if (GENERAL && E->S.n_media)
-            hm = apply_media(E->S.media, E->S.n_media, r.o, r.d, (uint32_t)pixel_index, (uint32_t)smp, (uint32_t)bounce, k0, k1, hm);
+            hm = apply_media(E->S.media, E->S.n_media, r.o, r.d, media_seed, hm);
           int inst = -1;
           HitAcc h = trace_closest<PROFILE, GENERAL, true, GENERAL>(E->S, r, E->sp.t_min, hm.t, &cnt, &inst);
           if (h.id < 0) { h = hm; inst = -1; }
           nseg++;
           if (h.id < 0) { L = L + beta * miss_radiance(E->sp, r.d); break; }
           Philox4 qq = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, k0, k1);
+          media_seed = qq.w;
           bool cont = shade_hit<PROFILE, GENERAL, GENERAL, GENERAL>(E->S, E->sp, r, h, beta, L, qq, inst);
           bounce++;
           if (!cont) break;
