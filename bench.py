@@ -11,6 +11,7 @@
   c4        rt_next_week BVH scene (moving spheres, checker, dielectric) 1200x800, 1000 spp
   c5        Weekend final scene 3840x2160, 5000 spp (the multi-GPU config)
   nw_final  rt_next_week final scene (boxes, 1000-sphere cluster, media, perlin, image) 800x800, 1000 spp
+  c3_instanced, nw_final_instanced   the same with translate / rotate_y as instances of the two-level BVH
 
 A "step" is one complete frame. N > 1 splits the SAMPLES of the frame over the ranks (strong scaling of one
 frame, as BASELINE.json's metric asks), each rank accumulating into its own frame, combined by the library's
@@ -47,6 +48,11 @@ CONFIGS = {
                workload="weekend_final_scene_487_spheres_3840x2160_5000spp_depth50"),
     "nw_final": dict(scene="next_week_final", kw={}, W=800, H=800, spp=1000,
                      workload="rt_next_week_final_scene_800x800_1000spp_depth50"),
+    # the same two scenes with translate / rotate_y as instances of the two-level BVH (rt_group / rt_instance)
+    "c3_instanced": dict(scene="obj_room", kw={"mesh": "blob968", "instanced": True}, W=800, H=800, spp=1500,
+                         workload="triangles_cuda_obj_room_968_triangle_mesh_as_instance_800x800_1500spp_depth50"),
+    "nw_final_instanced": dict(scene="next_week_final", kw={"instanced": True}, W=800, H=800, spp=1000,
+                               workload="rt_next_week_final_scene_cluster_as_instance_800x800_1000spp_depth50"),
 }
 DATA = {"weekend": "synthetic (the reference's random_scene() under glibc's default seed, float-rounded fixture)",
         "obj_room": "synthetic (procedural 968-triangle mesh in the room of obj_render.cu:384-524)",
