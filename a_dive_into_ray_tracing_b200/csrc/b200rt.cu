@@ -1132,6 +1132,8 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
     const char *lm = getenv("B200RT_LEAFMIN");
     P.leaf_min = lm ? atoi(lm) : 1; // measured: 1..5 within 0.5 %, larger values slower
     P.batch = std::max(1, std::min(P.batch, 32));
+    const char *bl = getenv("B200RT_BATCH_LONG");
+    P.batch_long = bl ? std::max(1, std::min(atoi(bl), 32)) : std::min(P.batch, 18);
     P.frac8 = std::max(0, std::min(P.frac8, 8));
   }
   const DevScene &S = ctx->S;

@@ -29,9 +29,12 @@
 // BVH steps between two warp votes in the search burst. Measured (B200, after the r1i instruction
 // diet): sphere-only kernel 2/3/4 steps -> 78.2/76.8/77.5 ms (config 2); general kernel
 // 173/171/167 ms (config 3, 150 spp).
-#ifndef RT_STEPS_PER_VOTE
-#define RT_STEPS_PER_VOTE(GENERAL) ((GENERAL) ? 4 : 3)
+// The extended kernel (media, noise / image textures) is bound by instruction fetch: a shorter unrolled burst is
+// faster there (final scene 106.9 -> 101.9 ms per 200 spp with 2 steps).
+#ifndef RT_SPV_EXT
+#define RT_SPV_EXT 2
 #endif
+#define RT_STEPS_PER_VOTE(GENERAL, EXT) ((EXT) ? RT_SPV_EXT : ((GENERAL) ? 4 : 3))
 #define RT_BLOCK_OF(GENERAL) ((GENERAL) ? RT_BLOCK_GENERAL : RT_BLOCK)
 #define RT_TILE_W 8
 #define RT_TILE_H 4
@@ -60,6 +63,7 @@ struct RenderParams {
   unsigned long long *stats;     // paths, segments, box tests, prim tests
   uint32_t seed_lo, seed_hi;
   int batch;  // shade/regenerate when this many lanes are DONE or DEAD (warp-voted scheduler)
+  int batch_long; // the same for warps whose paths run long (general kernels)
   int leaf_min; // run the pending primitive tests when this many lanes wait (or nobody searches)
   int frac8;  // a BVH burst ends when fewer than frac8/8 of its entry lanes are still searching
   // bytes of each array staged to shared memory (all multiples of 16)
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   // from the next item at once, so no lane idles through an item's drain tail. Two
   // 32-pixel accumulators per warp; a lane's path remembers its accumulator in bit 5 of pix.
   int pool_next = 0, pool_end = 0; // warp-uniform
+  int path_score = 0;              // warp-uniform: > 0 = this warp's paths are long (see the shading threshold)
   int tile_x0 = 0, tile_y0 = 0, s0 = 0, chunk = 0, chunk_n = 0, cur_buf = 0;
   int old_x0 = 0, old_y0 = 0, old_chunk = 0, old_chunk_n = 0, old_buf = 0, old_inflight = 0;
   bool have_cur = false, old_valid = false, more_work = true;
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       for (;;) {
         if (__popc(__ballot_sync(FULL, RT_SEARCHING(node))) < thr) break;
 #pragma unroll
-        for (int u = 0; u < RT_STEPS_PER_VOTE(GENERAL); u++) {
+        for (int u = 0; u < RT_STEPS_PER_VOTE(GENERAL, EXT); u++) {
           const bool searching = RT_SEARCHING(node);
           if (SMEM != 0) {
             // lanes that are not searching (node <= 0) fetch the first record and discard the result
@@ -462,7 +467,12 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     // ---- phase 3: shade + regenerate once enough lanes are out of the traversal
     const unsigned m_out = __ballot_sync(FULL, node == node_end);
     const int n_out = __popc(m_out);
-    if (n_out < P.batch && n_out < 32) continue;
+    // Long paths (closed, lit rooms: config 3 runs 20 segments per path) regenerate rarely - most lanes that leave the
+    // traversal only need the cheap hit shading - and do better with an earlier shading round; short paths end often
+    // and the expensive regeneration code wants a fuller batch. Each warp keeps a running score of (continuing hits)
+    // against (new paths) and switches thresholds: config 3 185 -> 172 ms per 150 spp, short-path scenes unchanged.
+    const int batch_w = (GENERAL && !EXT && path_score > 2048) ? P.batch_long : P.batch; // (the extended kernel: -3.5 % with it)
+    if (n_out < batch_w && n_out < 32) continue;
     // -- work-item management (warp-uniform)
     if (pool_next >= pool_end && !old_valid) {
       if (have_cur) { // the current item's pool is drained: it becomes the old item
@@ -553,7 +563,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       }
       // (c) ONE Philox call per lane: the bounce event of a hit, or the camera event of a new path
       if (!TRACE && (hit || fresh_path))
-        q = philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
+        q = philox_for_kernel<GENERAL>((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
       bool fresh_ray = false;
       if (hit) {
         const bool cont = shade_hit<PROFILE, GENERAL, EXT, INST>(S, P.sp, r, h, beta, L, q, hit_inst);
@@ -577,6 +587,10 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       }
       // ONE accumulation site for every path that ended in this round - rays that left the scene in (a), possibly
       // already re-assigned to a new (pixel, sample) whose L is reset only below, and paths the shading terminated
+      if (GENERAL && !EXT && !TRACE) { // hits that go on count 1, a new path counts 10 the other way, clamped
+        path_score += __popc(__ballot_sync(FULL, hit)) - 10 * __popc(__ballot_sync(FULL, fresh_path));
+        path_score = max(-4096, min(4096, path_score));
+      }
       if (TRACE && fresh_path) { // (a hit lane keeps its path: it never takes a new item in the same round)
         const float4 ra = __ldg(P.trace_rays + 2 * (size_t)pixel_index), rb = __ldg(P.trace_rays + 2 * (size_t)pixel_index + 1);
         r.o = v3(ra.x, ra.y, ra.z); r.tm = ra.w; r.d = v3(rb.x, rb.y, rb.z);
@@ -588,7 +602,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         const int i = tile_x0 + (px & 7), j = tile_y0 + (px >> 3);
         float x5 = 0.f;
         if (PROFILE == 2 && P.cam.time1 != P.cam.time0)
-          x5 = u01(philox4x32_10((uint32_t)pixel_index, (uint32_t)smp, 0u, 1u, P.seed_lo, P.seed_hi).x);
+          x5 = u01(philox_for_kernel<GENERAL>((uint32_t)pixel_index, (uint32_t)smp, 0u, 1u, P.seed_lo, P.seed_hi).x);
         r = gen_camera_ray<PROFILE>(P.cam, P.W, P.H, i, j, u01(q.x), u01(q.y), u01(q.z), u01(q.w), x5);
         beta = v3(1, 1, 1);
         L = v3(0, 0, 0);

@@ -59,6 +59,15 @@ static inline float rt_host_i2f(int i) { float x; memcpy(&x, &i, 4); return x; }
 #define RT_FDIV(a, b) ((a) / (b))
 #endif
 
+// Rarely executed or large straight-line code lives in out-of-line functions: the big general kernels are bound by
+// instruction fetch, and register allocation of the hot loop is not shaped by cold code. Arguments and
+// results travel BY VALUE (a reference would pin the caller's variables in local memory).
+#ifdef __CUDA_ARCH__
+#define RT_COLD __device__ __noinline__
+#else
+#define RT_COLD static inline
+#endif
+
 #define RT_NODE_SHIFT 5 // log2(sizeof packed node): node links are byte offsets
 
 struct V3f {

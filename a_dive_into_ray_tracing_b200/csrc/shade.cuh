@@ -78,13 +78,8 @@ RT_HD float rt_fast_sin(float x) {
 #endif
 }
 
-// ---- rarely used texture kinds live in out-of-line functions so that the render kernel's
-// register allocation is not shaped by them.
-#ifdef __CUDA_ARCH__
-#define RT_COLD __device__ __noinline__
-#else
-#define RT_COLD static inline
-#endif
+// ---- rarely used texture kinds live in out-of-line functions (RT_COLD, rt_common.cuh) so that the render
+// kernel's register allocation is not shaped by them.
 
 // perlin::noise with the trilinear Hermite interpolation of perlin.h:29-56,103-122 (as the reference
 // computes it: see the note at the weight vector)
