@@ -267,7 +267,10 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *scene);
 /* quality: 0 = LBVH (Morton + radix sort + Karras), 1 = + SAH refinement. */
 int rt_accel_build(rt_ctx *ctx, int quality);
 /* nodes: threaded BVH; leaf_prims: RT_PRIM_IDs in depth-first leaf order; big_prims: the
- * always-tested oversized primitives. Any output pointer may be NULL (counts only). */
+ * always-tested oversized primitives. Any output pointer may be NULL (counts only).
+ * Two-level scenes: the node array holds every tree - the top level first (root = node 0; its leaves may be
+ * RT_PRIM_INSTANCE ids), then one slot per group -, n_nodes counts the slots' records and records a tree does not
+ * use are undefined; leaves may also carry RT_PRIM_BOX ids (six rects of a box). */
 int rt_accel_download(rt_ctx *ctx, rt_bvh_node *nodes, int cap_nodes, int *n_nodes, int32_t *leaf_prims,
                       int cap_leaf, int *n_leaf, int32_t *big_prims, int cap_big, int *n_big);
 
