@@ -287,13 +287,6 @@ static int dev_reserve(rt_ctx *ctx, DevBuf &b, size_t bytes) {
   b.bytes = bytes;
   return RT_OK;
 }
-static int dev_upload(rt_ctx *ctx, DevBuf &b, const void *src, size_t bytes) {
-  int rc = dev_reserve(ctx, b, bytes);
-  if (rc) return rc;
-  CK(cudaMemsetAsync(b.p, 0, b.bytes, ctx->stream));
-  if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return RT_OK;
-}
 static void dev_free(DevBuf &b) {
   if (b.p) cudaFree(b.p);
   b.p = nullptr; b.bytes = 0;
