@@ -34,7 +34,10 @@
 #ifndef RT_SPV_EXT
 #define RT_SPV_EXT 2
 #endif
-#define RT_STEPS_PER_VOTE(GENERAL, EXT) ((EXT) ? RT_SPV_EXT : ((GENERAL) ? 4 : 3))
+#ifndef RT_SPV_SPHERE
+#define RT_SPV_SPHERE 3
+#endif
+#define RT_STEPS_PER_VOTE(GENERAL, EXT) ((EXT) ? RT_SPV_EXT : ((GENERAL) ? 4 : RT_SPV_SPHERE))
 #define RT_BLOCK_OF(GENERAL) ((GENERAL) ? RT_BLOCK_GENERAL : RT_BLOCK)
 #define RT_TILE_W 8
 #define RT_TILE_H 4
