@@ -220,6 +220,7 @@ struct rt_ctx {
   rt_scene_desc desc;
   bool general = false;
   bool ext = false; // media or noise/image textures: the extended kernel variant
+  bool spheres_only = false; // profile 2 with nothing but spheres (and no media / instances): the SPH instantiations
   // device scene
   // d_scene: ONE arena holding every flattened array of the scene (16-byte aligned slots, zero padded), filled by
   // one copy from the pinned staging block h_stage; the d_raw_* pointers (builder input) point into it too
@@ -454,6 +455,9 @@ int rt_scene_upload(rt_ctx *ctx, const rt_scene_desc *sc) {
   for (int i = 0; i < sc->n_materials; i++)
     if (sc->materials[i].texture >= RT_TEX_NOISE || sc->materials[i].type == RT_MAT_ISOTROPIC) ctx->ext = true;
   if (const char *e = getenv("B200RT_EXT")) ctx->ext = ctx->ext || (ctx->general && atoi(e) != 0); // measurement knob
+  ctx->spheres_only = ctx->general && !ctx->ext && sc->n_triangles == 0 && sc->n_quads == 0 && sc->n_groups == 0 &&
+                      sc->n_instances == 0;
+  if (const char *e = getenv("B200RT_SPH")) ctx->spheres_only = ctx->spheres_only && atoi(e) != 0; // measurement knob
 
   CK(cudaEventRecord(ctx->ev0, ctx->stream));
   const int ns = sc->n_spheres, nt = sc->n_triangles, nq = sc->n_quads, nm = sc->n_materials;
@@ -1091,7 +1095,16 @@ int rt_trace_closest_inst(rt_ctx *ctx, const float *rays, int n, float t_min, fl
 
 // ------------------------------------------------------------------ render
 typedef void (*render_kernel_t)(const RenderParams);
-static render_kernel_t pick_render_kernel(int profile, int smem, bool count, bool ext, bool inst) {
+static render_kernel_t pick_render_kernel(int profile, int smem, bool count, bool ext, bool inst, bool sph) {
+  if (sph) { // profile 2, spheres only (config 4)
+#define PICKS(C) \
+  return smem == 2 ? k_render<2, true, 2, C, false, false, false, true>                                 \
+                   : (smem == 1 ? k_render<2, true, 1, C, false, false, false, true>                    \
+                                : (smem == 3 ? k_render<2, true, 3, C, false, false, false, true> : k_render<2, true, 0, C, false, false, false, true>))
+    if (count) { PICKS(true); }
+    PICKS(false);
+#undef PICKS
+  }
   if (inst) { // two-level scenes: the general kernel's INST instantiations (the counting variant: global plan only)
     if (count) return ext ? k_render<2, true, 0, true, true, false, true> : k_render<2, true, 0, true, false, false, true>;
 #define PICKI(E) \
@@ -1214,10 +1227,14 @@ static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &s
                             (smem == 2 ? (RT_N_ORDERINGS - 1) * (size_t)P.b_nodes : (size_t)(P.n_copies - 1) * P.b_nodes);
   // staging order in k_render: node copies first, then the sphere array
   P.off_sph = (smem == 2 ? RT_N_ORDERINGS : P.n_copies) * P.b_nodes;
-  P.direct_leaf = (!ctx->general && (smem == 1 || smem == 2) && ctx->max_leaf == 1) ? 1 : 0;
+  P.direct_leaf = ((!ctx->general || ctx->spheres_only) && (smem == 1 || smem == 2) && ctx->max_leaf == 1) ? 1 : 0;
 }
 
-static render_kernel_t pick_trace_kernel(int profile, int smem, bool inst) {
+static render_kernel_t pick_trace_kernel(int profile, int smem, bool inst, bool sph) {
+  if (sph)
+    return smem == 2 ? k_render<2, true, 2, false, false, true, false, true>
+                     : (smem == 1 ? k_render<2, true, 1, false, false, true, false, true>
+                                  : (smem == 3 ? k_render<2, true, 3, false, false, true, false, true> : k_render<2, true, 0, false, false, true, false, true>));
   if (inst)
     return smem == 2 ? k_render<2, true, 2, false, false, true, true>
                      : (smem == 1 ? k_render<2, true, 1, false, false, true, true>
@@ -1263,7 +1280,7 @@ static int trace_through_render_kernel(rt_ctx *ctx, int n, float t_min, float t_
   int smem = 0;
   size_t smem_bytes = 0;
   plan_scene_residency(ctx, P, block, smem, smem_bytes);
-  render_kernel_t kern = pick_trace_kernel(ctx->cfg.profile, smem, ctx->two_level);
+  render_kernel_t kern = pick_trace_kernel(ctx->cfg.profile, smem, ctx->two_level, ctx->spheres_only);
   CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   CK(cudaMemsetAsync(P.work_counter, 0, 4, st));
   kern<<<grid, block, smem_bytes, st>>>(P);
@@ -1347,7 +1364,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   size_t smem_bytes = 0;
   plan_scene_residency(ctx, P, block, smem, smem_bytes);
   const bool count = (ctx->sp.flags & RT_FLAG_COUNTERS) != 0;
-  render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext, ctx->two_level);
+  render_kernel_t kern = pick_render_kernel(ctx->cfg.profile, smem, count, ctx->ext, ctx->two_level, ctx->spheres_only);
   CK(cudaFuncSetAttribute((const void *)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   cudaFuncAttributes fa;
   CK(cudaFuncGetAttributes(&fa, (const void *)kern));

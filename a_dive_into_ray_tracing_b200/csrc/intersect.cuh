@@ -206,7 +206,8 @@ RT_HD bool hit_box_xz_sorted(float4 lo, float4 hi, const RayPre &pre, float t_mi
 }
 
 // One primitive by RT_PRIM_ID. PROFILE selects the interval rule of static spheres.
-template <int PROFILE, bool GENERAL, bool BIG>
+// SPH: a profile-2 scene that holds spheres only (config 4: moving spheres, checker ground) - no type dispatch.
+template <int PROFILE, bool GENERAL, bool BIG, bool SPH = false>
 RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &pre, float t_min, HitAcc &h) {
   if (!GENERAL) {
     float4 s = S.sph[id];
@@ -216,7 +217,7 @@ RT_HD void hit_prim(const DevScene &S, int32_t id, const Ray &r, const RayPre &p
     else hit_sphere(s, xyz(s), PROFILE == 0, r, pre, t_min, h, id);
     return;
   }
-  int type = RT_PRIM_TYPE_OF(id), idx = RT_PRIM_INDEX_OF(id);
+  const int type = SPH ? (int)RT_PRIM_SPHERE : RT_PRIM_TYPE_OF(id), idx = SPH ? id : RT_PRIM_INDEX_OF(id);
   if (type == RT_PRIM_SPHERE) {
     float4 s = S.sph[idx];
     V3f c = xyz(s);

@@ -122,8 +122,13 @@ __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &o
 // translate::hit / rotate_y::hit do, rt_next_week/cuda/hittable.h:66-79,156-190), remembers where the top-level walk
 // goes on, and continues the SAME search bursts in the object's tree; that tree's end link (RT_POP_LINK) is a
 // fourth lane state handled in the primitive-test phase: restore the world ray, resume the top level.
-template <int PROFILE, bool GENERAL, int SMEM, bool COUNT, bool EXT, bool TRACE = false, bool INST = false>
+// SPH: a profile-2 scene of spheres only (config 4: moving spheres, checker texture, lights): the general kernel's
+// semantics with the sphere kernels' machinery - no primitive type dispatch, leaf payloads that name the sphere,
+// three steps per vote (the weekend scene under profile 2: 80.0 ms through the full general kernel, 68.1 ms through
+// the sphere kernel of profile 1).
+template <int PROFILE, bool GENERAL, int SMEM, bool COUNT, bool EXT, bool TRACE = false, bool INST = false, bool SPH = false>
 __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid_constant__ RenderParams P) {
+  constexpr bool PRIMS = GENERAL && !SPH; // primitives of several types (type dispatch, rect lists, leaf_prims indirection)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevScene S = P.S;
   int off = 0;
@@ -190,7 +195,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           const int esc = RT_F2I(lo.w) >> RT_NODE_SHIFT; // node index within the copy
           int pay = RT_F2I(hi.w), link;
           if (pay < 0) { // leaf
-            if (!GENERAL && P.direct_leaf) pay = ~(__ldg(P.S.leaf_prims + ((~pay) >> 3)) << 3);
+            if (!PRIMS && P.direct_leaf) pay = ~(__ldg(P.S.leaf_prims + ((~pay) >> 3)) << 3);
             link = pay;
           } else if (INST) { // a link that leaves the tree is its end code (global form: finished / RT_POP_LINK)
             link = esc >= nn ? u_code : base_q + (esc << 4);
@@ -343,11 +348,11 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     for (int i = 0; i < S.n_big; i++) {
       const int32_t id = S.big[i];
       if (COUNT) cnt.prim_tests++;
-      const bool is_sphere = !GENERAL || RT_PRIM_TYPE_OF(id) == RT_PRIM_SPHERE;
-      if (is_sphere) hit_prim<PROFILE, GENERAL, true>(S, id, r, pre, t_min, h);
-      else hit_prim<PROFILE, GENERAL, false>(S, id, r, pre, t_min, h);
+      const bool is_sphere = !PRIMS || RT_PRIM_TYPE_OF(id) == RT_PRIM_SPHERE;
+      if (is_sphere) hit_prim<PROFILE, GENERAL, true, SPH>(S, id, r, pre, t_min, h);
+      else hit_prim<PROFILE, GENERAL, false, SPH>(S, id, r, pre, t_min, h);
     }
-    if (GENERAL) { // always-tested rects (walls): decoded records, the same address for every lane
+    if (PRIMS) { // always-tested rects (walls): decoded records, the same address for every lane
       for (int i = 0; i < S.n_bigq; i++) {
         if (COUNT) cnt.prim_tests++;
         const float4 q0 = S.bigq[2 * i], q1 = S.bigq[2 * i + 1];
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       for (;;) {
         if (__popc(__ballot_sync(FULL, RT_SEARCHING(node))) < thr) break;
 #pragma unroll
-        for (int u = 0; u < RT_STEPS_PER_VOTE(GENERAL, EXT); u++) {
+        for (int u = 0; u < RT_STEPS_PER_VOTE(PRIMS, EXT); u++) {
           const bool searching = RT_SEARCHING(node);
           if (SMEM != 0) {
             // lanes that are not searching (node <= 0) fetch the first record and discard the result
@@ -452,16 +457,22 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         const int enc = ~node;
         if (COUNT) cnt.prim_tests++;
         const HitAcc h_before = h;
-        if (!GENERAL && SMEM != 0 && P.direct_leaf) {
+        if (!PRIMS && SMEM != 0 && P.direct_leaf) {
           // single-sphere leaf named by the payload itself: one LDS.128 from a 32-bit shared address
           const int id = enc >> 3;
           float4 s4;
           asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(s4.x), "=f"(s4.y), "=f"(s4.z), "=f"(s4.w)
               : "r"(nodes_s + (unsigned)P.off_sph + ((unsigned)id << 4)));
-          hit_sphere(s4, xyz(s4), PROFILE == 0, r, pre, t_min, h, id);
+          V3f c = xyz(s4);
+          bool closed = PROFILE == 0;
+          if (GENERAL && S.any_moving) { // moving_sphere::center (moving_sphere.h:34-36); its interval is closed
+            const float4 mv = S.sph_mv[id];
+            if (mv.w != 0.0f) { c = sphere_center_at(s4, mv, S.sph_t0[id], r.tm); closed = true; }
+          }
+          hit_sphere(s4, c, closed, r, pre, t_min, h, id);
           node = resume;
         } else {
-          hit_prim<PROFILE, GENERAL, false>(S, S.leaf_prims[enc >> 3], r, pre, t_min, h);
+          hit_prim<PROFILE, GENERAL, false, SPH>(S, S.leaf_prims[enc >> 3], r, pre, t_min, h);
           node = (enc & 7) ? node - 7 : resume; // next primitive of the leaf (first+1, count-1) or go on
         }
         if (INST && (h.id != h_before.id || h.t != h_before.t)) hit_inst = cur_inst;
@@ -569,7 +580,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         q = philox_for_kernel<GENERAL>((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
       bool fresh_ray = false;
       if (hit) {
-        const bool cont = shade_hit<PROFILE, GENERAL, EXT, INST>(S, P.sp, r, h, beta, L, q, hit_inst);
+        const bool cont = shade_hit<PROFILE, GENERAL, EXT, INST, SPH>(S, P.sp, r, h, beta, L, q, hit_inst);
         bounce++;
         if (cont && bounce < P.sp.max_depth) {
           fresh_ray = true;

@@ -246,10 +246,10 @@ RT_COLD HitAcc apply_media(const float4 *__restrict__ media, int n_media, V3f ro
 // Outward (nominal) normal and material of the primitive hit at p = r.at(h.t):
 // sphere (p - c)/r (sphere.h:57), triangle unit face normal (triangle.h:49), rect +axis
 // (aarect.h:54), medium arbitrary (constant_medium.h:69).
-template <bool GENERAL, bool EXT>
+template <bool GENERAL, bool EXT, bool SPH = false>
 RT_HD void surface_at(const DevScene &S, const Ray &r, const HitAcc &h, V3f p, V3f &outward, int &mat) {
-  int type = GENERAL ? RT_PRIM_TYPE_OF(h.id) : RT_PRIM_SPHERE;
-  int idx = GENERAL ? RT_PRIM_INDEX_OF(h.id) : h.id;
+  int type = (GENERAL && !SPH) ? RT_PRIM_TYPE_OF(h.id) : RT_PRIM_SPHERE;
+  int idx = (GENERAL && !SPH) ? RT_PRIM_INDEX_OF(h.id) : h.id;
   if (type == RT_PRIM_SPHERE) {
     float4 s = S.sph[idx];
     V3f c = xyz(s);
@@ -275,7 +275,7 @@ RT_HD void surface_at(const DevScene &S, const Ray &r, const HitAcc &h, V3f p, V
 // The same for a hit inside instance `inst` of a two-level scene (inst < 0: a world-level primitive): the
 // primitive lives in object space, so the hit point and the ray go there, and the normal comes back with the
 // rotation (rotate_y::hit, hittable.h:181-187). p_uv / n_uv = object-space hit point and normal (texture (u, v)).
-template <bool GENERAL, bool EXT, bool INST>
+template <bool GENERAL, bool EXT, bool INST, bool SPH = false>
 RT_HD void surface_at_inst(const DevScene &S, const Ray &r, const HitAcc &h, V3f p, int inst, V3f &outward, int &mat,
                            V3f &p_uv, V3f &n_uv) {
   if (INST && inst >= 0) {
@@ -287,7 +287,7 @@ RT_HD void surface_at_inst(const DevScene &S, const Ray &r, const HitAcc &h, V3f
     surface_at<GENERAL, EXT>(S, ro, h, p_uv, n_uv, mat);
     outward = inst_vector_to_world(rec, n_uv);
   } else {
-    surface_at<GENERAL, EXT>(S, r, h, p, outward, mat);
+    surface_at<GENERAL, EXT, SPH>(S, r, h, p, outward, mat);
     p_uv = p;
     n_uv = outward;
   }
@@ -346,13 +346,13 @@ RT_HD V3f dielectric_dir(V3f d, V3f n, float ir, float u1) {
 // new direction), the throughput `beta` and (profile 2) the radiance `L`.
 // Returns true when the path continues.
 //   rnd: the four random words of this bounce.
-template <int PROFILE, bool GENERAL, bool EXT = false, bool INST = false>
+template <int PROFILE, bool GENERAL, bool EXT = false, bool INST = false, bool SPH = false>
 RT_HD bool shade_hit(const DevScene &S, const ShadeParams &sp, Ray &r, const HitAcc &h, V3f &beta, V3f &L,
                      Philox4 rnd, int inst = -1) {
   const V3f p = madd(r.o, h.t, r.d);
   V3f outward, p_uv, n_uv;
   int mat;
-  surface_at_inst<GENERAL, EXT, INST>(S, r, h, p, inst, outward, mat, p_uv, n_uv);
+  surface_at_inst<GENERAL, EXT, INST, SPH>(S, r, h, p, inst, outward, mat, p_uv, n_uv);
   const float dn_out = dot(r.d, outward);
   const bool front_face = dn_out < 0.0f;
   V3f n = outward;
