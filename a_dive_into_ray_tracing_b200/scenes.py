@@ -768,7 +768,14 @@ def load_scene_file(path, width=None, height=None):
     images = [np.zeros((dims[2 * i + 1], dims[2 * i], 3), np.uint8) for i in range(n2[2])]
     ptrs = (C.c_void_p * max(len(images), 1))(*[im.ctypes.data for im in images])
     L.rtx_host_get2(media.ctypes.data, perlin.ctypes.data, C.addressof(ptrs))
+    n3 = np.zeros(2, np.int32)  # `flags instancing`: objects under an XFORM arrive as groups + instances
+    L.rtx_host_counts3.argtypes = [vp]
+    L.rtx_host_get3.argtypes = [vp, vp]
+    L.rtx_host_counts3(n3.ctypes.data)
+    groups, instances = np.zeros(n3[0], GROUP_DT), np.zeros(n3[1], INSTANCE_DT)
+    L.rtx_host_get3(groups.ctypes.data, instances.ctypes.data)
     sc = Scene(spheres=sph, triangles=tri, quads=quad, materials=mats, camera=cam, background=tuple(fopts[:3]),
                sky_gradient=int(opts[1]), t_min=float(fopts[3]), max_depth=int(opts[2]), flags=int(opts[3]),
-               name=os.path.basename(path), profile=int(opts[0]), media=media, perlin=perlin, images=images)
+               name=os.path.basename(path), profile=int(opts[0]), media=media, perlin=perlin, images=images,
+               groups=groups, instances=instances)
     return sc, (int(opts[4]), int(opts[5]), int(opts[6]))

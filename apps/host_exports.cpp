@@ -95,6 +95,7 @@ extern "C" int rtx_host_load_scene_file(const char *path, int width, int height,
     g_flat = fresh_flat();
     static scene_file keep; // the flattened image pointers refer to textures owned by the scene
     keep = sf;
+    if (keep.opt.instancing) g_flat.instancing = true; // the file's `flags instancing`
     keep.world.flatten(g_flat, transform());
     const int w = width > 0 ? width : keep.width, h = height > 0 ? height : keep.height;
     g_cam = keep.make_camera(w, h).describe();

@@ -66,7 +66,7 @@ int main(int argc, char **argv) {
     if (!spp) spp = 500;
     opt.device = device;
     opt.seed = seed;
-    opt.instancing = instancing;
+    opt.instancing = instancing || opt.instancing; // --instancing or the scene file's `flags instancing`
     const double aspect = double(W) / H;
     hittable_list world;
     hittable *root = nullptr;

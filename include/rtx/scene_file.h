@@ -8,11 +8,12 @@
 //   image W H SPP                                   default frame of the host program
 //   camera lookfrom x y z lookat x y z [vup x y z] vfov deg [aperture a] [focus d] [shutter t0 t1]
 //   sky | background r g b                          miss shader (gradient or constant)
-//   tmin t | depth n | flags [flip_normals] [depth_background] | seed s
+//   tmin t | depth n | flags [flip_normals] [depth_background] [reference_medium] [instancing] | seed s
+//                 (instancing: objects under an XFORM become instances of a two-level BVH instead of being baked)
 //   material NAME lambertian r g b | lambertian checker r g b r g b | lambertian noise scale [table-seed]
 //                 | lambertian image FILE.ppm | metal r g b fuzz | dielectric index | light r g b
-//   sphere cx cy cz r MAT
-//   moving_sphere x0 y0 z0 x1 y1 z1 t0 t1 r MAT
+//   sphere cx cy cz r MAT [XFORM]
+//   moving_sphere x0 y0 z0 x1 y1 z1 t0 t1 r MAT [XFORM]
 //   xy_rect x0 x1 y0 y1 k MAT | xz_rect x0 x1 z0 z1 k MAT | yz_rect y0 y1 z0 z1 k MAT   [XFORM]
 //   box x0 y0 z0 x1 y1 z1 MAT [XFORM]
 //   triangle x0 y0 z0 x1 y1 z1 x2 y2 z2 MAT [XFORM]      (geometric normal)
@@ -147,6 +148,8 @@ inline scene_file load_scene_file(const std::string &path) {
       while (L.more()) {
         if (L.accept("flip_normals")) sf.opt.flags |= RT_FLAG_FLIP_NORMALS;
         else if (L.accept("depth_background")) sf.opt.flags |= RT_FLAG_DEPTH_BACKGROUND;
+        else if (L.accept("reference_medium")) sf.opt.flags |= RT_FLAG_REFERENCE_MEDIUM;
+        else if (L.accept("instancing")) sf.opt.instancing = true;
         else L.fail("unknown flag '" + L.tok[L.pos] + "'");
       }
     } else if (kw == "material") {
@@ -174,11 +177,11 @@ inline scene_file load_scene_file(const std::string &path) {
     } else if (kw == "sphere") {
       point3 c = L.v3("center");
       double r = L.num("radius");
-      sf.world.add(make_shared<sphere>(c, r, mat(L.word("material"))));
+      sf.world.add(xform(make_shared<sphere>(c, r, mat(L.word("material")))));
     } else if (kw == "moving_sphere") {
       point3 c0 = L.v3("center0"), c1 = L.v3("center1");
       double t0 = L.num("time0"), t1 = L.num("time1"), r = L.num("radius");
-      sf.world.add(make_shared<moving_sphere>(c0, c1, t0, t1, r, mat(L.word("material"))));
+      sf.world.add(xform(make_shared<moving_sphere>(c0, c1, t0, t1, r, mat(L.word("material")))));
     } else if (kw == "xy_rect" || kw == "xz_rect" || kw == "yz_rect") {
       double a0 = L.num("a0"), a1 = L.num("a1"), b0 = L.num("b0"), b1 = L.num("b1"), k = L.num("k");
       auto m = mat(L.word("material"));

@@ -153,3 +153,41 @@ def test_parser_never_crashes_on_garbage(tmp_path):
         assert np.all(sc.spheres["material"] < len(sc.materials))
 
     run()
+
+
+def test_instancing_and_reference_medium_flags(tmp_path):
+    """`flags instancing`: objects under an XFORM arrive as rt_group + rt_instance (object-space geometry), and the
+    emulated two-level walk sees the same surfaces as the baked form of the same file; `flags reference_medium`
+    sets RT_FLAG_REFERENCE_MEDIUM"""
+    body = """profile next_week
+image 64 64 8
+camera lookfrom 278 278 -800 lookat 278 278 0 vfov 40
+background 0 0 0
+material white lambertian 0.73 0.73 0.73
+material lamp light 15 15 15
+xz_rect 213 343 227 332 554 lamp
+xz_rect 0 555 0 555 0 white
+box 0 0 0 165 330 165 white rotate_y 15 translate 265 0 295
+box 0 0 0 165 165 165 white rotate_y -18 translate 130 0 65
+sphere 400 100 100 60 white translate 0 20 0
+"""
+    a = tmp_path / "baked.scene"
+    b = tmp_path / "inst.scene"
+    a.write_text(body)
+    b.write_text(body + "flags instancing reference_medium\n")
+    sa, _ = scenes.load_scene_file(str(a))
+    sb, _ = scenes.load_scene_file(str(b))
+    assert len(sa.groups) == 0 and len(sa.instances) == 0 and len(sa.triangles) == 24
+    assert len(sb.groups) == 3 and len(sb.instances) == 3 and len(sb.triangles) == 0
+    assert sb.flags & D.RT_FLAG_REFERENCE_MEDIUM and not (sa.flags & D.RT_FLAG_REFERENCE_MEDIUM)
+    np.testing.assert_array_equal(sb.groups["n_quads"], [6, 6, 0])
+    np.testing.assert_array_equal(sb.groups["n_spheres"], [0, 0, 1])
+    np.testing.assert_allclose(sb.spheres["center0"][0], [400, 100, 100])         # object space
+    np.testing.assert_allclose(sb.instances["m"][2][[3, 7, 11]], [0, 20, 0])        # the translation
+    rays = D.primary_rays(sa.camera, 64, 64, 2)
+    ia, ta, _ = Emu(sa).trace(rays, t_min=sa.t_min)
+    ib, nb, tb = Emu(sb, max_leaf=1).trace_inst(rays, t_min=sb.t_min)
+    assert ((ia >= 0) != (ib >= 0)).mean() < 2e-3
+    k = (ia >= 0) & (ib >= 0)
+    assert np.quantile(np.abs(ta[k] - tb[k]) / ta[k], 0.999) < 1e-5
+    assert set(np.unique(nb[k]).tolist()) == {-1, 0, 1, 2}
