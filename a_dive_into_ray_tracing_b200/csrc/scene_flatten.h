@@ -302,8 +302,8 @@ static inline int flatten_scene(const rt_scene_desc *sc, int profile, HostFlat &
       if (is_box && sc->n_groups) {
         for (int g = 0; g < sc->n_groups && is_box; g++) {
           const int lo = sc->groups[g].first_quad, hi = lo + sc->groups[g].n_quads;
-          const bool first_in = i >= lo && i < hi, last_in = i + 5 >= lo && i + 5 < hi;
-          if (first_in != last_in) is_box = false;
+          const int inside = std::max(0, std::min(hi, i + 6) - std::max(lo, i)); // rects of this box the group owns
+          if (inside != 0 && inside != 6) is_box = false;
         }
       }
       if (!is_box) { i++; continue; }

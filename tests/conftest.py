@@ -9,6 +9,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# Property tests (hypothesis) draw the SAME examples on every run by default, so that the suite is repeatable (a red
+# test is a bug, not luck); RT_HYPOTHESIS_EXPLORE=1 switches to fresh random examples - the development loop that found
+# e.g. the box whose middle rects belong to a group (tests/test_random_scenes.py).
+try:
+    from hypothesis import settings as _hyp_settings
+    _hyp_settings.register_profile("repeatable", derandomize=True)
+    _hyp_settings.register_profile("explore", derandomize=False)
+    _hyp_settings.load_profile("explore" if os.environ.get("RT_HYPOTHESIS_EXPLORE") else "repeatable")
+except ImportError:  # hypothesis is optional for the rest of the suite
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 

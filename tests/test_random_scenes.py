@@ -4,7 +4,7 @@ the C ABI on the GPU (-m gpu). Covers duplicates, coincident and degenerate prim
 clustered Morton codes, mixed primitive types and every leaf size."""
 import numpy as np
 import pytest
-from hypothesis import HealthCheck, given, settings
+from hypothesis import HealthCheck, example, given, settings
 from hypothesis import strategies as st
 
 from a_dive_into_ray_tracing_b200 import ctypes_defs as D
@@ -212,6 +212,7 @@ two_level_args = dict(seed=st.integers(0, 10 ** 6), n_sph=st.integers(0, 40), n_
 
 @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(**two_level_args)
+@example(seed=186, n_sph=0, n_tri=4, n_quad=0, n_box=4, n_groups=3, n_inst=0, cluster=False)  # a group owns rects 2..4 of a box
 def test_emulated_two_level_builder_and_traversal(seed, n_sph, n_tri, n_quad, n_box, n_groups, n_inst, cluster):
     """tree walk == list-order brute force, bit for bit (primitive, instance, t), on random two-level scenes"""
     from tests.emu.pyemu import Emu
@@ -228,6 +229,7 @@ def test_emulated_two_level_builder_and_traversal(seed, n_sph, n_tri, n_quad, n_
 @pytest.mark.gpu
 @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow])
 @given(plan=st.sampled_from(["2", "1", "3", "0"]), **two_level_args)
+@example(plan="2", seed=186, n_sph=0, n_tri=4, n_quad=0, n_box=4, n_groups=3, n_inst=0, cluster=False)
 def test_gpu_two_level_builder_and_traversal(seed, n_sph, n_tri, n_quad, n_box, n_groups, n_inst, cluster, plan):
     """the same through the C ABI; the render kernel's own traversal (every residency plan) agrees with both except
     for exact ties, and a frame renders finite"""
