@@ -48,26 +48,25 @@
 // two-level scenes, shared-memory plans: the link that ends an object's tree (shared addresses are multiples of 16
 // above it, 0 = finished, negative = leaf payload)
 #define RT_POP_SHARED 8
-// Octant-copy plans (SMEM == 2): the planes of a shared-memory record as two fp16 numbers per word instead of two 16-bit
-// integers (RT_HALF_PLANES; 0 = the integer form, kept for A/B measurements).
-//  2 (default): sm_100's mixed-precision multiply-add, FHFMA (PTX fma.rn.f32.f16: f32 = f16 * f16 + f32, either half of
-//     a 32-bit register selected in the instruction), takes the plane straight from the loaded word:
-//     t = v_h * S_h + C is ONE instruction per plane and the record needs no decode at all - the step is LDS.128 +
-//     6 FHFMA + 4 min/max + the link selection (19-20 instructions against 25-26). The plane coordinate
-//     v = q / 23 >= 0 (q = the 16-bit coordinate over the tree's box, 0..46335; v < 2048) is rounded OUTWARDS to fp16 after
-//     the same two-step padding, and the ray keeps its slope per axis as an fp16 PAIR rounded apart, S_entry <= S <=
-//     S_exit (round-down / round-up; with v >= 0 the product errs to the conservative side for either sign of S; a slope
-//     beyond the fp16 range saturates to max-finite / infinity, i.e. a half-open slab, and 0 * inf = NaN is dropped by
-//     min / max): the boxes stay conservative, results are unchanged, and the looser planes cost 0.7 % more box tests.
-//  1: fp16 planes converted with HADD2.F32 (one FMA-pipe instruction per plane where the integer form needs LEA.HI on
-//     the half-rate ALU pipe + IMAD), then FFMA. ncu r2f had the ALU pipe as the limiter of the step (13 of 22).
-// Measured on config 2: 72.9 ms (0) -> 68.4 ms (1) -> see DESIGN.md (2).
+// Shared-memory plans: the planes of a node record as two fp16 numbers per word, taken STRAIGHT from the loaded word by
+// sm_100's mixed-precision multiply-add FHFMA (PTX fma.rn.f32.f16: f32 = f16 * f16 + f32, either half of a 32-bit
+// register selected in the instruction): t = v_h * S_h + C is ONE instruction per plane and the record needs no decode at
+// all - the step of the octant-copy plans is LDS.128 + 6 FHFMA + 4 min/max + the link selection (19-20 instructions
+// against 25-26 with 16-bit integer planes: 3 LEA.HI on the half-rate ALU pipe + 3 IMAD + 6 FFMA; ncu r2f had that pipe
+// as the limiter, 13 of the step's 22 instructions). The one-copy plans swap the halves of a word per lane by the sign
+// of the lane's direction (3 PRMT instead of 6) and run the same six FHFMA.
+// The plane coordinate v = q / 23 >= 0 (q = the 16-bit coordinate over the tree's box, 0..46335; v < 2048) is rounded
+// OUTWARDS to fp16 after the same two-step padding, and the ray keeps its slope per axis as an fp16 PAIR rounded apart,
+// S_entry <= S <= S_exit (round-down | round-up): with v >= 0 the product errs to the conservative side for either sign of
+// S; a slope beyond the fp16 range saturates to max-finite / infinity, i.e. a half-open slab, and 0 * inf = NaN is dropped
+// by min / max. The boxes stay conservative - results are unchanged (parity through this traversal is bit-exact against
+// brute force) - and the looser planes cost 0.7 % more box tests. Measured on config 2: 72.9 ms with integer planes,
+// 68.4 ms with fp16 planes converted by HADD2.F32 + FFMA, 65.9 ms with FHFMA. RT_HALF_PLANES=0 keeps the integer form
+// for A/B measurements.
 #ifndef RT_HALF_PLANES
-#define RT_HALF_PLANES 2
+#define RT_HALF_PLANES 1
 #endif
-#define RT_HALF_SCALE 0.03125f // form 1: v = q / 32 - 724
-#define RT_HALF_BIAS 724.0f
-#define RT_HALF_KINV 23.0f     // form 2: v = q / 23
+#define RT_HALF_KINV 23.0f // v = q / 23
 #ifndef RT_N_ORDERINGS
 #define RT_N_ORDERINGS 8 // node orderings = ray-direction octants (bvh_build.cuh body_order)
 #endif
@@ -149,6 +148,7 @@ __device__ __forceinline__ const void *stage_to_smem(unsigned char *smem, int &o
 // the sphere kernel of profile 1).
 template <int PROFILE, bool GENERAL, int SMEM, bool COUNT, bool EXT, bool TRACE = false, bool INST = false, bool SPH = false>
 __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid_constant__ RenderParams P) {
+  constexpr bool FH = RT_HALF_PLANES != 0; // fp16 planes + FHFMA in the shared-memory plans
   constexpr bool PRIMS = GENERAL && !SPH; // primitives of several types (type dispatch, rect lists, leaf_prims indirection)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   DevScene S = P.S;
@@ -157,9 +157,10 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   const uint32_t nodes_s = SMEM ? (uint32_t)__cvta_generic_to_shared(smem_raw) : 0u;
   if (SMEM) {
     // Nodes go to shared memory as 16-BYTE QUANTISED records (the global array keeps 32-byte float nodes):
-    //   {x planes, y planes, z planes, link}: each plane word = two 16-bit fixed-point coordinates over the
-    //   root box (entry | exit << 16), rounded outwards with two steps of padding, so the slab test stays
-    //   conservative: a quantised box only ever adds false-positive box hits, never changes a result.
+    //   {x planes, y planes, z planes, link}: each plane word = two 16-bit coordinates over the root box
+    //   (entry | exit << 16; fp16 numbers by default - see RT_HALF_PLANES above - or fixed-point integers), rounded
+    //   outwards with two steps of padding, so the slab test stays conservative: a quantised box only ever adds
+    //   false-positive box hits, never changes a result.
     // ONE LDS.128 per BVH step instead of two: ncu r1j had the shared-memory data pipe at 89 % of its
     // wavefront peak (13.5 wavefronts per step for 32 lanes fetching 32 bytes each at unrelated addresses).
     // One link word is enough in the depth-first threaded layout: the first child of an inner node and the
@@ -199,11 +200,12 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
           w = make_uint4((q & 1) ? bwd : fwd, (q & 2) ? bwd : fwd, (q & 4) ? bwd : fwd, 0u);
           // one-copy plans keep (low plane | high plane << 16): low = RT_Q_MAX, high = 0 is missed by either direction
           if (SMEM != 2) w = make_uint4((unsigned)RT_Q_MAX, (unsigned)RT_Q_MAX, (unsigned)RT_Q_MAX, 0u);
-          if (SMEM == 2 && RT_HALF_PLANES) { // entry = +60000 | exit = -60000 (fp16) for a positive direction, mirrored for a negative one
-            // (form 2: the slopes are finite or infinite, never zero or NaN on the entry / exit side that decides here -
-            // see the step: a sentinel's entry is +-inf or beyond every exit)
+          if (FH) {
+            // fp16: entry = +60000 | exit = -60000 for a positive direction, mirrored for a negative one (a slope is finite
+            // or infinite, never zero or NaN: the entry lies beyond the exit for every ray); the one-copy plans keep
+            // (low | high << 16) = (+60000 | -60000), which the per-lane swap turns into the same two cases
             const unsigned fwdh = 0xFB537B53u, bwdh = 0x7B53FB53u;
-            w = make_uint4((q & 1) ? bwdh : fwdh, (q & 2) ? bwdh : fwdh, (q & 4) ? bwdh : fwdh, 0u);
+            w = make_uint4((SMEM == 2 && (q & 1)) ? bwdh : fwdh, (SMEM == 2 && (q & 2)) ? bwdh : fwdh, (SMEM == 2 && (q & 4)) ? bwdh : fwdh, 0u);
           }
           if (INST) w.w = (unsigned)u_code; // (records between a tree's sentinel and the next tree are never reached)
         } else {
@@ -217,13 +219,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
             const unsigned ql = (unsigned)fminf(fmaxf(fl, 0.0f), (float)RT_Q_MAX), qh = (unsigned)fminf(fmaxf(fh, 0.0f), (float)RT_Q_MAX);
             const bool neg = SMEM == 2 && ((q >> a) & 1);
             pw[a] = (neg ? (qh | (ql << 16)) : (ql | (qh << 16))) + (SMEM == 2 ? 0x4B000000u : 0u);
-            if (SMEM == 2 && RT_HALF_PLANES == 1) {
-              // the padded, clamped 16-bit coordinates are exact in fp32; q / 32 - 724 is exact too (|v| < 1024, 5 fraction bits)
-              const unsigned hl = __half_as_ushort(__float2half_rd(RT_FMA((float)ql, RT_HALF_SCALE, -RT_HALF_BIAS)));
-              const unsigned hh = __half_as_ushort(__float2half_ru(RT_FMA((float)qh, RT_HALF_SCALE, -RT_HALF_BIAS)));
-              pw[a] = neg ? (hh | (hl << 16)) : (hl | (hh << 16));
-            }
-            if (SMEM == 2 && RT_HALF_PLANES == 2) { // v = q / 23, both roundings outwards
+            if (FH) { // v = q / 23, both roundings outwards
               const unsigned hl = __half_as_ushort(__float2half_rd(__fmul_rd((float)ql, 1.0f / RT_HALF_KINV)));
               const unsigned hh = __half_as_ushort(__float2half_ru(__fmul_ru((float)qh, 1.0f / RT_HALF_KINV)));
               pw[a] = neg ? (hh | (hl << 16)) : (hl | (hh << 16));
@@ -322,11 +318,13 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   h.t = INFINITY; h.id = -1;
   RayPre pre;
   pre.inv_d = v3(0, 0, 0); pre.ood = v3(0, 0, 0); pre.inv_a = 0.f;
-  // quantised-node slab test (shared copies): t(plane q) = (2^23 + q) * qS + qC per axis
+  // quantised-node slab test (shared copies), per axis: t(plane v) = v * qSh + qC, v and the slope pair qSh in fp16
+  // (integer form: t(plane q) = (2^23 + q) * qS + qC)
   V3f qS = v3(0, 0, 0), qC = v3(0, 0, 0);
-  // one-copy plans: per-lane byte-permute selectors of the entry / exit plane of each axis (see the step)
+  // one-copy plans: per-lane byte-permute selectors (fp16 form: selE swaps the halves of a plane word for a negative
+  // direction; integer form: selE / selX extract the entry / exit plane of each axis) - see the step
   struct U3 { unsigned x, y, z; } selE = {0x7610u, 0x7610u, 0x7610u}, selX = {0x7632u, 0x7632u, 0x7632u};
-  U3 qSh = {0u, 0u, 0u}; // RT_HALF_PLANES == 2: the slope per axis as an fp16 pair (entry: rounded down | exit: rounded up)
+  U3 qSh = {0u, 0u, 0u}; // RT_HALF_PLANES: the slope per axis as an fp16 pair (entry: rounded down | exit: rounded up)
   const float t_min = P.sp.t_min;
   // Work items (tile, chunk of samples) are OVERLAPPED: when the current item's pool is
   // drained its in-flight paths become the "old" item and the warp starts regenerating
@@ -366,26 +364,24 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
     } else { // the root's shared address in this ray's copy
       const unsigned copy = SMEM == 2 ? octant : ((P.oct_lut >> (4u * octant)) & 7u);
       node = (int)(nodes_s + copy * (unsigned)P.b_nodes) + (root_index << 4);
-      // plane q (16-bit) enters the slab test as the float 2^23 + q (one PRMT builds it: 0x4B00 | q), so
-      // t = (qbase + q * qscale - o) / d = (2^23 + q) * qS + qC with qS = qscale / d, qC = (qbase - o) / d - 2^23 qS
+      // (integer form: plane q enters the slab test as the float 2^23 + q - one PRMT builds it: 0x4B00 | q -, so
+      // t = (qbase + q * qscale - o) / d = (2^23 + q) * qS + qC with qS = qscale / d, qC = (qbase - o) / d - 2^23 qS)
       qS = v3(fs.x * pre.inv_d.x, fs.y * pre.inv_d.y, fs.z * pre.inv_d.z);
-      if (SMEM == 2 && RT_HALF_PLANES == 2) {
+      if (FH) {
         // x = fb + 23 v fs, so t = v * (23 fs / d) + (fb - o) / d; the slope as the fp16 pair (rounded down | rounded up << 16)
         const V3f sl = RT_HALF_KINV * qS;
         qC = v3((fb.x - r.o.x) * pre.inv_d.x, (fb.y - r.o.y) * pre.inv_d.y, (fb.z - r.o.z) * pre.inv_d.z);
         qSh.x = (unsigned)__half_as_ushort(__float2half_rd(sl.x)) | ((unsigned)__half_as_ushort(__float2half_ru(sl.x)) << 16);
         qSh.y = (unsigned)__half_as_ushort(__float2half_rd(sl.y)) | ((unsigned)__half_as_ushort(__float2half_ru(sl.y)) << 16);
         qSh.z = (unsigned)__half_as_ushort(__float2half_rd(sl.z)) | ((unsigned)__half_as_ushort(__float2half_ru(sl.z)) << 16);
-      } else if (SMEM == 2 && RT_HALF_PLANES) {
-        // fp16 planes: x = fb + (v + 724) * 32 * fs, so t = v * (32 qS) + ((fb - o) / d + 23168 qS)
-        qC = v3(RT_FMA(RT_HALF_BIAS / RT_HALF_SCALE, qS.x, (fb.x - r.o.x) * pre.inv_d.x),
-                RT_FMA(RT_HALF_BIAS / RT_HALF_SCALE, qS.y, (fb.y - r.o.y) * pre.inv_d.y),
-                RT_FMA(RT_HALF_BIAS / RT_HALF_SCALE, qS.z, (fb.z - r.o.z) * pre.inv_d.z));
-        qS = (1.0f / RT_HALF_SCALE) * qS;
       } else
       qC = v3(RT_FMA(-8388608.0f, qS.x, (fb.x - r.o.x) * pre.inv_d.x), RT_FMA(-8388608.0f, qS.y, (fb.y - r.o.y) * pre.inv_d.y),
               RT_FMA(-8388608.0f, qS.z, (fb.z - r.o.z) * pre.inv_d.z));
-      if (SMEM != 2) { // a negative direction enters through the HIGH plane
+      if (SMEM != 2 && FH) { // a negative direction enters through the HIGH plane: swap the halves of the word
+        selE.x = (octant & 1u) ? 0x1032u : 0x3210u;
+        selE.y = (octant & 2u) ? 0x1032u : 0x3210u;
+        selE.z = (octant & 4u) ? 0x1032u : 0x3210u;
+      } else if (SMEM != 2) {
         selE.x = (octant & 1u) ? 0x7632u : 0x7610u; selX.x = selE.x ^ 0x0022u;
         selE.y = (octant & 2u) ? 0x7632u : 0x7610u; selX.y = selE.y ^ 0x0022u;
         selE.z = (octant & 4u) ? 0x7632u : 0x7610u; selX.z = selE.z ^ 0x0022u;
@@ -436,15 +432,20 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
             int link;
             asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(link) : "r"(at));
             if (COUNT) cnt.box_tests += searching ? 1u : 0u;
-            // Decode on the FMA pipe (ncu r2e: with PRMT the half-rate ALU pipe was the limiter at 74 %, the FMA pipe
-            // at 25 %): the stored word is (exit << 16 | entry) + 0x4B000000, so
+            // Integer form (RT_HALF_PLANES=0), octant copies: decode on the FMA pipe (ncu r2e: with PRMT the half-rate ALU
+            // pipe was the limiter at 74 %, the FMA pipe at 25 %): the stored word is (exit << 16 | entry) + 0x4B000000, so
             //   exit bits  = mad.hi(w, 2^16, 0x4B000000 - 0x4B00) = 0x4B000000 + exit      (planes <= 46335: no carry)
             //   entry bits = mad.lo(exit bits, -2^16, w)          = 0x4B000000 + entry     (mod 2^32)
             // i.e. the floats 2^23 + q, two integer multiply-adds per word.
             unsigned bx1 = 0, by1 = 0, bz1 = 0, bx0 = 0, by0 = 0, bz0 = 0;
             float x0, x1, y0, y1, z0, z1;
-            if (SMEM == 2 && RT_HALF_PLANES == 2) {
+            if (FH) {
               // FHFMA: t = plane (fp16 half of the record word) * slope (fp16 half of the pair) + C, fp32 result
+              if (SMEM != 2) { // one copy for every direction: each lane puts its entry plane into the low half
+                asm("prmt.b32 %0, %0, %0, %1;" : "+r"(w0) : "r"(selE.x));
+                asm("prmt.b32 %0, %0, %0, %1;" : "+r"(w1) : "r"(selE.y));
+                asm("prmt.b32 %0, %0, %0, %1;" : "+r"(w2) : "r"(selE.z));
+              }
 #define RT_FHFMA(d, w, sh, c, HALF)                                                                                      \
   asm("{ .reg .b16 pl, ph, sl, sx; mov.b32 {pl, ph}, %1; mov.b32 {sl, sx}, %2; fma.rn.f32.f16 %0, " HALF ", %3; }"   \
       : "=f"(d) : "r"(w), "r"(sh), "f"(c))
@@ -452,12 +453,6 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
               RT_FHFMA(y0, w1, qSh.y, qC.y, "pl, sl"); RT_FHFMA(y1, w1, qSh.y, qC.y, "ph, sx");
               RT_FHFMA(z0, w2, qSh.z, qC.z, "pl, sl"); RT_FHFMA(z1, w2, qSh.z, qC.z, "ph, sx");
 #undef RT_FHFMA
-            } else if (SMEM == 2 && RT_HALF_PLANES) {
-              const __half2 hx = *reinterpret_cast<const __half2 *>(&w0), hy = *reinterpret_cast<const __half2 *>(&w1),
-                            hz = *reinterpret_cast<const __half2 *>(&w2);
-              bx0 = __float_as_uint(__low2float(hx)); bx1 = __float_as_uint(__high2float(hx));
-              by0 = __float_as_uint(__low2float(hy)); by1 = __float_as_uint(__high2float(hy));
-              bz0 = __float_as_uint(__low2float(hz)); bz1 = __float_as_uint(__high2float(hz));
             } else if (SMEM == 2) {
               asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(bx1) : "r"(w0));
               asm("mad.hi.u32 %0, %1, 65536, 0x4AFFB500;" : "=r"(by1) : "r"(w1));
@@ -477,7 +472,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
               asm("prmt.b32 %0, %1, 0x4B000000, %2;" : "=r"(by1) : "r"(w1), "r"(selX.y));
               asm("prmt.b32 %0, %1, 0x4B000000, %2;" : "=r"(bz1) : "r"(w2), "r"(selX.z));
             }
-            if (!(SMEM == 2 && RT_HALF_PLANES == 2)) {
+            if (!FH) {
               x0 = RT_FMA(__uint_as_float(bx0), qS.x, qC.x); x1 = RT_FMA(__uint_as_float(bx1), qS.x, qC.x);
               y0 = RT_FMA(__uint_as_float(by0), qS.y, qC.y); y1 = RT_FMA(__uint_as_float(by1), qS.y, qC.y);
               z0 = RT_FMA(__uint_as_float(bz0), qS.z, qC.z); z1 = RT_FMA(__uint_as_float(bz1), qS.z, qC.z);
