@@ -1133,8 +1133,10 @@ static render_kernel_t pick_render_kernel(int profile, int smem, bool count, boo
 static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &smem, size_t &smem_bytes) {
   {
     const char *e = getenv("B200RT_BATCH"), *f = getenv("B200RT_FRAC8"); // tuning knobs
-    P.batch = e ? atoi(e) : 24;
-    P.frac8 = f ? atoi(f) : 5;
+    // (re-swept after the FHFMA step made a BVH step cheaper against the other phases: the sphere kernels of profiles
+    // 0 / 1 are best at 26 / 4 - config 2 per 250 spp: 33.17 ms against 33.45 ms at 24 / 5; the optimum is flat)
+    P.batch = e ? atoi(e) : (ctx->general ? 24 : 26);
+    P.frac8 = f ? atoi(f) : (ctx->general ? 5 : 4);
     const char *lm = getenv("B200RT_LEAFMIN");
     P.leaf_min = lm ? atoi(lm) : 1; // measured: 1..5 within 0.5 %, larger values slower
     P.batch = std::max(1, std::min(P.batch, 32));

@@ -1,14 +1,5 @@
-mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r2i_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/r2i_pytest.log; tail -3 gpurun_out/r2i_pytest.log
-timeout 300 python bench.py --steps 5 --warmup 3 > gpurun_out/r2i_bench_c2.json 2> gpurun_out/r2i_bench_c2.err; echo "bench c2 rc=$?"
-for c in c1 c3 c4 c5 nw_final c3_instanced nw_final_instanced; do
-  timeout 300 python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2i_bench_$c.json 2> gpurun_out/r2i_bench_$c.err; echo "bench $c rc=$?"
-done
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2i_launches_bench.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2i_ncu_launches.log 2>&1; echo "launch list rc=$?"
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob('gpurun_out/r2i_bench_*.json')):
-    try:
-        d=json.loads(open(f).read().strip().splitlines()[-1]); print(f, d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], d['roofline']['frac'])
-    except Exception as e: print(f, 'ERR', e)
-PY
+mkdir -p gpurun_out; out=gpurun_out/x10_knobs.log; : > $out
+for b in 20 24 26 28 30; do for f in 3 4 5 6; do echo -n "BATCH=$b FRAC8=$f " >> $out; B200RT_BATCH=$b B200RT_FRAC8=$f timeout 60 python tools/profile_frame.py 250 2>&1 | tail -1 >> $out; done; done
+for v in S2 S4 S5; do echo -n "variant $v " >> $out; B200RT_LIB=$PWD/build/variants/libb200rt_$v.so timeout 60 python tools/profile_frame.py 250 2>&1 | tail -1 >> $out; done
+for f in 3 4 6; do echo -n "variant S4 FRAC8=$f " >> $out; B200RT_FRAC8=$f B200RT_LIB=$PWD/build/variants/libb200rt_S4.so timeout 60 python tools/profile_frame.py 250 2>&1 | tail -1 >> $out; done
+cat $out
