@@ -1,4 +1,3 @@
 mkdir -p gpurun_out
-timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2i_bench_n2.json 2> gpurun_out/r2i_bench_n2.err; echo "rc=$?"
-tail -c 1500 gpurun_out/r2i_bench_n2.json | head -c 1500; echo; tail -3 gpurun_out/r2i_bench_n2.err
-timeout 120 python -m pytest tests/test_reduce.py tests/test_cpp_host.py -m gpu -x -q 2>&1 | tail -3
+timeout 200 python -m pytest tests/test_render_kernel_traversal.py tests/test_instancing.py -m gpu -x -q > gpurun_out/x12_tests.log 2>&1; echo "rc=$?" >> gpurun_out/x12_tests.log; tail -3 gpurun_out/x12_tests.log
+EXP_NAME=x12 EXP_VARIANTS="D P0 D P0" EXP_CASES="c2 c3 c4 nw" bash tools/exp_variants.sh
