@@ -1362,6 +1362,7 @@ static int render_into(rt_ctx *ctx, int W, int H, int spp_begin, int spp_count, 
   P.stats = (unsigned long long *)ctx->d_stats.p;
   P.seed_lo = (uint32_t)(ctx->cfg.seed & 0xffffffffu);
   P.seed_hi = (uint32_t)(ctx->cfg.seed >> 32);
+  philox_round_keys(P.seed_lo, P.seed_hi, P.philox_rk);
   int smem = 0;
   size_t smem_bytes = 0;
   plan_scene_residency(ctx, P, block, smem, smem_bytes);

@@ -27,6 +27,25 @@ RT_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, 
   return o;
 }
 
+// The same function with the ten round keys given (k + r * W, r = 0..9: {k0, k1} pairs). The key schedule is the same for
+// every lane, warp and call of a launch: precomputed on the host and read as kernel-parameter constants it costs nothing,
+// where the bump per round is two (uniform-datapath) instructions that still take issue slots - 20 of a call's ~80.
+RT_HD Philox4 philox4x32_10_keys(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t *rk) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u;
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    uint32_t hi0 = RT_MULHI(M0, c0), lo0 = M0 * c0;
+    uint32_t hi1 = RT_MULHI(M1, c2), lo1 = M1 * c2;
+    uint32_t n0 = hi1 ^ c1 ^ rk[2 * r], n2 = hi0 ^ c3 ^ rk[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  Philox4 o = {c0, c1, c2, c3};
+  return o;
+}
+static inline void philox_round_keys(uint32_t k0, uint32_t k1, uint32_t rk[20]) {
+  for (int r = 0; r < 10; r++) { rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u; rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+}
+
 // The render kernel's call sites (camera event, bounce event, shutter time). OUTLINE: calls of ONE out-of-line copy
 // instead of three inlined ones - the general kernels are bound by instruction fetch (rt_next_week final scene
 // 106.9 -> 95.9 ms per 200 spp; configs 3 and 4 unchanged); the compact sphere-only kernels keep it inline.
@@ -36,13 +55,15 @@ static __device__ __noinline__ Philox4 philox_call(uint32_t c0, uint32_t c1, uin
 }
 #endif
 template <bool OUTLINE>
-RT_HD Philox4 philox_for_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+RT_HD Philox4 philox_for_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                const uint32_t *rk = nullptr) {
 #ifdef __CUDA_ARCH__
 #ifdef RT_PHILOX_OUTLINE_ALL
   return philox_call(c0, c1, c2, c3, k0, k1);
 #else
   if (OUTLINE) return philox_call(c0, c1, c2, c3, k0, k1);
 #endif
+  if (rk) return philox4x32_10_keys(c0, c1, c2, c3, rk); // inlined copies: round keys from the kernel parameters
 #endif
   return philox4x32_10(c0, c1, c2, c3, k0, k1);
 }

@@ -85,6 +85,7 @@ struct RenderParams {
   int *work_counter;
   unsigned long long *stats;     // paths, segments, box tests, prim tests
   uint32_t seed_lo, seed_hi;
+  uint32_t philox_rk[20]; // the ten Philox round keys of (seed_lo, seed_hi): philox_round_keys
   int batch;  // shade/regenerate when this many lanes are DONE or DEAD (warp-voted scheduler)
   int batch_long; // the same for warps whose paths run long (general kernels)
   int leaf_min; // run the pending primitive tests when this many lanes wait (or nobody searches)
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
       }
       // (c) ONE Philox call per lane: the bounce event of a hit, or the camera event of a new path
       if (!TRACE && (hit || fresh_path))
-        q = philox_for_kernel<GENERAL>((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi);
+        q = philox_for_kernel<GENERAL>((uint32_t)pixel_index, (uint32_t)smp, (uint32_t)(1 + bounce), 0u, P.seed_lo, P.seed_hi, P.philox_rk);
       bool fresh_ray = false;
       if (hit) {
         const bool cont = shade_hit<PROFILE, GENERAL, EXT, INST, SPH>(S, P.sp, r, h, beta, L, q, hit_inst);
@@ -682,7 +683,7 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
         const int i = tile_x0 + (px & 7), j = tile_y0 + (px >> 3);
         float x5 = 0.f;
         if (PROFILE == 2 && P.cam.time1 != P.cam.time0)
-          x5 = u01(philox_for_kernel<GENERAL>((uint32_t)pixel_index, (uint32_t)smp, 0u, 1u, P.seed_lo, P.seed_hi).x);
+          x5 = u01(philox_for_kernel<GENERAL>((uint32_t)pixel_index, (uint32_t)smp, 0u, 1u, P.seed_lo, P.seed_hi, P.philox_rk).x);
         r = gen_camera_ray<PROFILE>(P.cam, P.W, P.H, i, j, u01(q.x), u01(q.y), u01(q.z), u01(q.w), x5);
         beta = v3(1, 1, 1);
         L = v3(0, 0, 0);
