@@ -155,7 +155,11 @@ __global__ void __launch_bounds__(RT_BLOCK_OF(GENERAL), 1) k_render(const __grid
   DevScene S = P.S;
   int off = 0;
   // 32-bit shared-window address of the staged node copies (they start the dynamic segment)
-  const uint32_t nodes_s = SMEM ? (uint32_t)__cvta_generic_to_shared(smem_raw) : 0u;
+  // (asm volatile: computed ONCE. As a plain __cvta_generic_to_shared the compiler rematerialises it - S2UR CgaCtaId +
+  // UMOV + ULEA, a special-register read on the critical path - at every burst entry and phase: config 2 65.24 -> 64.49 ms,
+  // config 3 167.8 -> 166.3 ms per 150 spp, no additional spills.)
+  uint32_t nodes_s = 0u;
+  if (SMEM) asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(nodes_s) : "l"(smem_raw));
   if (SMEM) {
     // Nodes go to shared memory as 16-BYTE QUANTISED records (the global array keeps 32-byte float nodes):
     //   {x planes, y planes, z planes, link}: each plane word = two 16-bit coordinates over the root box
