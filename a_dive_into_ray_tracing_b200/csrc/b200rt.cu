@@ -1133,10 +1133,12 @@ static render_kernel_t pick_render_kernel(int profile, int smem, bool count, boo
 static void plan_scene_residency(rt_ctx *ctx, RenderParams &P, int block, int &smem, size_t &smem_bytes) {
   {
     const char *e = getenv("B200RT_BATCH"), *f = getenv("B200RT_FRAC8"); // tuning knobs
-    // (re-swept after the FHFMA step made a BVH step cheaper against the other phases: the sphere kernels of profiles
-    // 0 / 1 are best at 26 / 4 - config 2 per 250 spp: 33.17 ms against 33.45 ms at 24 / 5; the optimum is flat)
+    // (re-swept after the FHFMA step made a BVH step cheaper against the other phases: a burst now runs until fewer
+    // than 4/8 - before: 5/8 - of its entry lanes search; the sphere kernels of profiles 0 / 1 also shade a little
+    // later. Config 2 per 250 spp: 33.17 ms at 26 / 4 against 33.45 ms at 24 / 5; config 3 per 150 spp 166.4 -> 164.3 ms,
+    // config 4 per 200 spp 35.3 -> 34.9 ms, final scene per 200 spp 96.8 -> 95.2 ms at 24 / 4. The optimum is flat.)
     P.batch = e ? atoi(e) : (ctx->general ? 24 : 26);
-    P.frac8 = f ? atoi(f) : (ctx->general ? 5 : 4);
+    P.frac8 = f ? atoi(f) : 4;
     const char *lm = getenv("B200RT_LEAFMIN");
     P.leaf_min = lm ? atoi(lm) : 1; // measured: 1..5 within 0.5 %, larger values slower
     P.batch = std::max(1, std::min(P.batch, 32));
