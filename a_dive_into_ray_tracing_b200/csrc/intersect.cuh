@@ -173,6 +173,8 @@ RT_HD void hit_quad(float4 q0, float4 q1, const Ray &r, const RayPre &pre, float
 RT_HD HitAcc hit_box_sides(float4 b0, float4 b1, const Ray &r, const RayPre &pre, float t_min, HitAcc h) {
   const int first = RT_F2I(b0.w);
   const float lo[3] = {b0.x, b0.y, b0.z}, hi[3] = {b1.x, b1.y, b1.z};
+  const float o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z}, inv[3] = {pre.inv_d.x, pre.inv_d.y, pre.inv_d.z};
+#ifdef RT_BOX_SEQUENTIAL // the six rect tests one after the other against the running hit (the form this replaces; A/B builds)
 #pragma unroll
   for (int j = 0; j < 6; j++) {
     const int ax = 2 - (j >> 1), ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
@@ -181,6 +183,31 @@ RT_HD HitAcc hit_box_sides(float4 b0, float4 b1, const Ray &r, const RayPre &pre
     hit_quad(q0, q1, r, pre, t_min, h, RT_PRIM_ID(RT_PRIM_QUAD, first + j));
   }
   return h;
+#else
+  // The same six rect formulas in the same order, but the sides first compete among themselves - the smallest
+  // t >= t_min inside its rect wins, the LATER side on an exact tie (ids grow with j and the closed rule lets the later
+  // list item win) - and only the winner meets the running hit, under the list rule. Sequentially updating h through
+  // the six sides gives the same (id, t): the minimum over {h, valid sides} with the same tie-breaks. Per side this
+  // saves the comparison against h.t / h.id and the id arithmetic; few lanes run this code (3-4 of 32 in the
+  // rt_next_week final scene), so its length is what counts.
+  float bt = INFINITY;
+  int bj = -1;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    const int ax = 2 - (j >> 1), ia = ax == 0 ? 1 : 0, ib = ax == 2 ? 1 : 2;
+    const float k = (j & 1) ? lo[ax] : hi[ax];
+    const float t = (k - o[ax]) * inv[ax]; // hit_quad's own expressions: t, then the in-plane point by FMA
+    const float a = RT_FMA(t, d[ia], o[ia]), b = RT_FMA(t, d[ib], o[ib]);
+    const bool ok = (a >= lo[ia]) & (a <= hi[ia]) & (b >= lo[ib]) & (b <= hi[ib]) & (t >= t_min) & (t <= bt);
+    bt = ok ? t : bt;
+    bj = ok ? j : bj;
+  }
+  const int32_t id = RT_PRIM_ID(RT_PRIM_QUAD, first + bj);
+  const bool take = (bj >= 0) & ((bt < h.t) | ((bt == h.t) & (id > h.id)));
+  h.t = take ? bt : h.t;
+  h.id = take ? id : h.id;
+  return h;
+#endif
 }
 
 // Slab test against a packed node box (closed interval). 1/d is finite (rt_safe_dir), so the
