@@ -114,3 +114,96 @@ def test_gpu_final_scene_frame_with_box_leaves(monkeypatch):
             ctx.render(W, H, 16)
             frames.append(ctx.accum())
     np.testing.assert_array_equal(frames[0], frames[1])
+
+
+def _lattice_scene():
+    """a 4x3x4 lattice of boxes that TOUCH (coincident faces of neighbours: exact ties in t between rects of different
+    boxes and between the exit side of one box and the entry side of the next), plus two boxes nested exactly"""
+    from a_dive_into_ray_tracing_b200.ctypes_defs import MATERIAL_DT, QUAD_DT, Scene
+    mats = np.zeros(2, MATERIAL_DT)
+    mats["type"] = [D.RT_MAT_LAMBERTIAN, D.RT_MAT_METAL]
+    mats["albedo"] = [[0.7, 0.7, 0.7], [0.8, 0.6, 0.2]]
+    quads = []
+    for i in range(4):
+        for j in range(3):
+            for k in range(4):
+                p0 = (np.float32(i), np.float32(j), np.float32(k))
+                p1 = (np.float32(i + 1), np.float32(j + 1), np.float32(k + 1))
+                quads += scenes.box_as_quads(p0, p1, (i + j + k) & 1)
+    quads += scenes.box_as_quads((np.float32(1), np.float32(1), np.float32(1)), (np.float32(3), np.float32(2), np.float32(3)), 1)
+    quads += scenes.box_as_quads((np.float32(1), np.float32(1), np.float32(1)), (np.float32(3), np.float32(2), np.float32(3)), 0)
+    sc = Scene(quads=np.array(quads, QUAD_DT), materials=mats, background=(1, 1, 1), sky_gradient=0, t_min=1e-3,
+               profile=D.RT_PROFILE_NEXT_WEEK, name="lattice")
+    sc.camera = D.camera_from_lookat((2, 1.5, -6), (2, 1.5, 2), (0, 1, 0), 40.0, 1.0, 0.0, 10.0, dtype=np.float32)
+    return sc
+
+
+def _lattice_rays():
+    """axis-parallel rays ON the lattice planes and edges, diagonal rays through edges and corners, rays that start on a
+    shared face, and random ones"""
+    rng = np.random.default_rng(11)
+    rays = []
+    g = np.arange(0, 4.01, 0.5, dtype=np.float32)
+    for ax in range(3):
+        for u in g:
+            for v in g[:7]:
+                for s in (-1.0, 1.0):
+                    o = np.zeros(3, np.float32)
+                    d = np.zeros(3, np.float32)
+                    o[ax] = -2.0 if s > 0 else 6.0
+                    o[(ax + 1) % 3], o[(ax + 2) % 3] = u, v
+                    d[ax] = s
+                    rays.append(np.concatenate([o, [0.0], d, [0.0]]))
+    for _ in range(1500):  # through lattice points, in lattice directions
+        p = rng.integers(0, 5, 3).astype(np.float32)
+        d = rng.integers(-2, 3, 3).astype(np.float32)
+        if not d.any():
+            d[0] = 1
+        o = p - d * np.float32(rng.integers(1, 4))
+        rays.append(np.concatenate([o, [0.0], d, [0.0]]))
+    for _ in range(1500):  # starting on a shared face
+        o = np.array([rng.integers(0, 5), rng.random() * 3, rng.random() * 4], np.float32)
+        d = rng.normal(size=3).astype(np.float32)
+        rays.append(np.concatenate([o, [0.0], d, [0.0]]))
+    o = (rng.random((2000, 3)) * [6, 5, 6] - 1).astype(np.float32)
+    d = rng.normal(size=(2000, 3)).astype(np.float32)
+    rnd = np.concatenate([o, np.zeros((2000, 1), np.float32), d, np.zeros((2000, 1), np.float32)], axis=1)
+    return np.concatenate([np.array(rays, np.float32), rnd]).astype(np.float32)
+
+
+def test_box_sides_ties_and_edges_emulated(monkeypatch):
+    """the box leaf lets its six sides compete among themselves before the winner meets the running hit: on exact ties
+    (coincident faces, nested identical boxes) and on edges / corners that must still be the answer of six separate
+    rect leaves AND of the list-order brute force, bit for bit"""
+    sc, rays = _lattice_scene(), _lattice_rays()
+    out = {}
+    for on in ("0", "1"):
+        monkeypatch.setenv("B200RT_BOXES", on)
+        e = Emu(sc, max_leaf=1)
+        _, leaf, _ = e.accel()
+        ids, ts, _ = e.trace(rays, t_min=sc.t_min)
+        ib, tb, _ = e.trace(rays, t_min=sc.t_min, use_accel=0)
+        np.testing.assert_array_equal(ids, ib)
+        np.testing.assert_array_equal(ts, tb)
+        out[on] = (ids, ts, _types(leaf))
+    np.testing.assert_array_equal(out["0"][0], out["1"][0])
+    np.testing.assert_array_equal(out["0"][1], out["1"][1])
+    assert D.RT_PRIM_BOX in out["1"][2] and D.RT_PRIM_BOX not in out["0"][2]
+    assert (out["1"][0] >= 0).mean() > 0.5
+
+
+@pytest.mark.gpu
+def test_gpu_box_sides_ties_and_edges(monkeypatch):
+    sc, rays = _lattice_scene(), _lattice_rays()
+    res = []
+    for on in ("0", "1"):
+        monkeypatch.setenv("B200RT_BOXES", on)
+        with capi.Context(profile=2) as ctx:
+            ctx.upload(sc).build_accel(1)
+            ia, ta = ctx.trace_closest(rays, use_accel=1)
+            ib, tb = ctx.trace_closest(rays, use_accel=0)
+        np.testing.assert_array_equal(ia, ib)
+        np.testing.assert_array_equal(ta, tb)
+        res.append((ia, ta))
+    np.testing.assert_array_equal(res[0][0], res[1][0])
+    np.testing.assert_array_equal(res[0][1], res[1][1])
